@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the lift-and-query hot path (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic input of BASELINE config 2:
+  lift   8 frames of 240x320x32ch features into a 96x96x48 grid @ 4 cm  (voxel.frames/s)
+  query  1 Mi TSDF query points: trilinear sampler + ResNet-MLP decoder + TSDF head (points/s)
+`value` = TSDF query points per second over the whole step (lift included), inputs resident in
+HBM in the REFERENCE's layouts (NCHW feature maps: the NCHW->NHWC pass is inside the step).
+`e2e` = the same through the drop-in API with pinned HOST buffers (H2D of features/xyz and D2H
+of the TSDF inside the timed region).  `--impl reference` times the reference's CPU algorithm
+(the oracle port: same ATen CPU kernels the reference calls) on the host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from gennerf_b200 import synthetic as S   # noqa: E402
+
+VS = 0.04
+C_FEAT = 32
+MLP = dict(d_hidden=512, n_blocks=5, d_out=64, d_geo=32, num_freqs=2, freq_factor=0.5)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], bf16=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, bf16=1400.0, source="fallback")
+
+
+def flops_per_query(d_feat, d_code, d_hidden, n_blocks, d_out, d_geo):
+    return 2 * (d_feat * d_hidden + n_blocks * (d_code * d_hidden + 2 * d_hidden * d_hidden) + d_hidden * d_out + d_geo)
+
+
+def lift_bytes(T, C, H, W, V, n_valid):
+    """every input element once (or only the gathered ones if fewer), every output once."""
+    return min(T * C * H * W * 4, n_valid * C * 4) + V * C * 4 + V * 5 + T * 48
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        hi = [s for s in sm if s >= 0.5 * mx] or sm
+        return {"sm_mhz": hi[len(hi) // 2] if hi else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(rank, Q):
+    wl = S.WORKLOADS["cfg2"]
+    g = S.gen(1002 + rank)
+    P = S.projections(wl["T"], wl["H"], wl["W"], wl["voxel_dim"], VS, g).unsqueeze(0)
+    feats = S.frame_features(wl["T"], C_FEAT, wl["H"], wl["W"], g)
+    xyz = S.query_points(Q, wl["voxel_dim"], VS, g)
+    d_code = 3 + 6 * MLP["num_freqs"]
+    w, hw, hb = S.decoder_weights(g, C_FEAT, d_code, MLP["d_hidden"], MLP["n_blocks"], MLP["d_out"], MLP["d_geo"])
+    return wl, P, feats, xyz, (w, hw, hb)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_time(wl, P, feats, xyz, weights, sample_q, reps=1):
+    """seconds for lift (full size) and for `sample_q` queries, best of `reps`."""
+    from oracle import gennerf_oracle as O
+    w, hw, hb = weights
+    origin = torch.tensor([0, 0, 0]).view(1, 3)
+    t_lift = t_query = float("inf")
+    with torch.no_grad():
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            vol, valid, _ = O.encode_volume(wl["voxel_dim"], VS, origin, P, feats)
+            t1 = time.perf_counter()
+            # the reference answers a query list in chunks of 10 000 (model.py:769-777), re-normalising
+            # the volume inside every forward call (model.py:195-199)
+            for q0 in range(0, sample_q, 10000):
+                O.gennerf_forward(xyz[:, q0:min(sample_q, q0 + 10000)], w, hw, hb, volume=vol, valid=valid, voxel_size=VS,
+                                  num_freqs=MLP["num_freqs"], freq_factor=MLP["freq_factor"], n_blocks=MLP["n_blocks"],
+                                  d_out_geo=MLP["d_geo"], d_out_sem=MLP["d_out"] - MLP["d_geo"])
+            t2 = time.perf_counter()
+            t_lift, t_query = min(t_lift, t1 - t0), min(t_query, t2 - t1)
+    return t_lift, t_query
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    Q = 1 << 20
+    wl, P, feats, xyz, weights = make_inputs(0, Q)
+    sample_q = 20000
+    times = []
+    for i in range(args.warmup + args.steps):
+        tl, tq = cpu_step_time(wl, P, feats, xyz, weights, sample_q)
+        if i >= args.warmup:
+            times.append(tl + tq * (Q / sample_q))
+    t = sum(times) / len(times)
+    val = Q / t
+    line = {"impl": "reference", "metric": "tsdf_query_points_per_s", "value": val, "unit": "points/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(Q),
+            "cpu_baseline": {"value": val, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"lift at full size + {sample_q} of {Q} queries in the reference's 10k chunks, "
+                                       "query time scaled linearly to 1 Mi"},
+            "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def config_dict(Q):
+    wl = S.WORKLOADS["cfg2"]
+    return {"workload": "BASELINE config 2: volumetric encoder, 8 synthetic 240x320 frames x 32 ch -> 96x96x48 grid @4cm, "
+                        f"{Q} TSDF queries, sampler + ResNet-MLP decoder (d_hidden 512, 5 blocks, d_out 32+32)",
+            "frames": wl["T"], "image": [wl["H"], wl["W"]], "channels": C_FEAT, "grid": list(wl["voxel_dim"]),
+            "queries_per_gpu": Q, "l2": "256 MiB scratch written between timed steps (L2 flush)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch.distributed as dist
+    from gennerf_b200 import ops
+    from gennerf_b200._lib import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Q = 1 << 20
+    wl, P, feats_h, xyz_h, (w, hw, hb) = make_inputs(rank, Q)
+    origin = torch.tensor([0, 0, 0]).view(1, 3)
+    T, H, W = wl["T"], wl["H"], wl["W"]
+    V = wl["voxel_dim"][0] * wl["voxel_dim"][1] * wl["voxel_dim"][2]
+
+    feats = [f.to(dev) for f in feats_h]                    # reference layout: NCHW contiguous
+    xyz = xyz_h.to(dev)
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=MLP["n_blocks"], d_geo=MLP["d_geo"], use_code=True,
+                            num_freqs=MLP["num_freqs"], freq_factor=MLP["freq_factor"], device=dev)
+    precision = args.precision
+    if precision == "bf16":
+        try:
+            dw.pack()
+        except RuntimeError as e:
+            if args.strict:
+                raise
+            sys.stderr.write(f"[bench] bf16 tcgen05 decoder unavailable ({e}); timing the fp32 CUDA-core decoder\n")
+            precision = "fp32"
+    fused = precision == "bf16" and not args.unfused
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+
+    def step(record=None):
+        e = [ev() for _ in range(4)] if record is not None else None
+        if e: e[0].record()
+        vol, cnt, valid = ops.backproject_frames(wl["voxel_dim"], VS, origin, P, feats)
+        if e: e[1].record()
+        if fused:
+            out, tsdf, feat = ops.query_fused(dw, xyz, volume=vol, voxel_size=VS, origin=origin, want_feat=False)
+            if e: e[2].record()
+        else:
+            feat = ops.sample_features(xyz, volume=vol, voxel_size=VS, origin=origin)
+            if e: e[2].record()
+            out, tsdf = ops.decode(dw, xyz, feat, precision)
+        if e:
+            e[3].record()
+            record.append(e)
+        return vol, cnt, tsdf
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        vol, cnt, tsdf = step()
+        flush.fill_(1)
+    n_valid = int(cnt.sum().item())
+    barrier()
+    rec = []
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.fill_(1)                                  # L2 flush, outside the event pairs
+            step(rec)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    ms_lift = sum(e[0].elapsed_time(e[1]) for e in rec) / len(rec)
+    ms_samp = sum(e[1].elapsed_time(e[2]) for e in rec) / len(rec)
+    ms_dec = sum(e[2].elapsed_time(e[3]) for e in rec) / len(rec)
+    ms_step = sum(e[0].elapsed_time(e[3]) for e in rec) / len(rec)
+
+    # ---- end to end through the drop-in API with pinned host buffers ----------------------
+    feats_pin = [f.pin_memory() for f in feats_h]
+    xyz_pin = xyz_h.pin_memory()
+    tsdf_pin = torch.empty((1, Q, 1), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        fd = [f.to(dev, non_blocking=True) for f in feats_pin]
+        xd = xyz_pin.to(dev, non_blocking=True)
+        vol, cnt, valid = ops.backproject_frames(wl["voxel_dim"], VS, origin, P, fd)
+        if fused:
+            out, tsdf, _ = ops.query_fused(dw, xd, volume=vol, voxel_size=VS, origin=origin, want_feat=False)
+        else:
+            feat = ops.sample_features(xd, volume=vol, voxel_size=VS, origin=origin)
+            out, tsdf = ops.decode(dw, xd, feat, precision)
+        tsdf_pin.copy_(tsdf, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = ev(), ev()
+        a.record()
+        e2e_step()
+        b.record()
+        b.synchronize()
+        e2e_ms.append(a.elapsed_time(b))
+    barrier()
+    ms_e2e = sum(e2e_ms) / len(e2e_ms)
+
+    t = torch.tensor([ms_step, ms_e2e, ms_lift, ms_samp, ms_dec], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e, ms_lift, ms_samp, ms_dec = t.tolist()
+
+    if rank == 0:
+        pk = peaks()
+        d_code = 3 + 6 * MLP["num_freqs"]
+        fl = flops_per_query(C_FEAT, d_code, MLP["d_hidden"], MLP["n_blocks"], MLP["d_out"], MLP["d_geo"]) * Q
+        dec_ms = ms_dec if not fused else ms_samp
+        tf = fl / (dec_ms * 1e-3) / 1e12
+        lb = lift_bytes(T, C_FEAT, H, W, V, n_valid)
+        lift_gbs = lb / (ms_lift * 1e-3) / 1e9
+        line = {
+            "metric": "tsdf_query_points_per_s", "value": world * Q / (ms_step * 1e-3), "unit": "points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": dict(config_dict(Q), parallelism=f"replicas x{world} (queries and scenes sharded, no data-path collective)",
+                           decoder="bf16 tcgen05 fused sampler+MLP" if fused else f"{precision} sampler + decoder kernels"),
+            "roofline": {"kernel": "decoder", "bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
+                         "frac": tf / pk["bf16"], "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+                         "flops_per_launch": fl, "ms_per_launch": dec_ms},
+            "backprojection": {"metric": "voxel_frames_per_s", "value": world * V * T / (ms_lift * 1e-3), "ms": ms_lift,
+                               "includes": "NCHW->NHWC pass + fused lift kernel",
+                               "roofline": {"bound": "hbm", "achieved": lift_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                            "frac": lift_gbs / pk["hbm"], "algorithmic_bytes": lb}},
+            "breakdown_ms": {"lift": ms_lift, "sampler_or_fused_query": ms_samp, "decoder": ms_dec},
+            "e2e": {"value": world * Q / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": sum(f.numel() for f in feats_h) * 4 + xyz_h.numel() * 4,
+                    "d2h_bytes_per_step": Q * 4},
+            "gpu_launches": args.steps * (3 if fused else 4),
+            "clocks": clocks.summary(),
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu:
+            torch.set_num_threads(os.cpu_count() or 1)
+            sample_q = 20000
+            tl, tq = cpu_step_time(wl, P, feats_h, xyz_h, (w, hw, hb), sample_q)
+            line["cpu_baseline"] = {"value": Q / (tl + tq * (Q / sample_q)), "unit": "points/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "lift_voxel_frames_per_s": V * T / tl,
+                                    "sample": f"lift at full size + {sample_q} of {Q} queries in the reference's 10k chunks, "
+                                              "query time scaled linearly"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--unfused", action="store_true", help="separate sampler and decoder kernels")
+    ap.add_argument("--strict", action="store_true", help="fail instead of timing the fp32 decoder when bf16 is unavailable")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,339 @@
+// Fused volumetric back-projection ("lift") for sm_100a.
+//
+// Replaces, per scene and for all T frames in ONE pass over the voxels:
+//   coordinates()            reference src/data/tsdf.py:25-40       (never materialised)
+//   backproject()            reference src/models/utils.py:948-996
+//   accumulation in encode() reference src/models/model.py:121-127
+//   normalisation            reference src/models/model.py:195-199  (identity on the sum, trap T2)
+//
+// Data layout: features are channels-last (H,W,C): a voxel-frame reads one contiguous
+// C*4-byte run (one 128 B line at C=32).  G = min(32, C/4) lanes share a voxel, each lane one
+// float4.  A warp owns NVW consecutive voxels (consecutive z); lane i projects voxel i ONCE
+// per frame and the pixel offset is handed to the G lanes that fetch it with __shfl_sync, so
+// the projection arithmetic is not repeated per channel group.  Sums stay in registers over
+// the T frames (frame order == the reference's summation order => bit-exact) and are written
+// once with streaming stores.  HBM-bound: algorithmic bytes = features read once + volume
+// written once.
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace gnb {
+
+struct LiftKP {
+    const float* feat[GNB_MAX_FRAMES];   // per frame, this scene, NHWC
+    float P[GNB_MAX_FRAMES][12];
+    int T, H, W, C;
+    int nx, ny, nz;
+    long long V;
+    float vs, ox, oy, oz;
+    float* volume;
+    long long stride_v, stride_c;
+    int* count;
+    unsigned char* valid;
+    int accumulate, mean;
+};
+static_assert(sizeof(LiftKP) <= 4096, "kernel parameter block must stay below 4 KB");
+
+// Projection of one voxel by one 3x4 matrix with the reference's exact arithmetic
+// (SURVEY trap T3): torch.bmm(P, [w;1]) on the CPU is the FMA chain
+//   fma(P3, 1, fma(P2, wz, fma(P1, wy, P0*wx)));  px = rint(cx/cz) (round-half-even, T1).
+// Returns the pixel offset py*W+px, or -1 when the frame does not see the voxel.
+__device__ __forceinline__ int project_voxel(const float* __restrict__ P, float wx, float wy, float wz,
+                                             int H, int W, float* fx_out = nullptr, float* fy_out = nullptr) {
+    float cx = __fadd_rn(__fmaf_rn(P[2], wz, __fmaf_rn(P[1], wy, __fmul_rn(P[0], wx))), P[3]);
+    float cy = __fadd_rn(__fmaf_rn(P[6], wz, __fmaf_rn(P[5], wy, __fmul_rn(P[4], wx))), P[7]);
+    float cz = __fadd_rn(__fmaf_rn(P[10], wz, __fmaf_rn(P[9], wy, __fmul_rn(P[8], wx))), P[11]);
+    float fx = rintf(__fdiv_rn(cx, cz));
+    float fy = rintf(__fdiv_rn(cy, cz));
+    if (fx_out) { *fx_out = fx; *fy_out = fy; }
+    // float comparisons == the reference's int64 comparisons for every finite value; NaN/inf
+    // (cz == 0) compare false here and convert to INT64_MIN (invalid) there.
+    bool ok = (fx >= 0.0f) && (fy >= 0.0f) && (fx < (float)W) && (fy < (float)H) && (cz > 0.0f);
+    return ok ? (int)fy * W + (int)fx : -1;
+}
+
+__device__ __forceinline__ void voxel_world(long long v, int ny, int nz, float vs, float ox, float oy, float oz,
+                                            float& wx, float& wy, float& wz) {
+    int iz = (int)(v % nz);
+    long long r = v / nz;
+    int iy = (int)(r % ny);
+    int ix = (int)(r / ny);
+    // world = fl(i) * voxel_size + origin: two separately rounded operations (utils.py:974)
+    wx = __fadd_rn(__fmul_rn((float)ix, vs), ox);
+    wy = __fadd_rn(__fmul_rn((float)iy, vs), oy);
+    wz = __fadd_rn(__fmul_rn((float)iz, vs), oz);
+}
+
+// G lanes per voxel, VEC floats per lane (4: float4 path, needs C % 4 == 0; 1: scalar path).
+// grid.x = warps over voxels, grid.y = channel chunks of G*VEC.
+// CL: channels-last volume (stride_c == 1); otherwise the reference's (C,V) layout.
+template <int G, int VEC, bool CL>
+__global__ void __launch_bounds__(256) lift_kernel(const __grid_constant__ LiftKP p) {
+    constexpr int NVW = (256 / G) < 32 ? (256 / G) : 32;   // voxels per warp
+    constexpr int ITER = NVW * G / 32;                     // gathers per lane per frame
+    constexpr int VPI = 32 / G;                            // voxels per gather instruction
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long v0 = warp * NVW;
+    if (v0 >= p.V) return;
+    const int sub = lane % G;
+    const int c0 = (blockIdx.y * G + sub) * VEC;           // first channel of this lane
+    const bool c_ok = c0 < p.C;
+
+    // lane i (< NVW) owns voxel v0+i for the projection
+    const long long v_own = v0 + lane;
+    const bool own = (lane < NVW) && (v_own < p.V);
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (own) voxel_world(v_own, p.ny, p.nz, p.vs, p.ox, p.oy, p.oz, wx, wy, wz);
+
+    float acc[ITER][VEC];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < ITER; ++j) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[j][k] = 0.0f;
+    }
+    if (p.accumulate) {
+        if (own && p.count) cnt = p.count[v_own];
+#pragma unroll
+        for (int j = 0; j < ITER; ++j) {
+            long long v = v0 + j * VPI + lane / G;
+            if (v < p.V && c_ok) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[j][k] = p.volume[v * p.stride_v + (c0 + k) * p.stride_c];
+            }
+        }
+    }
+
+#pragma unroll 2
+    for (int t = 0; t < p.T; ++t) {
+        int off = -1;
+        if (own) off = project_voxel(p.P[t], wx, wy, wz, p.H, p.W);
+        cnt += (off >= 0);
+        if (__ballot_sync(FULL, off >= 0) == 0u) continue;          // warp-uniform
+        const float* __restrict__ f = p.feat[t];
+#pragma unroll
+        for (int j = 0; j < ITER; ++j) {
+            int o = __shfl_sync(FULL, off, j * VPI + lane / G);
+            if (o >= 0 && c_ok) {
+                const float* src = f + (long long)o * p.C + c0;
+                if constexpr (VEC == 4) {
+                    float4 x = ldg4(src);
+                    acc[j][0] = __fadd_rn(acc[j][0], x.x);
+                    acc[j][1] = __fadd_rn(acc[j][1], x.y);
+                    acc[j][2] = __fadd_rn(acc[j][2], x.z);
+                    acc[j][3] = __fadd_rn(acc[j][3], x.w);
+                } else {
+                    acc[j][0] = __fadd_rn(acc[j][0], __ldg(src));
+                }
+            }
+        }
+    }
+
+    if (p.mean) {
+#pragma unroll
+        for (int j = 0; j < ITER; ++j) {
+            int n = __shfl_sync(FULL, cnt, j * VPI + lane / G);
+            float d = (float)(n > 0 ? n : 1);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[j][k] = __fdiv_rn(acc[j][k], d);
+        }
+    }
+
+    // ---- write once ------------------------------------------------------------------
+    if (own && blockIdx.y == 0) {
+        if (p.count) p.count[v_own] = cnt;
+        if (p.valid) p.valid[v_own] = (unsigned char)(cnt > 0);
+    }
+    if constexpr (CL) {
+        // channels-last volume: the warp writes NVW * C*4 contiguous bytes
+#pragma unroll
+        for (int j = 0; j < ITER; ++j) {
+            long long v = v0 + j * VPI + lane / G;
+            if (v < p.V && c_ok) {
+                float* dst = p.volume + v * p.stride_v + c0;
+                if constexpr (VEC == 4) {
+                    stcs4(dst, make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+                } else {
+                    dst[0] = acc[j][0];
+                }
+            }
+        }
+    } else {
+        // reference layout (C,V): transpose the warp's NVW x (G*VEC) tile through shared memory
+        // so that every row of NVW voxels is written contiguously
+        constexpr int NC = G * VEC;
+        __shared__ float tile[8][NC][NVW + 1];
+        float(*tw)[NVW + 1] = tile[threadIdx.x >> 5];
+#pragma unroll
+        for (int j = 0; j < ITER; ++j) {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) tw[sub * VEC + k][j * VPI + lane / G] = acc[j][k];
+        }
+        __syncwarp();
+        const int cbase = blockIdx.y * NC;
+        for (int idx = lane; idx < NC * NVW; idx += 32) {
+            int c = idx / NVW, vv = idx % NVW;
+            if (cbase + c < p.C && v0 + vv < p.V)
+                p.volume[(v0 + vv) * p.stride_v + (long long)(cbase + c) * p.stride_c] = tw[c][vv];
+        }
+    }
+}
+
+// ---- NCHW -> NHWC ---------------------------------------------------------------------
+struct TransposeKP {
+    const float* src[GNB_MAX_FRAMES];
+    float* dst;
+    int T, B, C;
+    long long HW;
+};
+
+// One (b,t) image per blockIdx.z; 32 channels x 32 pixels tiles through shared memory.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant__ TransposeKP p) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z / p.B, b = blockIdx.z % p.B;
+    const float* __restrict__ src = p.src[t] + (long long)b * p.C * p.HW;
+    float* __restrict__ dst = p.dst + ((long long)t * p.B + b) * p.HW * p.C;
+    const long long px0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        int c = c0 + r;
+        long long px = px0 + tx;
+        tile[r][tx] = (c < p.C && px < p.HW) ? __ldg(src + (long long)c * p.HW + px) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        long long px = px0 + r;
+        int c = c0 + tx;
+        if (c < p.C && px < p.HW) dst[px * p.C + c] = tile[tx][r];
+    }
+}
+
+__global__ void project_indices_kernel(int nx, int ny, int nz, float vs, float ox, float oy, float oz,
+                                       const __grid_constant__ LiftKP p, int* px, int* py, unsigned char* valid) {
+    long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= p.V) return;
+    float wx, wy, wz, fx, fy;
+    voxel_world(v, ny, nz, vs, ox, oy, oz, wx, wy, wz);
+    int off = project_voxel(p.P[0], wx, wy, wz, p.H, p.W, &fx, &fy);
+    // (long) of a non-finite / out-of-range float is INT64_MIN on the CPU; report INT32_MIN
+    px[v] = (fabsf(fx) < 2147483520.0f) ? (int)fx : INT_MIN;
+    py[v] = (fabsf(fy) < 2147483520.0f) ? (int)fy : INT_MIN;
+    valid[v] = (unsigned char)(off >= 0);
+}
+
+template <int G, int VEC>
+static int launch_lift(const LiftKP& kp, int C, cudaStream_t st) {
+    constexpr int NVW = (256 / G) < 32 ? (256 / G) : 32;
+    long long warps = (kp.V + NVW - 1) / NVW;
+    dim3 grid((unsigned)((warps + 7) / 8), (unsigned)ceil_div(C, G * VEC));
+    if (kp.stride_c == 1)
+        lift_kernel<G, VEC, true><<<grid, 256, 0, st>>>(kp);
+    else
+        lift_kernel<G, VEC, false><<<grid, 256, 0, st>>>(kp);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int dispatch_lift(const LiftKP& kp, cudaStream_t st) {
+    const int C = kp.C;
+    if (C % 4 == 0) {
+        int g = C / 4;
+        if (g >= 32) return launch_lift<32, 4>(kp, C, st);
+        if (g > 8) return launch_lift<16, 4>(kp, C, st);
+        if (g > 4) return launch_lift<8, 4>(kp, C, st);
+        if (g > 2) return launch_lift<4, 4>(kp, C, st);
+        if (g > 1) return launch_lift<2, 4>(kp, C, st);
+        return launch_lift<1, 4>(kp, C, st);
+    }
+    if (C >= 32) return launch_lift<32, 1>(kp, C, st);
+    if (C > 8) return launch_lift<16, 1>(kp, C, st);
+    if (C > 4) return launch_lift<8, 1>(kp, C, st);
+    if (C > 2) return launch_lift<4, 1>(kp, C, st);
+    if (C > 1) return launch_lift<2, 1>(kp, C, st);
+    return launch_lift<1, 1>(kp, C, st);
+}
+
+}  // namespace gnb
+
+using namespace gnb;
+
+extern "C" int gnb_nchw_to_nhwc(const float* const* h_src, int n_frames, float* dst, int B, int C, int H, int W,
+                                void* stream) {
+    GNB_CHECK_ARG(h_src && dst, "gnb_nchw_to_nhwc: null pointer");
+    GNB_CHECK_ARG(n_frames >= 1 && n_frames <= GNB_MAX_FRAMES, "gnb_nchw_to_nhwc: n_frames %d not in [1,%d]", n_frames,
+                  GNB_MAX_FRAMES);
+    GNB_CHECK_ARG(B >= 1 && C >= 1 && H >= 1 && W >= 1, "gnb_nchw_to_nhwc: bad shape");
+    GNB_CHECK_ARG((long long)n_frames * B <= 65535, "gnb_nchw_to_nhwc: T*B too large");
+    TransposeKP kp;
+    for (int t = 0; t < n_frames; ++t) kp.src[t] = h_src[t];
+    kp.dst = dst;
+    kp.T = n_frames, kp.B = B, kp.C = C, kp.HW = (long long)H * W;
+    dim3 grid((unsigned)ceil_div(kp.HW, 32), (unsigned)ceil_div(C, 32), (unsigned)(n_frames * B));
+    nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kp);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_backproject_frames(const GnbLiftParams* p, void* stream) {
+    GNB_CHECK_ARG(p, "gnb_backproject_frames: null params");
+    GNB_CHECK_ARG(p->nx > 0 && p->ny > 0 && p->nz > 0, "gnb_backproject_frames: bad voxel grid %dx%dx%d", p->nx, p->ny, p->nz);
+    GNB_CHECK_ARG(p->n_frames >= 1 && p->n_frames <= GNB_MAX_FRAMES, "gnb_backproject_frames: n_frames %d not in [1,%d]",
+                  p->n_frames, GNB_MAX_FRAMES);
+    GNB_CHECK_ARG(p->batch >= 1 && p->C >= 1 && p->H >= 1 && p->W >= 1, "gnb_backproject_frames: bad feature shape");
+    GNB_CHECK_ARG((long long)p->H * p->W < INT_MAX, "gnb_backproject_frames: image too large");
+    GNB_CHECK_ARG(p->volume && p->h_projection, "gnb_backproject_frames: null volume/projection");
+    GNB_CHECK_ARG(p->feat_layout == GNB_LAYOUT_NHWC || p->feat_layout == GNB_LAYOUT_NCHW, "gnb_backproject_frames: bad layout");
+    for (int t = 0; t < p->n_frames; ++t) GNB_CHECK_ARG(p->features[t], "gnb_backproject_frames: features[%d] is null", t);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long V = (long long)p->nx * p->ny * p->nz;
+    const long long img = (long long)p->H * p->W * p->C;
+
+    const float* base[GNB_MAX_FRAMES];
+    long long frame_stride_b = img;       // elements between scenes inside one frame tensor
+    if (p->feat_layout == GNB_LAYOUT_NCHW) {
+        GNB_CHECK_ARG(p->scratch, "gnb_backproject_frames: NCHW features need a scratch buffer of T*B*H*W*C floats");
+        int rc = gnb_nchw_to_nhwc(p->features, p->n_frames, p->scratch, p->batch, p->C, p->H, p->W, stream);
+        if (rc) return rc;
+        for (int t = 0; t < p->n_frames; ++t) base[t] = p->scratch + (long long)t * p->batch * img;
+    } else {
+        for (int t = 0; t < p->n_frames; ++t) base[t] = p->features[t];
+    }
+    for (int b = 0; b < p->batch; ++b) {
+        LiftKP kp;
+        for (int t = 0; t < p->n_frames; ++t) {
+            kp.feat[t] = base[t] + (long long)b * frame_stride_b;
+            for (int k = 0; k < 12; ++k) kp.P[t][k] = p->h_projection[((long long)b * p->n_frames + t) * 12 + k];
+        }
+        kp.T = p->n_frames, kp.H = p->H, kp.W = p->W, kp.C = p->C;
+        kp.nx = p->nx, kp.ny = p->ny, kp.nz = p->nz, kp.V = V;
+        kp.vs = p->voxel_size, kp.ox = p->origin[0], kp.oy = p->origin[1], kp.oz = p->origin[2];
+        kp.volume = p->volume + (long long)b * p->vol_stride_b;
+        kp.stride_v = p->vol_stride_v, kp.stride_c = p->vol_stride_c;
+        kp.count = p->count ? p->count + (long long)b * V : nullptr;
+        kp.valid = p->valid ? p->valid + (long long)b * V : nullptr;
+        kp.accumulate = p->accumulate, kp.mean = p->mean;
+        int rc = dispatch_lift(kp, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int gnb_project_indices(int nx, int ny, int nz, float voxel_size, const float* h_origin3,
+                                   const float* h_projection12, int H, int W, int32_t* px, int32_t* py, uint8_t* valid,
+                                   void* stream) {
+    GNB_CHECK_ARG(nx > 0 && ny > 0 && nz > 0 && H > 0 && W > 0, "gnb_project_indices: bad shape");
+    GNB_CHECK_ARG(h_origin3 && h_projection12 && px && py && valid, "gnb_project_indices: null pointer");
+    LiftKP kp;
+    for (int k = 0; k < 12; ++k) kp.P[0][k] = h_projection12[k];
+    kp.T = 1, kp.H = H, kp.W = W, kp.C = 1;
+    kp.V = (long long)nx * ny * nz;
+    project_indices_kernel<<<ceil_div(kp.V, 256), 256, 0, (cudaStream_t)stream>>>(
+        nx, ny, nz, voxel_size, h_origin3[0], h_origin3[1], h_origin3[2], kp, px, py, valid);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}

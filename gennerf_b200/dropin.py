@@ -1,0 +1,415 @@
+"""Drop-in host layer: the reference's functions and modules for the lift-and-query path,
+same names, argument meaning, return layouts and state_dict keys, computed by the sm_100a
+kernels.  A maintainer swaps imports; configs/model/*.yaml load
+unchanged.
+
+    from gennerf_b200.dropin import backproject, trilinear_interpolation, \
+        normalize_coordinate, coordinate2index            # was: src.models.utils
+    from gennerf_b200.dropin import LocalPoolPointnet      # was: src.models.components.pointnet
+    from gennerf_b200.dropin import ResnetFC, PositionalEncoding, TSDFHeadSimple
+    from gennerf_b200.dropin import GenNerf                # hot-path methods of src.models.model
+
+CUDA tensors only.  Nothing here falls back to PyTorch arithmetic for the hot ops: the
+small per-point nn.Linear layers of the PointNet and the optional U-Net stay PyTorch, as
+SURVEY section 2 scopes them.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+
+PLANE_AXES = {"xz": [0, 2], "xy": [0, 1], "yz": [1, 2]}
+_PLANE_ID = {"xz": 0, "xy": 1, "yz": 2}
+
+
+# ------------------------------------------------------------------------------------------
+# functions of src/models/utils.py
+# ------------------------------------------------------------------------------------------
+def backproject(voxel_dim, voxel_size, origin, projection, features):
+    """reference src/models/utils.py:948-996 (per-frame shim over the fused kernel).
+    projection (B,3,4), features (B,C,H,W) -> volume (B,C,nx,ny,nz), valid (B,1,nx,ny,nz) bool."""
+    B = features.size(0)
+    volume, _, valid = ops.backproject_frames(voxel_dim, voxel_size, origin, projection.reshape(B, 1, 3, 4), [features])
+    return volume, valid
+
+
+def trilinear_interpolation(voxel_volume, xyz, origin, voxel_size, mode="bilinear"):
+    """reference src/models/utils.py:999-1042.  voxel_volume (B,nx,ny,nz,C) (any strides; the
+    permuted view of a channels-last volume is read in place), xyz (B,N,3) -> (B,N,C)."""
+    if mode != "bilinear":
+        raise NotImplementedError("gennerf_b200: only mode='bilinear' (the reference's default) is built")
+    vol = voxel_volume.permute(0, 4, 1, 2, 3)
+    return ops.sample_features(xyz, volume=vol, voxel_size=voxel_size, origin=origin)
+
+
+def normalize_coordinate(p, padding=0.1, plane="xz", encode=True):
+    """reference src/models/utils.py:75-98: (B,N,3) -> (B,N,2) in [0, 1-1e-5]."""
+    coord, _ = ops.plane_coords(p, padding, 1)
+    return coord[_PLANE_ID.get(plane, 2)]
+
+
+def coordinate2index(x, reso, coord_type="2d"):
+    """reference src/models/utils.py:57-72 ('2d' only): (B,N,2) in [0,1) -> int64 (B,1,N).
+    Integer arithmetic on an already-normalised tensor; kept as a thin torch expression
+    because the kernels compute the index together with the normalisation (plane_coords)."""
+    if coord_type != "2d":
+        raise NotImplementedError("gennerf_b200: grid ('3d') features are dead code in the reference config")
+    xi = (x * reso).long()
+    return (xi[:, :, 0] + reso * xi[:, :, 1])[:, None, :]
+
+
+# ------------------------------------------------------------------------------------------
+# src/models/components/positional_encoding.py
+# ------------------------------------------------------------------------------------------
+class PositionalEncoding(nn.Module):
+    def __init__(self, num_freqs=6, d_in=3, freq_factor=np.pi, include_input=True):
+        super().__init__()
+        if d_in != 3:
+            raise NotImplementedError("gennerf_b200: positional encoding of 3-D points only")
+        self.num_freqs, self.d_in, self.freq_factor, self.include_input = num_freqs, d_in, freq_factor, include_input
+        self.freqs = freq_factor * 2.0 ** torch.arange(0, num_freqs)
+        self.d_out = self.num_freqs * 2 * d_in + (d_in if include_input else 0)
+        # same (non-parameter) buffers as the reference, so state_dicts line up
+        self.register_buffer("_freqs", torch.repeat_interleave(self.freqs, 2).view(1, -1, 1))
+        _phases = torch.zeros(2 * self.num_freqs)
+        _phases[1::2] = np.pi * 0.5
+        self.register_buffer("_phases", _phases.view(1, -1, 1))
+
+    def forward(self, x):
+        return ops.positional_encoding(x, self.num_freqs, self.freq_factor, self.include_input)
+
+    @classmethod
+    def from_conf(cls, cfg, d_in=3):
+        return cls(cfg.num_freqs, d_in, cfg.freq_factor, cfg.include_input)
+
+
+# ------------------------------------------------------------------------------------------
+# src/models/components/resnetfc.py
+# ------------------------------------------------------------------------------------------
+class ResnetBlockFC(nn.Module):
+    """Parameter holder with the reference's names and initialisation (resnetfc.py:10-52)."""
+
+    def __init__(self, size_in, size_out=None, size_h=None, beta=0.0):
+        super().__init__()
+        size_out = size_in if size_out is None else size_out
+        size_h = min(size_in, size_out) if size_h is None else size_h
+        if size_in != size_out or size_h != size_in:
+            raise NotImplementedError("gennerf_b200: square ResNet blocks only (the reference decoder's)")
+        self.size_in, self.size_h, self.size_out = size_in, size_h, size_out
+        self.fc_0 = nn.Linear(size_in, size_h)
+        self.fc_1 = nn.Linear(size_h, size_out)
+        nn.init.constant_(self.fc_0.bias, 0.0)
+        nn.init.kaiming_normal_(self.fc_0.weight, a=0, mode="fan_in")
+        nn.init.constant_(self.fc_1.bias, 0.0)
+        nn.init.zeros_(self.fc_1.weight)
+        self.shortcut = None
+
+
+class ResnetFC(nn.Module):
+    def __init__(self, d_in, d_out=4, n_blocks=5, d_latent=0, d_hidden=128, beta=0.0, combine_layer=1000,
+                 combine_type="average", use_spade=False, use_layer_norm=False, alpha=1.0):
+        super().__init__()
+        if beta > 0 or use_spade or use_layer_norm or combine_layer < n_blocks or d_in <= 0 or d_latent <= 0:
+            raise NotImplementedError("gennerf_b200: only the reference's default decoder options are built "
+                                      "(ReLU, no spade / layer norm, combine_layer > n_blocks, d_in > 0, d_latent > 0)")
+        self.lin_in = nn.Linear(d_in, d_hidden)
+        nn.init.constant_(self.lin_in.bias, 0.0)
+        nn.init.kaiming_normal_(self.lin_in.weight, a=0, mode="fan_in")
+        self.lin_out = nn.Linear(d_hidden, d_out)
+        nn.init.constant_(self.lin_out.bias, 0.0)
+        nn.init.kaiming_normal_(self.lin_out.weight, a=0, mode="fan_in")
+        self.n_blocks, self.d_latent, self.d_in, self.d_out, self.d_hidden = n_blocks, d_latent, d_in, d_out, d_hidden
+        self.combine_layer, self.combine_type = combine_layer, combine_type
+        self.use_spade, self.use_layer_norm = use_spade, use_layer_norm
+        self.blocks = nn.ModuleList([ResnetBlockFC(d_hidden, beta=beta) for _ in range(n_blocks)])
+        n_lin_z = min(combine_layer, n_blocks)
+        self.lin_z = nn.ModuleList([nn.Linear(d_latent, d_hidden) for _ in range(n_lin_z)])
+        for i in range(n_lin_z):
+            nn.init.constant_(self.lin_z[i].bias, 0.0)
+            nn.init.kaiming_normal_(self.lin_z[i].weight, a=0, mode="fan_in")
+        self.activation = nn.ReLU()
+        self.alpha = nn.Parameter(torch.tensor(alpha))
+        self._dw = None
+
+    def device_weights(self, head=None, code=None, precision="fp32"):
+        """ops.DecoderWeights over the CURRENT parameter tensors (rebuilt on every call while
+        training; cache it yourself for inference)."""
+        sd = {k: v for k, v in self.state_dict().items()}
+        dev = self.lin_in.weight.device
+        if head is None:
+            hw, hb, d_geo = torch.zeros(1, 1, device=dev), torch.zeros(1, device=dev), 1
+        else:
+            hw, hb, d_geo = head.fc.weight, head.fc.bias, head.fc.weight.shape[1]
+        if code is None:
+            kw = dict(use_code=2, num_freqs=0, freq_factor=0.0, include_input=False, d_code=self.d_latent)
+        else:
+            kw = dict(use_code=1, num_freqs=code.num_freqs, freq_factor=code.freq_factor, include_input=code.include_input)
+        dw = ops.DecoderWeights(sd, hw, hb, n_blocks=self.n_blocks, d_geo=d_geo, device=dev, **kw)
+        if precision == "bf16":
+            dw.pack()
+        return dw
+
+    def forward(self, zx, combine_inner_dims=(1,), combine_index=None, dim_size=None, ret_last_feat=False,
+                precision="fp32"):
+        """reference resnetfc.py:134-189: zx (..., d_latent + d_in) -> (..., d_out)."""
+        if ret_last_feat:
+            raise NotImplementedError("gennerf_b200: ret_last_feat is not used on the path")
+        assert zx.size(-1) == self.d_latent + self.d_in
+        z, x = zx[..., : self.d_latent], zx[..., self.d_latent:]
+        dw = self.device_weights(precision=precision)
+        out, _ = _decode_given_code(dw, z, x, precision)
+        return out
+
+    @classmethod
+    def from_conf(cls, cfg, d_in, d_latent):
+        return cls(d_in=d_in, d_out=cfg.d_out_geo + cfg.d_out_sem, n_blocks=cfg.n_blocks, d_latent=d_latent,
+                   d_hidden=cfg.d_hidden, beta=cfg.beta, combine_layer=cfg.combine_layer, combine_type=cfg.combine_type,
+                   use_spade=cfg.use_spade, use_layer_norm=cfg.use_layer_norm, alpha=cfg.alpha)
+
+
+def _decode_given_code(dw, z, x, precision):
+    """decode with use_code=2: the `xyz` slot of the C ABI carries the (n, d_code) codes."""
+    import ctypes as C
+
+    from ._lib import check, lib
+    lead = z.shape[:-1]
+    z2 = z.float().reshape(-1, z.shape[-1]).contiguous()
+    x2 = x.float().reshape(-1, x.shape[-1]).contiguous()
+    n = z2.shape[0]
+    out = torch.empty((n, dw.w.d_out), device=z.device, dtype=torch.float32)
+    with torch.cuda.device(z.device):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if precision == "fp32":
+            check(lib().gnb_decode_fp32(C.byref(dw.w), z2.data_ptr(), x2.data_ptr(), n, out.data_ptr(), None, st),
+                  "gnb_decode_fp32")
+        else:
+            packed = dw.packed if dw.packed is not None else dw.pack()
+            check(lib().gnb_decode_bf16(C.byref(dw.w), packed.data_ptr(), z2.data_ptr(), x2.data_ptr(), n, out.data_ptr(),
+                                        None, st), "gnb_decode_bf16")
+    return out.reshape(*lead, -1), None
+
+
+# ------------------------------------------------------------------------------------------
+# src/models/components/heads3d.py
+# ------------------------------------------------------------------------------------------
+class TSDFHeadSimple(nn.Module):
+    def __init__(self, input_dim):
+        super().__init__()
+        self.fc = nn.Linear(input_dim, 1)
+        nn.init.xavier_uniform_(self.fc.weight, gain=nn.init.calculate_gain("tanh"))
+        nn.init.zeros_(self.fc.bias)
+
+    def forward(self, x):
+        return ops.tsdf_head(x, self.fc.weight, self.fc.bias)
+
+
+# ------------------------------------------------------------------------------------------
+# src/models/components/pointnet.py
+# ------------------------------------------------------------------------------------------
+class _PointBlockFC(nn.Module):
+    """src/models/components/layers.py:7-49 (hidden 32 linears; stays PyTorch)."""
+
+    def __init__(self, size_in, size_out=None, size_h=None):
+        super().__init__()
+        size_out = size_in if size_out is None else size_out
+        size_h = min(size_in, size_out) if size_h is None else size_h
+        self.size_in, self.size_h, self.size_out = size_in, size_h, size_out
+        self.fc_0 = nn.Linear(size_in, size_h)
+        self.fc_1 = nn.Linear(size_h, size_out)
+        self.actvn = nn.ReLU()
+        self.shortcut = None if size_in == size_out else nn.Linear(size_in, size_out, bias=False)
+        nn.init.zeros_(self.fc_1.weight)
+
+    def forward(self, x):
+        net = self.fc_0(self.actvn(x))
+        dx = self.fc_1(self.actvn(net))
+        return (x if self.shortcut is None else self.shortcut(x)) + dx
+
+
+class LocalPoolPointnet(nn.Module):
+    """reference src/models/components/pointnet.py:13-189.  The scatter_mean onto planes and the
+    scatter-max/gather local pooling run on the sm_100a kernels; `unet` (a user-supplied
+    nn.Module applied to every plane, reference pointnet.py:85-87) stays PyTorch."""
+
+    def __init__(self, c_dim=128, dim=3, hidden_dim=128, scatter_type="max", unet=None, unet_kwargs=None,
+                 unet3d=False, unet3d_kwargs=None, plane_resolution=None, grid_resolution=None, plane_type="xz",
+                 padding=0.1, n_blocks=5, scatter_mode="atomic"):
+        super().__init__()
+        if scatter_type not in ("max", "mean"):
+            raise ValueError("incorrect scatter type")
+        if "grid" in plane_type:
+            raise NotImplementedError("gennerf_b200: 'grid' features are not on the path")
+        self.c_dim, self.hidden_dim = c_dim, hidden_dim
+        self.fc_pos = nn.Linear(dim, 2 * hidden_dim)
+        self.blocks = nn.ModuleList([_PointBlockFC(2 * hidden_dim, hidden_dim) for _ in range(n_blocks)])
+        self.fc_c = nn.Linear(hidden_dim, c_dim)
+        self.actvn = nn.ReLU()
+        self.unet = unet if isinstance(unet, nn.Module) else None
+        self.unet3d = None
+        self.reso_plane, self.reso_grid = plane_resolution, grid_resolution
+        self.plane_type = [plane_type] if isinstance(plane_type, str) else list(plane_type)
+        self.padding = padding
+        self.scatter_type = scatter_type
+        self.scatter_mode = scatter_mode            # 'atomic' | 'deterministic' (extra knob, default = fast)
+
+    def generate_plane_features(self, p, c, plane="xz"):
+        """reference pointnet.py:72-89 for one plane (the kernel computes all three)."""
+        planes, _ = ops.scatter_mean_planes(p, c, self.reso_plane, self.padding, self.scatter_mode)
+        fea = planes[_PLANE_ID[plane]]
+        return self.unet(fea) if self.unet is not None else fea
+
+    def pool_local(self, xy, index, c):
+        """reference pointnet.py:105-121.  `xy`/`index` are accepted for signature parity; the
+        kernel recomputes the cells from the points stored by forward()."""
+        return ops.pool_local(self._p, c, self.reso_plane, self.padding, self.scatter_type)
+
+    def forward(self, p):
+        """reference pointnet.py:124-171: p (B,N,3) -> {'xz','xy','yz': (B,c_dim,R,R)}."""
+        self._p = p
+        net = self.fc_pos(p)
+        net = self.blocks[0](net)
+        for block in self.blocks[1:]:
+            pooled = self.pool_local(None, None, net)
+            net = block(torch.cat([net, pooled], dim=2))
+        c = self.fc_c(net)
+        planes, _ = ops.scatter_mean_planes(p, c, self.reso_plane, self.padding, self.scatter_mode)
+        fea = {}
+        for name in ("xz", "xy", "yz"):                           # reference key order (:164-169)
+            if name in self.plane_type:
+                f = planes[_PLANE_ID[name]]
+                fea[name] = self.unet(f) if self.unet is not None else f
+        return fea
+
+    @classmethod
+    def from_conf(cls, cfg, unet=None):
+        return cls(c_dim=cfg.c_dim, dim=cfg.dim, hidden_dim=cfg.hidden_dim, scatter_type=cfg.scatter_type, unet=unet,
+                   plane_resolution=cfg.plane_resolution, plane_type=cfg.plane_type, padding=cfg.padding,
+                   n_blocks=cfg.n_blocks)
+
+
+class FeaturePlaneMerger(nn.Module):
+    """reference src/models/components/plane_merger.py (adjacent, one elementwise op; PyTorch)."""
+
+    def __init__(self, strategy="average", alpha=0.5, c_dim=None):
+        super().__init__()
+        if strategy == "learn":
+            self.conv = nn.Conv2d(c_dim * 2, c_dim, kernel_size=1)
+        self.alpha, self.strategy = alpha, strategy
+
+    def forward(self, plane_1, plane_2):
+        if self.strategy == "average":
+            return {k: self.alpha * plane_1[k] + (1 - self.alpha) * plane_2[k] for k in plane_1}
+        if self.strategy == "learn":
+            return {k: self.conv(torch.cat([plane_1[k], plane_2[k]], dim=1)) for k in plane_1}
+        raise NotImplementedError(f"Feature plane merge strategy: {self.strategy}")
+
+    @classmethod
+    def from_conf(cls, cfg, c_dim=None):
+        return cls(cfg.strategy, cfg.alpha, c_dim)
+
+
+# ------------------------------------------------------------------------------------------
+# src/models/model.py -- the hot-path methods of GenNerf
+# ------------------------------------------------------------------------------------------
+class GenNerf(nn.Module):
+    """Encoder/decoder interface of the reference's GenNerf (model.py:25-248) on the B200 path.
+
+    Same cfg keys, submodule names (spatial, pointnet, merger, code, mlp, head_geo) and
+    attributes (.volume, .valid, .c_plane).  The 2D CNN (`spatial`) and the FPS front end are
+    outside the path: pass the CNN as `spatial=` (any nn.Module image -> (B,C,H,W)) and the
+    sparse point cloud through `encode(..., sparse_xyz=)`; Lightning orchestration, losses and
+    logging stay in the reference.  `precision`: 'bf16' (tcgen05 decoder, default for
+    inference) or 'fp32' (CUDA-core decoder, 1e-5 parity).
+    """
+
+    def __init__(self, cfg, spatial=None, unet=None, precision="bf16", fused=True):
+        super().__init__()
+        self.cfg = cfg
+        self.precision, self.fused = precision, fused
+        encoder_latent = 0
+        if cfg.encoder.use_spatial:
+            self.spatial = spatial
+            encoder_latent += [0, 64, 128, 256, 512, 1024][cfg.encoder.spatial.num_layers] \
+                if getattr(cfg.encoder.spatial, "latent_size", None) is None else cfg.encoder.spatial.latent_size
+        if cfg.encoder.use_pointnet:
+            self.pointnet = LocalPoolPointnet.from_conf(cfg.encoder.pointnet, unet=unet)
+            self.merger = FeaturePlaneMerger.from_conf(cfg.encoder.plane_merger, c_dim=cfg.encoder.pointnet.c_dim)
+            encoder_latent += cfg.encoder.pointnet.c_dim
+        d_in = 3
+        if cfg.use_code:
+            self.code = PositionalEncoding.from_conf(cfg.code, d_in=d_in)
+            d_in = self.code.d_out
+        self.mlp = ResnetFC.from_conf(cfg.mlp, d_in=encoder_latent, d_latent=d_in)
+        self.head_geo = TSDFHeadSimple(cfg.mlp.d_out_geo)
+        self.origin = torch.tensor([0, 0, 0]).view(1, 3)
+        self.voxel_sizes = [int(cfg.voxel_size * 100)]
+        self._dw = None
+        self.initialize_volume()
+
+    @property
+    def device(self):
+        return self.mlp.lin_in.weight.device
+
+    def initialize_volume(self):
+        self.volume = None
+        self.valid = None
+        self.count = None
+        self.c_plane = None
+
+    def refresh_weights(self):
+        """Re-read the decoder parameters (call after an optimiser step / load_state_dict)."""
+        self._dw = self.mlp.device_weights(head=self.head_geo, code=self.code if self.cfg.use_code else None,
+                                           precision=self.precision)
+        if not self.cfg.use_code:
+            self._dw.w.use_code, self._dw.w.d_code = 0, 3
+        return self._dw
+
+    def encode(self, projection, image, depth=None, mode="val", sparse_xyz=None):
+        """reference model.py:77-150.  projection (B,T,3,4), image (B,T,3,H,W) (or (B,T,C,H,W)
+        feature maps when no `spatial` CNN is attached).  All T frames are lifted by ONE fused
+        kernel; repeated calls keep accumulating, as in the reference."""
+        T = projection.size(1)
+        if self.cfg.encoder.use_spatial:
+            feats = []
+            for t in range(T):
+                img = image[:, t]
+                feats.append(self.spatial(img) if self.spatial is not None else img)
+            voxel_dim = self.cfg.voxel_dim_train if self.training else self.cfg.voxel_dim_val
+            out = None if self.volume is None else (self.volume, self.count, self.valid)
+            self.volume, self.count, self.valid = ops.backproject_frames(
+                voxel_dim, self.cfg.voxel_size, self.origin, projection, feats, out=out)
+        if self.cfg.encoder.use_pointnet:
+            if sparse_xyz is None:
+                raise NotImplementedError("gennerf_b200: pass the FPS point cloud as sparse_xyz= "
+                                          "(get_3d_points + farthest_point_sample are a 'next' row, SURVEY 8f-1)")
+            c_plane_new = self.pointnet(sparse_xyz)
+            self.c_plane = c_plane_new if self.c_plane is None else self.merger(c_plane_new, self.c_plane)
+
+    def sample_plane_feature(self, p, c, plane="xz"):
+        """reference model.py:153-161: (B,Q,3), (B,C_p,R,R) -> (B,C_p,Q)."""
+        out = ops.sample_features(p, planes={plane: c}, padding=self.cfg.encoder.pointnet.padding)
+        return out.transpose(1, 2)
+
+    def map_features(self, xyz):
+        """reference model.py:163-204: (B,Q,3) -> (B,Q,C_p + C), one kernel."""
+        return ops.sample_features(
+            xyz, volume=self.volume if self.cfg.encoder.use_spatial else None,
+            planes=self.c_plane if self.cfg.encoder.use_pointnet else None,
+            voxel_size=self.cfg.voxel_size, origin=self.origin,
+            padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1)
+
+    def forward(self, xyz):
+        """reference model.py:207-248: dict feat_geo, feat_sem, tsdf, feat."""
+        d_geo, d_sem = self.cfg.mlp.d_out_geo, self.cfg.mlp.d_out_sem
+        dw = self._dw if (self._dw is not None and not self.training) else self.refresh_weights()
+        if self.precision == "bf16" and self.fused:
+            out, tsdf, feat = ops.query_fused(
+                dw, xyz, volume=self.volume if self.cfg.encoder.use_spatial else None,
+                planes=self.c_plane if self.cfg.encoder.use_pointnet else None,
+                voxel_size=self.cfg.voxel_size, origin=self.origin,
+                padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1)
+        else:
+            feat = self.map_features(xyz)
+            out, tsdf = ops.decode(dw, xyz, feat, self.precision)
+        return {"feat_geo": out[..., :d_geo], "feat_sem": out[..., d_geo:d_geo + d_sem], "tsdf": tsdf, "feat": feat}

@@ -1,0 +1,387 @@
+"""Torch-facing operator layer over the C ABI (include/gennerf_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation below is a
+hand-written sm_100a kernel reached through ctypes with raw device pointers and the
+current CUDA stream.  CUDA tensors only -- no CPU path exists.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GnbDecoderWeights, GnbLiftParams, GnbSampleParams, check, lib
+
+PLANES = ("xz", "xy", "yz")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gennerf_b200 ops take CUDA tensors only (there is no CPU fallback)")
+
+
+def _f32(t):
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def _origin3(origin):
+    if origin is None:
+        return [0.0, 0.0, 0.0]
+    if torch.is_tensor(origin):
+        return [float(v) for v in origin.reshape(-1).tolist()]
+    return [float(v) for v in origin]
+
+
+# ------------------------------------------------------------------------------------------
+# lift
+# ------------------------------------------------------------------------------------------
+def backproject_frames(voxel_dim, voxel_size, origin, projections, features, *, mean=False,
+                       volume_layout="channels_last", out=None):
+    """Fused back-projection of T frames (reference utils.py:948 + model.py:121-127,195-199).
+
+    projections: (B,T,3,4) (CPU or CUDA; a CUDA tensor costs one small D2H copy);
+    features: sequence of T CUDA tensors (B,C,H,W), NCHW-contiguous (reference layout,
+    transposed on the fly) or channels_last (zero-copy).
+    Returns volume (B,C,nx,ny,nz) [channels_last_3d strides unless volume_layout='reference'],
+    count (B,nx,ny,nz) int32, valid (B,1,nx,ny,nz) bool.  volume == the reference's
+    accumulated self.volume (a SUM, bit-exact); mean=True divides by count instead.
+    `out=(volume, count, valid)` accumulates further frames into earlier results.
+    """
+    nx, ny, nz = (int(d) for d in voxel_dim)
+    feats = [_f32(f) for f in features]
+    _need_cuda(*feats)
+    T = len(feats)
+    B, Cc, H, W = feats[0].shape
+    P = torch.as_tensor(projections).detach().to("cpu", torch.float32).reshape(-1, T, 3, 4).contiguous()
+    if P.shape[0] != B:
+        raise RuntimeError(f"projections batch {P.shape[0]} != features batch {B}")
+    dev = feats[0].device
+    V = nx * ny * nz
+    if out is None:
+        if volume_layout == "channels_last":
+            vol_store = torch.empty((B, nx, ny, nz, Cc), device=dev, dtype=torch.float32)
+            volume = vol_store.permute(0, 4, 1, 2, 3)
+        elif volume_layout == "reference":
+            volume = torch.empty((B, Cc, nx, ny, nz), device=dev, dtype=torch.float32)
+        else:
+            raise ValueError(volume_layout)
+        count = torch.empty((B, nx, ny, nz), device=dev, dtype=torch.int32)
+        valid = torch.empty((B, 1, nx, ny, nz), device=dev, dtype=torch.bool)
+        accumulate = False
+    else:
+        volume, count, valid = out
+        accumulate = True
+    sb, sc, sx, sy, sz = volume.stride()
+    if not (sz * nz == sy and sy * ny == sx):
+        raise RuntimeError("volume must be dense over (nx,ny,nz)")
+    # channels_last (NHWC) feature maps are consumed in place; anything else is made NCHW-contiguous
+    # (the reference's layout) and transposed by the library
+    nhwc = all(f.is_contiguous(memory_format=torch.channels_last) and not f.is_contiguous() for f in feats)
+    if not nhwc:
+        feats = [f.contiguous() for f in feats]
+    with torch.cuda.device(dev):
+        for t0 in range(0, T, _lib.GNB_MAX_FRAMES):
+            chunk = feats[t0:t0 + _lib.GNB_MAX_FRAMES]
+            n = len(chunk)
+            p = GnbLiftParams()
+            p.nx, p.ny, p.nz = nx, ny, nz
+            p.voxel_size = float(voxel_size)
+            p.origin[:] = _origin3(origin)
+            p.batch, p.n_frames, p.C, p.H, p.W = B, n, Cc, H, W
+            p.feat_layout = _lib.LAYOUT_NHWC if nhwc else _lib.LAYOUT_NCHW
+            for i, f in enumerate(chunk):
+                p.features[i] = f.data_ptr()
+            Pc = P[:, t0:t0 + n].contiguous()
+            p.h_projection = Pc.data_ptr()
+            scratch = None
+            if not nhwc:
+                scratch = torch.empty(n * B * H * W * Cc, device=dev, dtype=torch.float32)
+                p.scratch = scratch.data_ptr()
+            p.volume = volume.data_ptr()
+            p.vol_stride_b, p.vol_stride_v, p.vol_stride_c = sb, sz, sc
+            p.count, p.valid = count.data_ptr(), valid.data_ptr()
+            p.accumulate = int(accumulate or t0 > 0)
+            p.mean = int(bool(mean) and t0 + n >= T)
+            check(lib().gnb_backproject_frames(C.byref(p), _stream()), "gnb_backproject_frames")
+    return volume, count, valid
+
+
+def project_indices(voxel_dim, voxel_size, origin, projection, H, W, device="cuda"):
+    """px, py (int32 (V,)), valid (bool (V,)) for ONE 3x4 projection: the integer part of the
+    reference's backproject (utils.py:979-985), for bit-exact parity tests."""
+    nx, ny, nz = (int(d) for d in voxel_dim)
+    V = nx * ny * nz
+    px = torch.empty(V, device=device, dtype=torch.int32)
+    py = torch.empty(V, device=device, dtype=torch.int32)
+    valid = torch.empty(V, device=device, dtype=torch.bool)
+    o = (C.c_float * 3)(*_origin3(origin))
+    P = (C.c_float * 12)(*[float(v) for v in torch.as_tensor(projection).reshape(-1).tolist()])
+    with torch.cuda.device(px.device):
+        check(lib().gnb_project_indices(nx, ny, nz, float(voxel_size), o, P, int(H), int(W), px.data_ptr(),
+                                        py.data_ptr(), valid.data_ptr(), _stream()), "gnb_project_indices")
+    return px, py, valid
+
+
+def nchw_to_nhwc(frames):
+    """T tensors (B,C,H,W) contiguous -> one (T,B,H,W,C) tensor (layout helper)."""
+    frames = [_f32(f).contiguous() for f in frames]
+    _need_cuda(*frames)
+    B, Cc, H, W = frames[0].shape
+    dst = torch.empty((len(frames), B, H, W, Cc), device=frames[0].device, dtype=torch.float32)
+    ptrs = (C.c_void_p * len(frames))(*[f.data_ptr() for f in frames])
+    with torch.cuda.device(dst.device):
+        check(lib().gnb_nchw_to_nhwc(ptrs, len(frames), dst.data_ptr(), B, Cc, H, W, _stream()), "gnb_nchw_to_nhwc")
+    return dst
+
+
+# ------------------------------------------------------------------------------------------
+# sampler
+# ------------------------------------------------------------------------------------------
+def _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding):
+    """volume: (B,C,nx,ny,nz) logical, any strides.  planes: dict name -> (B,C_p,R,R) logical,
+    any (common) strides, or None.  Returns (params, keepalive, B, Q, C_p, C)."""
+    _need_cuda(xyz, volume)
+    xyz = _f32(xyz).contiguous()
+    B, Q, _ = xyz.shape
+    s = GnbSampleParams()
+    keep = [xyz]
+    s.batch, s.n_query, s.xyz = B, Q, xyz.data_ptr()
+    Cv = Cp = 0
+    if volume is not None:
+        volume = _f32(volume)
+        if volume.shape[0] != B:
+            raise RuntimeError("volume batch != xyz batch")
+        _, Cv, nx, ny, nz = volume.shape
+        s.volume = volume.data_ptr()
+        s.nx, s.ny, s.nz, s.C = nx, ny, nz, Cv
+        s.vol_stride_b, s.vol_stride_c, s.vol_stride_x, s.vol_stride_y, s.vol_stride_z = volume.stride()
+        s.voxel_size = float(voxel_size)
+        s.origin[:] = _origin3(origin)
+        keep.append(volume)
+    if planes:
+        ref = None
+        for k, name in enumerate(PLANES):
+            pl = planes.get(name)
+            if pl is None:
+                continue
+            pl = _f32(pl)
+            _need_cuda(pl)
+            if ref is None:
+                ref = pl
+            elif pl.stride() != ref.stride() or pl.shape != ref.shape:
+                pl = pl.contiguous(memory_format=torch.channels_last) if ref.is_contiguous(
+                    memory_format=torch.channels_last) else pl.contiguous()
+                if pl.stride() != ref.stride():
+                    raise RuntimeError("the three planes must share shape and strides")
+            s.plane[k] = pl.data_ptr()
+            keep.append(pl)
+        if ref is not None:
+            if ref.shape[0] != B or ref.shape[2] != ref.shape[3]:
+                raise RuntimeError("planes must be (B,C_p,R,R)")
+            Cp, R = ref.shape[1], ref.shape[2]
+            s.R, s.Cp = R, Cp
+            s.pl_stride_b, s.pl_stride_c, s.pl_stride_h, s.pl_stride_w = ref.stride()
+            s.padding = float(padding)
+    return s, keep, B, Q, Cp, Cv
+
+
+def sample_features(xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1):
+    """GenNerf.map_features (reference model.py:163-204): (B,Q,3) -> (B,Q,C_p + C), plane
+    features first.  `volume` is the accumulated (already normalised == summed) volume."""
+    s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
+    out = torch.empty((B, Q, Cp + Cv), device=xyz.device, dtype=torch.float32)
+    s.out, s.out_stride = out.data_ptr(), Cp + Cv
+    with torch.cuda.device(out.device):
+        check(lib().gnb_sample_features(C.byref(s), _stream()), "gnb_sample_features")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# triplane projection
+# ------------------------------------------------------------------------------------------
+def plane_coords(p, padding, reso):
+    """normalize_coordinate + coordinate2index for the three planes (reference utils.py:57-98).
+    p (B,N,3) -> coord (3,B,N,2) fp32, index (3,B,N) int64; plane order xz, xy, yz."""
+    _need_cuda(p)
+    p = _f32(p).contiguous()
+    B, N, _ = p.shape
+    coord = torch.empty((3, B, N, 2), device=p.device, dtype=torch.float32)
+    index = torch.empty((3, B, N), device=p.device, dtype=torch.int64)
+    with torch.cuda.device(p.device):
+        check(lib().gnb_plane_coords(p.data_ptr(), B * N, float(padding), int(reso), coord.data_ptr(),
+                                     index.data_ptr(), _stream()), "gnb_plane_coords")
+    return coord, index
+
+
+def scatter_mean_planes(p, c, reso, padding=0.1, mode="atomic"):
+    """LocalPoolPointnet.generate_plane_features for xz, xy, yz at once (reference
+    pointnet.py:72-89, without the U-Net).  p (B,N,3), c (B,N,C_p) ->
+    planes (3,B,C_p,R,R) logical (channels-last storage), count (3,B,R,R) int32.
+    mode 'atomic' (fast) or 'deterministic' (bit-identical to the CPU scatter order)."""
+    _need_cuda(p, c)
+    p, c = _f32(p).contiguous(), _f32(c).contiguous()
+    B, N, _ = p.shape
+    Cp = c.shape[2]
+    R = int(reso)
+    m = {"atomic": _lib.SCATTER_ATOMIC, "deterministic": _lib.SCATTER_DETERMINISTIC}[mode]
+    store = torch.empty((3, B, R, R, Cp), device=p.device, dtype=torch.float32)
+    count = torch.empty((3, B, R, R), device=p.device, dtype=torch.int32)
+    nbytes = lib().gnb_scatter_scratch_bytes(B, N, R, m)
+    scratch = torch.empty(max(nbytes, 1), device=p.device, dtype=torch.uint8)
+    with torch.cuda.device(p.device):
+        check(lib().gnb_scatter_mean_planes(p.data_ptr(), c.data_ptr(), B, N, Cp, R, float(padding), m,
+                                            store.data_ptr(), count.data_ptr(), scratch.data_ptr(), nbytes,
+                                            _stream()), "gnb_scatter_mean_planes")
+    return store.permute(0, 1, 4, 2, 3), count
+
+
+def pool_local(p, c, reso, padding=0.1, scatter_type="max"):
+    """LocalPoolPointnet.pool_local (reference pointnet.py:105-121): c (B,N,Hd) -> (B,N,Hd)."""
+    _need_cuda(p, c)
+    p, c = _f32(p).contiguous(), _f32(c).contiguous()
+    B, N, _ = p.shape
+    Hd = c.shape[2]
+    t = {"max": _lib.POOL_MAX, "mean": _lib.POOL_MEAN}[scatter_type]
+    out = torch.empty_like(c)
+    nbytes = lib().gnb_pool_scratch_bytes(B, N, Hd, int(reso))
+    scratch = torch.empty(nbytes, device=p.device, dtype=torch.uint8)
+    with torch.cuda.device(p.device):
+        check(lib().gnb_pool_local(p.data_ptr(), c.data_ptr(), B, N, Hd, int(reso), float(padding), t,
+                                   out.data_ptr(), scratch.data_ptr(), nbytes, _stream()), "gnb_pool_local")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# decoder
+# ------------------------------------------------------------------------------------------
+class DecoderWeights:
+    """Device-side view of the reference's ResnetFC + TSDFHeadSimple parameters.
+
+    Built from state_dicts with the reference's keys (lin_in.*, lin_z.{i}.*,
+    blocks.{i}.fc_{0,1}.*, lin_out.*, alpha; fc.weight / fc.bias for the head).  The tensors
+    stay owned by the nn.Modules (checkpoint compatibility); this object only holds pointers
+    and, for the bf16 tcgen05 path, a packed copy refreshed by `pack()`.
+    """
+
+    def __init__(self, mlp_sd, head_w, head_b, *, n_blocks, d_geo, use_code=True, num_freqs=2,
+                 freq_factor=0.5, include_input=True, d_code=None, device="cuda"):
+        def dev(t):
+            return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+        self.t = {k: dev(v) for k, v in mlp_sd.items()}
+        self.head_w, self.head_b = dev(head_w).reshape(-1), dev(head_b).reshape(-1)
+        w = GnbDecoderWeights()
+        w.d_hidden, w.d_feat = self.t["lin_in.weight"].shape
+        w.d_out = self.t["lin_out.weight"].shape[0]
+        w.n_blocks, w.d_geo = int(n_blocks), int(d_geo)
+        w.alpha = float(self.t["alpha"].item()) if "alpha" in self.t else 1.0
+        w.use_code, w.num_freqs, w.freq_factor, w.include_input = int(use_code), int(num_freqs), float(freq_factor), int(include_input)
+        if int(use_code) == 2:         # codes are given (stand-alone ResnetFC.forward)
+            w.d_code = int(d_code)
+        else:
+            w.d_code = ((3 if include_input else 0) + 6 * int(num_freqs)) if use_code else 3
+        w.lin_in_w, w.lin_in_b = self.t["lin_in.weight"].data_ptr(), self.t["lin_in.bias"].data_ptr()
+        for i in range(w.n_blocks):
+            w.lin_z_w[i], w.lin_z_b[i] = self.t[f"lin_z.{i}.weight"].data_ptr(), self.t[f"lin_z.{i}.bias"].data_ptr()
+            w.fc0_w[i], w.fc0_b[i] = self.t[f"blocks.{i}.fc_0.weight"].data_ptr(), self.t[f"blocks.{i}.fc_0.bias"].data_ptr()
+            w.fc1_w[i], w.fc1_b[i] = self.t[f"blocks.{i}.fc_1.weight"].data_ptr(), self.t[f"blocks.{i}.fc_1.bias"].data_ptr()
+        w.lin_out_w, w.lin_out_b = self.t["lin_out.weight"].data_ptr(), self.t["lin_out.bias"].data_ptr()
+        w.head_w, w.head_b = self.head_w.data_ptr(), self.head_b.data_ptr()
+        self.w = w
+        self.device = torch.device(device)
+        self.packed = None
+
+    def pack(self):
+        """(Re)build the bf16 tcgen05 operand image of the weights."""
+        n = lib().gnb_decoder_packed_bytes(C.byref(self.w))
+        if n <= 0:
+            raise RuntimeError("gennerf_b200: this decoder shape has no bf16 tcgen05 path: "
+                               + lib().gnb_last_error().decode())
+        if self.packed is None or self.packed.numel() != n:
+            self.packed = torch.empty(n, device=self.device, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            check(lib().gnb_decoder_pack_bf16(C.byref(self.w), self.packed.data_ptr(), _stream()), "gnb_decoder_pack_bf16")
+        return self.packed
+
+
+def decode(weights, xyz, feat, precision="fp32"):
+    """PositionalEncoding -> ResnetFC -> TSDFHeadSimple (reference model.py:226-246).
+    xyz (..., 3), feat (..., d_feat) -> out (..., d_out), tsdf (..., 1)."""
+    _need_cuda(xyz, feat)
+    lead = xyz.shape[:-1]
+    xyz2 = _f32(xyz).reshape(-1, 3).contiguous()
+    feat2 = _f32(feat).reshape(-1, feat.shape[-1]).contiguous()
+    n = xyz2.shape[0]
+    out = torch.empty((n, weights.w.d_out), device=xyz.device, dtype=torch.float32)
+    tsdf = torch.empty((n, 1), device=xyz.device, dtype=torch.float32)
+    with torch.cuda.device(xyz.device):
+        if precision == "fp32":
+            check(lib().gnb_decode_fp32(C.byref(weights.w), xyz2.data_ptr(), feat2.data_ptr(), n, out.data_ptr(),
+                                        tsdf.data_ptr(), _stream()), "gnb_decode_fp32")
+        elif precision == "bf16":
+            packed = weights.packed if weights.packed is not None else weights.pack()
+            check(lib().gnb_decode_bf16(C.byref(weights.w), packed.data_ptr(), xyz2.data_ptr(), feat2.data_ptr(), n,
+                                        out.data_ptr(), tsdf.data_ptr(), _stream()), "gnb_decode_bf16")
+        else:
+            raise ValueError(precision)
+    return out.reshape(*lead, -1), tsdf.reshape(*lead, 1)
+
+
+def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
+                want_feat=True):
+    """GenNerf.forward in one kernel (sampler fused into the bf16 tcgen05 decoder).
+    Returns out (B,Q,d_out), tsdf (B,Q,1), feat (B,Q,C_lat) or None."""
+    s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
+    feat = None
+    if want_feat:
+        feat = torch.empty((B, Q, Cp + Cv), device=xyz.device, dtype=torch.float32)
+        s.out, s.out_stride = feat.data_ptr(), Cp + Cv
+    out = torch.empty((B, Q, weights.w.d_out), device=xyz.device, dtype=torch.float32)
+    tsdf = torch.empty((B, Q, 1), device=xyz.device, dtype=torch.float32)
+    packed = weights.packed if weights.packed is not None else weights.pack()
+    with torch.cuda.device(xyz.device):
+        check(lib().gnb_query_fused_bf16(C.byref(s), C.byref(weights.w), packed.data_ptr(), out.data_ptr(),
+                                         tsdf.data_ptr(), _stream()), "gnb_query_fused_bf16")
+    return out, tsdf, feat
+
+
+def positional_encoding(x, num_freqs, freq_factor, include_input=True):
+    """PositionalEncoding.forward (reference positional_encoding.py:28-40): (n,3) -> (n,d_code)."""
+    _need_cuda(x)
+    x = _f32(x).contiguous()
+    n = x.shape[0]
+    d = (3 if include_input else 0) + 6 * int(num_freqs)
+    out = torch.empty((n, d), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib().gnb_positional_encoding(x.data_ptr(), n, int(num_freqs), float(freq_factor), int(include_input),
+                                            out.data_ptr(), _stream()), "gnb_positional_encoding")
+    return out
+
+
+def tsdf_head(feat_geo, weight, bias):
+    """TSDFHeadSimple.forward (reference heads3d.py:36-50): (...,d_geo) -> (...,1) = tanh(fc(x))."""
+    _need_cuda(feat_geo, weight, bias)
+    lead = feat_geo.shape[:-1]
+    d_geo = feat_geo.shape[-1]
+    g = _f32(feat_geo)
+    if g.stride(-1) != 1 or not g.reshape(-1, d_geo).is_contiguous():
+        # a column slice of a row-major (n, d_out) tensor is fine: pass its row stride
+        if g.dim() >= 2 and g.stride(-1) == 1 and all(g.stride(i) == g.stride(i + 1) * g.shape[i + 1] for i in range(g.dim() - 2)):
+            pass
+        else:
+            g = g.contiguous()
+    n = 1
+    for s in lead:
+        n *= s
+    stride = g.stride(-2) if g.dim() >= 2 else d_geo
+    w = _f32(weight).reshape(-1).contiguous()
+    b = _f32(bias).reshape(-1).contiguous()
+    out = torch.empty((n,), device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device):
+        check(lib().gnb_tsdf_head(g.data_ptr(), n, d_geo, stride, w.data_ptr(), b.data_ptr(), out.data_ptr(), _stream()),
+              "gnb_tsdf_head")
+    return out.reshape(*lead, 1)

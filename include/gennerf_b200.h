@@ -1,0 +1,224 @@
+/*
+ * gennerf_b200 -- C ABI of the B200-native lift-and-query path of gen-nerf.
+ *
+ * The reference (mrchris7/gen-nerf) is pure Python and has no FFI layer; its boundary for
+ * this path is a set of Python call sites.  Each entry point below
+ * names the reference function it replaces (file:line relative to the reference root).
+ * gennerf_b200/ops.py binds these through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only
+ *     enqueue work on it: they never synchronise, allocate or free (the caller owns all
+ *     buffers, including scratch) and keep no mutable global state, so they are re-entrant
+ *     across streams and threads;
+ *   - return value 0 = success, otherwise a negative GNB_E_* code or a positive
+ *     cudaError_t; gnb_last_error() gives a thread-local message;
+ *   - sizes are element counts, strides are in elements, fp32 unless stated.
+ */
+#ifndef GENNERF_B200_H
+#define GENNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNB_VERSION 100
+#define GNB_MAX_FRAMES 64          /* frames per gnb_backproject_frames call               */
+
+#define GNB_E_INVALID (-1)         /* bad argument                                          */
+#define GNB_E_UNSUPPORTED (-2)     /* shape not supported by the sm_100a kernels            */
+#define GNB_E_ARCH (-3)            /* device is not sm_100                                  */
+
+/* feature-map layouts */
+#define GNB_LAYOUT_NCHW 0          /* reference layout (B,C,H,W) contiguous                 */
+#define GNB_LAYOUT_NHWC 1          /* channels-last: (B,H,W,C) contiguous                   */
+
+int gnb_version(void);
+const char* gnb_last_error(void);
+/* sizeof() of the parameter structs as compiled: 0 GnbLiftParams, 1 GnbSampleParams,
+ * 2 GnbDecoderWeights.  Lets a foreign-language binding verify its struct layout. */
+int gnb_struct_size(int which);
+
+/* -------------------------------------------------------------------------------------
+ * Layout helper: (T frames) NCHW -> NHWC, one launch.  src[t] is (B,C,H,W); dst is
+ * (T,B,H,W,C).  Not in the reference: it is the price of the reference's NCHW contract and
+ * is skipped when the CNN already runs channels-last.
+ * ----------------------------------------------------------------------------------- */
+int gnb_nchw_to_nhwc(const float* const* h_src, int n_frames, float* dst,
+                     int B, int C, int H, int W, void* stream);
+
+/* -------------------------------------------------------------------------------------
+ * Fused lift.  Replaces, for all T frames of one scene batch at once,
+ *   coordinates()                   src/data/tsdf.py:25-40        (never materialised)
+ *   backproject()                   src/models/utils.py:948-996
+ *   the accumulation in encode()    src/models/model.py:121-127, voxel_net.py:120-126
+ *   the normalisation               src/models/model.py:195-199, voxel_net.py:163-168
+ * volume[b,v,:] = sum over frames t (in frame order) of features_t[b,:,py,px] where frame t
+ * sees voxel v;  count[b,v] = number of such frames;  valid[b,v] = count > 0.
+ * With mean != 0 the sum is divided by count (the north-star's masked mean; the reference
+ * computes the SUM, SURVEY trap T2).
+ * ----------------------------------------------------------------------------------- */
+typedef struct GnbLiftParams {
+    int32_t nx, ny, nz;            /* voxel grid; linear id v = (x*ny + y)*nz + z           */
+    float voxel_size;
+    float origin[3];
+    int32_t batch;                 /* B scenes                                              */
+    int32_t n_frames;              /* T <= GNB_MAX_FRAMES                                   */
+    int32_t C, H, W;               /* feature maps                                          */
+    int32_t feat_layout;           /* GNB_LAYOUT_NHWC: features[t] is (B,H,W,C)             */
+                                   /* GNB_LAYOUT_NCHW: features[t] is (B,C,H,W); `scratch`  */
+                                   /*   must hold T*B*H*W*C floats                          */
+    const float* features[GNB_MAX_FRAMES];
+    const float* h_projection;     /* HOST (B,T,3,4) world->pixel, row-major                */
+    float* scratch;
+    /* outputs */
+    float* volume;                 /* element (b,v,c) at b*vol_stride_b + v*vol_stride_v +  */
+    int64_t vol_stride_b;          /*   c*vol_stride_c.  channels-last: (V*C, C, 1);        */
+    int64_t vol_stride_v;          /*   reference (B,C,nx,ny,nz): (C*V, 1, V)               */
+    int64_t vol_stride_c;
+    int32_t* count;                /* (B,V) or NULL                                         */
+    uint8_t* valid;                /* (B,V) 0/1 or NULL                                     */
+    int32_t accumulate;            /* != 0: volume/count already hold earlier frames        */
+    int32_t mean;                  /* != 0: divide by count at the end                      */
+} GnbLiftParams;
+
+int gnb_backproject_frames(const GnbLiftParams* p, void* stream);
+
+/* Parity probe for the integer part of backproject (utils.py:979-985): pixel indices of
+ * every voxel for ONE projection.  px,py are the int64 values the reference computes where
+ * they are finite and fit int32, else INT32_MIN.  valid as in the reference. */
+int gnb_project_indices(int nx, int ny, int nz, float voxel_size, const float* h_origin3,
+                        const float* h_projection12, int H, int W,
+                        int32_t* px, int32_t* py, uint8_t* valid, void* stream);
+
+/* -------------------------------------------------------------------------------------
+ * Point-query sampler.  Replaces
+ *   trilinear_interpolation()            src/models/utils.py:999-1042  (F.grid_sample 3-D)
+ *   GenNerf.sample_plane_feature() x3    src/models/model.py:153-161   (F.grid_sample 2-D)
+ *   normalize_coordinate()               src/models/utils.py:75-98
+ *   GenNerf.map_features()               src/models/model.py:163-204   (concat, planes first)
+ * out[b,q,:] = [ sum over planes of bilinear(plane, q) (C_p) | trilinear(volume, q) (C) ].
+ * Either part may be absent (pointer NULL).
+ * ----------------------------------------------------------------------------------- */
+typedef struct GnbSampleParams {
+    int32_t batch;
+    int64_t n_query;               /* Q per scene                                           */
+    const float* xyz;              /* (B,Q,3)                                               */
+    /* volume part */
+    const float* volume;           /* NULL = no volume part                                 */
+    int32_t nx, ny, nz, C;
+    int64_t vol_stride_b, vol_stride_x, vol_stride_y, vol_stride_z, vol_stride_c;
+    float voxel_size;
+    float origin[3];
+    /* plane part: planes in the reference order xz, xy, yz; NULL entries are skipped */
+    const float* plane[3];
+    int32_t R, Cp;
+    int64_t pl_stride_b, pl_stride_h, pl_stride_w, pl_stride_c;  /* (B,C_p,H=R,W=R) logical */
+    double padding;                /* python float, e.g. 0.1 (kept double: 1+padding+1e-5 is rounded once) */
+    /* output */
+    float* out;                    /* (B,Q,out_stride), plane part first                    */
+    int64_t out_stride;            /* >= Cp + C                                             */
+} GnbSampleParams;
+
+int gnb_sample_features(const GnbSampleParams* p, void* stream);
+
+/* -------------------------------------------------------------------------------------
+ * Plane coordinates and cell indices.  Replaces normalize_coordinate() + coordinate2index()
+ * src/models/utils.py:57-98 for the three planes at once.
+ * coord: (3,B,N,2) fp32 in [0, 1-1e-5];  index: (3,B,N) int64 = x0 + R*x1.
+ * ----------------------------------------------------------------------------------- */
+int gnb_plane_coords(const float* p, int64_t n_points_total, double padding, int R,
+                     float* coord, int64_t* index, void* stream);
+
+/* -------------------------------------------------------------------------------------
+ * Triplane scatter-mean.  Replaces LocalPoolPointnet.generate_plane_features() x3
+ * (src/models/components/pointnet.py:72-89) = torch_scatter.scatter_mean onto R*R cells.
+ * planes: (3,B,R,R,C_p) channels-last (logical (B,C_p,R,R) per plane);
+ * count: (3,B,R*R) int32 (exact in both modes).
+ * mode 0: warp-aggregated atomics (sums order-nondeterministic);
+ * mode 1: deterministic -- every cell sums its points in ascending point index, which is
+ *         bit-identical to the CPU scatter_add_ the oracle uses.  scratch >= result of
+ *         gnb_scatter_scratch_bytes().
+ * ----------------------------------------------------------------------------------- */
+#define GNB_SCATTER_ATOMIC 0
+#define GNB_SCATTER_DETERMINISTIC 1
+int64_t gnb_scatter_scratch_bytes(int B, int64_t N, int R, int mode);
+int gnb_scatter_mean_planes(const float* p, const float* c, int B, int64_t N, int Cp, int R,
+                            double padding, int mode, float* planes, int32_t* count,
+                            void* scratch, int64_t scratch_bytes, void* stream);
+
+/* -------------------------------------------------------------------------------------
+ * Local pooling.  Replaces LocalPoolPointnet.pool_local()
+ * (src/models/components/pointnet.py:105-121): for each plane scatter-(max|mean) the point
+ * features into cells, gather the cell value back to every point, sum over the 3 planes.
+ * c,out: (B,N,Hd);  scratch >= gnb_pool_scratch_bytes().
+ * ----------------------------------------------------------------------------------- */
+#define GNB_POOL_MAX 0
+#define GNB_POOL_MEAN 1
+int64_t gnb_pool_scratch_bytes(int B, int64_t N, int Hd, int R);
+int gnb_pool_local(const float* p, const float* c, int B, int64_t N, int Hd, int R,
+                   double padding, int pool_type, float* out,
+                   void* scratch, int64_t scratch_bytes, void* stream);
+
+/* -------------------------------------------------------------------------------------
+ * Decoder.  Replaces
+ *   PositionalEncoding.forward()   src/models/components/positional_encoding.py:28-40
+ *   ResnetFC.forward()             src/models/components/resnetfc.py:134-189 (default options:
+ *                                   ReLU, no spade / layer-norm, combine_layer > n_blocks)
+ *   TSDFHeadSimple.forward()       src/models/components/heads3d.py:36-50
+ *   the glue in GenNerf.forward()  src/models/model.py:226-246
+ * Weight layout is the reference's nn.Linear layout (out_features, in_features) row-major.
+ * ----------------------------------------------------------------------------------- */
+typedef struct GnbDecoderWeights {
+    int32_t d_feat;                /* lin_in in_features  (= encoder_latent)                */
+    int32_t d_code;                /* lin_z in_features   (= 3 + 6*num_freqs, or 3)         */
+    int32_t d_hidden;
+    int32_t n_blocks;              /* <= 8                                                  */
+    int32_t d_out;                 /* d_out_geo + d_out_sem                                 */
+    int32_t d_geo;                 /* head input = first d_geo outputs                      */
+    float alpha;                   /* ResnetFC.alpha (value of the learnable scalar)        */
+    /* positional encoding */
+    int32_t use_code;              /* 0: code = xyz; 1: positional encoding of xyz;         */
+                                   /* 2: the `xyz` argument already holds (n_rows, d_code)  */
+                                   /*    codes (stand-alone ResnetFC.forward(zx))           */
+    int32_t num_freqs;
+    float freq_factor;
+    int32_t include_input;
+    /* fp32 parameters */
+    const float* lin_in_w;  const float* lin_in_b;
+    const float* lin_z_w[8]; const float* lin_z_b[8];
+    const float* fc0_w[8];   const float* fc0_b[8];
+    const float* fc1_w[8];   const float* fc1_b[8];
+    const float* lin_out_w; const float* lin_out_b;
+    const float* head_w;    const float* head_b;
+} GnbDecoderWeights;
+
+/* Stand-alone pieces (the reference's modules called on their own). */
+int gnb_positional_encoding(const float* x, int64_t n_rows, int num_freqs, float freq_factor,
+                            int include_input, float* out, void* stream);      /* (n,3)->(n,d_code) */
+int gnb_tsdf_head(const float* feat_geo, int64_t n_rows, int d_geo, int64_t row_stride,
+                  const float* head_w, const float* head_b, float* tsdf, void* stream);
+
+/* fp32 CUDA-core decoder (exact mode, tolerance 1e-5 relative to the oracle). */
+int gnb_decode_fp32(const GnbDecoderWeights* w, const float* xyz, const float* feat,
+                    int64_t n_rows, float* out, float* tsdf, void* stream);
+
+/* bf16 tcgen05/TMEM decoder (fast mode, |tsdf - oracle| <= 1e-2).  `packed` is the
+ * device buffer written by gnb_decoder_pack_bf16 (gnb_decoder_packed_bytes bytes). */
+int64_t gnb_decoder_packed_bytes(const GnbDecoderWeights* w);
+int gnb_decoder_pack_bf16(const GnbDecoderWeights* w, void* packed, void* stream);
+int gnb_decode_bf16(const GnbDecoderWeights* w, const void* packed, const float* xyz,
+                    const float* feat, int64_t n_rows, float* out, float* tsdf, void* stream);
+
+/* Fused sampler + bf16 decoder (GenNerf.forward, model.py:207-248): xyz -> feat (optional
+ * output), out (feat_geo|feat_sem), tsdf, in one kernel. */
+int gnb_query_fused_bf16(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed,
+                         float* out, float* tsdf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENNERF_B200_H */
