@@ -30,6 +30,9 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a and link the shared library; returns its path."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "gennerf_b200.h")]
+    if not force and not verbose and not _stale(LIB, srcs):
+        return LIB                                   # up to date (e.g. the prebuilt .so on the GPU box)
     objdir = os.path.join(ROOT, "build", "obj")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
