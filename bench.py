@@ -192,15 +192,9 @@ def run_native(args):
     dw = ops.DecoderWeights(w, hw, hb, n_blocks=MLP["n_blocks"], d_geo=MLP["d_geo"], use_code=True,
                             num_freqs=MLP["num_freqs"], freq_factor=MLP["freq_factor"], device=dev)
     precision = args.precision
-    if precision == "bf16":
-        try:
-            dw.pack()
-        except RuntimeError as e:
-            if args.strict:
-                raise
-            sys.stderr.write(f"[bench] bf16 tcgen05 decoder unavailable ({e}); timing the fp32 CUDA-core decoder\n")
-            precision = "fp32"
-    fused = precision == "bf16" and not args.unfused
+    if precision != "fp32":
+        dw.pack(precision)                                  # raises if the tcgen05 path is unavailable: no fallback
+    fused = precision != "fp32" and not args.unfused
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
@@ -211,7 +205,8 @@ def run_native(args):
         vol, cnt, valid = ops.backproject_frames(wl["voxel_dim"], VS, origin, P, feats)
         if e: e[1].record()
         if fused:
-            out, tsdf, feat = ops.query_fused(dw, xyz, volume=vol, voxel_size=VS, origin=origin, want_feat=False)
+            out, tsdf, feat = ops.query_fused(dw, xyz, volume=vol, voxel_size=VS, origin=origin, want_feat=False,
+                                              precision=precision)
             if e: e[2].record()
         else:
             feat = ops.sample_features(xyz, volume=vol, voxel_size=VS, origin=origin)
@@ -256,7 +251,7 @@ def run_native(args):
         xd = xyz_pin.to(dev, non_blocking=True)
         vol, cnt, valid = ops.backproject_frames(wl["voxel_dim"], VS, origin, P, fd)
         if fused:
-            out, tsdf, _ = ops.query_fused(dw, xd, volume=vol, voxel_size=VS, origin=origin, want_feat=False)
+            out, tsdf, _ = ops.query_fused(dw, xd, volume=vol, voxel_size=VS, origin=origin, want_feat=False, precision=precision)
         else:
             feat = ops.sample_features(xd, volume=vol, voxel_size=VS, origin=origin)
             out, tsdf = ops.decode(dw, xd, feat, precision)
@@ -293,11 +288,11 @@ def run_native(args):
         line = {
             "metric": "tsdf_query_points_per_s", "value": world * Q / (ms_step * 1e-3), "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[precision], "data": "synthetic",
             "config": dict(config_dict(Q), parallelism=f"replicas x{world} (queries and scenes sharded, no data-path collective)",
-                           decoder="bf16 tcgen05 fused sampler+MLP" if fused else f"{precision} sampler + decoder kernels"),
+                           decoder=f"{precision} tcgen05 fused sampler+MLP" if fused else f"{precision} sampler + decoder kernels"),
             "roofline": {"kernel": "decoder", "bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": tf / pk["bf16"], "traffic": None, "peak_source": pk["source"] + " bf16 sustained",
+                         "frac": tf / pk["bf16"], "traffic": None, "peak_source": pk["source"] + " bf16 cuBLAS sustained (fp16 and bf16 share the tensor-core rate)",
                          "flops_per_launch": fl, "ms_per_launch": dec_ms},
             "backprojection": {"metric": "voxel_frames_per_s", "value": world * V * T / (ms_lift * 1e-3), "ms": ms_lift,
                                "includes": "NCHW->NHWC pass + fused lift kernel",
@@ -330,9 +325,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="decoder operands: fp16/bf16 = tcgen05 tensor cores (fp32 accumulate), fp32 = CUDA cores")
     ap.add_argument("--unfused", action="store_true", help="separate sampler and decoder kernels")
-    ap.add_argument("--strict", action="store_true", help="fail instead of timing the fp32 decoder when bf16 is unavailable")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

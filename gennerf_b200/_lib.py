@@ -13,6 +13,7 @@ GNB_MAX_FRAMES = 64
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 SCATTER_ATOMIC, SCATTER_DETERMINISTIC = 0, 1
 POOL_MAX, POOL_MEAN = 0, 1
+TC_FP16, TC_BF16 = 0, 1
 
 c_float_p = C.POINTER(C.c_float)
 
@@ -63,6 +64,7 @@ class GnbDecoderWeights(C.Structure):
         ("fc1_w", C.c_void_p * 8), ("fc1_b", C.c_void_p * 8),
         ("lin_out_w", C.c_void_p), ("lin_out_b", C.c_void_p),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+        ("tc_dtype", C.c_int32),
     ]
 
 
@@ -90,10 +92,10 @@ SIGNATURES = {
     "gnb_decode_fp32": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "gnb_decoder_packed_bytes": (C.c_int64, [C.POINTER(GnbDecoderWeights)]),
-    "gnb_decoder_pack_bf16": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p]),
-    "gnb_decode_bf16": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+    "gnb_decoder_pack_tc": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p]),
+    "gnb_decode_tc": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
-    "gnb_query_fused_bf16": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(GnbDecoderWeights), C.c_void_p,
+    "gnb_query_fused_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(GnbDecoderWeights), C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -1,21 +1,743 @@
-// placeholder: replaced by the tcgen05/TMEM decoder
-#include "common.cuh"
+// tcgen05 / TMEM tensor-core decoder (fp16 or bf16 operands, fp32 accumulate) with the point-query
+// sampler fused into its prologue (sm_100a).
+//
+// Replaces GenNerf.forward (reference src/models/model.py:207-248) in ONE kernel:
+//   map_features (sampler, sample.cuh)                      model.py:163-204
+//   PositionalEncoding                                      positional_encoding.py:28-40
+//   ResnetFC: lin_in, n_blocks x [lin_z, fc_0, fc_1], lin_out   resnetfc.py:134-189 (trap T8)
+//   TSDFHeadSimple                                          heads3d.py:36-50
+//
+// Tile: 128 query rows per cluster.  Hidden width d_hidden is split over NSPLIT = 1 or 2 CTAs
+// (2 when d_hidden > 256): CTA r owns hidden units [r*HN, (r+1)*HN), HN <= 256, because the
+// fp32 residual stream x (128 x HN) must stay resident in TMEM next to the fc_0 output
+// (128 x HN): 2*HN <= 512 columns.
+//
+// Per CTA:
+//   TMEM   cols [0,HN)      x    residual stream, fp32, accumulated in place by lin_in, lin_z, fc_1
+//          cols [256,256+HN) net  fc_0 output; reused for the lin_out tile
+//   SMEM   A buffer         128 x K bf16 activations, K-major, 128B-swizzled 64-column chunks
+//          code tile        positional encoding (+ two constant-1 columns that carry biases)
+//          W ring           NSTAGE x 16 KB weight tiles (<=128 n-rows x 64 k), pre-swizzled in HBM,
+//                           streamed with 1-D bulk async copies (no tensor map needed)
+//   warps  0: weight producer   1: MMA issuer   2: TMEM alloc + A-chunk exchange   3: idle
+//          4-7: epilogue / prologue (thread = query row = TMEM lane)
+//
+// Dataflow per tile: prologue samples features + encodes xyz -> bf16 operand tiles; then MMA groups
+//   G0 = [lin_in, lin_z_0] -> x;  per block: E(relu(x)) -> [fc_0] -> net;  E(relu(net+b0)) ->
+//   [fc_1, lin_z_next] -> x;  finally E(relu(x+b1_last)) -> [lin_out] -> epilogue (+b_out, tanh head).
+// An epilogue round converts one TMEM accumulator into the next layer's A operand chunk by
+// chunk; each chunk has its own mbarrier, so the MMA of a layer starts as soon as its first
+// chunk is ready.  With NSPLIT=2 each CTA produces half of the chunks and pushes them to its
+// peer with a bulk shared::cta -> shared::cluster copy that completes on the peer's barrier.
+// lin_in / lin_z biases (and fc_1's, folded into the next lin_z) ride in two extra K columns
+// as a bf16 hi+lo pair; fc_0 / lin_out / last fc_1 biases are added in fp32 by the epilogue.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "sample.cuh"
+
+namespace gnb {
+
+int check_decoder_weights(const GnbDecoderWeights* w, const char* who);
+
+namespace tc {
+
+constexpr int BM = 128;               // rows per tile
+constexpr int CHUNK = BM * 128;       // bytes of one 128-row x 64-col bf16 chunk
+constexpr int NET_COL = 256;          // TMEM column of the net / out accumulator
+constexpr int MAX_CHUNKS = 16;
+constexpr int MAX_STAGES = 8;
+constexpr int NTHREADS = 256;
+constexpr int EPI_WARP0 = 4;          // first epilogue warp (4 warps: one per TMEM lane quadrant)
+
+struct Dims {
+    int d_feat, d_code, Hd, nb, d_out, d_geo;
+    int nsplit, HN;                   // CTAs per tile, hidden units per CTA
+    int KF, KZ, KH;                   // 64-wide K chunks of lin_in, lin_z, hidden layers
+    int NOUT;                         // lin_out rows padded to a multiple of 16
+    int ACH;                          // chunks in the A buffer = max(KF, KH)
+    int nstage;
+    long long packed_per_rank;        // bytes
+};
+
+__host__ __device__ inline int n_tiles_of(int rows) { return (rows + 127) / 128; }
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+
+// global -> own shared memory, completion on an own mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// own shared memory -> peer CTA's shared memory, completion on the PEER's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+                 "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows x 64 bf16, 8-row groups 1024 B apart), sm_100 format:
+// start>>4 [0,14) | LBO=1 [16,30) | SBO=1024>>4 [32,46) | version=1 [46,48) | SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A format [7,10) and B format [10,13) (0 = f16,
+// 1 = bf16), K-major both, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc(int n, bool bf16) {
+    const uint32_t f = bf16 ? 1u : 0u;
+    return (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// two fp32 -> one packed pair of 16-bit operands (fp16 saturates at +-65504 instead of overflowing)
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+    if constexpr (BF16) {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    } else {
+        __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ float round16(float a) {
+    if constexpr (BF16) return __bfloat162float(__float2bfloat16_rn(a));
+    else return __half2float(__float2half_rn(fminf(fmaxf(a, -65504.0f), 65504.0f)));
+}
+// byte offset of the 16-byte unit u (8 columns) of row r inside a swizzled chunk
+__device__ __forceinline__ uint32_t chunk_off(int r, int u) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4)); }
+
+// ---------------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------------
+struct TcKP {
+    Dims d;
+    GnbDecoderWeights w;          // fp32 biases, head, encoding options (matrices are read from `packed`)
+    const unsigned char* packed;
+    const float* xyz;             // (n_rows,3), or (n_rows,d_code) codes when w.use_code == 2
+    const float* feat;            // (n_rows,d_feat) when !fused
+    int fused;
+    SampleKP s;                   // sampler (fused); s.out = optional fp32 feature output
+    long long n_rows;
+    float* out;                   // (n_rows,d_out) or null
+    float* tsdf;                  // (n_rows) or null
+    int n_tiles, n_clusters;
+};
+
+// shared-memory carve-up (offsets from the 1024-aligned base)
+struct Smem {
+    uint32_t a, code, ring, bias, bars;     // byte offsets
+    uint32_t total;
+};
+__host__ __device__ inline Smem smem_layout(const Dims& d) {
+    Smem s;
+    s.a = 0;
+    s.code = s.a + d.ACH * CHUNK;
+    s.ring = s.code + d.KZ * CHUNK;
+    s.bias = s.ring + d.nstage * CHUNK;
+    // fp32 table: b0[nb][HN] | b1_last[HN] | b_out[NOUT] | head_w[d_geo] | head_b
+    uint32_t nbias = (uint32_t)(d.nb * d.HN + d.HN + d.NOUT + d.d_geo + 1);
+    s.bars = (s.bias + nbias * 4 + 15) & ~15u;
+    // barriers: w_full[8] w_empty[8] a_ready[16] acc_ready in_ready | tmem base slot
+    s.total = s.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2) * 8 + 16;
+    return s;
+}
+
+// The per-tile program: every role walks the same sequence of GEMM ops.
+//   kind 0 lin_in (A = feature chunks), 1 lin_z (A = code chunks), 2 hidden (A = activation chunks)
+struct Op {
+    int a_kind, kchunks, rows, d_col, first_overwrites, group_end;
+};
+__device__ __forceinline__ int num_ops(const Dims& d) { return 2 + 3 * d.nb; }   // lin_in, nb x (lin_z, fc0, fc1), lin_out
+__device__ __forceinline__ Op get_op(const Dims& d, int o) {
+    Op op;
+    if (o == 0) return Op{0, d.KF, d.HN, 0, 1, 0};
+    if (o == 1 + 3 * d.nb) return Op{2, d.KH, d.NOUT, NET_COL, 1, 1};
+    int i = (o - 1) / 3, j = (o - 1) % 3;
+    // order inside a block as issued: lin_z_i (ends the group that feeds relu(x)), fc0_i, fc1_i
+    if (j == 0) return Op{1, d.KZ, d.HN, 0, 0, 1};
+    if (j == 1) return Op{2, d.KH, d.HN, NET_COL, 1, 1};
+    op = Op{2, d.KH, d.HN, 0, 0, (i == d.nb - 1) ? 1 : 0};
+    return op;
+}
+// k-chunk visiting order of an activation op: own chunks first, then the peer's
+__device__ __forceinline__ int act_chunk(const Dims& d, int rank, int t) { return (rank * (d.HN / 64) + t) % d.KH; }
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_constant__ TcKP p) {
+    extern __shared__ unsigned char smem_raw[];
+    const Dims& d = p.d;
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const Smem L = smem_layout(d);
+    const uint32_t sbase = smem_u32(sm);
+    const uint32_t bar0 = sbase + L.bars;
+    auto w_full = [&](int s) { return bar0 + 8u * s; };
+    auto w_empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+    auto a_ready = [&](int j) { return bar0 + 8u * (2 * MAX_STAGES + j); };
+    const uint32_t acc_ready = bar0 + 8u * (2 * MAX_STAGES + MAX_CHUNKS);
+    const uint32_t in_ready = acc_ready + 8;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2) * 8);
+    float* bias_s = reinterpret_cast<float*>(sm + L.bias);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (d.nsplit > 1) ? cluster_rank() : 0u;
+    const int cluster_id = blockIdx.x / d.nsplit;
+    const int own_chunks = d.HN / 64;
+
+    // ---- one-time setup ---------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < d.nstage; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+        for (int j = 0; j < d.KH; ++j) {
+            bool own = (j / own_chunks) == (int)rank;
+            mbar_init(a_ready(j), own ? 4 : 1);           // 4 epilogue warps, or the arming arrive for a pushed chunk
+        }
+        mbar_init(acc_ready, d.nsplit);                   // every CTA of the cluster commits to every CTA
+        mbar_init(in_ready, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // fp32 bias table
+        const GnbDecoderWeights& w = p.w;
+        const int h0 = rank * d.HN;
+        for (int i = threadIdx.x; i < d.nb * d.HN; i += NTHREADS) bias_s[i] = __ldg(w.fc0_b[i / d.HN] + h0 + i % d.HN);
+        float* b1 = bias_s + d.nb * d.HN;
+        for (int i = threadIdx.x; i < d.HN; i += NTHREADS) b1[i] = d.nb > 0 ? __ldg(w.fc1_b[d.nb - 1] + h0 + i) : 0.0f;
+        float* bo = b1 + d.HN;
+        for (int i = threadIdx.x; i < d.NOUT; i += NTHREADS) bo[i] = i < d.d_out ? __ldg(w.lin_out_b + i) : 0.0f;
+        float* hw = bo + d.NOUT;
+        for (int i = threadIdx.x; i < d.d_geo; i += NTHREADS) hw[i] = __ldg(w.head_w + i);
+        if (threadIdx.x == 0) hw[d.d_geo] = __ldg(w.head_b);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (d.nsplit > 1) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const unsigned char* wstream = p.packed + (long long)rank * d.packed_per_rank;
+    const int nops = num_ops(d);
+
+    if (warp == 0) {
+        // =============================== weight producer ======================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
+                const unsigned char* src = wstream;
+                for (int o = 0; o < nops; ++o) {
+                    Op op = get_op(d, o);
+                    for (int kc = 0; kc < op.kchunks; ++kc)
+                        for (int nt = 0; nt < n_tiles_of(op.rows); ++nt, ++it) {
+                            const int rows = min(128, op.rows - nt * 128);
+                            const uint32_t bytes = rows * 128;
+                            const int s = it % d.nstage;
+                            mbar_wait(w_empty(s), ((it / d.nstage) & 1) ^ 1);
+                            mbar_expect_tx(w_full(s), bytes);
+                            bulk_g2s(sbase + L.ring + s * CHUNK, src, bytes, w_full(s));
+                            src += bytes;
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ==========================================
+        if (lane == 0) {
+            uint32_t it = 0, round = 0, tiles_done = 0;
+            for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++tiles_done) {
+                mbar_wait(in_ready, tiles_done & 1);
+                tc_fence_after();
+                for (int o = 0; o < nops; ++o) {
+                    Op op = get_op(d, o);
+                    if (op.a_kind == 2 && d.nsplit > 1) {
+                        // arm the barriers of the chunks the peer will push into this CTA
+                        for (int j = 0; j < d.KH; ++j)
+                            if ((j / own_chunks) != (int)rank) mbar_expect_tx(a_ready(j), CHUNK);
+                    }
+                    for (int t = 0; t < op.kchunks; ++t) {
+                        uint32_t a_addr;
+                        if (op.a_kind == 0) a_addr = sbase + L.a + t * CHUNK;
+                        else if (op.a_kind == 1) a_addr = sbase + L.code + t * CHUNK;
+                        else {
+                            const int j = act_chunk(d, rank, t);
+                            mbar_wait(a_ready(j), round & 1);
+                            tc_fence_after();
+                            a_addr = sbase + L.a + j * CHUNK;
+                        }
+                        for (int nt = 0; nt < n_tiles_of(op.rows); ++nt, ++it) {
+                            const int rows = min(128, op.rows - nt * 128);
+                            const int s = it % d.nstage;
+                            mbar_wait(w_full(s), (it / d.nstage) & 1);
+                            tc_fence_after();
+                            const uint64_t da = umma_desc(a_addr), db = umma_desc(sbase + L.ring + s * CHUNK);
+                            const uint32_t idesc = umma_idesc(rows, BF16);
+                            const uint32_t dcol = tmem + op.d_col + nt * 128;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16(dcol, da + 2 * k, db + 2 * k, idesc, (op.first_overwrites && t == 0 && k == 0) ? 0u : 1u);
+                            umma_commit(w_empty(s));          // frees the ring slot when these MMAs retire
+                        }
+                    }
+                    if (op.a_kind == 2) ++round;
+                    if (op.group_end) {
+                        if (d.nsplit > 1) umma_commit_mc(acc_ready, (uint16_t)((1u << d.nsplit) - 1));
+                        else umma_commit(acc_ready);
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // =============================== A-chunk exchange (NSPLIT=2) ==========================
+        if (lane == 0 && d.nsplit > 1) {
+            const uint32_t peer = rank ^ 1u;
+            uint32_t round = 0;
+            for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
+                for (int r = 0; r < 2 * d.nb + 1; ++r, ++round) {
+                    for (int t = 0; t < own_chunks; ++t) {
+                        const int j = rank * own_chunks + t;
+                        mbar_wait(a_ready(j), round & 1);     // all four epilogue warps wrote + fenced chunk j
+                        const uint32_t src = sbase + L.a + j * CHUNK;
+                        bulk_s2peer(map_to_cta(src, peer), src, CHUNK, map_to_cta(a_ready(j), peer));
+                    }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // =============================== prologue + epilogue ===================================
+        const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        const int row = q * 32 + lane;                       // query row inside the tile == TMEM lane
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        const GnbDecoderWeights& w = p.w;
+        uint32_t grp = 0;                                    // acc_ready uses so far
+        for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
+            const long long grow = (long long)tile * BM + row;
+            const bool live = grow < p.n_rows;
+            // ---------------- prologue: operand tiles of lin_in and lin_z -------------------
+            {
+                float code[64 * 4];                          // d_code + 2 <= 64*KZ (KZ <= 4)
+                const int kz = d.KZ * 64;
+                for (int k = 0; k < kz; ++k) code[k] = 0.0f;
+                float xyz3[3] = {0.f, 0.f, 0.f};
+                if (live) {
+                    if (w.use_code == 2) {
+                        for (int k = 0; k < d.d_code; ++k) code[k] = __ldg(p.xyz + grow * d.d_code + k);
+                    } else {
+                        xyz3[0] = __ldg(p.xyz + grow * 3), xyz3[1] = __ldg(p.xyz + grow * 3 + 1), xyz3[2] = __ldg(p.xyz + grow * 3 + 2);
+                        if (w.use_code == 0) { code[0] = xyz3[0], code[1] = xyz3[1], code[2] = xyz3[2]; }
+                        else {
+                            int o = 0;
+                            if (w.include_input) { code[0] = xyz3[0], code[1] = xyz3[1], code[2] = xyz3[2]; o = 3; }
+                            const float half_pi = (float)(3.14159265358979323846 * 0.5);
+                            for (int f = 0; f < 2 * w.num_freqs; ++f) {
+                                const float freq = w.freq_factor * exp2f((float)(f >> 1));
+                                const float phase = (f & 1) ? half_pi : 0.0f;
+                                for (int dd = 0; dd < 3; ++dd) code[o + f * 3 + dd] = sinf(__fadd_rn(phase, __fmul_rn(xyz3[dd], freq)));
+                            }
+                        }
+                    }
+                }
+                code[d.d_code] = 1.0f, code[d.d_code + 1] = 1.0f;      // bias hi / lo columns
+                for (int c = 0; c < d.KZ; ++c)
+                    for (int u = 0; u < 8; ++u) {
+                        const float* v = code + c * 64 + u * 8;
+                        uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
+                        *reinterpret_cast<uint4*>(sm + L.code + c * CHUNK + chunk_off(row, u)) = pk;
+                    }
+                // features: sampled here (fused) or read from the feature tensor
+                TriCorners tcn;
+                BiCorners bc[3];
+                const int b = (p.fused && live) ? (int)(grow / p.s.Q) : 0;
+                if (p.fused && live) {
+                    if (p.s.volume) trilinear_setup(p.s, xyz3[0], xyz3[1], xyz3[2], tcn);
+                    if (p.s.Cp > 0) planes_setup(p.s, xyz3[0], xyz3[1], xyz3[2], bc);
+                }
+                for (int c = 0; c < d.KF; ++c)
+                    for (int u = 0; u < 8; ++u) {
+                        float v[8];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int k = c * 64 + u * 8 + h * 4;         // first of 4 feature columns
+                            float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live && k < d.d_feat) {
+                                if (!p.fused) {
+                                    const float* src = p.feat + grow * d.d_feat + k;
+                                    if ((d.d_feat & 3) == 0) f4 = ldg4(src);
+                                    else {
+                                        f4.x = __ldg(src);
+                                        if (k + 1 < d.d_feat) f4.y = __ldg(src + 1);
+                                        if (k + 2 < d.d_feat) f4.z = __ldg(src + 2);
+                                        if (k + 3 < d.d_feat) f4.w = __ldg(src + 3);
+                                    }
+                                } else {
+                                    // (host guarantees C_p % 4 == 0, C % 4 == 0 and unit channel strides here)
+                                    Vals<4> r = (k < p.s.Cp) ? sample_planes<4>(p.s, bc, b, k) : sample_volume<4>(p.s, tcn, b, k - p.s.Cp);
+                                    f4 = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+                                    if (p.s.out && rank == 0) *reinterpret_cast<float4*>(p.s.out + grow * p.s.out_stride + k) = f4;
+                                }
+                            }
+                            v[h * 4 + 0] = f4.x, v[h * 4 + 1] = f4.y, v[h * 4 + 2] = f4.z, v[h * 4 + 3] = f4.w;
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = c * 64 + u * 8 + e;
+                            if (k == d.d_feat || k == d.d_feat + 1) v[e] = 1.0f;       // bias hi / lo columns
+                        }
+                        uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
+                        *reinterpret_cast<uint4*>(sm + L.a + c * CHUNK + chunk_off(row, u)) = pk;
+                    }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(in_ready);
+            }
+            // ---------------- epilogue rounds: accumulator -> next A operand -----------------
+            const float* b0 = bias_s;
+            const float* b1_last = bias_s + d.nb * d.HN;
+            for (int r = 0; r < 2 * d.nb + 1; ++r) {
+                mbar_wait(acc_ready, grp & 1);
+                ++grp;
+                tc_fence_after();
+                const bool from_net = (r & 1) == 1;                       // rounds: x, net, x, net, ..., x(last)
+                const float* bias = from_net ? (b0 + (r >> 1) * d.HN) : ((r == 2 * d.nb) ? b1_last : nullptr);
+                const uint32_t src_col = from_net ? NET_COL : 0;
+                for (int t = 0; t < own_chunks; ++t) {
+                    const int j = rank * own_chunks + t;
+                    unsigned char* dst = sm + L.a + j * CHUNK;
+#pragma unroll
+                    for (int part = 0; part < 4; ++part) {               // 4 x 16 columns
+                        uint32_t v[16];
+                        tmem_ld16(tlane + src_col + t * 64 + part * 16, v);
+                        tmem_ld_wait();
+                        float f[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float x = __uint_as_float(v[e]);
+                            if (bias) x += bias[t * 64 + part * 16 + e];
+                            f[e] = fmaxf(x, 0.0f);
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 pk = make_uint4(pack16<BF16>(f[h * 8 + 0], f[h * 8 + 1]), pack16<BF16>(f[h * 8 + 2], f[h * 8 + 3]),
+                                                  pack16<BF16>(f[h * 8 + 4], f[h * 8 + 5]), pack16<BF16>(f[h * 8 + 6], f[h * 8 + 7]));
+                            *reinterpret_cast<uint4*>(dst + chunk_off(row, part * 2 + h)) = pk;
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_ready(j));
+                }
+            }
+            // ---------------- final epilogue: lin_out tile -> global, TSDF head -----------------
+            {
+                mbar_wait(acc_ready, grp & 1);
+                ++grp;
+                tc_fence_after();
+                const float* bo = bias_s + d.nb * d.HN + d.HN;
+                const float* hw = bo + d.NOUT;
+                float head = hw[d.d_geo];
+                for (int part = 0; part < d.NOUT / 16; ++part) {
+                    uint32_t v[16];
+                    tmem_ld16(tlane + NET_COL + part * 16, v);
+                    tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int n = part * 16 + e;
+                        f[e] = __uint_as_float(v[e]) + bo[n];
+                        if (n < d.d_geo) head = fmaf(f[e], hw[n], head);
+                    }
+                    if (live && rank == 0 && p.out) {
+                        float* o = p.out + grow * d.d_out + part * 16;
+                        if ((d.d_out & 3) == 0) {
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4)
+                                if (part * 16 + e < d.d_out) *reinterpret_cast<float4*>(o + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                if (part * 16 + e < d.d_out) o[e] = f[e];
+                        }
+                    }
+                }
+                if (live && rank == 0 && p.tsdf) p.tsdf[grow] = tanhf(head);
+                tc_fence_before();
+            }
+        }
+    }
+
+    // ---- teardown -----------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (d.nsplit > 1) cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 nn.Linear matrices -> bf16, K-major, 128B-swizzled tiles in stream order
+// ---------------------------------------------------------------------------------------------
+struct PackOp {
+    const float* W;       // (rows_true, K_true) row-major
+    int rows_true, K_true;
+    int n0;               // first row of this CTA's slice
+    int rows;             // rows of the op in this CTA (HN or NOUT)
+    int kchunks;
+    int kc_rot;           // activation ops: visiting order starts at this chunk (own chunks first)
+    float scale;          // multiplies W and biasA
+    const float* biasA;   // bias columns at k == K_true (hi) and K_true + 1 (lo): scale*biasA[n] + biasB[n]
+    const float* biasB;
+    int bias_cols;
+    long long dst_off;    // byte offset of the op inside the rank's stream
+};
+
+template <bool BF16>
+__global__ void pack_kernel(PackOp op, unsigned char* __restrict__ dst_rank) {
+    // one thread per 16-byte unit: (t, nt, n_local, u)
+    const int ntile = n_tiles_of(op.rows);
+    const long long units_per_k = (long long)op.rows * 8;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= units_per_k * op.kchunks) return;
+    const int t = (int)(idx / units_per_k);
+    int rem = (int)(idx % units_per_k);
+    const int n_in_op = rem / 8, u = rem % 8;
+    const int nt = n_in_op / 128, nl = n_in_op % 128;
+    const int kc = (op.kc_rot + t) % op.kchunks;
+    const int n = op.n0 + n_in_op;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = kc * 64 + u * 8 + e;
+        float x = 0.0f;
+        if (n < op.rows_true) {
+            if (k < op.K_true) x = op.scale * op.W[(long long)n * op.K_true + k];
+            else if (op.bias_cols && k < op.K_true + 2) {
+                float b = (op.biasA ? op.scale * op.biasA[n] : 0.0f) + (op.biasB ? op.biasB[n] : 0.0f);
+                float hi = round16<BF16>(b);
+                x = (k == op.K_true) ? hi : (b - hi);
+            }
+        }
+        v[e] = x;
+    }
+    // tiles of one k-chunk are consecutive: rows of earlier n-tiles precede
+    long long off = op.dst_off + ((long long)t * op.rows + (long long)nt * 128) * 128 + chunk_off(nl, u);
+    (void)ntile;
+    *reinterpret_cast<uint4*>(dst_rank + off) = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
+}
+
+static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
+    int rc = check_decoder_weights(w, who);
+    if (rc) return rc;
+    d.d_feat = w->d_feat, d.d_code = w->d_code, d.Hd = w->d_hidden, d.nb = w->n_blocks, d.d_out = w->d_out, d.d_geo = w->d_geo;
+    if (d.Hd % 64 != 0 || d.Hd > 512 || d.Hd < 64 || (d.Hd > 256 && d.Hd % 128 != 0)) {
+        set_error("%s: d_hidden %d is not supported by the tcgen05 path (multiple of 64 up to 256, or 384 / 512)", who, d.Hd);
+        return GNB_E_UNSUPPORTED;
+    }
+    if (w->tc_dtype != GNB_TC_FP16 && w->tc_dtype != GNB_TC_BF16) { set_error("%s: unknown tc_dtype %d", who, w->tc_dtype); return GNB_E_INVALID; }
+    if (d.nb < 1) { set_error("%s: n_blocks must be >= 1", who); return GNB_E_UNSUPPORTED; }
+    d.nsplit = d.Hd > 256 ? 2 : 1;
+    d.HN = d.Hd / d.nsplit;
+    d.KF = (d.d_feat + 2 + 63) / 64;
+    d.KZ = (d.d_code + 2 + 63) / 64;
+    d.KH = d.Hd / 64;
+    d.NOUT = (d.d_out + 15) / 16 * 16;
+    if (d.KZ > 4 || d.NOUT > 256 || d.KF > MAX_CHUNKS) {
+        set_error("%s: d_code %d / d_out %d / d_feat %d too large for the tcgen05 path", who, d.d_code, d.d_out, d.d_feat);
+        return GNB_E_UNSUPPORTED;
+    }
+    d.ACH = d.KF > d.KH ? d.KF : d.KH;
+    d.nstage = MAX_STAGES;
+    while (d.nstage >= 2 && smem_layout(d).total + 1024 > 227 * 1024) --d.nstage;
+    if (d.nstage < 2) { set_error("%s: tile does not fit in shared memory", who); return GNB_E_UNSUPPORTED; }
+    long long bytes = 0;
+    bytes += (long long)d.KF * d.HN * 128;
+    bytes += (long long)d.nb * ((long long)d.KZ * d.HN * 128 + 2LL * d.KH * d.HN * 128);
+    bytes += (long long)d.KH * d.NOUT * 128;
+    d.packed_per_rank = bytes;
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace gnb
+
 using namespace gnb;
-extern "C" int64_t gnb_decoder_packed_bytes(const GnbDecoderWeights* w) { (void)w; return 0; }
-extern "C" int gnb_decoder_pack_bf16(const GnbDecoderWeights* w, void* packed, void* stream) {
-    (void)w, (void)packed, (void)stream;
-    set_error("gnb_decoder_pack_bf16: not built yet");
-    return GNB_E_UNSUPPORTED;
+using namespace gnb::tc;
+
+extern "C" int64_t gnb_decoder_packed_bytes(const GnbDecoderWeights* w) {
+    Dims d;
+    if (make_dims(w, d, "gnb_decoder_packed_bytes")) return 0;
+    return d.packed_per_rank * d.nsplit;
 }
-extern "C" int gnb_decode_bf16(const GnbDecoderWeights* w, const void* packed, const float* xyz, const float* feat,
+
+extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, void* stream) {
+    Dims d;
+    int rc = make_dims(w, d, "gnb_decoder_pack_tc");
+    if (rc) return rc;
+    GNB_CHECK_ARG(packed, "gnb_decoder_pack_tc: null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int rank = 0; rank < d.nsplit; ++rank) {
+        unsigned char* dst = (unsigned char*)packed + (long long)rank * d.packed_per_rank;
+        long long off = 0;
+        auto launch = [&](PackOp op) -> int {
+            op.dst_off = off;
+            long long units = (long long)op.rows * 8 * op.kchunks;
+            if (w->tc_dtype == GNB_TC_BF16) pack_kernel<true><<<ceil_div(units, 256), 256, 0, st>>>(op, dst);
+            else pack_kernel<false><<<ceil_div(units, 256), 256, 0, st>>>(op, dst);
+            GNB_LAUNCH_CHECK();
+            off += (long long)op.kchunks * op.rows * 128;
+            return 0;
+        };
+        const int n0 = rank * d.HN, rot = rank * (d.HN / 64);
+        PackOp op;
+        op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.HN, d.KF, 0, 1.0f, w->lin_in_b, nullptr, 1, 0};
+        if ((rc = launch(op))) return rc;
+        for (int i = 0; i < d.nb; ++i) {
+            // x += alpha * (Wz code + bz)   [+ b1 of the previous block, folded here]
+            op = PackOp{w->lin_z_w[i], d.Hd, d.d_code, n0, d.HN, d.KZ, 0, w->alpha, w->lin_z_b[i], i > 0 ? w->fc1_b[i - 1] : nullptr, 1, 0};
+            if ((rc = launch(op))) return rc;
+            op = PackOp{w->fc0_w[i], d.Hd, d.Hd, n0, d.HN, d.KH, rot, 1.0f, nullptr, nullptr, 0, 0};
+            if ((rc = launch(op))) return rc;
+            op = PackOp{w->fc1_w[i], d.Hd, d.Hd, n0, d.HN, d.KH, rot, 1.0f, nullptr, nullptr, 0, 0};
+            if ((rc = launch(op))) return rc;
+        }
+        op = PackOp{w->lin_out_w, d.d_out, d.Hd, 0, d.NOUT, d.KH, rot, 1.0f, nullptr, nullptr, 0, 0};
+        if ((rc = launch(op))) return rc;
+        if (off != d.packed_per_rank) { set_error("gnb_decoder_pack_tc: internal size mismatch"); return GNB_E_INVALID; }
+    }
+    return 0;
+}
+
+static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, void* stream) {
+    int rc = make_dims(w, kp.d, "gnb_decode_tc");
+    if (rc) return rc;
+    GNB_CHECK_ARG(packed, "gnb_decode_tc: weights are not packed");
+    const Dims& d = kp.d;
+    kp.w = *w;
+    kp.packed = (const unsigned char*)packed;
+    if (kp.n_rows == 0) return 0;
+    int dev = 0, sms = 0, cc = 0;
+    GNB_CUDA(cudaGetDevice(&dev));
+    GNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GNB_CUDA(cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc != 10) { set_error("gnb_decode_tc: needs an sm_100 device (found sm_%d0)", cc); return GNB_E_ARCH; }
+    kp.n_tiles = (int)((kp.n_rows + BM - 1) / BM);
+    kp.n_clusters = sms / d.nsplit;
+    if (kp.n_clusters > kp.n_tiles) kp.n_clusters = kp.n_tiles;
+    const size_t smem = smem_layout(d).total + 1024;
+    auto kernel = (w->tc_dtype == GNB_TC_BF16) ? decoder_tc_kernel<true> : decoder_tc_kernel<false>;
+    GNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kp.n_clusters * d.nsplit);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = d.nsplit, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    GNB_CUDA(cudaLaunchKernelEx(&cfg, kernel, kp));
+    return 0;
+}
+
+extern "C" int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz, const float* feat,
                                int64_t n_rows, float* out, float* tsdf, void* stream) {
-    (void)w, (void)packed, (void)xyz, (void)feat, (void)n_rows, (void)out, (void)tsdf, (void)stream;
-    set_error("gnb_decode_bf16: not built yet");
-    return GNB_E_UNSUPPORTED;
+    GNB_CHECK_ARG(xyz && feat && n_rows >= 0 && (out || tsdf), "gnb_decode_tc: bad arguments");
+    TcKP kp = {};
+    kp.xyz = xyz, kp.feat = feat, kp.fused = 0, kp.n_rows = n_rows, kp.out = out, kp.tsdf = tsdf;
+    return launch_tc(w, packed, kp, stream);
 }
-extern "C" int gnb_query_fused_bf16(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed, float* out,
+
+extern "C" int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed, float* out,
                                     float* tsdf, void* stream) {
-    (void)s, (void)w, (void)packed, (void)out, (void)tsdf, (void)stream;
-    set_error("gnb_query_fused_bf16: not built yet");
-    return GNB_E_UNSUPPORTED;
+    TcKP kp = {};
+    int rc = fill_sample_kp(s, kp.s);
+    if (rc) return rc;
+    GNB_CHECK_ARG(w && w->use_code != 2, "gnb_query_fused_tc: the fused query encodes xyz itself (use_code 0 or 1)");
+    GNB_CHECK_ARG(w->d_feat == kp.s.C + kp.s.Cp, "gnb_query_fused_tc: d_feat %d != C_p + C = %d", w->d_feat, kp.s.C + kp.s.Cp);
+    GNB_CHECK_ARG(out || tsdf, "gnb_query_fused_tc: no output requested");
+    GNB_CHECK_ARG(!s->out || (s->out_stride >= w->d_feat && s->out_stride % 4 == 0), "gnb_query_fused_tc: bad feature output stride");
+    bool ok = true;
+    if (kp.s.volume) ok = ok && kp.s.vsc == 1 && kp.s.C % 4 == 0 && kp.s.vsb % 4 == 0 && kp.s.vsx % 4 == 0 && kp.s.vsy % 4 == 0 && kp.s.vsz % 4 == 0;
+    if (kp.s.Cp > 0) ok = ok && kp.s.psc == 1 && kp.s.Cp % 4 == 0 && kp.s.psb % 4 == 0 && kp.s.psh % 4 == 0 && kp.s.psw % 4 == 0;
+    if (!ok) {
+        set_error("gnb_query_fused_tc: the fused path needs channels-last volume / planes with channel counts % 4 == 0 "
+                  "(use gnb_sample_features + gnb_decode_tc otherwise)");
+        return GNB_E_UNSUPPORTED;
+    }
+    kp.xyz = s->xyz, kp.feat = nullptr, kp.fused = 1, kp.n_rows = kp.s.total, kp.out = out, kp.tsdf = tsdf;
+    return launch_tc(w, packed, kp, stream);
 }

@@ -146,8 +146,8 @@ class ResnetFC(nn.Module):
         else:
             kw = dict(use_code=1, num_freqs=code.num_freqs, freq_factor=code.freq_factor, include_input=code.include_input)
         dw = ops.DecoderWeights(sd, hw, hb, n_blocks=self.n_blocks, d_geo=d_geo, device=dev, **kw)
-        if precision == "bf16":
-            dw.pack()
+        if precision in ("fp16", "bf16"):
+            dw.pack(precision)
         return dw
 
     def forward(self, zx, combine_inner_dims=(1,), combine_index=None, dim_size=None, ret_last_feat=False,
@@ -184,9 +184,9 @@ def _decode_given_code(dw, z, x, precision):
             check(lib().gnb_decode_fp32(C.byref(dw.w), z2.data_ptr(), x2.data_ptr(), n, out.data_ptr(), None, st),
                   "gnb_decode_fp32")
         else:
-            packed = dw.packed if dw.packed is not None else dw.pack()
-            check(lib().gnb_decode_bf16(C.byref(dw.w), packed.data_ptr(), z2.data_ptr(), x2.data_ptr(), n, out.data_ptr(),
-                                        None, st), "gnb_decode_bf16")
+            packed = dw.tc_image(precision)
+            check(lib().gnb_decode_tc(C.byref(dw.w), packed.data_ptr(), z2.data_ptr(), x2.data_ptr(), n, out.data_ptr(),
+                                        None, st), "gnb_decode_tc")
     return out.reshape(*lead, -1), None
 
 
@@ -319,11 +319,11 @@ class GenNerf(nn.Module):
     attributes (.volume, .valid, .c_plane).  The 2D CNN (`spatial`) and the FPS front end are
     outside the path: pass the CNN as `spatial=` (any nn.Module image -> (B,C,H,W)) and the
     sparse point cloud through `encode(..., sparse_xyz=)`; Lightning orchestration, losses and
-    logging stay in the reference.  `precision`: 'bf16' (tcgen05 decoder, default for
-    inference) or 'fp32' (CUDA-core decoder, 1e-5 parity).
+    logging stay in the reference.  `precision`: 'fp16' (tcgen05 decoder, default) | 'bf16'
+    (tcgen05, wider range, coarser) | 'fp32' (CUDA-core decoder, 1e-5 parity).
     """
 
-    def __init__(self, cfg, spatial=None, unet=None, precision="bf16", fused=True):
+    def __init__(self, cfg, spatial=None, unet=None, precision="fp16", fused=True):
         super().__init__()
         self.cfg = cfg
         self.precision, self.fused = precision, fused
@@ -403,12 +403,13 @@ class GenNerf(nn.Module):
         """reference model.py:207-248: dict feat_geo, feat_sem, tsdf, feat."""
         d_geo, d_sem = self.cfg.mlp.d_out_geo, self.cfg.mlp.d_out_sem
         dw = self._dw if (self._dw is not None and not self.training) else self.refresh_weights()
-        if self.precision == "bf16" and self.fused:
+        if self.precision in ("fp16", "bf16") and self.fused:
             out, tsdf, feat = ops.query_fused(
                 dw, xyz, volume=self.volume if self.cfg.encoder.use_spatial else None,
                 planes=self.c_plane if self.cfg.encoder.use_pointnet else None,
                 voxel_size=self.cfg.voxel_size, origin=self.origin,
-                padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1)
+                padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1,
+                precision=self.precision)
         else:
             feat = self.map_features(xyz)
             out, tsdf = ops.decode(dw, xyz, feat, self.precision)

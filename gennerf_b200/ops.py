@@ -295,21 +295,29 @@ class DecoderWeights:
         self.device = torch.device(device)
         self.packed = None
 
-    def pack(self):
-        """(Re)build the bf16 tcgen05 operand image of the weights."""
+    def pack(self, dtype="fp16"):
+        """(Re)build the 16-bit tensor-core operand image of the weights ('fp16' or 'bf16')."""
+        self.w.tc_dtype = {"fp16": _lib.TC_FP16, "bf16": _lib.TC_BF16}[dtype]
         n = lib().gnb_decoder_packed_bytes(C.byref(self.w))
         if n <= 0:
-            raise RuntimeError("gennerf_b200: this decoder shape has no bf16 tcgen05 path: "
+            raise RuntimeError("gennerf_b200: this decoder shape has no tcgen05 path: "
                                + lib().gnb_last_error().decode())
         if self.packed is None or self.packed.numel() != n:
             self.packed = torch.empty(n, device=self.device, dtype=torch.uint8)
         with torch.cuda.device(self.device):
-            check(lib().gnb_decoder_pack_bf16(C.byref(self.w), self.packed.data_ptr(), _stream()), "gnb_decoder_pack_bf16")
+            check(lib().gnb_decoder_pack_tc(C.byref(self.w), self.packed.data_ptr(), _stream()), "gnb_decoder_pack_tc")
+        self.packed_dtype = dtype
+        return self.packed
+
+    def tc_image(self, dtype):
+        if self.packed is None or getattr(self, "packed_dtype", None) != dtype:
+            self.pack(dtype)
         return self.packed
 
 
 def decode(weights, xyz, feat, precision="fp32"):
     """PositionalEncoding -> ResnetFC -> TSDFHeadSimple (reference model.py:226-246).
+    precision: 'fp32' (CUDA cores, exact mode) | 'fp16' | 'bf16' (tcgen05, 16-bit operands).
     xyz (..., 3), feat (..., d_feat) -> out (..., d_out), tsdf (..., 1)."""
     _need_cuda(xyz, feat)
     lead = xyz.shape[:-1]
@@ -322,18 +330,18 @@ def decode(weights, xyz, feat, precision="fp32"):
         if precision == "fp32":
             check(lib().gnb_decode_fp32(C.byref(weights.w), xyz2.data_ptr(), feat2.data_ptr(), n, out.data_ptr(),
                                         tsdf.data_ptr(), _stream()), "gnb_decode_fp32")
-        elif precision == "bf16":
-            packed = weights.packed if weights.packed is not None else weights.pack()
-            check(lib().gnb_decode_bf16(C.byref(weights.w), packed.data_ptr(), xyz2.data_ptr(), feat2.data_ptr(), n,
-                                        out.data_ptr(), tsdf.data_ptr(), _stream()), "gnb_decode_bf16")
+        elif precision in ("fp16", "bf16"):
+            packed = weights.tc_image(precision)
+            check(lib().gnb_decode_tc(C.byref(weights.w), packed.data_ptr(), xyz2.data_ptr(), feat2.data_ptr(), n,
+                                        out.data_ptr(), tsdf.data_ptr(), _stream()), "gnb_decode_tc")
         else:
             raise ValueError(precision)
     return out.reshape(*lead, -1), tsdf.reshape(*lead, 1)
 
 
 def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
-                want_feat=True):
-    """GenNerf.forward in one kernel (sampler fused into the bf16 tcgen05 decoder).
+                want_feat=True, precision="fp16"):
+    """GenNerf.forward in one kernel (sampler fused into the tcgen05 decoder).
     Returns out (B,Q,d_out), tsdf (B,Q,1), feat (B,Q,C_lat) or None."""
     s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
     feat = None
@@ -342,10 +350,10 @@ def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
         s.out, s.out_stride = feat.data_ptr(), Cp + Cv
     out = torch.empty((B, Q, weights.w.d_out), device=xyz.device, dtype=torch.float32)
     tsdf = torch.empty((B, Q, 1), device=xyz.device, dtype=torch.float32)
-    packed = weights.packed if weights.packed is not None else weights.pack()
+    packed = weights.tc_image(precision)
     with torch.cuda.device(xyz.device):
-        check(lib().gnb_query_fused_bf16(C.byref(s), C.byref(weights.w), packed.data_ptr(), out.data_ptr(),
-                                         tsdf.data_ptr(), _stream()), "gnb_query_fused_bf16")
+        check(lib().gnb_query_fused_tc(C.byref(s), C.byref(weights.w), packed.data_ptr(), out.data_ptr(),
+                                         tsdf.data_ptr(), _stream()), "gnb_query_fused_tc")
     return out, tsdf, feat
 
 

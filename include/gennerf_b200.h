@@ -172,6 +172,8 @@ int gnb_pool_local(const float* p, const float* c, int B, int64_t N, int Hd, int
  *   the glue in GenNerf.forward()  src/models/model.py:226-246
  * Weight layout is the reference's nn.Linear layout (out_features, in_features) row-major.
  * ----------------------------------------------------------------------------------- */
+#define GNB_TC_FP16 0              /* 11-bit significand, |x| <= 65504 (saturated)          */
+#define GNB_TC_BF16 1              /* 8-bit significand, fp32 range                         */
 typedef struct GnbDecoderWeights {
     int32_t d_feat;                /* lin_in in_features  (= encoder_latent)                */
     int32_t d_code;                /* lin_z in_features   (= 3 + 6*num_freqs, or 3)         */
@@ -194,6 +196,7 @@ typedef struct GnbDecoderWeights {
     const float* fc1_w[8];   const float* fc1_b[8];
     const float* lin_out_w; const float* lin_out_b;
     const float* head_w;    const float* head_b;
+    int32_t tc_dtype;              /* tensor-core operand type: GNB_TC_FP16 (default) or GNB_TC_BF16 */
 } GnbDecoderWeights;
 
 /* Stand-alone pieces (the reference's modules called on their own). */
@@ -206,17 +209,19 @@ int gnb_tsdf_head(const float* feat_geo, int64_t n_rows, int d_geo, int64_t row_
 int gnb_decode_fp32(const GnbDecoderWeights* w, const float* xyz, const float* feat,
                     int64_t n_rows, float* out, float* tsdf, void* stream);
 
-/* bf16 tcgen05/TMEM decoder (fast mode, |tsdf - oracle| <= 1e-2).  `packed` is the
- * device buffer written by gnb_decoder_pack_bf16 (gnb_decoder_packed_bytes bytes). */
+/* tcgen05/TMEM tensor-core decoder (fast mode): 16-bit operands (w->tc_dtype), fp32
+ * accumulation and fp32 residual stream; |tsdf - oracle| <= 1e-2 with fp16 operands.
+ * `packed` is the device buffer written by gnb_decoder_pack_tc (gnb_decoder_packed_bytes
+ * bytes); it must be re-packed after the fp32 parameters change. */
 int64_t gnb_decoder_packed_bytes(const GnbDecoderWeights* w);
-int gnb_decoder_pack_bf16(const GnbDecoderWeights* w, void* packed, void* stream);
-int gnb_decode_bf16(const GnbDecoderWeights* w, const void* packed, const float* xyz,
-                    const float* feat, int64_t n_rows, float* out, float* tsdf, void* stream);
+int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, void* stream);
+int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz,
+                  const float* feat, int64_t n_rows, float* out, float* tsdf, void* stream);
 
-/* Fused sampler + bf16 decoder (GenNerf.forward, model.py:207-248): xyz -> feat (optional
- * output), out (feat_geo|feat_sem), tsdf, in one kernel. */
-int gnb_query_fused_bf16(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed,
-                         float* out, float* tsdf, void* stream);
+/* Fused sampler + tensor-core decoder (GenNerf.forward, model.py:207-248): xyz -> feat
+ * (optional output), out (feat_geo|feat_sem), tsdf, in one kernel. */
+int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed,
+                       float* out, float* tsdf, void* stream);
 
 #ifdef __cplusplus
 }

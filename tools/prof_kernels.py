@@ -20,7 +20,7 @@ T = wl["T"]
 P = S.projections(T, wl["H"], wl["W"], wl["voxel_dim"], VS, g).unsqueeze(0)
 feats = [torch.randn(1, C, wl["H"], wl["W"], device=dev) for _ in range(T)]
 feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
-Q = min(wl["Q"], 1 << 21)
+Q = int(os.environ.get("PROF_Q", min(wl["Q"], 1 << 21)))
 xyz = S.query_points(Q, wl["voxel_dim"], VS, g).to(dev)
 w, hw, hb = S.decoder_weights(g, C, 15, 512, 5, 64, 32)
 dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, use_code=True, num_freqs=2, freq_factor=0.5, device=dev)
