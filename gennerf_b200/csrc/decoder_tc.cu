@@ -20,7 +20,7 @@
 //          W ring           NSTAGE x 16 KB weight tiles (<=128 n-rows x 64 k), pre-swizzled in HBM,
 //                           streamed with 1-D bulk async copies (no tensor map needed)
 //   warps  0: weight producer   1: MMA issuer   2: TMEM alloc + A-chunk exchange   3: idle
-//          4-7: epilogue / prologue (thread = query row = TMEM lane)
+//          4-11: epilogue / prologue, two warps per TMEM lane quadrant (thread = query row = TMEM lane)
 //
 // Dataflow per tile: prologue samples features + encodes xyz -> bf16 operand tiles; then MMA groups
 //   G0 = [lin_in, lin_z_0] -> x;  per block: E(relu(x)) -> [fc_0] -> net;  E(relu(net+b0)) ->
@@ -32,6 +32,7 @@
 // lin_in / lin_z biases (and fc_1's, folded into the next lin_z) ride in two extra K columns
 // as a bf16 hi+lo pair; fc_0 / lin_out / last fc_1 biases are added in fp32 by the epilogue.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 #include "sample.cuh"
@@ -47,15 +48,19 @@ constexpr int CHUNK = BM * 128;       // bytes of one 128-row x 64-col bf16 chun
 constexpr int NET_COL = 256;          // TMEM column of the net / out accumulator
 constexpr int MAX_CHUNKS = 16;
 constexpr int MAX_STAGES = 8;
-constexpr int NTHREADS = 256;
-constexpr int EPI_WARP0 = 4;          // first epilogue warp (4 warps: one per TMEM lane quadrant)
+constexpr int NTHREADS = 384;
+constexpr int EPI_WARP0 = 4;          // epilogue warps 4..11: two per TMEM lane quadrant (warp & 3)
+constexpr int EPI_GROUPS = 2;         // group g = (warp - 4) / 4 converts the own chunks t with t % 2 == g
 
 struct Dims {
     int d_feat, d_code, Hd, nb, d_out, d_geo;
     int nsplit, HN;                   // CTAs per tile, hidden units per CTA
     int KF, KZ, KH;                   // 64-wide K chunks of lin_in, lin_z, hidden layers
     int NOUT;                         // lin_out rows padded to a multiple of 16
-    int ACH;                          // chunks in the A buffer = max(KF, KH)
+    int OWN;                          // activation chunks this CTA produces per layer = HN / 64
+    int AOWN;                         // A-buffer slots for own chunks (and the lin_in operand) = max(KF, OWN)
+    int RS;                           // A-buffer slots cycled through by the chunks the peer pushes (0, 1 or 2)
+    int ACH;                          // A-buffer slots in total = AOWN + RS
     int nstage;
     long long packed_per_rank;        // bytes
 };
@@ -155,6 +160,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // two fp32 -> one packed pair of 16-bit operands (fp16 saturates at +-65504 instead of overflowing)
@@ -164,9 +184,18 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
         __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&v);
     } else {
-        __half2 v = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
-        return *reinterpret_cast<uint32_t*>(&v);
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
     }
+}
+// relu + (fp16: saturate) + round + pack in ONE F2FP instruction
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack16_relu(float lo, float hi) {
+    uint32_t r;
+    if constexpr (BF16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 template <bool BF16>
 __device__ __forceinline__ float round16(float a) {
@@ -191,6 +220,7 @@ struct TcKP {
     float* out;                   // (n_rows,d_out) or null
     float* tsdf;                  // (n_rows) or null
     int n_tiles, n_clusters;
+    long long* dbg;               // optional per-phase clock64() trace of cluster 0 (profiling aid), or null
 };
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
@@ -207,7 +237,7 @@ __host__ __device__ inline Smem smem_layout(const Dims& d) {
     // fp32 table: b0[nb][HN] | b1_last[HN] | b_out[NOUT] | head_w[d_geo] | head_b
     uint32_t nbias = (uint32_t)(d.nb * d.HN + d.HN + d.NOUT + d.d_geo + 1);
     s.bars = (s.bias + nbias * 4 + 15) & ~15u;
-    // barriers: w_full[8] w_empty[8] a_ready[16] acc_ready in_ready | tmem base slot
+    // barriers: w_full[8] w_empty[8] a_ready[8] rready[4] rfree[4] acc_ready in_ready | tmem base slot
     s.total = s.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2) * 8 + 16;
     return s;
 }
@@ -232,6 +262,9 @@ __device__ __forceinline__ Op get_op(const Dims& d, int o) {
 // k-chunk visiting order of an activation op: own chunks first, then the peer's
 __device__ __forceinline__ int act_chunk(const Dims& d, int rank, int t) { return (rank * (d.HN / 64) + t) % d.KH; }
 
+// trace slot layout: dbg[role*4096 + k]; role 0 = MMA thread, 1 = epilogue warp 4 lane 0, 2 = producer
+#define GNB_TRACE(role, k) do { if (p.dbg && blockIdx.x == 0 && (k) < 4096) p.dbg[(role) * 4096 + (k)] = clock64(); } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -245,7 +278,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     const uint32_t bar0 = sbase + L.bars;
     auto w_full = [&](int s) { return bar0 + 8u * s; };
     auto w_empty = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
-    auto a_ready = [&](int j) { return bar0 + 8u * (2 * MAX_STAGES + j); };
+    auto a_ready = [&](int t) { return bar0 + 8u * (2 * MAX_STAGES + t); };          // own chunk t written (this CTA)
+    auto rready = [&](int sl) { return bar0 + 8u * (2 * MAX_STAGES + 8 + sl); };     // peer's chunk landed in remote slot sl
+    auto rfree = [&](int sl) { return bar0 + 8u * (2 * MAX_STAGES + 12 + sl); };     // the PEER has consumed what I pushed into its slot sl
     const uint32_t acc_ready = bar0 + 8u * (2 * MAX_STAGES + MAX_CHUNKS);
     const uint32_t in_ready = acc_ready + 8;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2) * 8);
@@ -254,17 +289,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = (d.nsplit > 1) ? cluster_rank() : 0u;
     const int cluster_id = blockIdx.x / d.nsplit;
-    const int own_chunks = d.HN / 64;
+    const int own_chunks = d.OWN;
+    const uint32_t peer = rank ^ 1u;
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int s = 0; s < d.nstage; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-        for (int j = 0; j < d.KH; ++j) {
-            bool own = (j / own_chunks) == (int)rank;
-            mbar_init(a_ready(j), own ? 4 : 1);           // 4 epilogue warps, or the arming arrive for a pushed chunk
-        }
+        for (int t = 0; t < 8; ++t) mbar_init(a_ready(t), 4 * EPI_GROUPS);   // all epilogue warps contribute to a chunk
+        for (int sl = 0; sl < 4; ++sl) { mbar_init(rready(sl), 1); mbar_init(rfree(sl), 1); }
         mbar_init(acc_ready, d.nsplit);                   // every CTA of the cluster commits to every CTA
-        mbar_init(in_ready, 4);
+        mbar_init(in_ready, 4 * EPI_GROUPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -295,82 +329,122 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     if (warp == 0) {
         // =============================== weight producer ======================================
         if (lane == 0) {
-            uint32_t it = 0;
+            int stage = 0;
+            uint32_t phase = 0;
             for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
                 const unsigned char* src = wstream;
                 for (int o = 0; o < nops; ++o) {
-                    Op op = get_op(d, o);
+                    const Op op = get_op(d, o);
+                    const int ntile = n_tiles_of(op.rows);
                     for (int kc = 0; kc < op.kchunks; ++kc)
-                        for (int nt = 0; nt < n_tiles_of(op.rows); ++nt, ++it) {
-                            const int rows = min(128, op.rows - nt * 128);
-                            const uint32_t bytes = rows * 128;
-                            const int s = it % d.nstage;
-                            mbar_wait(w_empty(s), ((it / d.nstage) & 1) ^ 1);
-                            mbar_expect_tx(w_full(s), bytes);
-                            bulk_g2s(sbase + L.ring + s * CHUNK, src, bytes, w_full(s));
+                        for (int nt = 0; nt < ntile; ++nt) {
+                            const uint32_t bytes = (uint32_t)min(128, op.rows - nt * 128) * 128u;
+                            mbar_wait(w_empty(stage), phase ^ 1);
+                            mbar_expect_tx(w_full(stage), bytes);
+                            bulk_g2s(sbase + L.ring + stage * CHUNK, src, bytes, w_full(stage));
                             src += bytes;
+                            if (++stage == d.nstage) { stage = 0; phase ^= 1; }
                         }
                 }
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ==========================================
-        if (lane == 0) {
-            uint32_t it = 0, round = 0, tiles_done = 0;
-            for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++tiles_done) {
-                mbar_wait(in_ready, tiles_done & 1);
-                tc_fence_after();
-                for (int o = 0; o < nops; ++o) {
-                    Op op = get_op(d, o);
-                    if (op.a_kind == 2 && d.nsplit > 1) {
-                        // arm the barriers of the chunks the peer will push into this CTA
-                        for (int j = 0; j < d.KH; ++j)
-                            if ((j / own_chunks) != (int)rank) mbar_expect_tx(a_ready(j), CHUNK);
-                    }
-                    for (int t = 0; t < op.kchunks; ++t) {
-                        uint32_t a_addr;
-                        if (op.a_kind == 0) a_addr = sbase + L.a + t * CHUNK;
-                        else if (op.a_kind == 1) a_addr = sbase + L.code + t * CHUNK;
-                        else {
-                            const int j = act_chunk(d, rank, t);
-                            mbar_wait(a_ready(j), round & 1);
-                            tc_fence_after();
-                            a_addr = sbase + L.a + j * CHUNK;
+        // The whole warp walks the program (warp-uniform control flow and operands); one elected
+        // lane issues.  Two adjacent ring slots holding the two 128-row halves of a 256-row slice
+        // are consumed by ONE N=256 instruction per k-step (half the issue work, 25% less
+        // shared-memory operand traffic than two N=128 instructions).
+        int stage = 0;
+        uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0;
+        for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++tiles_done) {
+            mbar_wait(in_ready, tiles_done & 1);
+            tc_fence_after();
+            int tk = tiles_done * 64;
+            if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
+            for (int o = 0; o < nops; ++o) {
+                const Op op = get_op(d, o);
+                if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
+                const int ntile = n_tiles_of(op.rows);
+                long long wait_a = 0, wait_w = 0;                  // trace only
+                for (int t = 0; t < op.kchunks; ++t) {
+                    uint32_t a_addr;
+                    int rslot = -1;                                // >= 0: this chunk sits in a remote slot
+                    if (op.a_kind == 0) a_addr = sbase + L.a + t * CHUNK;
+                    else if (op.a_kind == 1) a_addr = sbase + L.code + t * CHUNK;
+                    else {
+                        const long long c0 = p.dbg ? clock64() : 0;
+                        if (t < own_chunks) {                      // own chunks first ...
+                            mbar_wait(a_ready(t), round & 1);
+                            a_addr = sbase + L.a + t * CHUNK;
+                        } else {                                   // ... then the peer's, in the order it pushes them
+                            rslot = (int)(rtotal % (uint32_t)d.RS);
+                            if (lane == 0) mbar_expect_tx(rready(rslot), CHUNK);
+                            __syncwarp();
+                            mbar_wait(rready(rslot), (rtotal / (uint32_t)d.RS) & 1);
+                            a_addr = sbase + L.a + (d.AOWN + rslot) * CHUNK;
+                            ++rtotal;
                         }
-                        for (int nt = 0; nt < n_tiles_of(op.rows); ++nt, ++it) {
-                            const int rows = min(128, op.rows - nt * 128);
-                            const int s = it % d.nstage;
-                            mbar_wait(w_full(s), (it / d.nstage) & 1);
-                            tc_fence_after();
-                            const uint64_t da = umma_desc(a_addr), db = umma_desc(sbase + L.ring + s * CHUNK);
-                            const uint32_t idesc = umma_idesc(rows, BF16);
-                            const uint32_t dcol = tmem + op.d_col + nt * 128;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_f16(dcol, da + 2 * k, db + 2 * k, idesc, (op.first_overwrites && t == 0 && k == 0) ? 0u : 1u);
-                            umma_commit(w_empty(s));          // frees the ring slot when these MMAs retire
-                        }
+                        if (p.dbg) wait_a += clock64() - c0;
                     }
-                    if (op.a_kind == 2) ++round;
-                    if (op.group_end) {
+                    for (int nt = 0; nt < ntile;) {
+                        const int pair = (ntile - nt >= 2 && (stage & 1) == 0 && stage + 1 < d.nstage) ? 2 : 1;
+                        const long long c1 = p.dbg ? clock64() : 0;
+                        mbar_wait(w_full(stage), phase);
+                        if (pair == 2) mbar_wait(w_full(stage + 1), phase);
+                        if (p.dbg) wait_w += clock64() - c1;
+                        tc_fence_after();
+                        const int rows = min(128 * pair, op.rows - nt * 128);
+                        const uint64_t da = umma_desc(a_addr), db = umma_desc(sbase + L.ring + stage * CHUNK);
+                        const uint32_t idesc = umma_idesc(rows, BF16);
+                        const uint32_t dcol = tmem + op.d_col + nt * 128;
+                        const uint32_t first = (op.first_overwrites && t == 0) ? 0u : 1u;
+                        if (elect_one()) {
+                            umma_f16(dcol, da, db, idesc, first);
+                            umma_f16(dcol, da + 2, db + 2, idesc, 1u);
+                            umma_f16(dcol, da + 4, db + 4, idesc, 1u);
+                            umma_f16(dcol, da + 6, db + 6, idesc, 1u);
+                            umma_commit(w_empty(stage));          // frees the ring slot(s) when these MMAs retire
+                            if (pair == 2) umma_commit(w_empty(stage + 1));
+                            // last MMAs that read a remote slot: tell the PEER it may push into it again
+                            if (rslot >= 0 && nt + pair >= ntile) umma_commit_mc(rfree(rslot), (uint16_t)(1u << peer));
+                        }
+                        __syncwarp();
+                        stage += pair;
+                        if (stage == d.nstage) { stage = 0; phase ^= 1; }
+                        nt += pair;
+                    }
+                }
+                if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
+                if (lane == 0 && p.dbg && blockIdx.x == 0 && tiles_done < 8) {
+                    p.dbg[2 * 4096 + (tiles_done * 32 + o) * 2] = wait_a;
+                    p.dbg[2 * 4096 + (tiles_done * 32 + o) * 2 + 1] = wait_w;
+                }
+                if (op.a_kind == 2) ++round;
+                if (op.group_end) {
+                    if (elect_one()) {
                         if (d.nsplit > 1) umma_commit_mc(acc_ready, (uint16_t)((1u << d.nsplit) - 1));
                         else umma_commit(acc_ready);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 2) {
         // =============================== A-chunk exchange (NSPLIT=2) ==========================
+        // Pushes every own chunk into one of the peer's RS remote slots (cycled).  A slot is reused
+        // only after the peer's MMAs that read it have retired (rfree, signalled by the peer's
+        // multicast tcgen05.commit).
         if (lane == 0 && d.nsplit > 1) {
-            const uint32_t peer = rank ^ 1u;
-            uint32_t round = 0;
+            uint32_t round = 0, ptotal = 0;
             for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
                 for (int r = 0; r < 2 * d.nb + 1; ++r, ++round) {
-                    for (int t = 0; t < own_chunks; ++t) {
-                        const int j = rank * own_chunks + t;
-                        mbar_wait(a_ready(j), round & 1);     // all four epilogue warps wrote + fenced chunk j
-                        const uint32_t src = sbase + L.a + j * CHUNK;
-                        bulk_s2peer(map_to_cta(src, peer), src, CHUNK, map_to_cta(a_ready(j), peer));
+                    for (int t = 0; t < own_chunks; ++t, ++ptotal) {
+                        const uint32_t sl = ptotal % (uint32_t)d.RS, use = ptotal / (uint32_t)d.RS;
+                        mbar_wait(a_ready(t), round & 1);     // every epilogue warp wrote + fenced chunk t
+                        if (use > 0) mbar_wait(rfree(sl), (use - 1) & 1);
+                        const uint32_t src = sbase + L.a + t * CHUNK;
+                        const uint32_t dst = sbase + L.a + (d.AOWN + sl) * CHUNK;
+                        bulk_s2peer(map_to_cta(dst, peer), src, CHUNK, map_to_cta(rready(sl), peer));
                     }
                 }
             }
@@ -378,6 +452,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     } else if (warp >= EPI_WARP0) {
         // =============================== prologue + epilogue ===================================
         const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        const int eg = (warp - EPI_WARP0) >> 2;              // epilogue group 0 / 1
         const int row = q * 32 + lane;                       // query row inside the tile == TMEM lane
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const GnbDecoderWeights& w = p.w;
@@ -385,6 +460,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
         for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
             const long long grow = (long long)tile * BM + row;
             const bool live = grow < p.n_rows;
+            int ek = (int)(grp / (2 * d.nb + 2)) * 64;
+            if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             // ---------------- prologue: operand tiles of lin_in and lin_z -------------------
             {
                 float code[64 * 4];                          // d_code + 2 <= 64*KZ (KZ <= 4)
@@ -411,7 +488,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 }
                 code[d.d_code] = 1.0f, code[d.d_code + 1] = 1.0f;      // bias hi / lo columns
                 for (int c = 0; c < d.KZ; ++c)
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = eg; u < 8; u += EPI_GROUPS) {           // the two groups write alternate units
                         const float* v = code + c * 64 + u * 8;
                         uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
                         *reinterpret_cast<uint4*>(sm + L.code + c * CHUNK + chunk_off(row, u)) = pk;
@@ -425,7 +502,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                     if (p.s.Cp > 0) planes_setup(p.s, xyz3[0], xyz3[1], xyz3[2], bc);
                 }
                 for (int c = 0; c < d.KF; ++c)
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = eg; u < 8; u += EPI_GROUPS) {
                         float v[8];
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -461,6 +538,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(in_ready);
+                if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             }
             // ---------------- epilogue rounds: accumulator -> next A operand -----------------
             const float* b0 = bias_s;
@@ -469,36 +547,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 mbar_wait(acc_ready, grp & 1);
                 ++grp;
                 tc_fence_after();
+                if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
                 const bool from_net = (r & 1) == 1;                       // rounds: x, net, x, net, ..., x(last)
                 const float* bias = from_net ? (b0 + (r >> 1) * d.HN) : ((r == 2 * d.nb) ? b1_last : nullptr);
                 const uint32_t src_col = from_net ? NET_COL : 0;
-                for (int t = 0; t < own_chunks; ++t) {
-                    const int j = rank * own_chunks + t;
-                    unsigned char* dst = sm + L.a + j * CHUNK;
+                // both groups work on every chunk (group g converts its columns [32g, 32g+32)), so the
+                // first chunk -- which releases the MMAs of this layer -- is ready as early as possible
+                uint32_t v[2][32];
+                tmem_ld32(tlane + src_col + eg * 32, v[0]);
+#pragma unroll 1
+                for (int t = 0; t < own_chunks; t += 2) {
 #pragma unroll
-                    for (int part = 0; part < 4; ++part) {               // 4 x 16 columns
-                        uint32_t v[16];
-                        tmem_ld16(tlane + src_col + t * 64 + part * 16, v);
+                    for (int h = 0; h < 2; ++h) {
+                        if (t + h >= own_chunks) break;
                         tmem_ld_wait();
-                        float f[16];
+                        if (t + h + 1 < own_chunks) tmem_ld32(tlane + src_col + (t + h + 1) * 64 + eg * 32, v[(h + 1) & 1]);
+                        unsigned char* dst = sm + L.a + (t + h) * CHUNK;
+                        const float* bch = bias ? bias + (t + h) * 64 + eg * 32 : nullptr;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float x = __uint_as_float(v[e]);
-                            if (bias) x += bias[t * 64 + part * 16 + e];
-                            f[e] = fmaxf(x, 0.0f);
-                        }
+                        for (int u = 0; u < 4; ++u) {                    // 4 x 16-byte units of 8 columns
+                            float f[8];
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 pk = make_uint4(pack16<BF16>(f[h * 8 + 0], f[h * 8 + 1]), pack16<BF16>(f[h * 8 + 2], f[h * 8 + 3]),
-                                                  pack16<BF16>(f[h * 8 + 4], f[h * 8 + 5]), pack16<BF16>(f[h * 8 + 6], f[h * 8 + 7]));
-                            *reinterpret_cast<uint4*>(dst + chunk_off(row, part * 2 + h)) = pk;
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[h][u * 8 + e]);
+                            if (bch) {
+                                const float4 b0v = *reinterpret_cast<const float4*>(bch + u * 8);
+                                const float4 b1v = *reinterpret_cast<const float4*>(bch + u * 8 + 4);
+                                f[0] += b0v.x, f[1] += b0v.y, f[2] += b0v.z, f[3] += b0v.w;
+                                f[4] += b1v.x, f[5] += b1v.y, f[6] += b1v.z, f[7] += b1v.w;
+                            }
+                            uint4 pk = make_uint4(pack16_relu<BF16>(f[0], f[1]), pack16_relu<BF16>(f[2], f[3]),
+                                                  pack16_relu<BF16>(f[4], f[5]), pack16_relu<BF16>(f[6], f[7]));
+                            *reinterpret_cast<uint4*>(dst + chunk_off(row, eg * 4 + u)) = pk;
                         }
+                        tc_fence_before();
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a_ready(t + h));
                     }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(a_ready(j));
                 }
+                if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             }
             // ---------------- final epilogue: lin_out tile -> global, TSDF head -----------------
             {
@@ -508,7 +595,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 const float* bo = bias_s + d.nb * d.HN + d.HN;
                 const float* hw = bo + d.NOUT;
                 float head = hw[d.d_geo];
-                for (int part = 0; part < d.NOUT / 16; ++part) {
+                for (int part = 0; part < (eg == 0 ? d.NOUT / 16 : 0); ++part) {
                     uint32_t v[16];
                     tmem_ld16(tlane + NET_COL + part * 16, v);
                     tmem_ld_wait();
@@ -532,8 +619,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         }
                     }
                 }
-                if (live && rank == 0 && p.tsdf) p.tsdf[grow] = tanhf(head);
+                if (live && rank == 0 && eg == 0 && p.tsdf) p.tsdf[grow] = tanhf(head);
                 tc_fence_before();
+                if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             }
         }
     }
@@ -615,11 +703,14 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
     d.KZ = (d.d_code + 2 + 63) / 64;
     d.KH = d.Hd / 64;
     d.NOUT = (d.d_out + 15) / 16 * 16;
-    if (d.KZ > 4 || d.NOUT > 256 || d.KF > MAX_CHUNKS) {
+    if (d.KZ > 4 || d.NOUT > 256 || d.KF > 8) {
         set_error("%s: d_code %d / d_out %d / d_feat %d too large for the tcgen05 path", who, d.d_code, d.d_out, d.d_feat);
         return GNB_E_UNSUPPORTED;
     }
-    d.ACH = d.KF > d.KH ? d.KF : d.KH;
+    d.OWN = d.HN / 64;
+    d.AOWN = d.KF > d.OWN ? d.KF : d.OWN;
+    d.RS = d.nsplit > 1 ? (d.OWN >= 2 ? 2 : 1) : 0;
+    d.ACH = d.AOWN + d.RS;
     d.nstage = MAX_STAGES;
     while (d.nstage >= 2 && smem_layout(d).total + 1024 > 227 * 1024) --d.nstage;
     if (d.nstage < 2) { set_error("%s: tile does not fit in shared memory", who); return GNB_E_UNSUPPORTED; }
@@ -681,6 +772,11 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
     return 0;
 }
 
+static long long* g_trace = nullptr;
+// profiling aid (not part of the public header): device buffer of 3*4096 int64 that receives
+// clock64() stamps of cluster 0's roles; pass null to switch tracing off again
+extern "C" void gnb_debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+
 static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, void* stream) {
     int rc = make_dims(w, kp.d, "gnb_decode_tc");
     if (rc) return rc;
@@ -694,8 +790,13 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
     GNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     GNB_CUDA(cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev));
     if (cc != 10) { set_error("gnb_decode_tc: needs an sm_100 device (found sm_%d0)", cc); return GNB_E_ARCH; }
+    kp.dbg = g_trace;
     kp.n_tiles = (int)((kp.n_rows + BM - 1) / BM);
     kp.n_clusters = sms / d.nsplit;
+    if (const char* e = getenv("GNB_DEBUG_MAX_CLUSTERS")) {   // profiling aid: fewer resident clusters
+        int m = atoi(e);
+        if (m > 0 && m < kp.n_clusters) kp.n_clusters = m;
+    }
     if (kp.n_clusters > kp.n_tiles) kp.n_clusters = kp.n_tiles;
     const size_t smem = smem_layout(d).total + 1024;
     auto kernel = (w->tc_dtype == GNB_TC_BF16) ? decoder_tc_kernel<true> : decoder_tc_kernel<false>;
