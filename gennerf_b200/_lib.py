@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libgennerf_b200.so")
 
 GNB_MAX_FRAMES = 64
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
-SCATTER_ATOMIC, SCATTER_DETERMINISTIC = 0, 1
+SCATTER_ATOMIC, SCATTER_DETERMINISTIC, SCATTER_ATOMIC_SUM = 0, 1, 2
 POOL_MAX, POOL_MEAN = 0, 1
 TC_FP16, TC_BF16 = 0, 1
 
@@ -32,6 +32,7 @@ class GnbLiftParams(C.Structure):
         ("vol_stride_b", C.c_int64), ("vol_stride_v", C.c_int64), ("vol_stride_c", C.c_int64),
         ("count", C.c_void_p), ("valid", C.c_void_p),
         ("accumulate", C.c_int32), ("mean", C.c_int32),
+        ("x_begin", C.c_int32), ("x_end", C.c_int32),
     ]
 
 
@@ -83,6 +84,7 @@ SIGNATURES = {
     "gnb_scatter_scratch_bytes": (C.c_int64, [C.c_int, C.c_int64, C.c_int, C.c_int]),
     "gnb_scatter_mean_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "gnb_scatter_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "gnb_pool_scratch_bytes": (C.c_int64, [C.c_int, C.c_int64, C.c_int, C.c_int]),
     "gnb_pool_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

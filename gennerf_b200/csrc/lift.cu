@@ -15,6 +15,7 @@
 // once with streaming stores.  HBM-bound: algorithmic bytes = features read once + volume
 // written once.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -32,6 +33,7 @@ struct LiftKP {
     int* count;
     unsigned char* valid;
     int accumulate, mean;
+    int x_begin, x_end;                  // slab of the grid this launch computes
 };
 static_assert(sizeof(LiftKP) <= 4096, "kernel parameter block must stay below 4 KB");
 
@@ -66,26 +68,77 @@ __device__ __forceinline__ void voxel_world(long long v, int ny, int nz, float v
 }
 
 // G lanes per voxel, VEC floats per lane (4: float4 path, needs C % 4 == 0; 1: scalar path).
-// grid.x = warps over voxels, grid.y = channel chunks of G*VEC.
-// CL: channels-last volume (stride_c == 1); otherwise the reference's (C,V) layout.
-template <int G, int VEC, bool CL>
+// A block owns a compact BX x BY x 16 brick of voxels (8 warps x NVW voxels); grid.y = channel
+// chunks of G*VEC.  CL: channels-last volume (stride_c == 1); otherwise the reference's (C,V) layout.
+//
+// Frame culling: before the per-voxel work the block projects the 8 corner voxels of its brick by
+// every frame.  A frame whose 8 corners all lie behind the camera, or all lie (with cz > 0) more
+// than a pixel outside the same image border, cannot see any voxel of the brick (voxel centres
+// are convex combinations of the corner centres and x/z is linear-fractional), so it is skipped
+// for the whole block.  Frames are still visited in ascending order, so the sum order is kept.
+template <int G, int VEC, bool CL, int NVW>
 __global__ void __launch_bounds__(256) lift_kernel(const __grid_constant__ LiftKP p) {
-    constexpr int NVW = (256 / G) < 32 ? (256 / G) : 32;   // voxels per warp
+    // NVW = voxels per warp (power of two, 32/G <= NVW <= 32)
     constexpr int ITER = NVW * G / 32;                     // gathers per lane per frame
     constexpr int VPI = 32 / G;                            // voxels per gather instruction
-    const int lane = threadIdx.x & 31;
-    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long v0 = warp * NVW;
-    if (v0 >= p.V) return;
+    constexpr int NVB = 8 * NVW;                           // voxels per block: 256 / 128 / 64
+    constexpr int BZ = NVB >= 64 ? 16 : 8, BY = NVB >= 256 ? 4 : 2, BX = NVB / (BZ * BY);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nbz = (p.nz + BZ - 1) / BZ, nby = (p.ny + BY - 1) / BY;
+    const int bz = blockIdx.x % nbz, by = (blockIdx.x / nbz) % nby, bx = blockIdx.x / (nbz * nby);
+    const int x0 = p.x_begin + bx * BX, y0 = by * BY, z0 = bz * BZ;
+
+    // ---- which frames can see this brick ---------------------------------------------------
+    __shared__ unsigned long long s_vis;
+    if (threadIdx.x == 0) s_vis = 0ull;
+    __syncthreads();
+    {
+        const int x1 = min(x0 + BX, p.x_end) - 1, y1 = min(y0 + BY, p.ny) - 1, z1 = min(z0 + BZ, p.nz) - 1;
+        for (int base = 0; base < p.T * 8; base += 256) {
+            const int task = base + threadIdx.x;
+            const bool active = task < p.T * 8;               // whole 8-lane groups are active or not
+            const int t = active ? (task >> 3) : 0, corner = task & 7;
+            const float cwx = __fadd_rn(__fmul_rn((float)((corner & 1) ? x1 : x0), p.vs), p.ox);
+            const float cwy = __fadd_rn(__fmul_rn((float)((corner & 2) ? y1 : y0), p.vs), p.oy);
+            const float cwz = __fadd_rn(__fmul_rn((float)((corner & 4) ? z1 : z0), p.vs), p.oz);
+            const float* P = p.P[t];
+            const float cx = fmaf(P[2], cwz, fmaf(P[1], cwy, P[0] * cwx)) + P[3];
+            const float cy = fmaf(P[6], cwz, fmaf(P[5], cwy, P[4] * cwx)) + P[7];
+            const float cz = fmaf(P[10], cwz, fmaf(P[9], cwy, P[8] * cwx)) + P[11];
+            const bool front = cz > 1e-3f;
+            const float u = cx / cz, v = cy / cz;
+            const unsigned sh = lane & ~7u;
+            const bool all_behind = ((__ballot_sync(FULL, cz < -1e-3f) >> sh) & 0xffu) == 0xffu;
+            const bool all_left = ((__ballot_sync(FULL, front && u < -2.0f) >> sh) & 0xffu) == 0xffu;
+            const bool all_right = ((__ballot_sync(FULL, front && u > (float)p.W + 1.0f) >> sh) & 0xffu) == 0xffu;
+            const bool all_top = ((__ballot_sync(FULL, front && v < -2.0f) >> sh) & 0xffu) == 0xffu;
+            const bool all_bottom = ((__ballot_sync(FULL, front && v > (float)p.H + 1.0f) >> sh) & 0xffu) == 0xffu;
+            if (active && corner == 0 && !(all_behind || all_left || all_right || all_top || all_bottom))
+                atomicOr(&s_vis, 1ull << t);
+        }
+    }
+    __syncthreads();
+    unsigned long long vis = s_vis;
+
     const int sub = lane % G;
     const int c0 = (blockIdx.y * G + sub) * VEC;           // first channel of this lane
     const bool c_ok = c0 < p.C;
 
-    // lane i (< NVW) owns voxel v0+i for the projection
-    const long long v_own = v0 + lane;
-    const bool own = (lane < NVW) && (v_own < p.V);
+    // lane i (< NVW) owns voxel i of this warp's part of the brick for the projection
+    const int iv = warp * NVW + lane;
+    const int vx = x0 + iv / (BZ * BY), vy = y0 + (iv / BZ) % BY, vz = z0 + iv % BZ;
+    const bool own = (lane < NVW) && vx < p.x_end && vy < p.ny && vz < p.nz;
+    const int v_own = own ? (vx * p.ny + vy) * p.nz + vz : -1;
     float wx = 0.f, wy = 0.f, wz = 0.f;
-    if (own) voxel_world(v_own, p.ny, p.nz, p.vs, p.ox, p.oy, p.oz, wx, wy, wz);
+    if (own) {
+        // world = fl(i) * voxel_size + origin: two separately rounded operations (utils.py:974)
+        wx = __fadd_rn(__fmul_rn((float)vx, p.vs), p.ox);
+        wy = __fadd_rn(__fmul_rn((float)vy, p.vs), p.oy);
+        wz = __fadd_rn(__fmul_rn((float)vz, p.vs), p.oz);
+    }
+    int vj[ITER];                                          // voxel handled by gather slot j of this lane
+#pragma unroll
+    for (int j = 0; j < ITER; ++j) vj[j] = __shfl_sync(FULL, v_own, j * VPI + lane / G);
 
     float acc[ITER][VEC];
     int cnt = 0;
@@ -98,36 +151,47 @@ __global__ void __launch_bounds__(256) lift_kernel(const __grid_constant__ LiftK
         if (own && p.count) cnt = p.count[v_own];
 #pragma unroll
         for (int j = 0; j < ITER; ++j) {
-            long long v = v0 + j * VPI + lane / G;
-            if (v < p.V && c_ok) {
+            if (vj[j] >= 0 && c_ok) {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[j][k] = p.volume[v * p.stride_v + (c0 + k) * p.stride_c];
+                for (int k = 0; k < VEC; ++k) acc[j][k] = p.volume[(long long)vj[j] * p.stride_v + (c0 + k) * p.stride_c];
             }
         }
     }
 
-#pragma unroll 2
-    for (int t = 0; t < p.T; ++t) {
-        int off = -1;
-        if (own) off = project_voxel(p.P[t], wx, wy, wz, p.H, p.W);
-        cnt += (off >= 0);
-        if (__ballot_sync(FULL, off >= 0) == 0u) continue;          // warp-uniform
-        const float* __restrict__ f = p.feat[t];
+    while (vis) {                                          // ascending frame order == reference summation order
+        // two frames per trip: both projections, then all gathers of both frames in flight together
+        const int t0 = __ffsll((long long)vis) - 1;
+        vis &= vis - 1;
+        const int t1 = vis ? __ffsll((long long)vis) - 1 : -1;
+        if (t1 >= 0) vis &= vis - 1;
+        int off0 = -1, off1 = -1;
+        if (own) {
+            off0 = project_voxel(p.P[t0], wx, wy, wz, p.H, p.W);
+            if (t1 >= 0) off1 = project_voxel(p.P[t1], wx, wy, wz, p.H, p.W);
+        }
+        cnt += (off0 >= 0) + (off1 >= 0);
+        if (__ballot_sync(FULL, (off0 & off1) >= 0 || off0 >= 0 || off1 >= 0) == 0u) continue;      // warp-uniform
+        const float* __restrict__ f0 = p.feat[t0];
+        const float* __restrict__ f1 = p.feat[t1 >= 0 ? t1 : t0];
 #pragma unroll
         for (int j = 0; j < ITER; ++j) {
-            int o = __shfl_sync(FULL, off, j * VPI + lane / G);
-            if (o >= 0 && c_ok) {
-                const float* src = f + (long long)o * p.C + c0;
-                if constexpr (VEC == 4) {
-                    float4 x = ldg4(src);
-                    acc[j][0] = __fadd_rn(acc[j][0], x.x);
-                    acc[j][1] = __fadd_rn(acc[j][1], x.y);
-                    acc[j][2] = __fadd_rn(acc[j][2], x.z);
-                    acc[j][3] = __fadd_rn(acc[j][3], x.w);
-                } else {
-                    acc[j][0] = __fadd_rn(acc[j][0], __ldg(src));
-                }
+            const int o0 = __shfl_sync(FULL, off0, j * VPI + lane / G);
+            const int o1 = __shfl_sync(FULL, off1, j * VPI + lane / G);
+            float x0[VEC], x1[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) x0[k] = x1[k] = 0.0f;       // + 0.0f leaves the sum bit-identical
+            if (o0 >= 0 && c_ok) {
+                const float* src = f0 + (long long)o0 * p.C + c0;
+                if constexpr (VEC == 4) { const float4 v = ldg4(src); x0[0] = v.x, x0[1] = v.y, x0[2] = v.z, x0[3] = v.w; }
+                else x0[0] = __ldg(src);
             }
+            if (o1 >= 0 && c_ok) {
+                const float* src = f1 + (long long)o1 * p.C + c0;
+                if constexpr (VEC == 4) { const float4 v = ldg4(src); x1[0] = v.x, x1[1] = v.y, x1[2] = v.z, x1[3] = v.w; }
+                else x1[0] = __ldg(src);
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[j][k] = __fadd_rn(__fadd_rn(acc[j][k], x0[k]), x1[k]);
         }
     }
 
@@ -147,12 +211,11 @@ __global__ void __launch_bounds__(256) lift_kernel(const __grid_constant__ LiftK
         if (p.valid) p.valid[v_own] = (unsigned char)(cnt > 0);
     }
     if constexpr (CL) {
-        // channels-last volume: the warp writes NVW * C*4 contiguous bytes
+        // channels-last volume: every voxel is one contiguous C*4-byte run
 #pragma unroll
         for (int j = 0; j < ITER; ++j) {
-            long long v = v0 + j * VPI + lane / G;
-            if (v < p.V && c_ok) {
-                float* dst = p.volume + v * p.stride_v + c0;
+            if (vj[j] >= 0 && c_ok) {
+                float* dst = p.volume + (long long)vj[j] * p.stride_v + c0;
                 if constexpr (VEC == 4) {
                     stcs4(dst, make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
                 } else {
@@ -161,11 +224,11 @@ __global__ void __launch_bounds__(256) lift_kernel(const __grid_constant__ LiftK
             }
         }
     } else {
-        // reference layout (C,V): transpose the warp's NVW x (G*VEC) tile through shared memory
-        // so that every row of NVW voxels is written contiguously
+        // reference layout (C,V): transpose the warp's NVW x (G*VEC) tile through shared memory so
+        // that each channel row is written as runs of consecutive z
         constexpr int NC = G * VEC;
         __shared__ float tile[8][NC][NVW + 1];
-        float(*tw)[NVW + 1] = tile[threadIdx.x >> 5];
+        float(*tw)[NVW + 1] = tile[warp];
 #pragma unroll
         for (int j = 0; j < ITER; ++j) {
 #pragma unroll
@@ -173,10 +236,11 @@ __global__ void __launch_bounds__(256) lift_kernel(const __grid_constant__ LiftK
         }
         __syncwarp();
         const int cbase = blockIdx.y * NC;
-        for (int idx = lane; idx < NC * NVW; idx += 32) {
-            int c = idx / NVW, vv = idx % NVW;
-            if (cbase + c < p.C && v0 + vv < p.V)
-                p.volume[(v0 + vv) * p.stride_v + (long long)(cbase + c) * p.stride_c] = tw[c][vv];
+#pragma unroll 4
+        for (int idx = lane; idx < NC * NVW; idx += 32) {           // NC * NVW is a multiple of 32
+            const int c = idx / NVW, vv = idx % NVW;
+            const int v = __shfl_sync(FULL, v_own, vv);
+            if (cbase + c < p.C && v >= 0) p.volume[(long long)v * p.stride_v + (long long)(cbase + c) * p.stride_c] = tw[c][vv];
         }
     }
 }
@@ -226,17 +290,31 @@ __global__ void project_indices_kernel(int nx, int ny, int nz, float vs, float o
     valid[v] = (unsigned char)(off >= 0);
 }
 
-template <int G, int VEC>
-static int launch_lift(const LiftKP& kp, int C, cudaStream_t st) {
-    constexpr int NVW = (256 / G) < 32 ? (256 / G) : 32;
-    long long warps = (kp.V + NVW - 1) / NVW;
-    dim3 grid((unsigned)((warps + 7) / 8), (unsigned)ceil_div(C, G * VEC));
+template <int G, int VEC, int NVW>
+static int launch_lift_nvw(const LiftKP& kp, int C, cudaStream_t st) {
+    constexpr int NVB = 8 * NVW, BZ = NVB >= 64 ? 16 : 8, BY = NVB >= 256 ? 4 : 2, BX = NVB / (BZ * BY);
+    long long bricks = (long long)ceil_div(kp.x_end - kp.x_begin, BX) * ceil_div(kp.ny, BY) * ceil_div(kp.nz, BZ);
+    dim3 grid((unsigned)bricks, (unsigned)ceil_div(C, G * VEC));
     if (kp.stride_c == 1)
-        lift_kernel<G, VEC, true><<<grid, 256, 0, st>>>(kp);
+        lift_kernel<G, VEC, true, NVW><<<grid, 256, 0, st>>>(kp);
     else
-        lift_kernel<G, VEC, false><<<grid, 256, 0, st>>>(kp);
+        lift_kernel<G, VEC, false, NVW><<<grid, 256, 0, st>>>(kp);
     GNB_LAUNCH_CHECK();
     return 0;
+}
+
+// voxels per warp: fewer voxels per warp = fewer accumulator registers, more resident warps and a
+// finer culling brick; GNB_LIFT_NVW overrides the default for tuning
+template <int G, int VEC>
+static int launch_lift(const LiftKP& kp, int C, cudaStream_t st) {
+    constexpr int NVMAX = (256 / G) < 32 ? (256 / G) : 32;
+    constexpr int NVMIN = (32 / G) > 4 ? (32 / G) : 4;      // bricks are at least 2 x 2 x 8
+    int nvw = NVMAX >= 16 ? 16 : NVMAX;
+    if (const char* e = getenv("GNB_LIFT_NVW")) nvw = atoi(e);
+    if (nvw <= NVMIN) return launch_lift_nvw<G, VEC, NVMIN>(kp, C, st);
+    if constexpr (NVMAX >= 2 * NVMIN) { if (nvw <= 2 * NVMIN || NVMAX == 2 * NVMIN) return launch_lift_nvw<G, VEC, 2 * NVMIN>(kp, C, st); }
+    if constexpr (NVMAX >= 4 * NVMIN) { if (nvw <= 4 * NVMIN || NVMAX == 4 * NVMIN) return launch_lift_nvw<G, VEC, 4 * NVMIN>(kp, C, st); }
+    return launch_lift_nvw<G, VEC, NVMAX>(kp, C, st);
 }
 
 static int dispatch_lift(const LiftKP& kp, cudaStream_t st) {
@@ -286,7 +364,9 @@ extern "C" int gnb_backproject_frames(const GnbLiftParams* p, void* stream) {
                   p->n_frames, GNB_MAX_FRAMES);
     GNB_CHECK_ARG(p->batch >= 1 && p->C >= 1 && p->H >= 1 && p->W >= 1, "gnb_backproject_frames: bad feature shape");
     GNB_CHECK_ARG((long long)p->H * p->W < INT_MAX, "gnb_backproject_frames: image too large");
+    GNB_CHECK_ARG((long long)p->nx * p->ny * p->nz < INT_MAX, "gnb_backproject_frames: voxel grid too large");
     GNB_CHECK_ARG(p->volume && p->h_projection, "gnb_backproject_frames: null volume/projection");
+    GNB_CHECK_ARG(p->x_begin >= 0 && p->x_end <= p->nx && (p->x_end == 0 || p->x_end >= p->x_begin), "gnb_backproject_frames: bad x range");
     GNB_CHECK_ARG(p->feat_layout == GNB_LAYOUT_NHWC || p->feat_layout == GNB_LAYOUT_NCHW, "gnb_backproject_frames: bad layout");
     for (int t = 0; t < p->n_frames; ++t) GNB_CHECK_ARG(p->features[t], "gnb_backproject_frames: features[%d] is null", t);
     cudaStream_t st = (cudaStream_t)stream;
@@ -317,6 +397,8 @@ extern "C" int gnb_backproject_frames(const GnbLiftParams* p, void* stream) {
         kp.count = p->count ? p->count + (long long)b * V : nullptr;
         kp.valid = p->valid ? p->valid + (long long)b * V : nullptr;
         kp.accumulate = p->accumulate, kp.mean = p->mean;
+        kp.x_begin = p->x_begin, kp.x_end = (p->x_end > 0) ? p->x_end : p->nx;
+        if (kp.x_end <= kp.x_begin) continue;
         int rc = dispatch_lift(kp, st);
         if (rc) return rc;
     }

@@ -361,7 +361,7 @@ extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, in
     const float den = (float)(1.0 + padding + 10e-6);
     const long long RR = (long long)R * R, cells = 3LL * B * RR;
     GNB_CUDA(cudaMemsetAsync(count, 0, cells * sizeof(int), st));
-    if (mode == GNB_SCATTER_ATOMIC) {
+    if (mode == GNB_SCATTER_ATOMIC || mode == GNB_SCATTER_ATOMIC_SUM) {
         GNB_CHECK_ARG(Cp <= 256, "gnb_scatter_mean_planes: C_p %d > 256 not supported", Cp);
         GNB_CUDA(cudaMemsetAsync(planes, 0, cells * Cp * sizeof(float), st));
         if (N > 0) {
@@ -372,8 +372,10 @@ extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, in
             else if (Cp <= 128) scatter_atomic_kernel<4><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
             else scatter_atomic_kernel<8><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
             GNB_LAUNCH_CHECK();
-            scatter_finalize_kernel<<<ceil_div(cells * Cp, 256), 256, 0, st>>>(planes, count, cells, Cp);
-            GNB_LAUNCH_CHECK();
+            if (mode == GNB_SCATTER_ATOMIC) {
+                scatter_finalize_kernel<<<ceil_div(cells * Cp, 256), 256, 0, st>>>(planes, count, cells, Cp);
+                GNB_LAUNCH_CHECK();
+            }
         }
         return 0;
     }
@@ -402,6 +404,14 @@ extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, in
         GNB_LAUNCH_CHECK();
     }
     det_reduce_kernel<<<ceil_div(cells, 8), 256, 0, st>>>(c, s.vals[cur], s.start, count, B, N, Cp, RR, planes);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_scatter_finalize(float* planes, const int32_t* count, int64_t n_cells, int Cp, void* stream) {
+    GNB_CHECK_ARG(planes && count && n_cells >= 0 && Cp >= 1, "gnb_scatter_finalize: bad arguments");
+    if (n_cells == 0) return 0;
+    scatter_finalize_kernel<<<ceil_div(n_cells * Cp, 256), 256, 0, (cudaStream_t)stream>>>(planes, count, n_cells, Cp);
     GNB_LAUNCH_CHECK();
     return 0;
 }

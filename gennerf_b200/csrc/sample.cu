@@ -2,6 +2,8 @@
 // Replaces GenNerf.map_features (reference src/models/model.py:163-204).  HBM/L2-bound gather:
 // G lanes share a query, each lane one float4 of channels, so every corner fetch of a
 // channels-last volume/plane is one contiguous C*4-byte run.
+#include <stdlib.h>
+
 #include "sample.cuh"
 
 namespace gnb {
@@ -34,6 +36,124 @@ __global__ void __launch_bounds__(256) sample_kernel(const __grid_constant__ Sam
             if constexpr (VEC == 4) *reinterpret_cast<float4*>(out + c_off + c) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
             else out[c_off + c] = r.v[0];
         }
+    }
+}
+
+// Fast path (channels-last, C % 4 == 0, < 2^31 elements): a warp takes 32 queries.  Lane i sets up
+// query i ONCE (normalisation, clip, floor, 8 + 12 corner offsets and weights) and parks the result
+// in shared memory; then the warp walks the 32 queries with G lanes per query, each lane one
+// float4 of channels, reading the corner table with broadcast LDS.128.  The setup arithmetic is
+// the same device functions as the generic kernel, so both produce identical bits.
+constexpr int ST_WORDS = 20;     // per query: 8 offsets + 8 weights (+4 pad: conflict-free LDS.128)
+
+template <bool PLANES>
+__device__ __forceinline__ void staged_part(const SampleKP& p, float* __restrict__ tab, int lane, int G, long long q0,
+                                            long long nq, float* __restrict__ out_base, int c_off) {
+    // tab: [32][ST_WORDS] for this warp.  PLANES: three tables are processed one after the other.
+    const int sub = lane % G, qpi = 32 / G;
+    const int Cn = PLANES ? p.Cp : p.C;
+    for (int it = 0; it < G; ++it) {
+        const int ql = it * qpi + lane / G;
+        const long long q = q0 + ql;
+        if (q >= nq) continue;
+        const float* e = tab + ql * ST_WORDS;
+        const int4 o0 = *reinterpret_cast<const int4*>(e), o1 = *reinterpret_cast<const int4*>(e + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(e + 8), w1 = *reinterpret_cast<const float4*>(e + 12);
+        const int b = (int)(q / p.Q);
+        float* out = out_base + q * p.out_stride + c_off;
+        for (int c = sub * 4; c < Cn; c += G * 4) {
+            if constexpr (!PLANES) {
+                const float* base = p.volume + b * p.vsb + c;
+                const float4 v0 = ldg4(base + o0.x), v1 = ldg4(base + o0.y), v2 = ldg4(base + o0.z), v3 = ldg4(base + o0.w);
+                const float4 v4 = ldg4(base + o1.x), v5 = ldg4(base + o1.y), v6 = ldg4(base + o1.z), v7 = ldg4(base + o1.w);
+                float4 r = make_float4(__fmul_rn(v0.x, w0.x), __fmul_rn(v0.y, w0.x), __fmul_rn(v0.z, w0.x), __fmul_rn(v0.w, w0.x));
+                r.x = fmaf(v1.x, w0.y, r.x), r.y = fmaf(v1.y, w0.y, r.y), r.z = fmaf(v1.z, w0.y, r.z), r.w = fmaf(v1.w, w0.y, r.w);
+                r.x = fmaf(v2.x, w0.z, r.x), r.y = fmaf(v2.y, w0.z, r.y), r.z = fmaf(v2.z, w0.z, r.z), r.w = fmaf(v2.w, w0.z, r.w);
+                r.x = fmaf(v3.x, w0.w, r.x), r.y = fmaf(v3.y, w0.w, r.y), r.z = fmaf(v3.z, w0.w, r.z), r.w = fmaf(v3.w, w0.w, r.w);
+                r.x = fmaf(v4.x, w1.x, r.x), r.y = fmaf(v4.y, w1.x, r.y), r.z = fmaf(v4.z, w1.x, r.z), r.w = fmaf(v4.w, w1.x, r.w);
+                r.x = fmaf(v5.x, w1.y, r.x), r.y = fmaf(v5.y, w1.y, r.y), r.z = fmaf(v5.z, w1.y, r.z), r.w = fmaf(v5.w, w1.y, r.w);
+                r.x = fmaf(v6.x, w1.z, r.x), r.y = fmaf(v6.y, w1.z, r.y), r.z = fmaf(v6.z, w1.z, r.z), r.w = fmaf(v6.w, w1.z, r.w);
+                r.x = fmaf(v7.x, w1.w, r.x), r.y = fmaf(v7.y, w1.w, r.y), r.z = fmaf(v7.z, w1.w, r.z), r.w = fmaf(v7.w, w1.w, r.w);
+                *reinterpret_cast<float4*>(out + c) = r;
+            }
+        }
+    }
+}
+
+constexpr int PT_WORDS = 28;     // per query: 3 planes x (4 offsets + 4 weights) (+4 pad)
+constexpr int ST_WARPS = 4;      // warps per block of the staged kernel
+
+// one plane's 4 corners: words 0-3 offsets, 4-7 weights
+__device__ __forceinline__ float4 staged_plane(const SampleKP& p, const float* __restrict__ e, const float* __restrict__ base) {
+    const int4 o = *reinterpret_cast<const int4*>(e);
+    const float4 w = *reinterpret_cast<const float4*>(e + 4);
+    const float4 v0 = ldg4(base + o.x), v1 = ldg4(base + o.y), v2 = ldg4(base + o.z), v3 = ldg4(base + o.w);
+    float4 r = make_float4(__fmul_rn(v0.x, w.x), __fmul_rn(v0.y, w.x), __fmul_rn(v0.z, w.x), __fmul_rn(v0.w, w.x));
+    r.x = fmaf(v1.x, w.y, r.x), r.y = fmaf(v1.y, w.y, r.y), r.z = fmaf(v1.z, w.y, r.z), r.w = fmaf(v1.w, w.y, r.w);
+    r.x = fmaf(v2.x, w.z, r.x), r.y = fmaf(v2.y, w.z, r.y), r.z = fmaf(v2.z, w.z, r.z), r.w = fmaf(v2.w, w.z, r.w);
+    r.x = fmaf(v3.x, w.w, r.x), r.y = fmaf(v3.y, w.w, r.y), r.z = fmaf(v3.z, w.w, r.z), r.w = fmaf(v3.w, w.w, r.w);
+    return r;
+}
+
+__global__ void __launch_bounds__(32 * ST_WARPS) sample_staged_kernel(const __grid_constant__ SampleKP p, int Gv, int Gp) {
+    __shared__ __align__(16) float s_tab[ST_WARPS][32 * ST_WORDS];      // per warp: volume corner table
+    __shared__ __align__(16) float s_ptab[ST_WARPS][32 * PT_WORDS];     // per warp: plane corner tables
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tv = s_tab[warp];
+    const long long ngroups = (p.total + 31) / 32;
+    for (long long grp = (long long)blockIdx.x * ST_WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * ST_WARPS) {
+        const long long q0 = grp * 32, q = q0 + lane;
+        // ---- setup: one lane per query --------------------------------------------------
+        if (q < p.total) {
+            const float x = __ldg(p.xyz + q * 3), y = __ldg(p.xyz + q * 3 + 1), z = __ldg(p.xyz + q * 3 + 2);
+            if (p.volume) {
+                TriCorners tc;
+                trilinear_setup(p, x, y, z, tc);
+                float* e = tv + lane * ST_WORDS;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    reinterpret_cast<int*>(e)[k] = (int)tc.off[k];
+                    e[8 + k] = tc.w[k];
+                }
+            }
+            if (p.Cp > 0) {
+                BiCorners bc[3];
+                planes_setup(p, x, y, z, bc);
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                    float* e = s_ptab[warp] + lane * PT_WORDS + pl * 8;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        reinterpret_cast<int*>(e)[k] = (int)bc[pl].off[k];
+                        e[4 + k] = bc[pl].w[k];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---- gather: G lanes per query, one float4 of channels per lane ---------------------
+        if (p.Cp > 0) {
+            const int sub = lane % Gp, qpi = 32 / Gp;
+            for (int it = 0; it < Gp; ++it) {
+                const int ql = it * qpi + lane / Gp;
+                const long long qq = q0 + ql;
+                if (qq >= p.total) continue;
+                const int b = (int)(qq / p.Q);
+                float* out = p.out + qq * p.out_stride;
+                for (int c = sub * 4; c < p.Cp; c += Gp * 4) {
+                    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) {
+                        if (p.plane[pl] == nullptr) continue;
+                        const float4 a = staged_plane(p, s_ptab[warp] + ql * PT_WORDS + pl * 8, p.plane[pl] + b * p.psb + c);
+                        r.x = __fadd_rn(r.x, a.x), r.y = __fadd_rn(r.y, a.y), r.z = __fadd_rn(r.z, a.z), r.w = __fadd_rn(r.w, a.w);
+                    }
+                    *reinterpret_cast<float4*>(out + c) = r;
+                }
+            }
+        }
+        if (p.volume) staged_part<false>(p, tv, lane, Gv, q0, p.total, p.out, p.Cp);
+        __syncwarp();
     }
 }
 
@@ -92,6 +212,23 @@ extern "C" int gnb_sample_features(const GnbSampleParams* s, void* stream) {
     if (kp.Cp > 0) {
         vec = vec && kp.psc == 1 && kp.Cp % 4 == 0 && kp.psb % 4 == 0 && kp.psh % 4 == 0 && kp.psw % 4 == 0;
         for (int k = 0; k < 3; ++k) vec = vec && aligned16(kp.plane[k]);
+    }
+    // staged fast path: float4 channels-last and every element offset fits int32
+    auto pow2_lanes = [](int n) { int g = 1; while (g < n && g < 32) g <<= 1; return g; };
+    bool small = true;
+    if (kp.volume) small = small && ((long long)kp.nx * kp.vsx + (long long)kp.ny * kp.vsy + (long long)kp.nz * kp.vsz < 0x7fffffffLL);
+    if (kp.Cp > 0) small = small && ((long long)kp.R * kp.psh + (long long)kp.R * kp.psw < 0x7fffffffLL);
+    if (vec && small && !getenv("GNB_SAMPLE_GENERIC")) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        long long groups = (kp.total + 31) / 32;
+        long long want = (groups + ST_WARPS - 1) / ST_WARPS;
+        unsigned blocks = (unsigned)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+        sample_staged_kernel<<<blocks, 32 * ST_WARPS, 0, (cudaStream_t)stream>>>(kp, pow2_lanes(kp.C / 4 > 0 ? kp.C / 4 : 1),
+                                                                        pow2_lanes(kp.Cp / 4 > 0 ? kp.Cp / 4 : 1));
+        GNB_LAUNCH_CHECK();
+        return 0;
     }
     int cmax = kp.C > kp.Cp ? kp.C : kp.Cp;
     int lanes = vec ? cmax / 4 : cmax;

@@ -40,7 +40,7 @@ def _origin3(origin):
 # lift
 # ------------------------------------------------------------------------------------------
 def backproject_frames(voxel_dim, voxel_size, origin, projections, features, *, mean=False,
-                       volume_layout="channels_last", out=None):
+                       volume_layout="channels_last", out=None, x_range=None, accumulate=None):
     """Fused back-projection of T frames (reference utils.py:948 + model.py:121-127,195-199).
 
     projections: (B,T,3,4) (CPU or CUDA; a CUDA tensor costs one small D2H copy);
@@ -49,7 +49,9 @@ def backproject_frames(voxel_dim, voxel_size, origin, projections, features, *, 
     Returns volume (B,C,nx,ny,nz) [channels_last_3d strides unless volume_layout='reference'],
     count (B,nx,ny,nz) int32, valid (B,1,nx,ny,nz) bool.  volume == the reference's
     accumulated self.volume (a SUM, bit-exact); mean=True divides by count instead.
-    `out=(volume, count, valid)` accumulates further frames into earlier results.
+    `out=(volume, count, valid)` accumulates further frames into earlier results
+    (accumulate=False: just write into those buffers).  `x_range=(x0, x1)` computes and writes only
+    that slab of the grid (multi-GPU sharding); the rest of the buffers is left untouched.
     """
     nx, ny, nz = (int(d) for d in voxel_dim)
     feats = [_f32(f) for f in features]
@@ -74,7 +76,7 @@ def backproject_frames(voxel_dim, voxel_size, origin, projections, features, *, 
         accumulate = False
     else:
         volume, count, valid = out
-        accumulate = True
+        accumulate = True if accumulate is None else bool(accumulate)
     sb, sc, sx, sy, sz = volume.stride()
     if not (sz * nz == sy and sy * ny == sx):
         raise RuntimeError("volume must be dense over (nx,ny,nz)")
@@ -106,6 +108,10 @@ def backproject_frames(voxel_dim, voxel_size, origin, projections, features, *, 
             p.count, p.valid = count.data_ptr(), valid.data_ptr()
             p.accumulate = int(accumulate or t0 > 0)
             p.mean = int(bool(mean) and t0 + n >= T)
+            if x_range is not None:
+                p.x_begin, p.x_end = int(x_range[0]), int(x_range[1])
+                if p.x_end <= p.x_begin:
+                    continue
             check(lib().gnb_backproject_frames(C.byref(p), _stream()), "gnb_backproject_frames")
     return volume, count, valid
 
@@ -227,7 +233,7 @@ def scatter_mean_planes(p, c, reso, padding=0.1, mode="atomic"):
     B, N, _ = p.shape
     Cp = c.shape[2]
     R = int(reso)
-    m = {"atomic": _lib.SCATTER_ATOMIC, "deterministic": _lib.SCATTER_DETERMINISTIC}[mode]
+    m = {"atomic": _lib.SCATTER_ATOMIC, "deterministic": _lib.SCATTER_DETERMINISTIC, "sum": _lib.SCATTER_ATOMIC_SUM}[mode]
     store = torch.empty((3, B, R, R, Cp), device=p.device, dtype=torch.float32)
     count = torch.empty((3, B, R, R), device=p.device, dtype=torch.int32)
     nbytes = lib().gnb_scatter_scratch_bytes(B, N, R, m)
@@ -237,6 +243,17 @@ def scatter_mean_planes(p, c, reso, padding=0.1, mode="atomic"):
                                             store.data_ptr(), count.data_ptr(), scratch.data_ptr(), nbytes,
                                             _stream()), "gnb_scatter_mean_planes")
     return store.permute(0, 1, 4, 2, 3), count
+
+
+def scatter_finalize(planes, count):
+    """sums (3,B,C_p,R,R) [channels-last storage] / max(count,1) in place (after an all-reduce)."""
+    store = planes.permute(0, 1, 3, 4, 2)
+    if not store.is_contiguous():
+        raise RuntimeError("scatter_finalize expects the channels-last storage scatter_mean_planes returns")
+    with torch.cuda.device(planes.device):
+        check(lib().gnb_scatter_finalize(store.data_ptr(), count.data_ptr(), count.numel(), planes.shape[2], _stream()),
+              "gnb_scatter_finalize")
+    return planes
 
 
 def pool_local(p, c, reso, padding=0.1, scatter_type="max"):

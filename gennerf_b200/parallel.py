@@ -1,0 +1,121 @@
+"""Multi-GPU partitioning of the lift-and-query path.
+
+One process per GPU (torchrun), torch.distributed (NCCL over NVLink on the B200 box, gloo in
+the CPU tests).  The path shards naturally, so collectives appear only where the data really
+has to move:
+
+  lift      voxels are independent -> contiguous x-slabs of the channels-last volume per rank,
+            then ONE all-gather so every rank can answer arbitrary queries
+  triplane  points split across ranks -> partial sums (fp32) + counts (int32) -> all-reduce,
+            divide locally (counts stay exact; fp32 sums are order-dependent as in atomic mode)
+  query     points are independent -> contiguous ranges of Q per rank, no collective
+            (optionally gathered to every rank)
+
+The compute backend is injected (`backend`): gennerf_b200.ops on the GPU; the CPU tests pass
+an oracle-backed stand-in so the partition / collective logic is covered with world_size 2
+on gloo.  Nothing here falls back to the CPU on its own.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous [begin, end) of n items for `rank`: sizes differ by at most one."""
+    base, rem = divmod(int(n), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def _ws(group):
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def lift_sharded(backend, voxel_dim, voxel_size, origin, projections, features, group=None, gather=True):
+    """Every rank holds the frame features (broadcast them first if only one rank ran the CNN,
+    see broadcast_features) and lifts the x-slab shard_range(nx) of the grid; with gather=True the
+    slabs are all-gathered so every rank ends up with the complete (volume, count, valid).
+
+    Returns volume (B,C,nx,ny,nz) [channels-last storage], count (B,nx,ny,nz) int32,
+    valid (B,1,nx,ny,nz) bool -- bit-identical to the single-GPU result (voxels are independent).
+    """
+    rank, world = _ws(group)
+    nx, ny, nz = (int(d) for d in voxel_dim)
+    B, C = features[0].shape[0], features[0].shape[1]
+    dev = features[0].device
+    x0, x1 = shard_range(nx, rank, world)
+    store = torch.empty((B, nx, ny, nz, C), device=dev, dtype=torch.float32)
+    count = torch.empty((B, nx, ny, nz), device=dev, dtype=torch.int32)
+    valid = torch.empty((B, 1, nx, ny, nz), device=dev, dtype=torch.bool)
+    volume = store.permute(0, 4, 1, 2, 3)
+    backend.backproject_frames(voxel_dim, voxel_size, origin, projections, features, out=(volume, count, valid),
+                               accumulate=False, x_range=(x0, x1))
+    if gather and world > 1:
+        for b in range(B):                       # a slab is one contiguous block per scene
+            _all_gather_slabs(store[b], nx, world, group)
+            _all_gather_slabs(count[b], nx, world, group)
+            _all_gather_slabs(valid[b, 0].view(torch.uint8), nx, world, group)
+    return volume, count, valid
+
+
+def _all_gather_slabs(t, nx, world, group):
+    """In-place all-gather of the x-slabs of t (nx, ...): rank r owns rows shard_range(nx, r)."""
+    rank, _ = _ws(group)
+    bounds = [shard_range(nx, r, world) for r in range(world)]
+    if nx % world == 0:
+        x0, x1 = bounds[rank]
+        dist.all_gather_into_tensor(t, t[x0:x1].clone(), group=group)       # equal slabs: one fused collective
+        return
+    # ragged slabs: pad to the largest, gather, copy back (works on every backend)
+    parts = _all_gather_ragged(t[bounds[rank][0]:bounds[rank][1]], [b - a for a, b in bounds], group)
+    for r, (a, b) in enumerate(bounds):
+        if r != rank:
+            t[a:b] = parts[r]
+
+
+def _all_gather_ragged(local, sizes, group):
+    """all-gather of tensors whose dim 0 differs per rank (sizes[r]); returns the list of pieces."""
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+    pad[: local.shape[0]] = local
+    buf = torch.empty((len(sizes) * mx,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    return [buf[r * mx: r * mx + n] for r, n in enumerate(sizes)]
+
+
+def broadcast_features(features, src=0, group=None):
+    """Frame features live on the rank that ran the 2D CNN: broadcast them (NCCL over NVLink)."""
+    rank, world = _ws(group)
+    if world > 1:
+        for f in features:
+            dist.broadcast(f, src=src, group=group)
+    return features
+
+
+def scatter_planes_sharded(backend, p, c, reso, padding=0.1, group=None):
+    """p (B,N,3), c (B,N,C_p): every rank scatters ITS points (the caller passes the rank's
+    shard); partial sums and counts are all-reduced, then divided locally.
+    Returns planes (3,B,C_p,R,R) [channels-last storage], count (3,B,R,R) int32 on every rank."""
+    rank, world = _ws(group)
+    sums, count = backend.scatter_mean_planes(p, c, reso, padding, "sum")
+    if world > 1:
+        store = sums.permute(0, 1, 3, 4, 2)
+        dist.all_reduce(store, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=group)
+    return backend.scatter_finalize(sums, count), count
+
+
+def query_sharded(query_fn, xyz, group=None, gather=False):
+    """xyz (B,Q,3) replicated on every rank (or only the rank's range if pre-sharded=False is not
+    needed): each rank answers the contiguous range shard_range(Q) with `query_fn(xyz_shard)` ->
+    tensor (B,q,...) and, with gather=True, the ranges are concatenated on every rank."""
+    rank, world = _ws(group)
+    Q = xyz.shape[1]
+    q0, q1 = shard_range(Q, rank, world)
+    out = query_fn(xyz[:, q0:q1].contiguous())
+    if not gather or world == 1:
+        return out, (q0, q1)
+    sizes = [shard_range(Q, r, world)[1] - shard_range(Q, r, world)[0] for r in range(world)]
+    parts = _all_gather_ragged(out.transpose(0, 1).contiguous(), sizes, group)       # ranges along dim 0
+    return torch.cat(parts, dim=0).transpose(0, 1).contiguous(), (0, Q)

@@ -83,6 +83,8 @@ typedef struct GnbLiftParams {
     uint8_t* valid;                /* (B,V) 0/1 or NULL                                     */
     int32_t accumulate;            /* != 0: volume/count already hold earlier frames        */
     int32_t mean;                  /* != 0: divide by count at the end                      */
+    int32_t x_begin, x_end;        /* only voxels with x_begin <= x < x_end are computed and  */
+                                   /* written (slab sharding across GPUs); 0,0 = whole grid  */
 } GnbLiftParams;
 
 int gnb_backproject_frames(const GnbLiftParams* p, void* stream);
@@ -145,10 +147,16 @@ int gnb_plane_coords(const float* p, int64_t n_points_total, double padding, int
  * ----------------------------------------------------------------------------------- */
 #define GNB_SCATTER_ATOMIC 0
 #define GNB_SCATTER_DETERMINISTIC 1
+#define GNB_SCATTER_ATOMIC_SUM 2   /* like ATOMIC but leaves SUMS in `planes` (no division): the  */
+                                   /* partial result a rank all-reduces before gnb_scatter_finalize */
 int64_t gnb_scatter_scratch_bytes(int B, int64_t N, int R, int mode);
 int gnb_scatter_mean_planes(const float* p, const float* c, int B, int64_t N, int Cp, int R,
                             double padding, int mode, float* planes, int32_t* count,
                             void* scratch, int64_t scratch_bytes, void* stream);
+
+/* planes[cell,:] /= max(count[cell],1) over n_cells = 3*B*R*R cells (after an all-reduce of
+ * GNB_SCATTER_ATOMIC_SUM partial sums and counts). */
+int gnb_scatter_finalize(float* planes, const int32_t* count, int64_t n_cells, int Cp, void* stream);
 
 /* -------------------------------------------------------------------------------------
  * Local pooling.  Replaces LocalPoolPointnet.pool_local()
