@@ -41,6 +41,17 @@ def peaks():
     return dict(hbm=6650.0, bf16=1400.0, source="fallback")
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write of the kernel's bench launch, from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)[kernel]
+        return {"dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+    except Exception:
+        return None
+
+
 def flops_per_query(d_feat, d_code, d_hidden, n_blocks, d_out, d_geo):
     return 2 * (d_feat * d_hidden + n_blocks * (d_code * d_hidden + 2 * d_hidden * d_hidden) + d_hidden * d_out + d_geo)
 
@@ -315,7 +326,7 @@ def run_native(args):
             "config": dict(config_dict(Q), parallelism=f"replicas x{world} (queries and scenes sharded, no data-path collective)",
                            decoder=f"{precision} tcgen05 fused sampler+MLP" if fused else f"{precision} sampler + decoder kernels"),
             "roofline": {"kernel": "decoder_tc_kernel (fused sampler + MLP)" if fused else "sampler + decoder", "bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": tf / pk["bf16"], "traffic": None, "peak_source": pk["source"] + " bf16 cuBLAS sustained (fp16 and bf16 share the tensor-core rate)",
+                         "frac": tf / pk["bf16"], "traffic": measured_traffic("decoder_tc_kernel") if fused else None, "peak_source": pk["source"] + " bf16 cuBLAS sustained (fp16 and bf16 share the tensor-core rate)",
                          "flops_per_launch": fl, "ms_per_launch": dec_ms},
             "backprojection": {"metric": "voxel_frames_per_s", "value": world * V * T / (ms_lift * 1e-3), "ms": ms_lift,
                                "includes": "NCHW->NHWC pass + fused lift kernel",
