@@ -277,6 +277,165 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Backward of the fused lift (autograd of utils.py:991 `volume[b,:,valid] = features[b,:,py,px]`,
+// i.e. index_put_(accumulate=True) into the feature maps, summed over what encode() accumulates):
+//   grad_features_t[b, py, px, :] += grad_volume[b, v, :]   for every frame t that sees voxel v.
+// Same brick / culling / projection code as the forward, so exactly the forward's voxel-frame
+// pairs receive gradient.  Many voxels along a ray hit the same pixel: the adds are 128-bit vector
+// reductions (red.global.add.v4.f32) into channels-last gradient maps; their order is not
+// deterministic (as in the reference's CUDA index_put_).
+// ---------------------------------------------------------------------------------------
+struct LiftBwdKP {
+    float* gfeat[GNB_MAX_FRAMES];        // per frame, this scene, NHWC, zero-initialised by the caller
+    float P[GNB_MAX_FRAMES][12];
+    int T, H, W, C;
+    int nx, ny, nz;
+    float vs, ox, oy, oz;
+    const float* gvol;
+    long long stride_v, stride_c;
+    const int* count;                    // mean mode: divide the incoming gradient by count
+    int mean;
+    int x_begin, x_end;
+};
+static_assert(sizeof(LiftBwdKP) <= 4096, "kernel parameter block must stay below 4 KB");
+
+template <int G, int VEC>
+__global__ void __launch_bounds__(256) lift_bwd_kernel(const __grid_constant__ LiftBwdKP p) {
+    constexpr int NVW = (256 / G) < 16 ? (256 / G) : 16;
+    constexpr int ITER = NVW * G / 32, VPI = 32 / G, NVB = 8 * NVW;
+    constexpr int BZ = NVB >= 64 ? 16 : 8, BY = NVB >= 256 ? 4 : 2, BX = NVB / (BZ * BY);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nbz = (p.nz + BZ - 1) / BZ, nby = (p.ny + BY - 1) / BY;
+    const int bz = blockIdx.x % nbz, by = (blockIdx.x / nbz) % nby, bx = blockIdx.x / (nbz * nby);
+    const int x0 = p.x_begin + bx * BX, y0 = by * BY, z0 = bz * BZ;
+    __shared__ unsigned long long s_vis;
+    if (threadIdx.x == 0) s_vis = 0ull;
+    __syncthreads();
+    {
+        const int x1 = min(x0 + BX, p.x_end) - 1, y1 = min(y0 + BY, p.ny) - 1, z1 = min(z0 + BZ, p.nz) - 1;
+        for (int base = 0; base < p.T * 8; base += 256) {
+            const int task = base + threadIdx.x;
+            const bool active = task < p.T * 8;
+            const int t = active ? (task >> 3) : 0, corner = task & 7;
+            const float cwx = __fadd_rn(__fmul_rn((float)((corner & 1) ? x1 : x0), p.vs), p.ox);
+            const float cwy = __fadd_rn(__fmul_rn((float)((corner & 2) ? y1 : y0), p.vs), p.oy);
+            const float cwz = __fadd_rn(__fmul_rn((float)((corner & 4) ? z1 : z0), p.vs), p.oz);
+            const float* P = p.P[t];
+            const float cx = fmaf(P[2], cwz, fmaf(P[1], cwy, P[0] * cwx)) + P[3];
+            const float cy = fmaf(P[6], cwz, fmaf(P[5], cwy, P[4] * cwx)) + P[7];
+            const float cz = fmaf(P[10], cwz, fmaf(P[9], cwy, P[8] * cwx)) + P[11];
+            const bool front = cz > 1e-3f;
+            const float u = cx / cz, v = cy / cz;
+            const unsigned sh = lane & ~7u;
+            const bool c0 = ((__ballot_sync(FULL, cz < -1e-3f) >> sh) & 0xffu) == 0xffu;
+            const bool c1 = ((__ballot_sync(FULL, front && u < -2.0f) >> sh) & 0xffu) == 0xffu;
+            const bool c2 = ((__ballot_sync(FULL, front && u > (float)p.W + 1.0f) >> sh) & 0xffu) == 0xffu;
+            const bool c3 = ((__ballot_sync(FULL, front && v < -2.0f) >> sh) & 0xffu) == 0xffu;
+            const bool c4 = ((__ballot_sync(FULL, front && v > (float)p.H + 1.0f) >> sh) & 0xffu) == 0xffu;
+            if (active && corner == 0 && !(c0 || c1 || c2 || c3 || c4)) atomicOr(&s_vis, 1ull << t);
+        }
+    }
+    __syncthreads();
+    unsigned long long vis = s_vis;
+    if (vis == 0ull) return;
+    const int sub = lane % G;
+    const int c0 = (blockIdx.y * G + sub) * VEC;
+    const bool c_ok = c0 < p.C;
+    const int iv = warp * NVW + lane;
+    const int vx = x0 + iv / (BZ * BY), vy = y0 + (iv / BZ) % BY, vz = z0 + iv % BZ;
+    const bool own = (lane < NVW) && vx < p.x_end && vy < p.ny && vz < p.nz;
+    const int v_own = own ? (vx * p.ny + vy) * p.nz + vz : -1;
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (own) {
+        wx = __fadd_rn(__fmul_rn((float)vx, p.vs), p.ox);
+        wy = __fadd_rn(__fmul_rn((float)vy, p.vs), p.oy);
+        wz = __fadd_rn(__fmul_rn((float)vz, p.vs), p.oz);
+    }
+    float g[ITER][VEC];
+#pragma unroll
+    for (int j = 0; j < ITER; ++j) {
+        const int v = __shfl_sync(FULL, v_own, j * VPI + lane / G);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) g[j][k] = 0.0f;
+        if (v >= 0 && c_ok) {
+            float sc = 1.0f;
+            if (p.mean) { const int n = p.count[v]; sc = 1.0f / (float)(n > 0 ? n : 1); }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) g[j][k] = sc * __ldg(p.gvol + (long long)v * p.stride_v + (c0 + k) * p.stride_c);
+        }
+    }
+    while (vis) {
+        const int t = __ffsll((long long)vis) - 1;
+        vis &= vis - 1;
+        int off = -1;
+        if (own) off = project_voxel(p.P[t], wx, wy, wz, p.H, p.W);
+        if (__ballot_sync(FULL, off >= 0) == 0u) continue;
+        float* __restrict__ f = p.gfeat[t];
+#pragma unroll
+        for (int j = 0; j < ITER; ++j) {
+            const int o = __shfl_sync(FULL, off, j * VPI + lane / G);
+            if (o >= 0 && c_ok) {
+                float* dst = f + (long long)o * p.C + c0;
+                if constexpr (VEC == 4) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(g[j][0], g[j][1], g[j][2], g[j][3]));
+                else atomicAdd(dst, g[j][0]);
+            }
+        }
+    }
+}
+
+template <int G, int VEC>
+static int launch_lift_bwd(const LiftBwdKP& kp, cudaStream_t st) {
+    constexpr int NVW = (256 / G) < 16 ? (256 / G) : 16;
+    constexpr int NVB = 8 * NVW, BZ = NVB >= 64 ? 16 : 8, BY = NVB >= 256 ? 4 : 2, BX = NVB / (BZ * BY);
+    long long bricks = (long long)ceil_div(kp.x_end - kp.x_begin, BX) * ceil_div(kp.ny, BY) * ceil_div(kp.nz, BZ);
+    dim3 grid((unsigned)bricks, (unsigned)ceil_div(kp.C, G * VEC));
+    lift_bwd_kernel<G, VEC><<<grid, 256, 0, st>>>(kp);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int dispatch_lift_bwd(const LiftBwdKP& kp, cudaStream_t st) {
+    const int C = kp.C;
+    if (C % 4 == 0) {
+        int g = C / 4;
+        if (g >= 32) return launch_lift_bwd<32, 4>(kp, st);
+        if (g > 8) return launch_lift_bwd<16, 4>(kp, st);
+        if (g > 4) return launch_lift_bwd<8, 4>(kp, st);
+        if (g > 2) return launch_lift_bwd<4, 4>(kp, st);
+        return launch_lift_bwd<2, 4>(kp, st);
+    }
+    if (C >= 32) return launch_lift_bwd<32, 1>(kp, st);
+    if (C > 8) return launch_lift_bwd<16, 1>(kp, st);
+    if (C > 4) return launch_lift_bwd<8, 1>(kp, st);
+    if (C > 2) return launch_lift_bwd<4, 1>(kp, st);
+    return launch_lift_bwd<2, 1>(kp, st);
+}
+
+// NHWC -> NCHW (gradient maps back to the reference layout)
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __grid_constant__ TransposeKP p) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z / p.B, b = blockIdx.z % p.B;
+    float* __restrict__ dst = const_cast<float*>(p.src[t]) + (long long)b * p.C * p.HW;      // (C,HW) output
+    const float* __restrict__ src = p.dst + ((long long)t * p.B + b) * p.HW * p.C;           // (HW,C) input
+    const long long px0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        long long px = px0 + r;
+        int c = c0 + tx;
+        tile[r][tx] = (c < p.C && px < p.HW) ? __ldg(src + px * p.C + c) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        int c = c0 + r;
+        long long px = px0 + tx;
+        if (c < p.C && px < p.HW) dst[(long long)c * p.HW + px] = tile[tx][r];
+    }
+}
+
 __global__ void project_indices_kernel(int nx, int ny, int nz, float vs, float ox, float oy, float oz,
                                        const __grid_constant__ LiftKP p, int* px, int* py, unsigned char* valid) {
     long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -417,5 +576,56 @@ extern "C" int gnb_project_indices(int nx, int ny, int nz, float voxel_size, con
     project_indices_kernel<<<ceil_div(kp.V, 256), 256, 0, (cudaStream_t)stream>>>(
         nx, ny, nz, voxel_size, h_origin3[0], h_origin3[1], h_origin3[2], kp, px, py, valid);
     GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_backproject_frames_bwd(const GnbLiftParams* p, const float* grad_volume, float* const* h_grad_features,
+                                          void* stream) {
+    GNB_CHECK_ARG(p && grad_volume && h_grad_features, "gnb_backproject_frames_bwd: null argument");
+    GNB_CHECK_ARG(p->nx > 0 && p->ny > 0 && p->nz > 0 && p->batch >= 1 && p->C >= 1 && p->H >= 1 && p->W >= 1,
+                  "gnb_backproject_frames_bwd: bad shape");
+    GNB_CHECK_ARG(p->n_frames >= 1 && p->n_frames <= GNB_MAX_FRAMES, "gnb_backproject_frames_bwd: n_frames %d not in [1,%d]",
+                  p->n_frames, GNB_MAX_FRAMES);
+    GNB_CHECK_ARG(p->h_projection, "gnb_backproject_frames_bwd: null projection");
+    GNB_CHECK_ARG(!p->mean || p->count, "gnb_backproject_frames_bwd: mean mode needs the forward's count");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long V = (long long)p->nx * p->ny * p->nz;
+    const long long img = (long long)p->H * p->W * p->C;
+    // gradient maps are accumulated channels-last; for the reference layout they are built in `scratch`
+    float* base[GNB_MAX_FRAMES];
+    const bool nchw = p->feat_layout == GNB_LAYOUT_NCHW;
+    GNB_CHECK_ARG(!nchw || p->scratch, "gnb_backproject_frames_bwd: NCHW gradients need a scratch buffer of T*B*H*W*C floats");
+    for (int t = 0; t < p->n_frames; ++t) {
+        GNB_CHECK_ARG(h_grad_features[t], "gnb_backproject_frames_bwd: grad_features[%d] is null", t);
+        base[t] = nchw ? p->scratch + (long long)t * p->batch * img : h_grad_features[t];
+        GNB_CUDA(cudaMemsetAsync(base[t], 0, sizeof(float) * p->batch * img, st));
+    }
+    for (int b = 0; b < p->batch; ++b) {
+        LiftBwdKP kp;
+        for (int t = 0; t < p->n_frames; ++t) {
+            kp.gfeat[t] = base[t] + (long long)b * img;
+            for (int k = 0; k < 12; ++k) kp.P[t][k] = p->h_projection[((long long)b * p->n_frames + t) * 12 + k];
+        }
+        kp.T = p->n_frames, kp.H = p->H, kp.W = p->W, kp.C = p->C;
+        kp.nx = p->nx, kp.ny = p->ny, kp.nz = p->nz;
+        kp.vs = p->voxel_size, kp.ox = p->origin[0], kp.oy = p->origin[1], kp.oz = p->origin[2];
+        kp.gvol = grad_volume + (long long)b * p->vol_stride_b;
+        kp.stride_v = p->vol_stride_v, kp.stride_c = p->vol_stride_c;
+        kp.count = p->count ? p->count + (long long)b * V : nullptr;
+        kp.mean = p->mean;
+        kp.x_begin = p->x_begin, kp.x_end = (p->x_end > 0) ? p->x_end : p->nx;
+        if (kp.x_end <= kp.x_begin) continue;
+        int rc = dispatch_lift_bwd(kp, st);
+        if (rc) return rc;
+    }
+    if (nchw) {
+        TransposeKP kp;
+        for (int t = 0; t < p->n_frames; ++t) kp.src[t] = h_grad_features[t];     // destination of the inverse transpose
+        kp.dst = p->scratch;
+        kp.T = p->n_frames, kp.B = p->batch, kp.C = p->C, kp.HW = (long long)p->H * p->W;
+        dim3 grid((unsigned)ceil_div(kp.HW, 32), (unsigned)ceil_div(p->C, 32), (unsigned)(p->n_frames * p->batch));
+        nhwc_to_nchw_kernel<<<grid, 256, 0, st>>>(kp);
+        GNB_LAUNCH_CHECK();
+    }
     return 0;
 }

@@ -308,6 +308,72 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ p, 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Backward passes.
+// scatter_mean (pointnet.py:82): grad_c[b,n,:] = sum over planes of grad_plane[cell(n),:] / max(count,1).
+// pool_local  (pointnet.py:113-119): out[n] = sum_k fea_k[cell_k(n)], fea_k = scatter_(max|mean)(c):
+//   gsum_k[cell] = sum of grad_out over the points of the cell (backward of the gather);
+//   mean: grad_c[n] = sum_k gsum_k[cell_k(n)] / count;   max: gsum goes to the ONE point that attains
+//   the maximum (torch_scatter's arg); exact ties are broken towards the smallest point index.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scatter_mean_bwd_kernel(const float* __restrict__ p, const float* __restrict__ gplanes,
+                                                               const int* __restrict__ count, int B, long long N, int Cp, int R,
+                                                               float den, long long psb_unused, float* __restrict__ gc) {
+    const int lane = threadIdx.x & 31;
+    const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= (long long)B * N) return;
+    const int b = (int)(pt / N);
+    const long long RR = (long long)R * R;
+    int cell[3];
+    plane_cells(__ldg(p + pt * 3), __ldg(p + pt * 3 + 1), __ldg(p + pt * 3 + 2), den, R, cell);
+    for (int ch = lane; ch < Cp; ch += 32) {
+        float g = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const long long cg = ((long long)k * B + b) * RR + cell[k];
+            const int n = count[cg];
+            g += __ldg(gplanes + cg * Cp + ch) / (float)(n > 0 ? n : 1);
+        }
+        gc[pt * Cp + ch] = g;
+    }
+}
+
+// phases: 0 init touched cells (gsum = 0, arg = INT_MAX); 1 gsum += grad_out and (max) arg = min index
+// among the points whose value equals the cell maximum; 2 route to the points
+template <int PHASE>
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ p, const float* __restrict__ c,
+                                                       const float* __restrict__ gout, int B, long long N, int Hd, int R, float den,
+                                                       int pool_type, const unsigned* __restrict__ cellmax, const int* __restrict__ cnt,
+                                                       float* __restrict__ gsum, int* __restrict__ arg, float* __restrict__ gc) {
+    const int lane = threadIdx.x & 31;
+    const long long pt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= (long long)B * N) return;
+    const int b = (int)(pt / N);
+    const long long RR = (long long)R * R;
+    int cell[3];
+    plane_cells(__ldg(p + pt * 3), __ldg(p + pt * 3 + 1), __ldg(p + pt * 3 + 2), den, R, cell);
+    for (int h = lane; h < Hd; h += 32) {
+        float o = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const long long cg = ((long long)k * B + b) * RR + cell[k];
+            const long long slot = cg * Hd + h;
+            if (PHASE == 0) {
+                gsum[slot] = 0.0f;
+                if (pool_type == GNB_POOL_MAX) arg[slot] = 0x7fffffff;
+            } else if (PHASE == 1) {
+                atomicAdd(gsum + slot, __ldg(gout + pt * Hd + h));
+                if (pool_type == GNB_POOL_MAX && enc_max(__ldg(c + pt * Hd + h)) == cellmax[slot]) atomicMin(arg + slot, (int)(pt % N));
+            } else {
+                if (pool_type == GNB_POOL_MAX) o += (arg[slot] == (int)(pt % N)) ? gsum[slot] : 0.0f;
+                else o += gsum[slot] / (float)cnt[cg];
+            }
+        }
+        if (PHASE == 2) gc[pt * Hd + h] = o;
+    }
+}
+
 static int radix_bits(long long RR) {
     int bits = 1;
     while ((1LL << bits) < RR) ++bits;
@@ -440,6 +506,50 @@ extern "C" int gnb_pool_local(const float* p, const float* c, int B, int64_t N, 
     pool_kernel<1><<<blocks, 256, 0, st>>>(p, c, B, N, Hd, R, den, pool_type, cellbuf, cnt, out);
     GNB_LAUNCH_CHECK();
     pool_kernel<2><<<blocks, 256, 0, st>>>(p, c, B, N, Hd, R, den, pool_type, cellbuf, cnt, out);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_scatter_mean_planes_bwd(const float* p, const float* grad_planes, const int32_t* count, int B, int64_t N,
+                                           int Cp, int R, double padding, float* grad_c, void* stream) {
+    GNB_CHECK_ARG(p && grad_planes && count && grad_c, "gnb_scatter_mean_planes_bwd: null pointer");
+    GNB_CHECK_ARG(B >= 1 && N >= 0 && Cp >= 1 && R >= 1, "gnb_scatter_mean_planes_bwd: bad shape");
+    if (N == 0) return 0;
+    const float den = (float)(1.0 + padding + 10e-6);
+    scatter_mean_bwd_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(p, grad_planes, count, B, N, Cp,
+                                                                                                      R, den, 0, grad_c);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t gnb_pool_bwd_scratch_bytes(int B, int64_t N, int Hd, int R) {
+    (void)N;
+    const long long cells = 3LL * B * R * R;
+    return 2 * ((cells * Hd * 4 + 255) / 256 * 256);
+}
+
+extern "C" int gnb_pool_local_bwd(const float* p, const float* c, const float* grad_out, int B, int64_t N, int Hd, int R,
+                                  double padding, int pool_type, const void* fwd_scratch, float* grad_c, void* scratch,
+                                  int64_t scratch_bytes, void* stream) {
+    GNB_CHECK_ARG(p && c && grad_out && grad_c && fwd_scratch, "gnb_pool_local_bwd: null pointer");
+    GNB_CHECK_ARG(B >= 1 && N >= 0 && Hd >= 1 && R >= 1, "gnb_pool_local_bwd: bad shape");
+    GNB_CHECK_ARG(pool_type == GNB_POOL_MAX || pool_type == GNB_POOL_MEAN, "gnb_pool_local_bwd: unknown pool type %d", pool_type);
+    GNB_CHECK_ARG(scratch && scratch_bytes >= gnb_pool_bwd_scratch_bytes(B, N, Hd, R), "gnb_pool_local_bwd: scratch too small");
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float den = (float)(1.0 + padding + 10e-6);
+    const long long cells = 3LL * B * R * R;
+    const long long half = (cells * Hd * 4 + 255) / 256 * 256;
+    const unsigned* cellmax = (const unsigned*)fwd_scratch;                          // layout of gnb_pool_local's scratch
+    const int* cnt = (const int*)((const char*)fwd_scratch + half);
+    float* gsum = (float*)scratch;
+    int* arg = (int*)((char*)scratch + half);
+    const unsigned blocks = (unsigned)(((long long)B * N + 7) / 8);
+    pool_bwd_kernel<0><<<blocks, 256, 0, st>>>(p, c, grad_out, B, N, Hd, R, den, pool_type, cellmax, cnt, gsum, arg, grad_c);
+    GNB_LAUNCH_CHECK();
+    pool_bwd_kernel<1><<<blocks, 256, 0, st>>>(p, c, grad_out, B, N, Hd, R, den, pool_type, cellmax, cnt, gsum, arg, grad_c);
+    GNB_LAUNCH_CHECK();
+    pool_bwd_kernel<2><<<blocks, 256, 0, st>>>(p, c, grad_out, B, N, Hd, R, den, pool_type, cellmax, cnt, gsum, arg, grad_c);
     GNB_LAUNCH_CHECK();
     return 0;
 }

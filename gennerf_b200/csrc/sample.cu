@@ -157,6 +157,167 @@ __global__ void __launch_bounds__(32 * ST_WARPS) sample_staged_kernel(const __gr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Backward of the sampler (ATen grid_sampler_{3d,2d}_backward with bilinear / border /
+// align_corners=True, chained through the reference's coordinate normalisations):
+//   grad_volume[corner_k, :] += w_k * grad_out[q, C_p:]        (8 corners, vector reductions)
+//   grad_plane_p[corner_k,:] += w_k * grad_out[q, :C_p]        (4 corners x 3 planes)
+//   grad_xyz[q] = sum_c grad_out[q,c] * d feat_c / d xyz       (optional)
+// The coordinate gradient is zero where the border clip is active (ATen
+// clip_coordinates_set_grad) and where normalize_coordinate clamps (masked assignment,
+// utils.py:94-97).  One lane group of G lanes per query, as in the forward.
+// ---------------------------------------------------------------------------------------
+struct SampleBwdKP {
+    SampleKP s;                    // forward parameters (volume / planes are read only for grad_xyz)
+    const float* gout;             // (B,Q,gout_stride): [planes C_p | volume C]
+    long long gout_stride;
+    float* gvolume;                // same strides as the forward volume, or null
+    float* gplane[3];              // same strides as the forward planes, or null
+    float* gxyz;                   // (B,Q,3) or null
+};
+
+// d(unnormalised, clipped coordinate)/d(grid coordinate g): (size-1)/2 inside the open interval, else 0
+__device__ __forceinline__ float unnorm_clip_grad(float g, int size) {
+    const float x = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(size - 1));
+    return (x <= 0.0f || x >= (float)(size - 1)) ? 0.0f : 0.5f * (float)(size - 1);
+}
+
+__global__ void __launch_bounds__(256) sample_bwd_kernel(const __grid_constant__ SampleBwdKP p, int G) {
+    const SampleKP& s = p.s;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long q = tid / G;
+    const int sub = (int)(tid % G);
+    const bool live = q < s.total;                        // keep every lane for the group shuffles
+    const long long qq = live ? q : 0;
+    const int b = (int)(qq / s.Q);
+    const float x = __ldg(s.xyz + qq * 3 + 0), y = __ldg(s.xyz + qq * 3 + 1), z = __ldg(s.xyz + qq * 3 + 2);
+    const float* __restrict__ go = p.gout + qq * p.gout_stride;
+    float gx = 0.f, gy = 0.f, gz = 0.f;                   // d loss / d (x,y,z), partial over this lane's channels
+    if (s.Cp > 0 && live) {
+        BiCorners bc[3];
+        planes_setup(s, x, y, z, bc);
+        const float ux = plane_unit(x, s.den), uy = plane_unit(y, s.den), uz = plane_unit(z, s.den);
+        const float u0[3] = {ux, ux, uy}, u1[3] = {uz, uy, uz};
+        float gu[3] = {0.f, 0.f, 0.f};                    // gradient w.r.t. the unit coordinates ux, uy, uz
+        const int a0[3] = {0, 0, 1}, a1[3] = {2, 1, 2};
+        for (int c = sub * 4; c < s.Cp; c += G * 4) {
+            float g4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) g4[e] = (c + e < s.Cp) ? __ldg(go + c + e) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (s.plane[k] == nullptr) continue;
+                if (p.gplane[k]) {
+                    float* gb = p.gplane[k] + b * s.psb + c * s.psc;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (bc[k].w[j] == 0.0f) continue;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < s.Cp) atomicAdd(gb + bc[k].off[j] + e * s.psc, bc[k].w[j] * g4[e]);
+                    }
+                }
+                if (p.gxyz) {
+                    // weights: nw = e*s, ne = w*s, sw = e*n, se = w*n with w = ix-x0, e = 1-w, n = iy-y0, s = 1-n
+                    const float ix = unnorm_clip(__fsub_rn(__fmul_rn(2.0f, u0[k]), 1.0f), s.R);
+                    const float iy = unnorm_clip(__fsub_rn(__fmul_rn(2.0f, u1[k]), 1.0f), s.R);
+                    const float w = ix - floorf(ix), e = 1.0f - w, n = iy - floorf(iy), sth = 1.0f - n;
+                    const float* pb = s.plane[k] + b * s.psb + c * s.psc;
+                    float dix = 0.f, diy = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        if (c + ch >= s.Cp) continue;
+                        const float v0 = bc[k].w[0] != 0.f || true ? __ldg(pb + bc[k].off[0] + ch * s.psc) : 0.f;
+                        const float v1 = __ldg(pb + bc[k].off[1] + ch * s.psc), v2 = __ldg(pb + bc[k].off[2] + ch * s.psc),
+                                    v3 = __ldg(pb + bc[k].off[3] + ch * s.psc);
+                        // corners beyond the border carry weight 0 in the forward and no gradient here
+                        const float m1 = bc[k].off[1] != bc[k].off[0] ? 1.f : 0.f, m2 = bc[k].off[2] != bc[k].off[0] ? 1.f : 0.f;
+                        const float m3 = (m1 != 0.f && m2 != 0.f) ? 1.f : 0.f;
+                        dix += g4[ch] * (-v0 * sth + m1 * v1 * sth - m2 * v2 * n + m3 * v3 * n);
+                        diy += g4[ch] * (-v0 * e - m1 * v1 * w + m2 * v2 * e + m3 * v3 * w);
+                    }
+                    // chain: vgrid = 2u - 1 (x2), unnormalise + clip
+                    gu[a0[k]] += dix * unnorm_clip_grad(__fsub_rn(__fmul_rn(2.0f, u0[k]), 1.0f), s.R) * 2.0f;
+                    gu[a1[k]] += diy * unnorm_clip_grad(__fsub_rn(__fmul_rn(2.0f, u1[k]), 1.0f), s.R) * 2.0f;
+                }
+            }
+        }
+        if (p.gxyz) {
+            // u = p/den + 0.5, masked to constants where u >= 1 or u < 0
+            const float raw[3] = {__fadd_rn(__fdiv_rn(x, s.den), 0.5f), __fadd_rn(__fdiv_rn(y, s.den), 0.5f),
+                                  __fadd_rn(__fdiv_rn(z, s.den), 0.5f)};
+            gx += (raw[0] >= 1.0f || raw[0] < 0.0f) ? 0.0f : gu[0] / s.den;
+            gy += (raw[1] >= 1.0f || raw[1] < 0.0f) ? 0.0f : gu[1] / s.den;
+            gz += (raw[2] >= 1.0f || raw[2] < 0.0f) ? 0.0f : gu[2] / s.den;
+        }
+    }
+    if (s.volume && live) {
+        TriCorners tc;
+        trilinear_setup(s, x, y, z, tc);
+        const float gxn = query_grid(x, s.ox, s.ext_x), gyn = query_grid(y, s.oy, s.ext_y), gzn = query_grid(z, s.oz, s.ext_z);
+        const float ix = unnorm_clip(gxn, s.nx), iy = unnorm_clip(gyn, s.ny), iz = unnorm_clip(gzn, s.nz);
+        const float fx = ix - floorf(ix), fy = iy - floorf(iy), fz = iz - floorf(iz);
+        const float wx[2] = {1.0f - fx, fx}, wy[2] = {1.0f - fy, fy}, wz[2] = {1.0f - fz, fz};
+        float dix = 0.f, diy = 0.f, diz = 0.f;
+        for (int c = sub * 4; c < s.C; c += G * 4) {
+            float g4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) g4[e] = (c + e < s.C) ? __ldg(go + s.Cp + c + e) : 0.0f;
+            if (p.gvolume) {
+                float* gb = p.gvolume + b * s.vsb + c * s.vsc;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (tc.w[k] == 0.0f) continue;
+                    if (s.vsc == 1 && (c + 3 < s.C) && ((reinterpret_cast<uintptr_t>(gb + tc.off[k]) & 15) == 0)) {
+                        atomicAdd(reinterpret_cast<float4*>(gb + tc.off[k]),
+                                  make_float4(tc.w[k] * g4[0], tc.w[k] * g4[1], tc.w[k] * g4[2], tc.w[k] * g4[3]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (c + e < s.C) atomicAdd(gb + tc.off[k] + e * s.vsc, tc.w[k] * g4[e]);
+                    }
+                }
+            }
+            if (p.gxyz) {
+                const float* vb = s.volume + b * s.vsb + c * s.vsc;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int bx = k & 1, byy = (k >> 1) & 1, bzz = (k >> 2) & 1;
+                    // a corner beyond the border (clamped offset) has no value in the forward
+                    const bool inb = (!bx || tc.off[k] != tc.off[k & ~1]) && (!byy || tc.off[k] != tc.off[k & ~2]) &&
+                                     (!bzz || tc.off[k] != tc.off[k & ~4]);
+                    if (!inb) continue;
+                    float dot = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (c + e < s.C) dot += g4[e] * __ldg(vb + tc.off[k] + e * s.vsc);
+                    dix += dot * (bx ? 1.0f : -1.0f) * wy[byy] * wz[bzz];
+                    diy += dot * (byy ? 1.0f : -1.0f) * wx[bx] * wz[bzz];
+                    diz += dot * (bzz ? 1.0f : -1.0f) * wx[bx] * wy[byy];
+                }
+            }
+        }
+        if (p.gxyz) {
+            // chain: g = 2*((x - o)/ext) - 1, then unnormalise + clip
+            gx += __fdiv_rn(2.0f * dix * unnorm_clip_grad(gxn, s.nx), s.ext_x);
+            gy += __fdiv_rn(2.0f * diy * unnorm_clip_grad(gyn, s.ny), s.ext_y);
+            gz += __fdiv_rn(2.0f * diz * unnorm_clip_grad(gzn, s.nz), s.ext_z);
+        }
+    }
+    if (p.gxyz) {
+        // reduce over the G lanes of the query (G is a power of two, groups are lane-aligned)
+        for (int d = G >> 1; d > 0; d >>= 1) {
+            gx += __shfl_xor_sync(FULL, gx, d);
+            gy += __shfl_xor_sync(FULL, gy, d);
+            gz += __shfl_xor_sync(FULL, gz, d);
+        }
+        if (live && sub == 0) {
+            p.gxyz[q * 3 + 0] = gx, p.gxyz[q * 3 + 1] = gy, p.gxyz[q * 3 + 2] = gz;
+        }
+    }
+}
+
 int fill_sample_kp(const GnbSampleParams* s, SampleKP& kp) {
     GNB_CHECK_ARG(s, "sample: null params");
     GNB_CHECK_ARG(s->batch >= 1 && s->n_query >= 0 && s->xyz, "sample: bad batch / n_query / xyz");
@@ -240,6 +401,27 @@ extern "C" int gnb_sample_features(const GnbSampleParams* s, void* stream) {
         sample_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(kp, G);
     else
         sample_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(kp, G);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_sample_features_bwd(const GnbSampleParams* s, const float* grad_out, int64_t grad_out_stride,
+                                       float* grad_volume, float* const* h_grad_planes3, float* grad_xyz, void* stream) {
+    SampleBwdKP kp;
+    int rc = fill_sample_kp(s, kp.s);
+    if (rc) return rc;
+    GNB_CHECK_ARG(grad_out && grad_out_stride >= kp.s.C + kp.s.Cp, "gnb_sample_features_bwd: bad grad_out");
+    GNB_CHECK_ARG(grad_volume || h_grad_planes3 || grad_xyz, "gnb_sample_features_bwd: nothing to compute");
+    if (kp.s.total == 0) return 0;
+    kp.gout = grad_out, kp.gout_stride = grad_out_stride;
+    kp.gvolume = kp.s.volume ? grad_volume : nullptr;
+    for (int k = 0; k < 3; ++k) kp.gplane[k] = (h_grad_planes3 && kp.s.plane[k]) ? h_grad_planes3[k] : nullptr;
+    kp.gxyz = grad_xyz;
+    int cmax = kp.s.C > kp.s.Cp ? kp.s.C : kp.s.Cp;
+    int lanes = (cmax + 3) / 4, G = 1;
+    while (G < lanes && G < 32) G <<= 1;
+    long long threads = kp.s.total * G;
+    sample_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kp, G);
     GNB_LAUNCH_CHECK();
     return 0;
 }

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 from torch import nn
 
+from . import autograd as ag
 from . import ops
 
 PLANE_AXES = {"xz": [0, 2], "xy": [0, 1], "yz": [1, 2]}
@@ -41,6 +42,15 @@ def trilinear_interpolation(voxel_volume, xyz, origin, voxel_size, mode="bilinea
         raise NotImplementedError("gennerf_b200: only mode='bilinear' (the reference's default) is built")
     vol = voxel_volume.permute(0, 4, 1, 2, 3)
     return ops.sample_features(xyz, volume=vol, voxel_size=voxel_size, origin=origin)
+
+
+def get_grid_coordinates(nx, ny, nz, volume_size, origin=None, device="cuda"):
+    """reference src/models/utils.py:926-935: (nx,ny,nz,3) query grid, linspace(0, size, n) per axis.
+    The three 1-D axes are generated on the CPU (bit-identical to the CPU reference) and expanded on
+    the device."""
+    ax = [torch.linspace(0, float(volume_size[i]), n).to(device) for i, n in enumerate((nx, ny, nz))]
+    gx, gy, gz = torch.meshgrid(ax[0], ax[1], ax[2], indexing="ij")
+    return torch.stack([gx, gy, gz], dim=-1)
 
 
 def normalize_coordinate(p, padding=0.1, plane="xz", encode=True):
@@ -161,6 +171,20 @@ class ResnetFC(nn.Module):
         out, _ = _decode_given_code(dw, z, x, precision)
         return out
 
+    def forward_torch(self, zx):
+        """The same network with torch.nn.functional.linear (cuBLAS) -- used for TRAINING steps, where
+        autograd needs the dgrad/wgrad GEMMs; the query counts of a training step (a few thousand
+        points, gen_nerf.yaml:23-36) make this launch-bound, not a hot path.  Inference goes through the
+        tcgen05 kernel."""
+        import torch.nn.functional as F
+        z, x = zx[..., : self.d_latent], zx[..., self.d_latent:]
+        x = self.lin_in(x)
+        for i in range(self.n_blocks):
+            x = x + self.alpha * self.lin_z[i](z)
+            net = self.blocks[i].fc_0(F.relu(x))
+            x = x + self.blocks[i].fc_1(F.relu(net))
+        return self.lin_out(F.relu(x))
+
     @classmethod
     def from_conf(cls, cfg, d_in, d_latent):
         return cls(d_in=d_in, d_out=cfg.d_out_geo + cfg.d_out_sem, n_blocks=cfg.n_blocks, d_latent=d_latent,
@@ -255,14 +279,14 @@ class LocalPoolPointnet(nn.Module):
 
     def generate_plane_features(self, p, c, plane="xz"):
         """reference pointnet.py:72-89 for one plane (the kernel computes all three)."""
-        planes, _ = ops.scatter_mean_planes(p, c, self.reso_plane, self.padding, self.scatter_mode)
+        planes, _ = ag.scatter_mean_planes(p, c, self.reso_plane, self.padding, self.scatter_mode)
         fea = planes[_PLANE_ID[plane]]
         return self.unet(fea) if self.unet is not None else fea
 
     def pool_local(self, xy, index, c):
         """reference pointnet.py:105-121.  `xy`/`index` are accepted for signature parity; the
         kernel recomputes the cells from the points stored by forward()."""
-        return ops.pool_local(self._p, c, self.reso_plane, self.padding, self.scatter_type)
+        return ag.pool_local(self._p, c, self.reso_plane, self.padding, self.scatter_type)
 
     def forward(self, p):
         """reference pointnet.py:124-171: p (B,N,3) -> {'xz','xy','yz': (B,c_dim,R,R)}."""
@@ -273,7 +297,7 @@ class LocalPoolPointnet(nn.Module):
             pooled = self.pool_local(None, None, net)
             net = block(torch.cat([net, pooled], dim=2))
         c = self.fc_c(net)
-        planes, _ = ops.scatter_mean_planes(p, c, self.reso_plane, self.padding, self.scatter_mode)
+        planes, _ = ag.scatter_mean_planes(p, c, self.reso_plane, self.padding, self.scatter_mode)
         fea = {}
         for name in ("xz", "xy", "yz"):                           # reference key order (:164-169)
             if name in self.plane_type:
@@ -376,9 +400,17 @@ class GenNerf(nn.Module):
                 img = image[:, t]
                 feats.append(self.spatial(img) if self.spatial is not None else img)
             voxel_dim = self.cfg.voxel_dim_train if self.training else self.cfg.voxel_dim_val
-            out = None if self.volume is None else (self.volume, self.count, self.valid)
-            self.volume, self.count, self.valid = ops.backproject_frames(
-                voxel_dim, self.cfg.voxel_size, self.origin, projection, feats, out=out)
+            if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
+                # training: differentiable lift (gradients scatter-add back into the feature maps)
+                vol, cnt, val = ag.backproject_frames(voxel_dim, self.cfg.voxel_size, self.origin, projection, feats)
+                if self.volume is None:
+                    self.volume, self.count, self.valid = vol, cnt, val
+                else:
+                    self.volume, self.count, self.valid = self.volume + vol, self.count + cnt, self.valid + val
+            else:
+                out = None if self.volume is None else (self.volume, self.count, self.valid)
+                self.volume, self.count, self.valid = ops.backproject_frames(
+                    voxel_dim, self.cfg.voxel_size, self.origin, projection, feats, out=out)
         if self.cfg.encoder.use_pointnet:
             if sparse_xyz is None:
                 raise NotImplementedError("gennerf_b200: pass the FPS point cloud as sparse_xyz= "
@@ -402,6 +434,8 @@ class GenNerf(nn.Module):
     def forward(self, xyz):
         """reference model.py:207-248: dict feat_geo, feat_sem, tsdf, feat."""
         d_geo, d_sem = self.cfg.mlp.d_out_geo, self.cfg.mlp.d_out_sem
+        if torch.is_grad_enabled() and (self.training or xyz.requires_grad):
+            return self._forward_train(xyz)
         dw = self._dw if (self._dw is not None and not self.training) else self.refresh_weights()
         if self.precision in ("fp16", "bf16") and self.fused:
             out, tsdf, feat = ops.query_fused(
@@ -414,3 +448,42 @@ class GenNerf(nn.Module):
             feat = self.map_features(xyz)
             out, tsdf = ops.decode(dw, xyz, feat, self.precision)
         return {"feat_geo": out[..., :d_geo], "feat_sem": out[..., d_geo:d_geo + d_sem], "tsdf": tsdf, "feat": feat}
+
+    @torch.no_grad()
+    def predict_tsdf(self, nx, ny, nz, volume_size=None):
+        """reference model.py:752-790 without its 10 000-point chunk loop, per-chunk volume
+        re-normalisation and per-chunk D2H copies: the whole (nx,ny,nz) grid is decoded by one fused
+        kernel launch.  Returns tsdf (1,nx,ny,nz) on the device."""
+        if volume_size is None:
+            volume_size = [self.cfg.voxel_size * d for d in self.cfg.voxel_dim_test]
+        grid = get_grid_coordinates(nx, ny, nz, volume_size, self.origin, device=self.device).reshape(1, -1, 3)
+        was_training = self.training
+        self.eval()
+        try:
+            return self.forward(grid)["tsdf"].reshape(1, nx, ny, nz)
+        finally:
+            self.train(was_training)
+
+    def _forward_train(self, xyz):
+        """Differentiable forward (reference model.py:207-248 under autograd): the sampler runs on the
+        sm_100a kernels with their hand-written backward (scatter-add into volume / planes, d/dxyz);
+        the small MLP goes through ResnetFC.forward_torch so that autograd provides dgrad / wgrad."""
+        d_geo, d_sem = self.cfg.mlp.d_out_geo, self.cfg.mlp.d_out_sem
+        B, N, _ = xyz.shape
+        feat = ag.sample_features(
+            xyz, volume=self.volume if self.cfg.encoder.use_spatial else None,
+            planes=self.c_plane if self.cfg.encoder.use_pointnet else None,
+            voxel_size=self.cfg.voxel_size, origin=self.origin,
+            padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1)
+        code = xyz
+        if self.cfg.use_code:
+            # positional encoding with torch ops so that d/dxyz flows (eikonal / gradient losses)
+            f = self.code._freqs.to(xyz.device)
+            ph = self.code._phases.to(xyz.device)
+            x2 = xyz.reshape(-1, 3)
+            emb = torch.sin(torch.addcmul(ph, x2.unsqueeze(1).repeat(1, self.code.num_freqs * 2, 1), f)).view(x2.shape[0], -1)
+            code = (torch.cat((x2, emb), dim=-1) if self.code.include_input else emb).reshape(B, N, -1)
+        out = self.mlp.forward_torch(torch.cat((code, feat), dim=-1))
+        feat_geo, feat_sem = out[..., :d_geo], out[..., d_geo:d_geo + d_sem]
+        tsdf = torch.tanh(torch.nn.functional.linear(feat_geo, self.head_geo.fc.weight, self.head_geo.fc.bias))
+        return {"feat_geo": feat_geo, "feat_sem": feat_sem, "tsdf": tsdf, "feat": feat}

@@ -410,3 +410,123 @@ def tsdf_head(feat_geo, weight, bias):
         check(lib().gnb_tsdf_head(g.data_ptr(), n, d_geo, stride, w.data_ptr(), b.data_ptr(), out.data_ptr(), _stream()),
               "gnb_tsdf_head")
     return out.reshape(*lead, 1)
+
+
+# ------------------------------------------------------------------------------------------
+# backward passes -- raw ops; gennerf_b200.autograd wires them into torch.autograd
+# ------------------------------------------------------------------------------------------
+def backproject_frames_bwd(voxel_dim, voxel_size, origin, projections, grad_volume, feat_shape, n_frames, *,
+                           nhwc=False, mean=False, count=None, x_range=None):
+    """grad_volume (B,C,nx,ny,nz) logical (any dense strides) -> list of T gradient maps (B,C,H,W) logical, in
+    channels_last memory when `nhwc` else NCHW-contiguous."""
+    nx, ny, nz = (int(d) for d in voxel_dim)
+    B, Cc, H, W = feat_shape
+    _need_cuda(grad_volume)
+    gv = _f32(grad_volume)
+    sb, sc, sx, sy, sz = gv.stride()
+    if not (sz * nz == sy and sy * ny == sx):
+        gv = gv.contiguous()
+        sb, sc, sx, sy, sz = gv.stride()
+    P = torch.as_tensor(projections).detach().to("cpu", torch.float32).reshape(-1, n_frames, 3, 4).contiguous()
+    dev = gv.device
+    grads = []
+    with torch.cuda.device(dev):
+        for t0 in range(0, n_frames, _lib.GNB_MAX_FRAMES):
+            n = min(_lib.GNB_MAX_FRAMES, n_frames - t0)
+            if nhwc:
+                chunk = [torch.empty((B, H, W, Cc), device=dev, dtype=torch.float32).permute(0, 3, 1, 2) for _ in range(n)]
+            else:
+                chunk = [torch.empty((B, Cc, H, W), device=dev, dtype=torch.float32) for _ in range(n)]
+            p = GnbLiftParams()
+            p.nx, p.ny, p.nz = nx, ny, nz
+            p.voxel_size = float(voxel_size)
+            p.origin[:] = _origin3(origin)
+            p.batch, p.n_frames, p.C, p.H, p.W = B, n, Cc, H, W
+            p.feat_layout = _lib.LAYOUT_NHWC if nhwc else _lib.LAYOUT_NCHW
+            Pc = P[:, t0:t0 + n].contiguous()
+            p.h_projection = Pc.data_ptr()
+            scratch = None
+            if not nhwc:
+                scratch = torch.empty(n * B * H * W * Cc, device=dev, dtype=torch.float32)
+                p.scratch = scratch.data_ptr()
+            p.vol_stride_b, p.vol_stride_v, p.vol_stride_c = sb, sz, sc
+            p.mean = int(bool(mean))
+            if mean:
+                p.count = count.data_ptr()
+            if x_range is not None:
+                p.x_begin, p.x_end = int(x_range[0]), int(x_range[1])
+            ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in chunk])
+            check(lib().gnb_backproject_frames_bwd(C.byref(p), gv.data_ptr(), ptrs, _stream()), "gnb_backproject_frames_bwd")
+            grads.extend(chunk)
+    return grads
+
+
+def sample_features_bwd(grad_out, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
+                        need_volume=True, need_planes=True, need_xyz=True):
+    """Backward of sample_features: returns (grad_xyz | None, grad_volume | None, {plane: grad} | None) with the
+    strides of the forward inputs."""
+    s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
+    go = _f32(grad_out).contiguous()
+    gvol = torch.zeros_like(volume, memory_format=torch.preserve_format) if (volume is not None and need_volume) else None
+    if gvol is not None and gvol.stride() != volume.stride():
+        raise RuntimeError("gradient volume must share the forward strides")
+    gpl, ptrs = None, None
+    if planes and need_planes:
+        gpl, ptrs = {}, (C.c_void_p * 3)()
+        fwd = {t.data_ptr(): t for t in keep}                     # the tensors the forward pointers refer to
+        for k, name in enumerate(PLANES):
+            if planes.get(name) is not None:
+                g = torch.zeros_like(fwd[s.plane[k]], memory_format=torch.preserve_format)
+                gpl[name] = g
+                ptrs[k] = g.data_ptr()
+    gxyz = torch.empty((B, Q, 3), device=go.device, dtype=torch.float32) if need_xyz else None
+    with torch.cuda.device(go.device):
+        check(lib().gnb_sample_features_bwd(C.byref(s), go.data_ptr(), go.shape[-1], gvol.data_ptr() if gvol is not None else None,
+                                            ptrs, gxyz.data_ptr() if gxyz is not None else None, _stream()),
+              "gnb_sample_features_bwd")
+    return gxyz, gvol, gpl
+
+
+def scatter_mean_planes_bwd(p, grad_planes, count, padding=0.1):
+    """grad_planes (3,B,C_p,R,R) logical -> grad_c (B,N,C_p)."""
+    _need_cuda(p, grad_planes, count)
+    p = _f32(p).contiguous()
+    B, N, _ = p.shape
+    store = _f32(grad_planes).permute(0, 1, 3, 4, 2).contiguous()                 # (3,B,R,R,C_p)
+    Cp, R = store.shape[-1], store.shape[2]
+    gc = torch.empty((B, N, Cp), device=p.device, dtype=torch.float32)
+    with torch.cuda.device(p.device):
+        check(lib().gnb_scatter_mean_planes_bwd(p.data_ptr(), store.data_ptr(), count.data_ptr(), B, N, Cp, R, float(padding),
+                                                gc.data_ptr(), _stream()), "gnb_scatter_mean_planes_bwd")
+    return gc
+
+
+def pool_local_fwd_keep(p, c, reso, padding=0.1, scatter_type="max"):
+    """pool_local that also returns the scratch buffer the backward needs."""
+    _need_cuda(p, c)
+    p, c = _f32(p).contiguous(), _f32(c).contiguous()
+    B, N, _ = p.shape
+    Hd = c.shape[2]
+    t = {"max": _lib.POOL_MAX, "mean": _lib.POOL_MEAN}[scatter_type]
+    out = torch.empty_like(c)
+    nbytes = lib().gnb_pool_scratch_bytes(B, N, Hd, int(reso))
+    scratch = torch.empty(nbytes, device=p.device, dtype=torch.uint8)
+    with torch.cuda.device(p.device):
+        check(lib().gnb_pool_local(p.data_ptr(), c.data_ptr(), B, N, Hd, int(reso), float(padding), t,
+                                   out.data_ptr(), scratch.data_ptr(), nbytes, _stream()), "gnb_pool_local")
+    return out, scratch
+
+
+def pool_local_bwd(p, c, grad_out, fwd_scratch, reso, padding=0.1, scatter_type="max"):
+    p, c, go = _f32(p).contiguous(), _f32(c).contiguous(), _f32(grad_out).contiguous()
+    B, N, _ = p.shape
+    Hd = c.shape[2]
+    t = {"max": _lib.POOL_MAX, "mean": _lib.POOL_MEAN}[scatter_type]
+    gc = torch.empty_like(c)
+    nbytes = lib().gnb_pool_bwd_scratch_bytes(B, N, Hd, int(reso))
+    scratch = torch.empty(nbytes, device=p.device, dtype=torch.uint8)
+    with torch.cuda.device(p.device):
+        check(lib().gnb_pool_local_bwd(p.data_ptr(), c.data_ptr(), go.data_ptr(), B, N, Hd, int(reso), float(padding), t,
+                                       fwd_scratch.data_ptr(), gc.data_ptr(), scratch.data_ptr(), nbytes, _stream()),
+              "gnb_pool_local_bwd")
+    return gc

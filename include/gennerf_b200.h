@@ -89,6 +89,14 @@ typedef struct GnbLiftParams {
 
 int gnb_backproject_frames(const GnbLiftParams* p, void* stream);
 
+/* Backward of gnb_backproject_frames (autograd of utils.py:991, an index_put_ with accumulate):
+ * grad_features_t[b,:,py,px] += grad_volume[b,v,:] for every frame t that sees voxel v.
+ * `p` as in the forward call (volume strides now describe grad_volume; `count` is read in mean
+ * mode); h_grad_features: HOST array of n_frames device pointers in p->feat_layout, fully
+ * overwritten.  Atomic, order-nondeterministic sums like the reference's CUDA index_put_. */
+int gnb_backproject_frames_bwd(const GnbLiftParams* p, const float* grad_volume,
+                               float* const* h_grad_features, void* stream);
+
 /* Parity probe for the integer part of backproject (utils.py:979-985): pixel indices of
  * every voxel for ONE projection.  px,py are the int64 values the reference computes where
  * they are finite and fit int32, else INT32_MIN.  valid as in the reference. */
@@ -126,6 +134,15 @@ typedef struct GnbSampleParams {
 } GnbSampleParams;
 
 int gnb_sample_features(const GnbSampleParams* p, void* stream);
+
+/* Backward of gnb_sample_features (ATen grid_sampler_{3d,2d}_backward chained through the
+ * reference's coordinate normalisations).  grad_out: (B,Q,grad_out_stride) = [planes | volume].
+ * grad_volume / grad_planes (HOST array of 3 device pointers) use the forward strides and must be
+ * zero-initialised by the caller (they are accumulated into); grad_xyz (B,Q,3) is overwritten.
+ * Any of the three may be null. */
+int gnb_sample_features_bwd(const GnbSampleParams* s, const float* grad_out, int64_t grad_out_stride,
+                            float* grad_volume, float* const* h_grad_planes3, float* grad_xyz,
+                            void* stream);
 
 /* -------------------------------------------------------------------------------------
  * Plane coordinates and cell indices.  Replaces normalize_coordinate() + coordinate2index()
@@ -170,6 +187,18 @@ int64_t gnb_pool_scratch_bytes(int B, int64_t N, int Hd, int R);
 int gnb_pool_local(const float* p, const float* c, int B, int64_t N, int Hd, int R,
                    double padding, int pool_type, float* out,
                    void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Backward passes of the triplane projection.
+ * scatter-mean: grad_c[b,n,:] = sum over planes of grad_planes[cell(n),:] / max(count,1);
+ *   grad_planes (3,B,R,R,C_p) channels-last, count from the forward.
+ * pool_local: grad_c from grad_out (B,N,Hd); `fwd_scratch` is the scratch buffer the forward
+ *   gnb_pool_local call filled (it holds the cell maxima / sums and counts) and `c` its input. */
+int gnb_scatter_mean_planes_bwd(const float* p, const float* grad_planes, const int32_t* count, int B,
+                                int64_t N, int Cp, int R, double padding, float* grad_c, void* stream);
+int64_t gnb_pool_bwd_scratch_bytes(int B, int64_t N, int Hd, int R);
+int gnb_pool_local_bwd(const float* p, const float* c, const float* grad_out, int B, int64_t N, int Hd,
+                       int R, double padding, int pool_type, const void* fwd_scratch, float* grad_c,
+                       void* scratch, int64_t scratch_bytes, void* stream);
 
 /* -------------------------------------------------------------------------------------
  * Decoder.  Replaces

@@ -142,3 +142,27 @@ def test_gennerf_dropin_tc_golden(golden_dir):
         out = model(i["xyz"].to(DEV))
     assert (out["tsdf"].cpu() - o["tsdf"]).abs().max().item() <= 1e-2
     assert ((out["feat"].cpu() - o["feat"]).abs().max() / o["feat"].abs().max()).item() <= 1e-5
+
+
+def test_predict_tsdf_dense_grid(golden_dir):
+    """dense TSDF extraction in one launch == the oracle answering the same grid."""
+    from test_gpu_parity import _gennerf_from_golden, load
+    G = load(golden_dir, "gennerf_forward.pt")
+    i = G["in"]
+    model = _gennerf_from_golden(G, "fp16", True)
+    T = i["projection"].shape[1]
+    image = i["features"].view(1, T, *i["features"].shape[1:]).to(DEV)
+    model.cfg.encoder.use_pointnet = False
+    model.encode(i["projection"], image, None, "val")
+    model.cfg.encoder.use_pointnet = True
+    model.c_plane = {k: v.to(DEV).contiguous(memory_format=torch.channels_last) for k, v in i["planes"].items()}
+    nx, ny, nz = 20, 18, 9
+    size = [d * i["voxel_size"] for d in i["voxel_dim"]]
+    tsdf = model.predict_tsdf(nx, ny, nz, size)
+    assert tsdf.shape == (1, nx, ny, nz)
+    feats = [i["features"][t:t + 1] for t in range(T)]
+    vol, valid, _ = O.encode_volume(i["voxel_dim"], i["voxel_size"], ORIGIN, i["projection"], feats)
+    grid = O.get_grid_coordinates(nx, ny, nz, size).reshape(1, -1, 3)
+    ref = O.gennerf_forward(grid, i["weights"], i["head_w"], i["head_b"], volume=vol, valid=valid, planes=i["planes"],
+                            voxel_size=i["voxel_size"], padding=i["padding"], num_freqs=i["num_freqs"], freq_factor=i["freq_factor"])
+    assert (tsdf.cpu().reshape(-1) - ref["tsdf"].reshape(-1)).abs().max().item() <= 1e-2
