@@ -19,8 +19,8 @@
 //          code tile        positional encoding (+ two constant-1 columns that carry biases)
 //          W ring           NSTAGE x 16 KB weight tiles (<=128 n-rows x 64 k), pre-swizzled in HBM,
 //                           streamed with 1-D bulk async copies (no tensor map needed)
-//   warps  0: weight producer   1: MMA issuer   2: TMEM alloc + A-chunk exchange   3: idle
-//          4-11: epilogue / prologue, two warps per TMEM lane quadrant (thread = query row = TMEM lane)
+//   warps  0-7: epilogue / prologue, two warps per TMEM lane quadrant (thread = query row = TMEM lane)
+//          8: weight producer   9: MMA issuer   10: TMEM alloc + A-chunk exchange   11: arrival forwarder
 //
 // Dataflow per tile: prologue samples features + encodes xyz -> bf16 operand tiles; then MMA groups
 //   G0 = [lin_in, lin_z_0] -> x;  per block: E(relu(x)) -> [fc_0] -> net;  E(relu(net+b0)) ->
@@ -49,12 +49,18 @@ constexpr int NET_COL = 256;          // TMEM column of the net / out accumulato
 constexpr int MAX_CHUNKS = 16;
 constexpr int MAX_STAGES = 8;
 constexpr int NTHREADS = 384;
-constexpr int EPI_WARP0 = 4;          // epilogue warps 4..11: two per TMEM lane quadrant (warp & 3)
+constexpr int EPI_WARP0 = 4;          // epilogue warps 0..7: two per TMEM lane quadrant (warp & 3)
+constexpr int ROLE_WARP0 = 0;         // 8 weight producer, 9 MMA issuer, 10 TMEM alloc + exchange, 11 forwarder
+                                      // (the warp scheduler favours higher warp ids: the issuer outranks the epilogue)
 constexpr int EPI_GROUPS = 2;         // group g = (warp - 4) / 4 converts the own chunks t with t % 2 == g
 
 struct Dims {
     int d_feat, d_code, Hd, nb, d_out, d_geo;
-    int nsplit, HN;                   // CTAs per tile, hidden units per CTA
+    int nsplit, HN;                   // N-halves of the hidden width (1 or 2), hidden units (TMEM columns) per half
+    int two;                          // 1: cta_group::2 pairs (256 query rows per cluster, each CTA loads half of B)
+    int csize;                        // CTAs per cluster = nsplit * (two ? 2 : 1)
+    int WN;                           // weight rows one CTA streams per k-chunk of a hidden layer = HN / (two ? 2 : 1)
+    int NOUTC;                        // lin_out weight rows per CTA
     int KF, KZ, KH;                   // 64-wide K chunks of lin_in, lin_z, hidden layers
     int NOUT;                         // lin_out rows padded to a multiple of 16
     int OWN;                          // activation chunks this CTA produces per layer = HN / 64
@@ -81,7 +87,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.  try_wait parks the thread in
+// hardware between polls, so waiting roles do not take issue slots from the warps that have work.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
@@ -94,6 +101,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (!done && spin > (1u << 24)) __trap();
     }
+}
+// Parking wait for a whole warp (epilogue): lane 0 waits, the others sleep at the warp barrier.
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+// Whole-warp wait with warp-uniform control flow and ONE polling lane.  An mbarrier query is a per-thread
+// operation on one shared-memory word: a full warp polling costs ~32 serialised queries (measured ~390 cycles per
+// wait even on a completed barrier), and 256 epilogue threads polling slow every other waiter of the SM down.
+// Lane 0 queries, the vote makes the result (and the loop) uniform, so operands of the following tcgen05
+// instructions stay in uniform registers.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+// Two barriers at once: both queries are in flight together (one query costs ~150 cycles of latency), which is
+// what the MMA issuer needs per k-step -- "A chunk ready" and "weight stage landed".
+__device__ __forceinline__ void mbar_wait2_warp(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+    mbar_wait(bar_a, par_a);
+    mbar_wait(bar_b, par_b);
+}
+// Up to three barriers (bar == 0: skip), all queries in flight together.
+__device__ __forceinline__ void mbar_wait3_warp(uint32_t b0, uint32_t p0, uint32_t b1, uint32_t p1, uint32_t b2, uint32_t p2) {
+    if (b0) mbar_wait(b0, p0);
+    if (b1) mbar_wait(b1, p1);
+    mbar_wait(b2, p2);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -134,9 +161,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 }
 // kind::f16 instruction descriptor: D=f32 [4,6)=1, A format [7,10) and B format [10,13) (0 = f16,
 // 1 = bf16), K-major both, N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t umma_idesc(int n, bool bf16) {
+__device__ __forceinline__ uint32_t umma_idesc(int n, bool bf16, int m = BM) {
     const uint32_t f = bf16 ? 1u : 0u;
-    return (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    return (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -152,6 +179,24 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                  "h"(mask)
                  : "memory");
+}
+// 2-CTA variants: one instruction drives the tensor cores of both SMs of the pair (M = 256: 128 rows from
+// each CTA's A tile, each CTA supplies half of the N rows of B); commits can signal any set of CTAs
+__device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_2cta(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+// arrive on a barrier that lives in another CTA of the cluster (address from map_to_cta)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -237,8 +282,8 @@ __host__ __device__ inline Smem smem_layout(const Dims& d) {
     // fp32 table: b0[nb][HN] | b1_last[HN] | b_out[NOUT] | head_w[d_geo] | head_b
     uint32_t nbias = (uint32_t)(d.nb * d.HN + d.HN + d.NOUT + d.d_geo + 1);
     s.bars = (s.bias + nbias * 4 + 15) & ~15u;
-    // barriers: w_full[8] w_empty[8] a_ready[8] rready[4] rfree[4] acc_ready in_ready | tmem base slot
-    s.total = s.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2) * 8 + 16;
+    // barriers: w_full[8] w_empty[8] a_ready[8] rready[4] rfree[4] acc_ready in_ready pw_full[8] prready[4] | tmem slot
+    s.total = s.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2 + 12) * 8 + 16;
     return s;
 }
 
@@ -250,25 +295,42 @@ struct Op {
 __device__ __forceinline__ int num_ops(const Dims& d) { return 2 + 3 * d.nb; }   // lin_in, nb x (lin_z, fc0, fc1), lin_out
 __device__ __forceinline__ Op get_op(const Dims& d, int o) {
     Op op;
-    if (o == 0) return Op{0, d.KF, d.HN, 0, 1, 0};
-    if (o == 1 + 3 * d.nb) return Op{2, d.KH, d.NOUT, NET_COL, 1, 1};
+    if (o == 0) return Op{0, d.KF, d.WN, 0, 1, 0};
+    if (o == 1 + 3 * d.nb) return Op{2, d.KH, d.NOUTC, NET_COL, 1, 1};
     int i = (o - 1) / 3, j = (o - 1) % 3;
     // order inside a block as issued: lin_z_i (ends the group that feeds relu(x)), fc0_i, fc1_i
-    if (j == 0) return Op{1, d.KZ, d.HN, 0, 0, 1};
-    if (j == 1) return Op{2, d.KH, d.HN, NET_COL, 1, 1};
-    op = Op{2, d.KH, d.HN, 0, 0, (i == d.nb - 1) ? 1 : 0};
+    if (j == 0) return Op{1, d.KZ, d.WN, 0, 0, 1};
+    if (j == 1) return Op{2, d.KH, d.WN, NET_COL, 1, 1};
+    op = Op{2, d.KH, d.WN, 0, 0, (i == d.nb - 1) ? 1 : 0};
     return op;
 }
-// k-chunk visiting order of an activation op: own chunks first, then the peer's
-__device__ __forceinline__ int act_chunk(const Dims& d, int rank, int t) { return (rank * (d.HN / 64) + t) % d.KH; }
+// k-chunk visiting order of an activation op on N-half `half`: own chunk 0, the peer's chunk 0, own 1, peer 1, ...
+// (the peer's r-th chunk lands about one copy latency after the own r-th is written, so the MMAs never wait
+// for a whole half).  Returns the global 64-wide k-chunk index; t even = own, t odd = pushed by the peer.
+__host__ __device__ inline int act_kchunk(int nsplit, int own, int half, int t, int interleave) {
+    if (nsplit == 1) return t;
+    if (!interleave) return (half * own + t) % (2 * own);          // own chunks first, then the peer's
+    const int r = t >> 1;
+    return (t & 1) ? ((half ^ 1) * own + r) : (half * own + r);
+}
 
 // trace slot layout: dbg[role*4096 + k]; role 0 = MMA thread, 1 = epilogue warp 4 lane 0, 2 = producer
+// (compiled in only with -DGNB_TC_TRACE: even a predicated clock read per k-step costs the single-thread MMA
+//  issue loop ~10 %)
+#ifdef GNB_TC_TRACE
 #define GNB_TRACE(role, k) do { if (p.dbg && blockIdx.x == 0 && (k) < 4096) p.dbg[(role) * 4096 + (k)] = clock64(); } while (0)
+#define GNB_TRACE_ON(p) ((p).dbg != nullptr)
+#else
+#define GNB_TRACE(role, k) do { } while (0)
+#define GNB_TRACE_ON(p) false
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool BF16>
+// TWO = cta_group::2: ranks (2i, 2i+1) of the cluster form an MMA pair working on 256 query rows (128 each);
+// rank>>1 selects the N-half of the hidden width, the even rank ("leader") issues every MMA of the pair.
+template <bool BF16, bool TWO>
 __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_constant__ TcKP p) {
     extern __shared__ unsigned char smem_raw[];
     const Dims& d = p.d;
@@ -283,31 +345,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     auto rfree = [&](int sl) { return bar0 + 8u * (2 * MAX_STAGES + 12 + sl); };     // the PEER has consumed what I pushed into its slot sl
     const uint32_t acc_ready = bar0 + 8u * (2 * MAX_STAGES + MAX_CHUNKS);
     const uint32_t in_ready = acc_ready + 8;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2) * 8);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2 + 12) * 8);
     float* bias_s = reinterpret_cast<float*>(sm + L.bias);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = (d.nsplit > 1) ? cluster_rank() : 0u;
-    const int cluster_id = blockIdx.x / d.nsplit;
+    const uint32_t rank = (d.csize > 1) ? cluster_rank() : 0u;
+    const int cluster_id = blockIdx.x / d.csize;
     const int own_chunks = d.OWN;
-    const uint32_t peer = rank ^ 1u;
+    const uint32_t half = TWO ? (rank >> 1) : rank;          // which N-half of the hidden width this CTA works on
+    const uint32_t mrow = TWO ? (rank & 1u) : 0u;             // which 128-row tile of the cluster's rows
+    const bool leader = !TWO || mrow == 0;                    // issues the MMAs
+    const uint32_t peer = TWO ? (rank ^ 2u) : (rank ^ 1u);    // same rows, other N-half: chunk exchange partner
+    const uint32_t lead_rank = rank & ~1u;                    // (TWO) leader of my pair
+    const int rows_per_cluster = TWO ? 2 * BM : BM;
 
     // ---- one-time setup ---------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int s = 0; s < d.nstage; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
-        for (int t = 0; t < 8; ++t) mbar_init(a_ready(t), 4 * EPI_GROUPS);   // all epilogue warps contribute to a chunk
-        for (int sl = 0; sl < 4; ++sl) { mbar_init(rready(sl), 1); mbar_init(rfree(sl), 1); }
-        mbar_init(acc_ready, d.nsplit);                   // every CTA of the cluster commits to every CTA
-        mbar_init(in_ready, 4 * EPI_GROUPS);
+        // on a pair leader a weight stage / pushed chunk is "full" when its own copy AND the partner's have landed:
+        // the partner forwards its local completion as a second arrival on the leader's barrier (one wait per k-step)
+        const int both = (TWO && leader) ? 2 : 1;
+        for (int s = 0; s < d.nstage; ++s) { mbar_init(w_full(s), both); mbar_init(w_empty(s), 1); }
+        // a chunk / the input tiles are complete when every epilogue warp of the CTA -- and, on a pair leader,
+        // of its partner too -- has arrived
+        const int warps_in = 4 * EPI_GROUPS * ((TWO && leader) ? 2 : 1);
+        for (int t = 0; t < 8; ++t) mbar_init(a_ready(t), warps_in);
+        for (int sl = 0; sl < 4; ++sl) { mbar_init(rready(sl), both); mbar_init(rfree(sl), 1); }
+        mbar_init(acc_ready, d.nsplit);                   // every issuing CTA of the cluster commits to every CTA
+        mbar_init(in_ready, warps_in);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == ROLE_WARP0 + 2) {
+        if constexpr (TWO) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32((const void*)tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     {   // fp32 bias table
         const GnbDecoderWeights& w = p.w;
-        const int h0 = rank * d.HN;
+        const int h0 = half * d.HN;
         for (int i = threadIdx.x; i < d.nb * d.HN; i += NTHREADS) bias_s[i] = __ldg(w.fc0_b[i / d.HN] + h0 + i % d.HN);
         float* b1 = bias_s + d.nb * d.HN;
         for (int i = threadIdx.x; i < d.HN; i += NTHREADS) b1[i] = d.nb > 0 ? __ldg(w.fc1_b[d.nb - 1] + h0 + i) : 0.0f;
@@ -319,45 +397,172 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     }
     tc_fence_before();
     __syncthreads();
-    if (d.nsplit > 1) cluster_sync_all();
+    if (d.csize > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
     const unsigned char* wstream = p.packed + (long long)rank * d.packed_per_rank;
     const int nops = num_ops(d);
+    const int my_tiles = cluster_id < p.n_tiles ? (p.n_tiles - 1 - cluster_id) / p.n_clusters + 1 : 0;
 
-    if (warp == 0) {
+    if (warp == ROLE_WARP0) {
         // =============================== weight producer ======================================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
-                const unsigned char* src = wstream;
-                for (int o = 0; o < nops; ++o) {
-                    const Op op = get_op(d, o);
-                    const int ntile = n_tiles_of(op.rows);
-                    for (int kc = 0; kc < op.kchunks; ++kc)
-                        for (int nt = 0; nt < ntile; ++nt) {
-                            const uint32_t bytes = (uint32_t)min(128, op.rows - nt * 128) * 128u;
+            if constexpr (TWO) {
+                // cta_group::2: a stage is a pair of 16 KB slots holding TWO consecutive k-chunks of the op (they are
+                // contiguous in the packed stream: one bulk copy); one barrier round-trip per 128 columns of K
+                const int nst = d.nstage / 2;
+                for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
+                    const unsigned char* src = wstream;
+                    for (int o = 0; o < nops; ++o) {
+                        const Op op = get_op(d, o);
+                        for (int kc = 0; kc < op.kchunks; kc += 2) {
+                            const uint32_t bytes = (uint32_t)min(2, op.kchunks - kc) * (uint32_t)op.rows * 128u;
                             mbar_wait(w_empty(stage), phase ^ 1);
                             mbar_expect_tx(w_full(stage), bytes);
-                            bulk_g2s(sbase + L.ring + stage * CHUNK, src, bytes, w_full(stage));
+                            bulk_g2s(sbase + L.ring + stage * 2 * CHUNK, src, bytes, w_full(stage));
                             src += bytes;
-                            if (++stage == d.nstage) { stage = 0; phase ^= 1; }
+                            if (++stage == nst) { stage = 0; phase ^= 1; }
                         }
+                    }
+                }
+            } else {
+                for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
+                    const unsigned char* src = wstream;
+                    for (int o = 0; o < nops; ++o) {
+                        const Op op = get_op(d, o);
+                        const int ntile = n_tiles_of(op.rows);
+                        for (int kc = 0; kc < op.kchunks; ++kc)
+                            for (int nt = 0; nt < ntile; ++nt) {
+                                const uint32_t bytes = (uint32_t)min(128, op.rows - nt * 128) * 128u;
+                                mbar_wait(w_empty(stage), phase ^ 1);
+                                mbar_expect_tx(w_full(stage), bytes);
+                                bulk_g2s(sbase + L.ring + stage * CHUNK, src, bytes, w_full(stage));
+                                src += bytes;
+                                if (++stage == d.nstage) { stage = 0; phase ^= 1; }
+                            }
+                    }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == ROLE_WARP0 + 1 && !leader) {
+        // ===================== (cta_group::2 partner) forward pushed-chunk arrivals to the leader ===========
+        // one lane per remote slot, so that forwarding never queues behind another slot
+        if (d.nsplit > 1 && lane < d.RS) {
+            const uint32_t total = (uint32_t)my_tiles * (uint32_t)(2 * d.nb + 1) * (uint32_t)own_chunks;
+            uint32_t use = 0;
+            for (uint32_t i = lane; i < total; i += d.RS, ++use) {
+                mbar_expect_tx(rready(lane), CHUNK);
+                mbar_wait(rready(lane), use & 1);
+                mbar_arrive_remote(map_to_cta(rready(lane), lead_rank));
+            }
+        }
+    } else if (warp == ROLE_WARP0 + 3 && !leader) {
+        // ===================== (cta_group::2 partner) forward weight-stage arrivals to the leader ============
+        // one lane per ring stage (a stage = two k-chunks)
+        const int nst = d.nstage / 2;
+        if (lane < nst) {
+            uint32_t per_tile = 0;
+            for (int o = 0; o < nops; ++o) { const Op op = get_op(d, o); per_tile += (op.kchunks + 1) / 2; }
+            const uint32_t total = (uint32_t)my_tiles * per_tile;
+            uint32_t use = 0;
+            for (uint32_t i = lane; i < total; i += nst, ++use) {
+                mbar_wait(w_full(lane), use & 1);
+                mbar_arrive_remote(map_to_cta(w_full(lane), lead_rank));
+            }
+        }
+    } else if (warp == ROLE_WARP0 + 1) {
         // =============================== MMA issuer ==========================================
         // The whole warp walks the program (warp-uniform control flow and operands); one elected
         // lane issues.  Two adjacent ring slots holding the two 128-row halves of a 256-row slice
         // are consumed by ONE N=256 instruction per k-step (half the issue work, 25% less
         // shared-memory operand traffic than two N=128 instructions).
+        if constexpr (TWO) {
+            // ---- cta_group::2 leader: steps of TWO k-chunks (128 columns of K): one combined wait on
+            //      [first chunk ready, second chunk ready, weight stage landed], 8 MMAs, the commits ----
+            const int nst = d.nstage / 2;
+            const uint16_t pairmask = (uint16_t)(3u << (half * 2)), othermask = (uint16_t)(3u << ((half ^ 1u) * 2));
+            int stage = 0;
+            uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0;
+            for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++tiles_done) {
+                mbar_wait_warp(in_ready, tiles_done & 1);
+                tc_fence_after();
+                int tk = tiles_done * 64;
+                if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
+                for (int o = 0; o < nops; ++o) {
+                    const Op op = get_op(d, o);
+                    if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
+                    long long wait_all = 0;
+                    const uint32_t idesc = umma_idesc(2 * op.rows, BF16, 2 * BM);
+                    const uint32_t dcol = tmem + op.d_col;
+                    for (int t = 0; t < op.kchunks; t += 2) {
+                        const int nchunk = min(2, op.kchunks - t);
+                        uint32_t a_addr[2] = {0, 0}, a_bar[2] = {0, 0}, a_par[2] = {0, 0};
+                        int rslot = -1;
+                        for (int c = 0; c < nchunk; ++c) {
+                            const int tt = t + c;
+                            if (op.a_kind == 0) a_addr[c] = sbase + L.a + tt * CHUNK;
+                            else if (op.a_kind == 1) a_addr[c] = sbase + L.code + tt * CHUNK;
+                            else {
+                                const bool own_chunk = d.nsplit == 1 || (tt & 1) == 0;
+                                const int r = d.nsplit == 1 ? tt : (tt >> 1);
+                                if (own_chunk) {
+                                    a_bar[c] = a_ready(r), a_par[c] = round & 1;
+                                    a_addr[c] = sbase + L.a + r * CHUNK;
+                                } else {
+                                    rslot = (int)(rtotal % (uint32_t)d.RS);
+                                    if (lane == 0) mbar_expect_tx(rready(rslot), CHUNK);
+                                    __syncwarp();
+                                    a_bar[c] = rready(rslot), a_par[c] = (rtotal / (uint32_t)d.RS) & 1;
+                                    a_addr[c] = sbase + L.a + (d.AOWN + rslot) * CHUNK;
+                                    ++rtotal;
+                                }
+                            }
+                        }
+                        const long long c1 = GNB_TRACE_ON(p) ? clock64() : 0;
+                        mbar_wait3_warp(a_bar[0], a_par[0], a_bar[1], a_par[1], w_full(stage), phase);
+                        if (GNB_TRACE_ON(p)) wait_all += clock64() - c1;
+                        tc_fence_after();
+                        const uint32_t b_base = sbase + L.ring + stage * 2 * CHUNK;
+                        const uint32_t first = (op.first_overwrites && t == 0) ? 0u : 1u;
+                        if (elect_one()) {
+                            const uint64_t da0 = umma_desc(a_addr[0]), db0 = umma_desc(b_base);
+                            umma_f16_2cta(dcol, da0, db0, idesc, first);
+                            umma_f16_2cta(dcol, da0 + 2, db0 + 2, idesc, 1u);
+                            umma_f16_2cta(dcol, da0 + 4, db0 + 4, idesc, 1u);
+                            umma_f16_2cta(dcol, da0 + 6, db0 + 6, idesc, 1u);
+                            if (nchunk == 2) {
+                                const uint64_t da1 = umma_desc(a_addr[1]), db1 = umma_desc(b_base + op.rows * 128);
+                                umma_f16_2cta(dcol, da1, db1, idesc, 1u);
+                                umma_f16_2cta(dcol, da1 + 2, db1 + 2, idesc, 1u);
+                                umma_f16_2cta(dcol, da1 + 4, db1 + 4, idesc, 1u);
+                                umma_f16_2cta(dcol, da1 + 6, db1 + 6, idesc, 1u);
+                            }
+                            umma_commit_mc_2cta(w_empty(stage), pairmask);     // both CTAs of the pair refill this stage
+                            if (rslot >= 0) umma_commit_mc_2cta(rfree(rslot), othermask);
+                        }
+                        __syncwarp();
+                        if (++stage == nst) { stage = 0; phase ^= 1; }
+                    }
+                    if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
+                    if (GNB_TRACE_ON(p) && lane == 0 && blockIdx.x == 0 && tiles_done < 8) {
+                        p.dbg[2 * 4096 + (tiles_done * 32 + o) * 2] = wait_all;
+                        p.dbg[2 * 4096 + (tiles_done * 32 + o) * 2 + 1] = 0;
+                    }
+                    if (op.a_kind == 2) ++round;
+                    if (op.group_end) {
+                        if (elect_one()) umma_commit_mc_2cta(acc_ready, (uint16_t)((1u << d.csize) - 1));
+                        __syncwarp();
+                    }
+                }
+            }
+        } else {
         int stage = 0;
         uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0;
         for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++tiles_done) {
-            mbar_wait(in_ready, tiles_done & 1);
+            mbar_wait_warp(in_ready, tiles_done & 1);
             tc_fence_after();
             int tk = tiles_done * 64;
             if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
@@ -369,44 +574,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 for (int t = 0; t < op.kchunks; ++t) {
                     uint32_t a_addr;
                     int rslot = -1;                                // >= 0: this chunk sits in a remote slot
+                    uint32_t a_bar = 0, a_par = 0;                 // barrier that says the A chunk is in shared memory
                     if (op.a_kind == 0) a_addr = sbase + L.a + t * CHUNK;
                     else if (op.a_kind == 1) a_addr = sbase + L.code + t * CHUNK;
                     else {
-                        const long long c0 = p.dbg ? clock64() : 0;
-                        if (t < own_chunks) {                      // own chunks first ...
-                            mbar_wait(a_ready(t), round & 1);
-                            a_addr = sbase + L.a + t * CHUNK;
-                        } else {                                   // ... then the peer's, in the order it pushes them
+                        const bool own_chunk = t < own_chunks;     // single-CTA issue: own chunks first, then the peer's
+                        const int r = own_chunk ? t : t - own_chunks;
+                        if (own_chunk) {                           // own chunk r ...
+                            a_bar = a_ready(r), a_par = round & 1;
+                            a_addr = sbase + L.a + r * CHUNK;
+                        } else {                                   // ... then the peer's r-th, in the order it pushes them
                             rslot = (int)(rtotal % (uint32_t)d.RS);
                             if (lane == 0) mbar_expect_tx(rready(rslot), CHUNK);
                             __syncwarp();
-                            mbar_wait(rready(rslot), (rtotal / (uint32_t)d.RS) & 1);
+                            a_bar = rready(rslot), a_par = (rtotal / (uint32_t)d.RS) & 1;
                             a_addr = sbase + L.a + (d.AOWN + rslot) * CHUNK;
                             ++rtotal;
                         }
-                        if (p.dbg) wait_a += clock64() - c0;
                     }
                     for (int nt = 0; nt < ntile;) {
                         const int pair = (ntile - nt >= 2 && (stage & 1) == 0 && stage + 1 < d.nstage) ? 2 : 1;
-                        const long long c1 = p.dbg ? clock64() : 0;
-                        mbar_wait(w_full(stage), phase);
-                        if (pair == 2) mbar_wait(w_full(stage + 1), phase);
-                        if (p.dbg) wait_w += clock64() - c1;
+                        const long long c1 = GNB_TRACE_ON(p) ? clock64() : 0;
+                        if (a_bar && nt == 0) mbar_wait2_warp(a_bar, a_par, w_full(stage), phase);      // both queries in flight together
+                        else mbar_wait_warp(w_full(stage), phase);
+                        if (pair == 2) mbar_wait_warp(w_full(stage + 1), phase);
+                        if (GNB_TRACE_ON(p)) wait_w += clock64() - c1;
                         tc_fence_after();
                         const int rows = min(128 * pair, op.rows - nt * 128);
                         const uint64_t da = umma_desc(a_addr), db = umma_desc(sbase + L.ring + stage * CHUNK);
-                        const uint32_t idesc = umma_idesc(rows, BF16);
-                        const uint32_t dcol = tmem + op.d_col + nt * 128;
                         const uint32_t first = (op.first_overwrites && t == 0) ? 0u : 1u;
-                        if (elect_one()) {
-                            umma_f16(dcol, da, db, idesc, first);
-                            umma_f16(dcol, da + 2, db + 2, idesc, 1u);
-                            umma_f16(dcol, da + 4, db + 4, idesc, 1u);
-                            umma_f16(dcol, da + 6, db + 6, idesc, 1u);
-                            umma_commit(w_empty(stage));          // frees the ring slot(s) when these MMAs retire
-                            if (pair == 2) umma_commit(w_empty(stage + 1));
-                            // last MMAs that read a remote slot: tell the PEER it may push into it again
-                            if (rslot >= 0 && nt + pair >= ntile) umma_commit_mc(rfree(rslot), (uint16_t)(1u << peer));
+                        if constexpr (TWO) {
+                            // N = rows held by this CTA + the same number held by its partner; M = 256
+                            const uint32_t idesc = umma_idesc(2 * rows, BF16, 2 * BM);
+                            const uint32_t dcol = tmem + op.d_col;
+                            const uint16_t pairmask = (uint16_t)(3u << (half * 2)), othermask = (uint16_t)(3u << ((half ^ 1u) * 2));
+                            if (elect_one()) {
+                                umma_f16_2cta(dcol, da, db, idesc, first);
+                                umma_f16_2cta(dcol, da + 2, db + 2, idesc, 1u);
+                                umma_f16_2cta(dcol, da + 4, db + 4, idesc, 1u);
+                                umma_f16_2cta(dcol, da + 6, db + 6, idesc, 1u);
+                                umma_commit_mc_2cta(w_empty(stage), pairmask);     // both CTAs of the pair refill this slot
+                                if (rslot >= 0) umma_commit_mc_2cta(rfree(rslot), othermask);
+                            }
+                        } else {
+                            const uint32_t idesc = umma_idesc(rows, BF16);
+                            const uint32_t dcol = tmem + op.d_col + nt * 128;
+                            if (elect_one()) {
+                                umma_f16(dcol, da, db, idesc, first);
+                                umma_f16(dcol, da + 2, db + 2, idesc, 1u);
+                                umma_f16(dcol, da + 4, db + 4, idesc, 1u);
+                                umma_f16(dcol, da + 6, db + 6, idesc, 1u);
+                                umma_commit(w_empty(stage));          // frees the ring slot(s) when these MMAs retire
+                                if (pair == 2) umma_commit(w_empty(stage + 1));
+                                // last MMAs that read a remote slot: tell the PEER it may push into it again
+                                if (rslot >= 0 && nt + pair >= ntile) umma_commit_mc(rfree(rslot), (uint16_t)(1u << peer));
+                            }
                         }
                         __syncwarp();
                         stage += pair;
@@ -415,21 +637,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                     }
                 }
                 if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
-                if (lane == 0 && p.dbg && blockIdx.x == 0 && tiles_done < 8) {
+                if (GNB_TRACE_ON(p) && lane == 0 && blockIdx.x == 0 && tiles_done < 8) {
                     p.dbg[2 * 4096 + (tiles_done * 32 + o) * 2] = wait_a;
                     p.dbg[2 * 4096 + (tiles_done * 32 + o) * 2 + 1] = wait_w;
                 }
                 if (op.a_kind == 2) ++round;
                 if (op.group_end) {
                     if (elect_one()) {
-                        if (d.nsplit > 1) umma_commit_mc(acc_ready, (uint16_t)((1u << d.nsplit) - 1));
+                        if constexpr (TWO) umma_commit_mc_2cta(acc_ready, (uint16_t)((1u << d.csize) - 1));
+                        else if (d.nsplit > 1) umma_commit_mc(acc_ready, (uint16_t)((1u << d.nsplit) - 1));
                         else umma_commit(acc_ready);
                     }
                     __syncwarp();
                 }
             }
         }
-    } else if (warp == 2) {
+        }   // !TWO
+    } else if (warp == ROLE_WARP0 + 2) {
         // =============================== A-chunk exchange (NSPLIT=2) ==========================
         // Pushes every own chunk into one of the peer's RS remote slots (cycled).  A slot is reused
         // only after the peer's MMAs that read it have retired (rfree, signalled by the peer's
@@ -458,7 +682,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
         const GnbDecoderWeights& w = p.w;
         uint32_t grp = 0;                                    // acc_ready uses so far
         for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
-            const long long grow = (long long)tile * BM + row;
+            const long long grow = (long long)tile * rows_per_cluster + mrow * BM + row;
             const bool live = grow < p.n_rows;
             int ek = (int)(grp / (2 * d.nb + 2)) * 64;
             if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
@@ -522,7 +746,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                                     // (host guarantees C_p % 4 == 0, C % 4 == 0 and unit channel strides here)
                                     Vals<4> r = (k < p.s.Cp) ? sample_planes<4>(p.s, bc, b, k) : sample_volume<4>(p.s, tcn, b, k - p.s.Cp);
                                     f4 = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-                                    if (p.s.out && rank == 0) *reinterpret_cast<float4*>(p.s.out + grow * p.s.out_stride + k) = f4;
+                                    if (p.s.out && half == 0) *reinterpret_cast<float4*>(p.s.out + grow * p.s.out_stride + k) = f4;
                                 }
                             }
                             v[h * 4 + 0] = f4.x, v[h * 4 + 1] = f4.y, v[h * 4 + 2] = f4.z, v[h * 4 + 3] = f4.w;
@@ -537,14 +761,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                     }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(in_ready);
+                if (lane == 0) {
+                    if (leader) mbar_arrive(in_ready);
+                    else mbar_arrive_remote(map_to_cta(in_ready, lead_rank));      // the pair leader issues for both
+                }
                 if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             }
             // ---------------- epilogue rounds: accumulator -> next A operand -----------------
             const float* b0 = bias_s;
             const float* b1_last = bias_s + d.nb * d.HN;
             for (int r = 0; r < 2 * d.nb + 1; ++r) {
-                mbar_wait(acc_ready, grp & 1);
+                mbar_wait_park(acc_ready, grp & 1);
                 ++grp;
                 tc_fence_after();
                 if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
@@ -582,14 +809,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         tc_fence_before();
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(a_ready(t + h));
+                        if (lane == 0) {
+                            mbar_arrive(a_ready(t + h));                             // local: exchange thread (+ MMA on a leader)
+                            if (!leader) mbar_arrive_remote(map_to_cta(a_ready(t + h), lead_rank));
+                        }
                     }
                 }
                 if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             }
             // ---------------- final epilogue: lin_out tile -> global, TSDF head -----------------
             {
-                mbar_wait(acc_ready, grp & 1);
+                mbar_wait_park(acc_ready, grp & 1);
                 ++grp;
                 tc_fence_after();
                 const float* bo = bias_s + d.nb * d.HN + d.HN;
@@ -606,7 +836,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         f[e] = __uint_as_float(v[e]) + bo[n];
                         if (n < d.d_geo) head = fmaf(f[e], hw[n], head);
                     }
-                    if (live && rank == 0 && p.out) {
+                    if (live && half == 0 && p.out) {
                         float* o = p.out + grow * d.d_out + part * 16;
                         if ((d.d_out & 3) == 0) {
 #pragma unroll
@@ -619,7 +849,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         }
                     }
                 }
-                if (live && rank == 0 && eg == 0 && p.tsdf) p.tsdf[grow] = tanhf(head);
+                if (live && half == 0 && eg == 0 && p.tsdf) p.tsdf[grow] = tanhf(head);
                 tc_fence_before();
                 if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             }
@@ -629,10 +859,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     // ---- teardown -----------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (d.nsplit > 1) cluster_sync_all();
-    if (warp == 2) {
+    if (d.csize > 1) cluster_sync_all();
+    if (warp == ROLE_WARP0 + 2) {
+        __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+        if constexpr (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
 }
 
@@ -645,7 +877,8 @@ struct PackOp {
     int n0;               // first row of this CTA's slice
     int rows;             // rows of the op in this CTA (HN or NOUT)
     int kchunks;
-    int kc_rot;           // activation ops: visiting order starts at this chunk (own chunks first)
+    int order_half;       // activation ops: N-half whose visiting order (act_kchunk) is used; -1 = identity
+    int nsplit, own, interleave;
     float scale;          // multiplies W and biasA
     const float* biasA;   // bias columns at k == K_true (hi) and K_true + 1 (lo): scale*biasA[n] + biasB[n]
     const float* biasB;
@@ -664,7 +897,7 @@ __global__ void pack_kernel(PackOp op, unsigned char* __restrict__ dst_rank) {
     int rem = (int)(idx % units_per_k);
     const int n_in_op = rem / 8, u = rem % 8;
     const int nt = n_in_op / 128, nl = n_in_op % 128;
-    const int kc = (op.kc_rot + t) % op.kchunks;
+    const int kc = op.order_half < 0 ? t : act_kchunk(op.nsplit, op.own, op.order_half, t, op.interleave);
     const int n = op.n0 + n_in_op;
     float v[8];
 #pragma unroll
@@ -699,10 +932,18 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
     if (d.nb < 1) { set_error("%s: n_blocks must be >= 1", who); return GNB_E_UNSUPPORTED; }
     d.nsplit = d.Hd > 256 ? 2 : 1;
     d.HN = d.Hd / d.nsplit;
+    // cta_group::2 pairs (each CTA streams half of B, 256 rows per cluster) are built and parity-tested but opt-in:
+    // measured this round they run at 0.91x of the single-CTA issue because a cluster of 4 leaves 16 SMs idle
+    // and the per-layer epilogue -> exchange -> MMA latency chain, not the weight ingest, then bounds a layer
+    d.two = getenv("GNB_TC_TWO_CTA") ? 1 : 0;
+    if (d.HN % 32 != 0) d.two = 0;
+    d.csize = d.nsplit * (d.two ? 2 : 1);
+    d.WN = d.two ? d.HN / 2 : d.HN;
     d.KF = (d.d_feat + 2 + 63) / 64;
     d.KZ = (d.d_code + 2 + 63) / 64;
     d.KH = d.Hd / 64;
-    d.NOUT = (d.d_out + 15) / 16 * 16;
+    d.NOUT = d.two ? (d.d_out + 31) / 32 * 32 : (d.d_out + 15) / 16 * 16;     // each CTA of a pair holds NOUT/2 rows
+    d.NOUTC = d.two ? d.NOUT / 2 : d.NOUT;
     if (d.KZ > 4 || d.NOUT > 256 || d.KF > 8) {
         set_error("%s: d_code %d / d_out %d / d_feat %d too large for the tcgen05 path", who, d.d_code, d.d_out, d.d_feat);
         return GNB_E_UNSUPPORTED;
@@ -713,11 +954,12 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
     d.ACH = d.AOWN + d.RS;
     d.nstage = MAX_STAGES;
     while (d.nstage >= 2 && smem_layout(d).total + 1024 > 227 * 1024) --d.nstage;
+    if (d.two) d.nstage &= ~1;          // cta_group::2 stages are pairs of 16 KB slots
     if (d.nstage < 2) { set_error("%s: tile does not fit in shared memory", who); return GNB_E_UNSUPPORTED; }
     long long bytes = 0;
-    bytes += (long long)d.KF * d.HN * 128;
-    bytes += (long long)d.nb * ((long long)d.KZ * d.HN * 128 + 2LL * d.KH * d.HN * 128);
-    bytes += (long long)d.KH * d.NOUT * 128;
+    bytes += (long long)d.KF * d.WN * 128;
+    bytes += (long long)d.nb * ((long long)d.KZ * d.WN * 128 + 2LL * d.KH * d.WN * 128);
+    bytes += (long long)d.KH * d.NOUTC * 128;
     d.packed_per_rank = bytes;
     return 0;
 }
@@ -731,7 +973,7 @@ using namespace gnb::tc;
 extern "C" int64_t gnb_decoder_packed_bytes(const GnbDecoderWeights* w) {
     Dims d;
     if (make_dims(w, d, "gnb_decoder_packed_bytes")) return 0;
-    return d.packed_per_rank * d.nsplit;
+    return d.packed_per_rank * d.csize;
 }
 
 extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, void* stream) {
@@ -740,7 +982,8 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
     if (rc) return rc;
     GNB_CHECK_ARG(packed, "gnb_decoder_pack_tc: null output");
     cudaStream_t st = (cudaStream_t)stream;
-    for (int rank = 0; rank < d.nsplit; ++rank) {
+    for (int rank = 0; rank < d.csize; ++rank) {
+        const int half = d.two ? rank >> 1 : rank, mrow = d.two ? (rank & 1) : 0;
         unsigned char* dst = (unsigned char*)packed + (long long)rank * d.packed_per_rank;
         long long off = 0;
         auto launch = [&](PackOp op) -> int {
@@ -752,20 +995,21 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
             off += (long long)op.kchunks * op.rows * 128;
             return 0;
         };
-        const int n0 = rank * d.HN, rot = rank * (d.HN / 64);
+        const int n0 = half * d.HN + mrow * d.WN;
         PackOp op;
-        op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.HN, d.KF, 0, 1.0f, w->lin_in_b, nullptr, 1, 0};
+        op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.WN, d.KF, -1, d.nsplit, d.OWN, d.two, 1.0f, w->lin_in_b, nullptr, 1, 0};
         if ((rc = launch(op))) return rc;
         for (int i = 0; i < d.nb; ++i) {
             // x += alpha * (Wz code + bz)   [+ b1 of the previous block, folded here]
-            op = PackOp{w->lin_z_w[i], d.Hd, d.d_code, n0, d.HN, d.KZ, 0, w->alpha, w->lin_z_b[i], i > 0 ? w->fc1_b[i - 1] : nullptr, 1, 0};
+            op = PackOp{w->lin_z_w[i], d.Hd, d.d_code, n0, d.WN, d.KZ, -1, d.nsplit, d.OWN, d.two, w->alpha, w->lin_z_b[i],
+                        i > 0 ? w->fc1_b[i - 1] : nullptr, 1, 0};
             if ((rc = launch(op))) return rc;
-            op = PackOp{w->fc0_w[i], d.Hd, d.Hd, n0, d.HN, d.KH, rot, 1.0f, nullptr, nullptr, 0, 0};
+            op = PackOp{w->fc0_w[i], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
             if ((rc = launch(op))) return rc;
-            op = PackOp{w->fc1_w[i], d.Hd, d.Hd, n0, d.HN, d.KH, rot, 1.0f, nullptr, nullptr, 0, 0};
+            op = PackOp{w->fc1_w[i], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
             if ((rc = launch(op))) return rc;
         }
-        op = PackOp{w->lin_out_w, d.d_out, d.Hd, 0, d.NOUT, d.KH, rot, 1.0f, nullptr, nullptr, 0, 0};
+        op = PackOp{w->lin_out_w, d.d_out, d.Hd, mrow * d.NOUTC, d.NOUTC, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
         if ((rc = launch(op))) return rc;
         if (off != d.packed_per_rank) { set_error("gnb_decoder_pack_tc: internal size mismatch"); return GNB_E_INVALID; }
     }
@@ -791,25 +1035,37 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
     GNB_CUDA(cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev));
     if (cc != 10) { set_error("gnb_decode_tc: needs an sm_100 device (found sm_%d0)", cc); return GNB_E_ARCH; }
     kp.dbg = g_trace;
-    kp.n_tiles = (int)((kp.n_rows + BM - 1) / BM);
-    kp.n_clusters = sms / d.nsplit;
+    const int rows_per_cluster = d.two ? 2 * BM : BM;
+    kp.n_tiles = (int)((kp.n_rows + rows_per_cluster - 1) / rows_per_cluster);
+    kp.n_clusters = sms / d.csize;
     if (const char* e = getenv("GNB_DEBUG_MAX_CLUSTERS")) {   // profiling aid: fewer resident clusters
         int m = atoi(e);
         if (m > 0 && m < kp.n_clusters) kp.n_clusters = m;
     }
     if (kp.n_clusters > kp.n_tiles) kp.n_clusters = kp.n_tiles;
     const size_t smem = smem_layout(d).total + 1024;
-    auto kernel = (w->tc_dtype == GNB_TC_BF16) ? decoder_tc_kernel<true> : decoder_tc_kernel<false>;
+    auto kernel = d.two ? ((w->tc_dtype == GNB_TC_BF16) ? decoder_tc_kernel<true, true> : decoder_tc_kernel<false, true>)
+                        : ((w->tc_dtype == GNB_TC_BF16) ? decoder_tc_kernel<true, false> : decoder_tc_kernel<false, false>);
     GNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kp.n_clusters * d.nsplit);
+    cfg.gridDim = dim3(kp.n_clusters * d.csize);
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = d.nsplit, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = d.csize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
+    {
+        // persistent kernel with a static tile walk: never launch more clusters than can be co-resident
+        // (clusters must fit inside one GPC, so fewer than SMs / cluster size may be available)
+        int max_clusters = 0;
+        cfg.gridDim = dim3(sms / d.csize * d.csize);
+        GNB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+        if (getenv("GNB_DEBUG_PRINT")) fprintf(stderr, "[gnb] decoder: cluster size %d, max co-resident clusters %d\n", d.csize, max_clusters);
+        if (max_clusters > 0 && kp.n_clusters > max_clusters) kp.n_clusters = max_clusters;
+        cfg.gridDim = dim3(kp.n_clusters * d.csize);
+    }
     GNB_CUDA(cudaLaunchKernelEx(&cfg, kernel, kp));
     return 0;
 }

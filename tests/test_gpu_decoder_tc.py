@@ -166,3 +166,23 @@ def test_predict_tsdf_dense_grid(golden_dir):
     ref = O.gennerf_forward(grid, i["weights"], i["head_w"], i["head_b"], volume=vol, valid=valid, planes=i["planes"],
                             voxel_size=i["voxel_size"], padding=i["padding"], num_freqs=i["num_freqs"], freq_factor=i["freq_factor"])
     assert (tsdf.cpu().reshape(-1) - ref["tsdf"].reshape(-1)).abs().max().item() <= 1e-2
+
+
+def test_decode_tc_cta_group2_variant(monkeypatch):
+    """The opt-in cta_group::2 variant (256 rows per cluster of 4, each CTA streams half of B) against the
+    default single-CTA issue: same numerics up to accumulation order."""
+    from gennerf_b200 import ops
+    g = S.gen(46)
+    w, hw, hb = S.decoder_weights(g, 32, 15, 512, 5, 64, 32)
+    n = 5000
+    xyz = S.query_points(n, (96, 96, 48), VS, g)[0].to(DEV)
+    feat = torch.randn(n, 32, generator=g).to(DEV)
+    dw1 = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    a, ta = ops.decode(dw1, xyz, feat, "fp16")
+    monkeypatch.setenv("GNB_TC_TWO_CTA", "1")
+    dw2 = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    b, tb = ops.decode(dw2, xyz, feat, "fp16")
+    torch.cuda.synchronize()
+    assert dw2.packed.numel() == dw1.packed.numel()
+    assert ((a - b).abs().max() / a.abs().max()).item() < 2e-3
+    assert (ta - tb).abs().max().item() < 5e-3

@@ -18,7 +18,7 @@ n = 148 * 128 * 3
 xyz = S.query_points(n, (96, 96, 48), 0.04, g)[0].to(dev)
 feat = torch.randn(n, 32, device=dev)
 ops.decode(dw, xyz, feat, "fp16")
-buf = torch.zeros(3 * 4096, dtype=torch.int64, device=dev)
+buf = torch.zeros(4 * 4096, dtype=torch.int64, device=dev)
 L = lib()._handle
 raw = C.CDLL(None)
 fn = lib().gnb_debug_set_trace
@@ -27,7 +27,7 @@ fn(buf.data_ptr())
 ops.decode(dw, xyz, feat, "fp16")
 torch.cuda.synchronize()
 fn(None)
-t = buf.cpu().view(3, 4096)
+t = buf.cpu().view(4, 4096)
 nb = 5
 for tile in range(2):
     m = t[0, tile * 64: tile * 64 + 64].tolist()
@@ -44,3 +44,4 @@ for tile in range(2):
         print(f"   E round {r:2d}: acc_ready seen +{e[k]-t0:7d}  chunks written +{e[k+1]-t0:7d}  (dur {e[k+1]-e[k]})")
         k += 2
     print(f"   final: acc_ready +{e[k]-t0:7d} done +{e[k+1]-t0:7d}")
+
