@@ -253,27 +253,57 @@ struct TransposeKP {
     long long HW;
 };
 
-// One (b,t) image per blockIdx.z; 32 channels x 32 pixels tiles through shared memory.
+// One (b,t) image per blockIdx.z; a block moves a 32-channel x 128-pixel tile through shared memory:
+// float4 loads along the pixel axis (NCHW rows), float4 stores along the channel axis (NHWC rows).  The tile row
+// stride of 129 floats keeps the transposed reads conflict-free.
+constexpr int TP_PX = 128;
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const __grid_constant__ TransposeKP p) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[32][TP_PX + 1];
     const int t = blockIdx.z / p.B, b = blockIdx.z % p.B;
     const float* __restrict__ src = p.src[t] + (long long)b * p.C * p.HW;
     float* __restrict__ dst = p.dst + ((long long)t * p.B + b) * p.HW * p.C;
-    const long long px0 = (long long)blockIdx.x * 32;
+    const long long px0 = (long long)blockIdx.x * TP_PX;
     const int c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    const bool vec_in = (p.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    // ---- load: 32 rows (channels) x 32 float4 (128 pixels) = 1024 float4, 4 per thread ----
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        int c = c0 + r;
-        long long px = px0 + tx;
-        tile[r][tx] = (c < p.C && px < p.HW) ? __ldg(src + (long long)c * p.HW + px) : 0.0f;
+    for (int i = 0; i < 4; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        const int r = idx >> 5, q = idx & 31;              // channel row, float4 column
+        const int c = c0 + r;
+        const long long px = px0 + q * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < p.C) {
+            const float* s = src + (long long)c * p.HW + px;
+            if (vec_in && px + 3 < p.HW) v = ldg4(s);
+            else {
+                if (px < p.HW) v.x = __ldg(s);
+                if (px + 1 < p.HW) v.y = __ldg(s + 1);
+                if (px + 2 < p.HW) v.z = __ldg(s + 2);
+                if (px + 3 < p.HW) v.w = __ldg(s + 3);
+            }
+        }
+        tile[r][q * 4 + 0] = v.x, tile[r][q * 4 + 1] = v.y, tile[r][q * 4 + 2] = v.z, tile[r][q * 4 + 3] = v.w;
     }
     __syncthreads();
+    // ---- store: 128 pixels x 8 float4 (32 channels) = 1024 float4, 4 per thread ----
+    const bool vec_out = (p.C % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-        long long px = px0 + r;
-        int c = c0 + tx;
-        if (c < p.C && px < p.HW) dst[px * p.C + c] = tile[tx][r];
+    for (int i = 0; i < 4; ++i) {
+        const int idx = threadIdx.x + i * 256;
+        const int pl = idx >> 3, cq = idx & 7;             // pixel in tile, channel quad
+        const long long px = px0 + pl;
+        const int c = c0 + cq * 4;
+        if (px >= p.HW || c >= p.C) continue;
+        float* d = dst + px * p.C + c;
+        const float v0 = tile[cq * 4 + 0][pl], v1 = tile[cq * 4 + 1][pl], v2 = tile[cq * 4 + 2][pl], v3 = tile[cq * 4 + 3][pl];
+        if (vec_out && c + 3 < p.C) *reinterpret_cast<float4*>(d) = make_float4(v0, v1, v2, v3);
+        else {
+            d[0] = v0;
+            if (c + 1 < p.C) d[1] = v1;
+            if (c + 2 < p.C) d[2] = v2;
+            if (c + 3 < p.C) d[3] = v3;
+        }
     }
 }
 
@@ -510,7 +540,7 @@ extern "C" int gnb_nchw_to_nhwc(const float* const* h_src, int n_frames, float* 
     for (int t = 0; t < n_frames; ++t) kp.src[t] = h_src[t];
     kp.dst = dst;
     kp.T = n_frames, kp.B = B, kp.C = C, kp.HW = (long long)H * W;
-    dim3 grid((unsigned)ceil_div(kp.HW, 32), (unsigned)ceil_div(C, 32), (unsigned)(n_frames * B));
+    dim3 grid((unsigned)ceil_div(kp.HW, TP_PX), (unsigned)ceil_div(C, 32), (unsigned)(n_frames * B));
     nchw_to_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kp);
     GNB_LAUNCH_CHECK();
     return 0;
