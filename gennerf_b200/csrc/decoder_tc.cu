@@ -19,8 +19,8 @@
 //          code tile        positional encoding (+ two constant-1 columns that carry biases)
 //          W ring           NSTAGE x 16 KB weight tiles (<=128 n-rows x 64 k), pre-swizzled in HBM,
 //                           streamed with 1-D bulk async copies (no tensor map needed)
-//   warps  0-7: epilogue / prologue, two warps per TMEM lane quadrant (thread = query row = TMEM lane)
-//          8: weight producer   9: MMA issuer   10: TMEM alloc + A-chunk exchange   11: arrival forwarder
+//   warps  0: weight producer   1: MMA issuer   2: TMEM alloc + A-chunk exchange   3: arrival forwarder (2-CTA)
+//          4-11: epilogue / prologue, two warps per TMEM lane quadrant (thread = query row = TMEM lane)
 //
 // Dataflow per tile: prologue samples features + encodes xyz -> bf16 operand tiles; then MMA groups
 //   G0 = [lin_in, lin_z_0] -> x;  per block: E(relu(x)) -> [fc_0] -> net;  E(relu(net+b0)) ->
@@ -49,10 +49,9 @@ constexpr int NET_COL = 256;          // TMEM column of the net / out accumulato
 constexpr int MAX_CHUNKS = 16;
 constexpr int MAX_STAGES = 8;
 constexpr int NTHREADS = 384;
-constexpr int EPI_WARP0 = 4;          // epilogue warps 0..7: two per TMEM lane quadrant (warp & 3)
-constexpr int ROLE_WARP0 = 0;         // 8 weight producer, 9 MMA issuer, 10 TMEM alloc + exchange, 11 forwarder
-                                      // (the warp scheduler favours higher warp ids: the issuer outranks the epilogue)
-constexpr int EPI_GROUPS = 2;         // group g = (warp - 4) / 4 converts the own chunks t with t % 2 == g
+constexpr int EPI_WARP0 = 4;          // epilogue warps 4..11: two per TMEM lane quadrant (warp & 3)
+constexpr int ROLE_WARP0 = 0;         // warp 0 weight producer, 1 MMA issuer, 2 TMEM alloc + chunk exchange, 3 forwarder
+constexpr int EPI_GROUPS = 2;         // group g = (warp - 4) / 4 converts columns [32g, 32g+32) of every own chunk
 
 struct Dims {
     int d_feat, d_code, Hd, nb, d_out, d_geo;

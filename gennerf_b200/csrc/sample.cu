@@ -46,12 +46,11 @@ __global__ void __launch_bounds__(256) sample_kernel(const __grid_constant__ Sam
 // the same device functions as the generic kernel, so both produce identical bits.
 constexpr int ST_WORDS = 20;     // per query: 8 offsets + 8 weights (+4 pad: conflict-free LDS.128)
 
-template <bool PLANES>
-__device__ __forceinline__ void staged_part(const SampleKP& p, float* __restrict__ tab, int lane, int G, long long q0,
-                                            long long nq, float* __restrict__ out_base, int c_off) {
-    // tab: [32][ST_WORDS] for this warp.  PLANES: three tables are processed one after the other.
+// volume part of 32 staged queries: tab = [32][ST_WORDS] corner table of this warp
+__device__ __forceinline__ void staged_volume(const SampleKP& p, float* __restrict__ tab, int lane, int G, long long q0,
+                                              long long nq, float* __restrict__ out_base, int c_off) {
     const int sub = lane % G, qpi = 32 / G;
-    const int Cn = PLANES ? p.Cp : p.C;
+    const int Cn = p.C;
     for (int it = 0; it < G; ++it) {
         const int ql = it * qpi + lane / G;
         const long long q = q0 + ql;
@@ -62,7 +61,7 @@ __device__ __forceinline__ void staged_part(const SampleKP& p, float* __restrict
         const int b = (int)(q / p.Q);
         float* out = out_base + q * p.out_stride + c_off;
         for (int c = sub * 4; c < Cn; c += G * 4) {
-            if constexpr (!PLANES) {
+            {
                 const float* base = p.volume + b * p.vsb + c;
                 const float4 v0 = ldg4(base + o0.x), v1 = ldg4(base + o0.y), v2 = ldg4(base + o0.z), v3 = ldg4(base + o0.w);
                 const float4 v4 = ldg4(base + o1.x), v5 = ldg4(base + o1.y), v6 = ldg4(base + o1.z), v7 = ldg4(base + o1.w);
@@ -152,7 +151,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS) sample_staged_kernel(const __gr
                 }
             }
         }
-        if (p.volume) staged_part<false>(p, tv, lane, Gv, q0, p.total, p.out, p.Cp);
+        if (p.volume) staged_volume(p, tv, lane, Gv, q0, p.total, p.out, p.Cp);
         __syncwarp();
     }
 }
