@@ -1,0 +1,145 @@
+// Front end of the triplane branch ("next" row 1):
+//   get_3d_points()          reference src/models/utils.py:120-175  depth map -> world points
+//   farthest_point_sample()  reference src/models/utils.py:178-202  512 sequential arg-max steps per frame
+// The reference runs FPS as npoint Python iterations of ~6 small kernels each (308 ms per 240x320 frame on the
+// CPU); here one CTA per cloud keeps the whole iteration on chip: distance update, running arg-max and the
+// block-wide reduction with two barriers per step.
+#include "common.cuh"
+
+namespace gnb {
+
+// out[b,h,w,:] = M_b . [u*d, v*d, d, 1]  with M_b = the first three rows of inverse([P_b; 0 0 0 1]) (computed on the
+// host in double precision); the fourth homogeneous coordinate is exactly 1, so the reference's final division
+// (utils.py:170) is the identity.
+struct UnprojectKP {
+    float M[8][12];
+};
+__global__ void unproject_kernel(const float* __restrict__ depth, const __grid_constant__ UnprojectKP kp, int b0, int nb, int H,
+                                 int W, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)H * W;
+    if (i >= per * nb) return;
+    const int bl = (int)(i / per);
+    const long long r = i % per;
+    const float u = (float)(r % W), v = (float)(r / W);
+    const long long gi = (long long)(b0 + bl) * per + r;
+    const float d = __ldg(depth + gi);
+    const float a0 = __fmul_rn(u, d), a1 = __fmul_rn(v, d);
+    const float* M = kp.M[bl];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        out[gi * 3 + k] = __fadd_rn(fmaf(M[k * 4 + 2], d, fmaf(M[k * 4 + 1], a1, __fmul_rn(M[k * 4 + 0], a0))), M[k * 4 + 3]);
+}
+
+// One CTA per cloud.  dist lives in global scratch (L2-resident: N * 4 bytes per cloud).
+// Arithmetic of the reference: dist = ((dx*dx + dy*dy) + dz*dz); distance = min(distance, dist) through the
+// `dist < distance` mask; farthest = FIRST index of the maximum (torch.max).
+__global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ xyz, long long N, int npoint,
+                                                   const long long* __restrict__ start, float* __restrict__ dist,
+                                                   long long* __restrict__ out_idx, float* __restrict__ out_xyz) {
+    __shared__ float s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_far;
+    const int b = blockIdx.x;
+    const float* __restrict__ p = xyz + (long long)b * N * 3;
+    float* __restrict__ dd = dist + (long long)b * N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) dd[i] = 1e10f;
+    int far = (int)start[b];
+    __syncthreads();
+    for (int it = 0; it < npoint; ++it) {
+        if (threadIdx.x == 0) {
+            out_idx[(long long)b * npoint + it] = far;
+            out_xyz[((long long)b * npoint + it) * 3 + 0] = p[far * 3LL + 0];
+            out_xyz[((long long)b * npoint + it) * 3 + 1] = p[far * 3LL + 1];
+            out_xyz[((long long)b * npoint + it) * 3 + 2] = p[far * 3LL + 2];
+        }
+        const float cx = __ldg(p + far * 3LL), cy = __ldg(p + far * 3LL + 1), cz = __ldg(p + far * 3LL + 2);
+        float best = -1.0f;
+        int besti = 0x7fffffff;
+        for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+            const float dx = __fsub_rn(p[i * 3], cx), dy = __fsub_rn(p[i * 3 + 1], cy), dz = __fsub_rn(p[i * 3 + 2], cz);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            float cur = dd[i];
+            if (d < cur) { cur = d; dd[i] = d; }
+            if (cur > best) { best = cur; besti = (int)i; }       // ascending i: keeps the first maximum
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, best, o);
+            const int oi = __shfl_xor_sync(FULL, besti, o);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = besti; }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < (int)(blockDim.x >> 5) ? s_val[lane] : -1.0f;
+            besti = lane < (int)(blockDim.x >> 5) ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, best, o);
+                const int oi = __shfl_xor_sync(FULL, besti, o);
+                if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+            }
+            if (lane == 0) s_far = besti;
+        }
+        __syncthreads();
+        far = s_far;
+    }
+}
+
+// 4x4 inverse of [P; 0 0 0 1] in double precision (Gauss-Jordan with partial pivoting); returns the first 3 rows
+static bool inverse_rows(const float* P12, float* M12) {
+    double a[4][8];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            a[r][c] = r < 3 ? (double)P12[r * 4 + c] : (c == 3 ? 1.0 : 0.0);
+            a[r][4 + c] = r == c ? 1.0 : 0.0;
+        }
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r)
+            if ((a[r][c] < 0 ? -a[r][c] : a[r][c]) > (a[piv][c] < 0 ? -a[piv][c] : a[piv][c])) piv = r;
+        if (a[piv][c] == 0.0) return false;
+        if (piv != c)
+            for (int k = 0; k < 8; ++k) { double t = a[c][k]; a[c][k] = a[piv][k]; a[piv][k] = t; }
+        const double inv = 1.0 / a[c][c];
+        for (int k = 0; k < 8; ++k) a[c][k] *= inv;
+        for (int r = 0; r < 4; ++r)
+            if (r != c) {
+                const double f = a[r][c];
+                if (f != 0.0)
+                    for (int k = 0; k < 8; ++k) a[r][k] -= f * a[c][k];
+            }
+    }
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) M12[r * 4 + c] = (float)a[r][4 + c];
+    return true;
+}
+
+}  // namespace gnb
+
+using namespace gnb;
+
+extern "C" int gnb_get_3d_points(const float* depth, const float* h_projection, int B, int H, int W, float* out, void* stream) {
+    GNB_CHECK_ARG(depth && h_projection && out && B >= 1 && H >= 1 && W >= 1, "gnb_get_3d_points: bad arguments");
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        const int nb = B - b0 < 8 ? B - b0 : 8;
+        UnprojectKP kp;
+        for (int b = 0; b < nb; ++b)
+            GNB_CHECK_ARG(inverse_rows(h_projection + (long long)(b0 + b) * 12, kp.M[b]), "gnb_get_3d_points: singular projection %d", b0 + b);
+        const long long n = (long long)nb * H * W;
+        unproject_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(depth, kp, b0, nb, H, W, out);
+        GNB_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int npoint, const int64_t* start, float* scratch,
+                                         int64_t* out_idx, float* out_xyz, void* stream) {
+    GNB_CHECK_ARG(xyz && start && scratch && out_idx && out_xyz, "gnb_farthest_point_sample: null pointer");
+    GNB_CHECK_ARG(B >= 1 && N >= 1 && N < 0x7fffffffLL / 3 && npoint >= 1, "gnb_farthest_point_sample: bad shape");
+    fps_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(xyz, N, npoint, (const long long*)start, scratch, (long long*)out_idx, out_xyz);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}

@@ -53,6 +53,16 @@ def get_grid_coordinates(nx, ny, nz, volume_size, origin=None, device="cuda"):
     return torch.stack([gx, gy, gz], dim=-1)
 
 
+def get_3d_points(depth_map, projection):
+    """reference src/models/utils.py:120-175."""
+    return ops.get_3d_points(depth_map, projection)
+
+
+def farthest_point_sample(xyz, npoint, start=None):
+    """reference src/models/utils.py:178-202 (`start`: optional first indices instead of torch.randint)."""
+    return ops.farthest_point_sample(xyz, npoint, start)
+
+
 def normalize_coordinate(p, padding=0.1, plane="xz", encode=True):
     """reference src/models/utils.py:75-98: (B,N,3) -> (B,N,2) in [0, 1-1e-5]."""
     coord, _ = ops.plane_coords(p, padding, 1)
@@ -413,8 +423,15 @@ class GenNerf(nn.Module):
                     voxel_dim, self.cfg.voxel_size, self.origin, projection, feats, out=out)
         if self.cfg.encoder.use_pointnet:
             if sparse_xyz is None:
-                raise NotImplementedError("gennerf_b200: pass the FPS point cloud as sparse_xyz= "
-                                          "(get_3d_points + farthest_point_sample are a 'next' row, SURVEY 8f-1)")
+                # reference model.py:131-136: unproject every frame, FPS to num_sparse_points, concatenate
+                if depth is None:
+                    raise RuntimeError("gennerf_b200: encode() needs `depth` (or sparse_xyz=) for the triplane branch")
+                B = projection.size(0)
+                parts = []
+                for t in range(T):
+                    pts = get_3d_points(depth[:, t], projection[:, t]).reshape(B, -1, 3)
+                    parts.append(farthest_point_sample(pts, self.cfg.encoder.pointnet.num_sparse_points)[0])
+                sparse_xyz = torch.cat(parts, dim=1)
             c_plane_new = self.pointnet(sparse_xyz)
             self.c_plane = c_plane_new if self.c_plane is None else self.merger(c_plane_new, self.c_plane)
 

@@ -530,3 +530,36 @@ def pool_local_bwd(p, c, grad_out, fwd_scratch, reso, padding=0.1, scatter_type=
                                        fwd_scratch.data_ptr(), gc.data_ptr(), scratch.data_ptr(), nbytes, _stream()),
               "gnb_pool_local_bwd")
     return gc
+
+
+# ------------------------------------------------------------------------------------------
+# front end of the triplane branch
+# ------------------------------------------------------------------------------------------
+def get_3d_points(depth_map, projection):
+    """get_3d_points (reference utils.py:120-175): depth (B,H,W), projection (B,3,4) -> (B,H,W,3)."""
+    _need_cuda(depth_map)
+    d = _f32(depth_map).contiguous()
+    B, H, W = d.shape
+    P = torch.as_tensor(projection).detach().to("cpu", torch.float32).reshape(B, 3, 4).contiguous()
+    out = torch.empty((B, H, W, 3), device=d.device, dtype=torch.float32)
+    with torch.cuda.device(d.device):
+        check(lib().gnb_get_3d_points(d.data_ptr(), P.data_ptr(), B, H, W, out.data_ptr(), _stream()), "gnb_get_3d_points")
+    return out
+
+
+def farthest_point_sample(xyz, npoint, start=None):
+    """farthest_point_sample (reference utils.py:178-202): xyz (B,N,3) -> sampled (B,npoint,3), indices (B,npoint).
+    `start` (B,) int64 is the first index; the reference draws it with torch.randint(0, N, (B,))."""
+    _need_cuda(xyz)
+    x = _f32(xyz).contiguous()
+    B, N, _ = x.shape
+    if start is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long, device=x.device)
+    start = start.to(device=x.device, dtype=torch.long).contiguous()
+    idx = torch.empty((B, npoint), device=x.device, dtype=torch.long)
+    out = torch.empty((B, npoint, 3), device=x.device, dtype=torch.float32)
+    scratch = torch.empty((B, N), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(lib().gnb_farthest_point_sample(x.data_ptr(), B, N, int(npoint), start.data_ptr(), scratch.data_ptr(),
+                                              idx.data_ptr(), out.data_ptr(), _stream()), "gnb_farthest_point_sample")
+    return out, idx

@@ -201,6 +201,19 @@ int gnb_pool_local_bwd(const float* p, const float* c, const float* grad_out, in
                        void* scratch, int64_t scratch_bytes, void* stream);
 
 /* -------------------------------------------------------------------------------------
+ * Front end of the triplane branch (SURVEY 8f "next" row 1).
+ * gnb_get_3d_points replaces get_3d_points() (src/models/utils.py:120-175): depth (B,H,W) and HOST
+ *   projections (B,3,4) -> world points (B,H,W,3).
+ * gnb_farthest_point_sample replaces farthest_point_sample() (src/models/utils.py:178-202): xyz (B,N,3),
+ *   start (B) int64 = the first index (the reference draws it with torch.randint) -> out_idx (B,npoint)
+ *   int64, out_xyz (B,npoint,3); scratch >= B*N floats.  Bit-identical to the reference's iteration.
+ * ----------------------------------------------------------------------------------- */
+int gnb_get_3d_points(const float* depth, const float* h_projection, int B, int H, int W, float* out,
+                      void* stream);
+int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int npoint, const int64_t* start,
+                              float* scratch, int64_t* out_idx, float* out_xyz, void* stream);
+
+/* -------------------------------------------------------------------------------------
  * Decoder.  Replaces
  *   PositionalEncoding.forward()   src/models/components/positional_encoding.py:28-40
  *   ResnetFC.forward()             src/models/components/resnetfc.py:134-189 (default options:

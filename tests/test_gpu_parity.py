@@ -332,3 +332,27 @@ def test_gennerf_forward_fp32_golden(golden_dir):
     for k in ("feat_geo", "feat_sem", "tsdf"):
         assert out[k].shape == o[k].shape
         close(out[k], o[k], 2e-5, k)
+
+
+# ---------------------------------------------------------------------------------------------
+# front end of the triplane branch
+# ---------------------------------------------------------------------------------------------
+def test_get_3d_points_and_fps():
+    g = S.gen(61)
+    H, W, T = 60, 80, 3
+    P = S.projections(T, H, W, (24, 24, 12), VS, g, pull_back=0.8)
+    depth = S.depth_maps(T, H, W, g)[0]
+    ref = O.get_3d_points(depth, P)
+    out = ops().get_3d_points(depth.to(DEV), P)
+    close(out, ref, 1e-5, "get_3d_points")
+    # FPS is bit-identical on identical inputs (same arithmetic, first-maximum tie rule)
+    xyz = ref.reshape(T, -1, 3)
+    start = torch.tensor([5, 0, H * W - 1])
+    s_o, c_o = O.farthest_point_sample(xyz, 64, start)
+    s, c = ops().farthest_point_sample(xyz.to(DEV), 64, start.to(DEV))
+    assert torch.equal(c.cpu(), c_o) and torch.equal(s.cpu(), s_o)
+    # duplicates (exact ties): still the first maximum
+    dup = torch.cat([xyz[:, :100], xyz[:, :100]], dim=1)
+    s_o, c_o = O.farthest_point_sample(dup, 32, torch.tensor([1, 2, 3]))
+    s, c = ops().farthest_point_sample(dup.to(DEV), 32, torch.tensor([1, 2, 3]).to(DEV))
+    assert torch.equal(c.cpu(), c_o)
