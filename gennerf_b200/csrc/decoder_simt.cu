@@ -221,7 +221,9 @@ extern "C" int gnb_decode_fp32(const GnbDecoderWeights* w, const float* xyz, con
                                float* tsdf, void* stream) {
     int rc = check_decoder_weights(w, "gnb_decode_fp32");
     if (rc) return rc;
-    GNB_CHECK_ARG(xyz && feat && n_rows >= 0 && (out || tsdf), "gnb_decode_fp32: bad arguments");
+    GNB_CHECK_ARG(n_rows >= 0, "gnb_decode_fp32: bad arguments");
+    if (n_rows == 0) return 0;
+    GNB_CHECK_ARG(xyz && feat && (out || tsdf), "gnb_decode_fp32: bad arguments");
     if (w->d_hidden % 32 != 0 || w->d_hidden > 512) {
         set_error("gnb_decode_fp32: d_hidden %d must be a multiple of 32 and <= 512", w->d_hidden);
         return GNB_E_UNSUPPORTED;

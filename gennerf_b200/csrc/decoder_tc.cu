@@ -1071,7 +1071,9 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
 
 extern "C" int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz, const float* feat,
                                int64_t n_rows, float* out, float* tsdf, void* stream) {
-    GNB_CHECK_ARG(xyz && feat && n_rows >= 0 && (out || tsdf), "gnb_decode_tc: bad arguments");
+    GNB_CHECK_ARG(n_rows >= 0, "gnb_decode_tc: bad arguments");
+    if (n_rows == 0) return 0;
+    GNB_CHECK_ARG(xyz && feat && (out || tsdf), "gnb_decode_tc: bad arguments");
     TcKP kp = {};
     kp.xyz = xyz, kp.feat = feat, kp.fused = 0, kp.n_rows = n_rows, kp.out = out, kp.tsdf = tsdf;
     return launch_tc(w, packed, kp, stream);
@@ -1084,6 +1086,7 @@ extern "C" int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeig
     if (rc) return rc;
     GNB_CHECK_ARG(w && w->use_code != 2, "gnb_query_fused_tc: the fused query encodes xyz itself (use_code 0 or 1)");
     GNB_CHECK_ARG(w->d_feat == kp.s.C + kp.s.Cp, "gnb_query_fused_tc: d_feat %d != C_p + C = %d", w->d_feat, kp.s.C + kp.s.Cp);
+    if (kp.s.total == 0) return 0;
     GNB_CHECK_ARG(out || tsdf, "gnb_query_fused_tc: no output requested");
     GNB_CHECK_ARG(!s->out || (s->out_stride >= w->d_feat && s->out_stride % 4 == 0), "gnb_query_fused_tc: bad feature output stride");
     bool ok = true;

@@ -404,7 +404,7 @@ static DetScratch det_layout(void* base, int B, long long N, int R) {
 using namespace gnb;
 
 extern "C" int gnb_plane_coords(const float* p, int64_t n, double padding, int R, float* coord, int64_t* index, void* stream) {
-    GNB_CHECK_ARG(p && n >= 0 && R > 0 && (coord || index), "gnb_plane_coords: bad arguments");
+    GNB_CHECK_ARG((p || n == 0) && n >= 0 && R > 0 && (coord || index || n == 0), "gnb_plane_coords: bad arguments");
     if (n == 0) return 0;
     float den = (float)(1.0 + padding + 10e-6);
     plane_coords_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p, n, den, R, coord, (long long*)index);
@@ -420,7 +420,7 @@ extern "C" int64_t gnb_scatter_scratch_bytes(int B, int64_t N, int R, int mode) 
 extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, int64_t N, int Cp, int R, double padding,
                                        int mode, float* planes, int32_t* count, void* scratch, int64_t scratch_bytes,
                                        void* stream) {
-    GNB_CHECK_ARG(p && c && planes && count, "gnb_scatter_mean_planes: null pointer");
+    GNB_CHECK_ARG(((p && c) || N == 0) && planes && count, "gnb_scatter_mean_planes: null pointer");
     GNB_CHECK_ARG(B >= 1 && N >= 0 && Cp >= 1 && R >= 1 && R <= 4096, "gnb_scatter_mean_planes: bad shape");
     GNB_CHECK_ARG((long long)B * N < 0x7fffffffLL, "gnb_scatter_mean_planes: too many points");
     cudaStream_t st = (cudaStream_t)stream;
@@ -490,7 +490,7 @@ extern "C" int64_t gnb_pool_scratch_bytes(int B, int64_t N, int Hd, int R) {
 
 extern "C" int gnb_pool_local(const float* p, const float* c, int B, int64_t N, int Hd, int R, double padding, int pool_type,
                               float* out, void* scratch, int64_t scratch_bytes, void* stream) {
-    GNB_CHECK_ARG(p && c && out, "gnb_pool_local: null pointer");
+    GNB_CHECK_ARG((p && c && out) || N == 0, "gnb_pool_local: null pointer");
     GNB_CHECK_ARG(B >= 1 && N >= 0 && Hd >= 1 && R >= 1, "gnb_pool_local: bad shape");
     GNB_CHECK_ARG(pool_type == GNB_POOL_MAX || pool_type == GNB_POOL_MEAN, "gnb_pool_local: unknown pool type %d", pool_type);
     GNB_CHECK_ARG(scratch && scratch_bytes >= gnb_pool_scratch_bytes(B, N, Hd, R), "gnb_pool_local: scratch too small");

@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(const __grid_constant__
 
 int fill_sample_kp(const GnbSampleParams* s, SampleKP& kp) {
     GNB_CHECK_ARG(s, "sample: null params");
-    GNB_CHECK_ARG(s->batch >= 1 && s->n_query >= 0 && s->xyz, "sample: bad batch / n_query / xyz");
+    GNB_CHECK_ARG(s->batch >= 1 && s->n_query >= 0 && (s->xyz || s->n_query == 0), "sample: bad batch / n_query / xyz");
     bool has_planes = s->plane[0] || s->plane[1] || s->plane[2];
     GNB_CHECK_ARG(s->volume || has_planes, "sample: neither a volume nor planes given");
     kp.xyz = s->xyz;
@@ -362,8 +362,8 @@ extern "C" int gnb_sample_features(const GnbSampleParams* s, void* stream) {
     SampleKP kp;
     int rc = fill_sample_kp(s, kp);
     if (rc) return rc;
-    GNB_CHECK_ARG(s->out && s->out_stride >= kp.C + kp.Cp, "sample: bad output");
     if (kp.total == 0) return 0;
+    GNB_CHECK_ARG(s->out && s->out_stride >= kp.C + kp.Cp, "sample: bad output");
     // float4 path: unit channel stride, channel counts and every base/stride a multiple of 4
     bool vec = (s->out_stride % 4 == 0) && aligned16(s->out);
     if (kp.volume)

@@ -221,7 +221,7 @@ def _decode_given_code(dw, z, x, precision):
             packed = dw.tc_image(precision)
             check(lib().gnb_decode_tc(C.byref(dw.w), packed.data_ptr(), z2.data_ptr(), x2.data_ptr(), n, out.data_ptr(),
                                         None, st), "gnb_decode_tc")
-    return out.reshape(*lead, -1), None
+    return out.reshape(*lead, dw.w.d_out), None
 
 
 # ------------------------------------------------------------------------------------------

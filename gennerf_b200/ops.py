@@ -353,7 +353,7 @@ def decode(weights, xyz, feat, precision="fp32"):
                                         out.data_ptr(), tsdf.data_ptr(), _stream()), "gnb_decode_tc")
         else:
             raise ValueError(precision)
-    return out.reshape(*lead, -1), tsdf.reshape(*lead, 1)
+    return out.reshape(*lead, weights.w.d_out), tsdf.reshape(*lead, 1)
 
 
 def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
