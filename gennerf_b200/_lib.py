@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgennerf_b200.so")
+# GNB_LIB_PATH selects another build of the same library (e.g. the tracing variant, `python -m gennerf_b200.build --trace`)
+LIB_PATH = os.environ.get("GNB_LIB_PATH") or os.path.join(HERE, "libgennerf_b200.so")
 
 GNB_MAX_FRAMES = 64
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1

@@ -28,12 +28,18 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+TRACE_LIB = os.path.join(HERE, "libgennerf_b200_trace.so")
+
+
 def build(force=False, verbose=False, trace=False):
-    """Compile every CUDA source for sm_100a and link the shared library; returns its path."""
+    """Compile every CUDA source for sm_100a and link the shared library; returns its path.
+    trace=True builds a second library (libgennerf_b200_trace.so, loaded when GNB_LIB_PATH points at it) with the
+    decoder's per-phase clock64() tracing compiled in -- a profiling aid for tools/trace_decoder.py."""
+    LIB = TRACE_LIB if trace else globals()["LIB"]
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "gennerf_b200.h")]
     if not force and not verbose and not _stale(LIB, srcs):
         return LIB                                   # up to date (e.g. the prebuilt .so on the GPU box)
-    objdir = os.path.join(ROOT, "build", "obj")
+    objdir = os.path.join(ROOT, "build", "obj_trace" if trace else "obj")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "gennerf_b200.h"))
@@ -61,5 +67,5 @@ def build(force=False, verbose=False, trace=False):
 
 
 if __name__ == "__main__":
-    # --trace: compile the decoder's per-phase clock64() tracing in (tools/trace_decoder.py); forces a rebuild
-    print(build(force="--force" in sys.argv or "--trace" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))
+    # --trace: build the tracing variant of the library (see build())
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -434,13 +434,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         const Op op = get_op(d, o);
                         const int ntile = n_tiles_of(op.rows);
                         for (int kc = 0; kc < op.kchunks; ++kc)
-                            for (int nt = 0; nt < ntile; ++nt) {
-                                const uint32_t bytes = (uint32_t)min(128, op.rows - nt * 128) * 128u;
+                            for (int nt = 0; nt < ntile;) {
+                                // Two adjacent ring slots (the two 128-row halves of a 256-row slice) are filled by ONE
+                                // bulk copy: a copy costs ~400 cycles whatever its size (16 KB -> 40 B/clk, 32 KB ->
+                                // 80 B/clk per SM, tools/microbench/l2_stream.cu), so bigger copies double the ingest rate.
+                                // The issuer pairs slots by the same rule and waits on the first slot's barrier only.
+                                const int pair = (ntile - nt >= 2 && (stage & 1) == 0 && stage + 1 < d.nstage) ? 2 : 1;
+                                const uint32_t bytes = (uint32_t)min(128 * pair, op.rows - nt * 128) * 128u;
                                 mbar_wait(w_empty(stage), phase ^ 1);
+                                if (pair == 2) mbar_wait(w_empty(stage + 1), phase ^ 1);
                                 mbar_expect_tx(w_full(stage), bytes);
                                 bulk_g2s(sbase + L.ring + stage * CHUNK, src, bytes, w_full(stage));
+                                if (pair == 2) mbar_arrive(w_full(stage + 1));     // nobody waits on it: keeps its phase in step with the ring
                                 src += bytes;
-                                if (++stage == d.nstage) { stage = 0; phase ^= 1; }
+                                stage += pair;
+                                if (stage == d.nstage) { stage = 0; phase ^= 1; }
+                                nt += pair;
                             }
                     }
                 }
@@ -595,8 +604,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         const int pair = (ntile - nt >= 2 && (stage & 1) == 0 && stage + 1 < d.nstage) ? 2 : 1;
                         const long long c1 = GNB_TRACE_ON(p) ? clock64() : 0;
                         if (a_bar && nt == 0) mbar_wait2_warp(a_bar, a_par, w_full(stage), phase);      // both queries in flight together
-                        else mbar_wait_warp(w_full(stage), phase);
-                        if (pair == 2) mbar_wait_warp(w_full(stage + 1), phase);
+                        else mbar_wait_warp(w_full(stage), phase);     // (a slot pair arrives as one copy on the first slot's barrier)
                         if (GNB_TRACE_ON(p)) wait_w += clock64() - c1;
                         tc_fence_after();
                         const int rows = min(128 * pair, op.rows - nt * 128);

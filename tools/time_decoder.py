@@ -1,0 +1,56 @@
+"""Tuning aid: tcgen05 decoder time at 1 Mi rows (config-2 shape) for the kernel variants selected by environment
+variables, each in a child process.  Prints ms, TFLOP/s and the max abs difference to the default variant."""
+import os
+import subprocess
+import sys
+
+VARIANTS = {
+    "default": {},
+    "two_cta": {"GNB_TC_TWO_CTA": "1"},
+    "one_cta": {"GNB_TC_TWO_CTA": "0"},
+}
+
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from gennerf_b200 import ops, synthetic as S
+    dev = "cuda"
+    Hd = int(os.environ.get("TD_HIDDEN", "512"))
+    n = int(os.environ.get("TD_ROWS", str(1 << 20)))
+    g = S.gen(1)
+    w, hw, hb = S.decoder_weights(g, 32, 15, Hd, 5, 64, 32)
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=dev)
+    xyz = S.query_points(n, (96, 96, 48), 0.04, g)[0].to(dev)
+    feat = torch.randn(n, 32, generator=g).to(dev)
+    out, tsdf = ops.decode(dw, xyz, feat, "fp16")
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms = []
+    for _ in range(7):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.decode(dw, xyz, feat, "fp16"); b.record(); b.synchronize()
+        ms.append(a.elapsed_time(b))
+    m = sorted(ms)[len(ms) // 2]
+    flops = 2.0 * (32 * Hd + 5 * (15 * Hd + 2 * Hd * Hd) + Hd * 64 + 32) * n
+    ck = os.environ.get("TD_CHECK")
+    diff = ""
+    if ck and os.path.exists(ck):
+        ref = torch.load(ck)
+        diff = f"  max|tsdf - default| {(tsdf.cpu() - ref['tsdf']).abs().max().item():.2e}  max|out - default| {(out.cpu() - ref['out']).abs().max().item():.2e}"
+    elif ck:
+        torch.save({"tsdf": tsdf.cpu(), "out": out.cpu()}, ck)
+    print(f"  Hd={Hd} rows={n}: {m:.3f} ms  {flops / m / 1e9:.1f} TFLOP/s  ({flops / m / 1e9 / 1389.9:.3f} of sustained bf16 peak){diff}", flush=True)
+else:
+    names = sys.argv[1:] or list(VARIANTS)
+    ck = "/tmp/td_check.pt"
+    if os.path.exists(ck):
+        os.remove(ck)
+    for name in names:
+        print(name, flush=True)
+        env = dict(os.environ)
+        env.update(VARIANTS.get(name, {}))
+        if VARIANTS.get(name, {}).get("GNB_TC_TWO_CTA") == "0":
+            env.pop("GNB_TC_TWO_CTA", None)
+        env["TD_CHECK"] = ck
+        subprocess.run([sys.executable, __file__, "child"], env=env, timeout=300)
