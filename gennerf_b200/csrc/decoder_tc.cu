@@ -66,7 +66,9 @@ struct Dims {
     int AOWN;                         // A-buffer slots for own chunks (and the lin_in operand) = max(KF, OWN)
     int RS;                           // A-buffer slots cycled through by the chunks the peer pushes (0, 1 or 2)
     int ACH;                          // A-buffer slots in total = AOWN + RS
-    int nstage;
+    int nstage;                       // weight-ring stages
+    int stage_bytes;                  // bytes of one stage: the weight rows of one step x 64 k (single-CTA issue: one k-chunk
+                                      // of <= 256 rows; cta_group::2: two k-chunks of <= 128 rows)
     long long packed_per_rank;        // bytes
 };
 
@@ -88,7 +90,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 // Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.  try_wait parks the thread in
 // hardware between polls, so waiting roles do not take issue slots from the warps that have work.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Before trapping, the first thread to time out leaves {1, block, thread, source line, barrier, parity} in the
+// host-mapped report buffer (gnb_debug_hang_report), which stays readable after the context has died.
+__device__ int* g_hang_report = nullptr;
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int line) {
+    int* r = g_hang_report;
+    if (r) {
+        const int i = atomicAdd(r, 1);
+        if (i < 160) {
+            int* e = r + 8 + i * 6;
+            e[0] = (int)blockIdx.x, e[1] = (int)threadIdx.x, e[2] = line, e[3] = (int)bar, e[4] = (int)parity, e[5] = 0;
+            __threadfence_system();
+        }
+    }
+    for (int k = 0; k < 200; ++k) __nanosleep(1000000);      // let the other stuck threads report too
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity, int line) {
     uint32_t done = 0;
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
@@ -98,19 +116,37 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (!done && spin > (1u << 24)) __trap();
+        if (!done && spin > (1u << 22)) mbar_timeout(bar, parity, line);
     }
 }
+#define mbar_wait(bar, parity) mbar_wait_((bar), (parity), __LINE__)
 // Parking wait for a whole warp (epilogue): lane 0 waits, the others sleep at the warp barrier.
-__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+#define mbar_wait_park(bar, parity) mbar_wait_((bar), (parity), __LINE__)
 // Whole-warp wait with warp-uniform control flow and ONE polling lane.  An mbarrier query is a per-thread
 // operation on one shared-memory word: a full warp polling costs ~32 serialised queries (measured ~390 cycles per
 // wait even on a completed barrier), and 256 epilogue threads polling slow every other waiter of the SM down.
 // Lane 0 queries, the vote makes the result (and the loop) uniform, so operands of the following tcgen05
 // instructions stay in uniform registers.
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
-// Two barriers at once: both queries are in flight together (one query costs ~150 cycles of latency), which is
-// what the MMA issuer needs per k-step -- "A chunk ready" and "weight stage landed".
+#define mbar_wait_warp(bar, parity) mbar_wait_((bar), (parity), __LINE__)
+// Two barriers at once with both queries in flight together (one query costs ~180 cycles of latency on the issuing
+// thread even when the phase is complete, tools/microbench/mma_rate.cu) -- what an MMA issuer needs per k-step:
+// "A chunk ready" and "weight stage landed".
+__device__ __forceinline__ void mbar_wait2_(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b, int line) {
+    uint32_t da = 0, db = 0;
+    for (uint32_t spin = 0; !(da & db); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "selp.u32 %1, 1, 0, q;\n\t}"
+            : "=r"(da), "=r"(db)
+            : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b)
+            : "memory");
+        if (!(da & db) && spin > (1u << 22)) mbar_timeout(da ? bar_b : bar_a, da ? par_b : par_a, line);
+    }
+}
+#define mbar_wait2(a, pa, b, pb) mbar_wait2_((a), (pa), (b), (pb), __LINE__)
 __device__ __forceinline__ void mbar_wait2_warp(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
     mbar_wait(bar_a, par_a);
     mbar_wait(bar_b, par_b);
@@ -168,6 +204,23 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a, uint64_t b
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// One 64-wide k-step = four K16 MMAs in ONE asm block: the descriptors of the 2nd..4th are derived inside (+32 bytes of
+// K each, i.e. +2 in the 16-byte address field), so the issuing thread moves one set of operands to uniform registers
+// per step instead of one per MMA.
+__device__ __forceinline__ void umma_f16_x4(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+        "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+        "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, 1;\n\t}" ::"r"(d_tmem),
         "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -277,31 +330,39 @@ __host__ __device__ inline Smem smem_layout(const Dims& d) {
     s.a = 0;
     s.code = s.a + d.ACH * CHUNK;
     s.ring = s.code + d.KZ * CHUNK;
-    s.bias = s.ring + d.nstage * CHUNK;
+    s.bias = s.ring + d.nstage * d.stage_bytes;
     // fp32 table: b0[nb][HN] | b1_last[HN] | b_out[NOUT] | head_w[d_geo] | head_b
     uint32_t nbias = (uint32_t)(d.nb * d.HN + d.HN + d.NOUT + d.d_geo + 1);
     s.bars = (s.bias + nbias * 4 + 15) & ~15u;
-    // barriers: w_full[8] w_empty[8] a_ready[8] rready[4] rfree[4] acc_ready in_ready pw_full[8] prready[4] | tmem slot
+    // barriers: w_full[8] w_empty[8] a_ready[8] rready[4] rfree[4] acc_ready in_ready (12 spare) | tmem slot
     s.total = s.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2 + 12) * 8 + 16;
     return s;
 }
 
-// The per-tile program: every role walks the same sequence of GEMM ops.
+// The per-tile program: every role (and the host-side packer) walks the same sequence of GEMM ops.
 //   kind 0 lin_in (A = feature chunks), 1 lin_z (A = code chunks), 2 hidden (A = activation chunks)
+// Order: lin_in, lin_z_0 | fc0_0 | lin_z_1, fc1_0 | fc0_1 | lin_z_2, fc1_1 | ... | fc0_last | fc1_last | lin_out
+// ("|" = end of an accumulation group: the epilogue converts the accumulator).  lin_z_{i+1} is issued BEFORE fc1_i:
+// its operand (the code tile) is always there, so its MMAs run while the epilogue is still converting fc0_i's
+// output -- the tensor pipe has work during that layer-to-layer bubble.  x is free at that point: the round that
+// read x (the operand of fc0_i) had written all its chunks before fc0_i's MMAs could be issued.
+enum : int { M_LIN_IN = 0, M_LIN_Z = 1, M_FC0 = 2, M_FC1 = 3, M_LIN_OUT = 4 };
 struct Op {
     int a_kind, kchunks, rows, d_col, first_overwrites, group_end;
+    int mat, blk;                     // which matrix (M_*) of which block
 };
-__device__ __forceinline__ int num_ops(const Dims& d) { return 2 + 3 * d.nb; }   // lin_in, nb x (lin_z, fc0, fc1), lin_out
-__device__ __forceinline__ Op get_op(const Dims& d, int o) {
-    Op op;
-    if (o == 0) return Op{0, d.KF, d.WN, 0, 1, 0};
-    if (o == 1 + 3 * d.nb) return Op{2, d.KH, d.NOUTC, NET_COL, 1, 1};
-    int i = (o - 1) / 3, j = (o - 1) % 3;
-    // order inside a block as issued: lin_z_i (ends the group that feeds relu(x)), fc0_i, fc1_i
-    if (j == 0) return Op{1, d.KZ, d.WN, 0, 0, 1};
-    if (j == 1) return Op{2, d.KH, d.WN, NET_COL, 1, 1};
-    op = Op{2, d.KH, d.WN, 0, 0, (i == d.nb - 1) ? 1 : 0};
-    return op;
+__host__ __device__ inline int num_ops(const Dims& d) { return 2 + 3 * d.nb; }
+__host__ __device__ inline Op get_op(const Dims& d, int o) {
+    if (o == 0) return Op{0, d.KF, d.WN, 0, 1, 0, M_LIN_IN, 0};
+    if (o == 1) return Op{1, d.KZ, d.WN, 0, 0, 1, M_LIN_Z, 0};
+    if (o == 1 + 3 * d.nb) return Op{2, d.KH, d.NOUTC, NET_COL, 1, 1, M_LIN_OUT, 0};
+    const int q = o - 2;
+    int i, j;                         // j: 0 fc0_i, 1 lin_z_{i+1}, 2 fc1_i
+    if (q < 3 * (d.nb - 1)) { i = q / 3, j = q % 3; }
+    else { i = d.nb - 1, j = (q - 3 * (d.nb - 1)) == 0 ? 0 : 2; }
+    if (j == 0) return Op{2, d.KH, d.WN, NET_COL, 1, 1, M_FC0, i};
+    if (j == 1) return Op{1, d.KZ, d.WN, 0, 0, 0, M_LIN_Z, i + 1};
+    return Op{2, d.KH, d.WN, 0, 0, 1, M_FC1, i};
 }
 // k-chunk visiting order of an activation op on N-half `half`: own chunk 0, the peer's chunk 0, own 1, peer 1, ...
 // (the peer's r-th chunk lands about one copy latency after the own r-th is written, so the MMAs never wait
@@ -412,7 +473,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
             if constexpr (TWO) {
                 // cta_group::2: a stage is a pair of 16 KB slots holding TWO consecutive k-chunks of the op (they are
                 // contiguous in the packed stream: one bulk copy); one barrier round-trip per 128 columns of K
-                const int nst = d.nstage / 2;
+                const int nst = d.nstage;
                 for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
                     const unsigned char* src = wstream;
                     for (int o = 0; o < nops; ++o) {
@@ -421,36 +482,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                             const uint32_t bytes = (uint32_t)min(2, op.kchunks - kc) * (uint32_t)op.rows * 128u;
                             mbar_wait(w_empty(stage), phase ^ 1);
                             mbar_expect_tx(w_full(stage), bytes);
-                            bulk_g2s(sbase + L.ring + stage * 2 * CHUNK, src, bytes, w_full(stage));
+                            bulk_g2s(sbase + L.ring + stage * d.stage_bytes, src, bytes, w_full(stage));
                             src += bytes;
                             if (++stage == nst) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
             } else {
+                // one step = one k-chunk of an op: its rows x 64 k slice (<= 256 rows = 32 KB) arrives as ONE bulk copy into
+                // one ring stage.  A copy costs the issuing thread ~400 cycles whatever its size (16 KB -> 40 B/clk, 32 KB ->
+                // 80 B/clk per SM, tools/microbench/l2_stream.cu), so big copies are what keeps the ingest rate up.
                 for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
                     const unsigned char* src = wstream;
                     for (int o = 0; o < nops; ++o) {
                         const Op op = get_op(d, o);
-                        const int ntile = n_tiles_of(op.rows);
-                        for (int kc = 0; kc < op.kchunks; ++kc)
-                            for (int nt = 0; nt < ntile;) {
-                                // Two adjacent ring slots (the two 128-row halves of a 256-row slice) are filled by ONE
-                                // bulk copy: a copy costs ~400 cycles whatever its size (16 KB -> 40 B/clk, 32 KB ->
-                                // 80 B/clk per SM, tools/microbench/l2_stream.cu), so bigger copies double the ingest rate.
-                                // The issuer pairs slots by the same rule and waits on the first slot's barrier only.
-                                const int pair = (ntile - nt >= 2 && (stage & 1) == 0 && stage + 1 < d.nstage) ? 2 : 1;
-                                const uint32_t bytes = (uint32_t)min(128 * pair, op.rows - nt * 128) * 128u;
-                                mbar_wait(w_empty(stage), phase ^ 1);
-                                if (pair == 2) mbar_wait(w_empty(stage + 1), phase ^ 1);
-                                mbar_expect_tx(w_full(stage), bytes);
-                                bulk_g2s(sbase + L.ring + stage * CHUNK, src, bytes, w_full(stage));
-                                if (pair == 2) mbar_arrive(w_full(stage + 1));     // nobody waits on it: keeps its phase in step with the ring
-                                src += bytes;
-                                stage += pair;
-                                if (stage == d.nstage) { stage = 0; phase ^= 1; }
-                                nt += pair;
-                            }
+                        const uint32_t bytes = (uint32_t)op.rows * 128u;
+                        for (int kc = 0; kc < op.kchunks; ++kc) {
+                            mbar_wait(w_empty(stage), phase ^ 1);
+                            mbar_expect_tx(w_full(stage), bytes);
+                            bulk_g2s(sbase + L.ring + stage * d.stage_bytes, src, bytes, w_full(stage));
+                            src += bytes;
+                            if (++stage == d.nstage) { stage = 0; phase ^= 1; }
+                        }
                     }
                 }
             }
@@ -470,7 +523,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     } else if (warp == ROLE_WARP0 + 3 && !leader) {
         // ===================== (cta_group::2 partner) forward weight-stage arrivals to the leader ============
         // one lane per ring stage (a stage = two k-chunks)
-        const int nst = d.nstage / 2;
+        const int nst = d.nstage;
         if (lane < nst) {
             uint32_t per_tile = 0;
             for (int o = 0; o < nops; ++o) { const Op op = get_op(d, o); per_tile += (op.kchunks + 1) / 2; }
@@ -490,7 +543,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
         if constexpr (TWO) {
             // ---- cta_group::2 leader: steps of TWO k-chunks (128 columns of K): one combined wait on
             //      [first chunk ready, second chunk ready, weight stage landed], 8 MMAs, the commits ----
-            const int nst = d.nstage / 2;
+            const int nst = d.nstage;
             const uint16_t pairmask = (uint16_t)(3u << (half * 2)), othermask = (uint16_t)(3u << ((half ^ 1u) * 2));
             int stage = 0;
             uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0;
@@ -533,7 +586,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         mbar_wait3_warp(a_bar[0], a_par[0], a_bar[1], a_par[1], w_full(stage), phase);
                         if (GNB_TRACE_ON(p)) wait_all += clock64() - c1;
                         tc_fence_after();
-                        const uint32_t b_base = sbase + L.ring + stage * 2 * CHUNK;
+                        const uint32_t b_base = sbase + L.ring + stage * d.stage_bytes;
                         const uint32_t first = (op.first_overwrites && t == 0) ? 0u : 1u;
                         if (elect_one()) {
                             const uint64_t da0 = umma_desc(a_addr[0]), db0 = umma_desc(b_base);
@@ -567,95 +620,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 }
             }
         } else {
-        int stage = 0;
-        uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0;
-        for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++tiles_done) {
-            mbar_wait_warp(in_ready, tiles_done & 1);
-            tc_fence_after();
-            int tk = tiles_done * 64;
-            if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
-            for (int o = 0; o < nops; ++o) {
-                const Op op = get_op(d, o);
-                if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
-                const int ntile = n_tiles_of(op.rows);
-                long long wait_a = 0, wait_w = 0;                  // trace only
-                for (int t = 0; t < op.kchunks; ++t) {
-                    uint32_t a_addr;
-                    int rslot = -1;                                // >= 0: this chunk sits in a remote slot
-                    uint32_t a_bar = 0, a_par = 0;                 // barrier that says the A chunk is in shared memory
-                    if (op.a_kind == 0) a_addr = sbase + L.a + t * CHUNK;
-                    else if (op.a_kind == 1) a_addr = sbase + L.code + t * CHUNK;
-                    else {
-                        const bool own_chunk = t < own_chunks;     // single-CTA issue: own chunks first, then the peer's
-                        const int r = own_chunk ? t : t - own_chunks;
-                        if (own_chunk) {                           // own chunk r ...
-                            a_bar = a_ready(r), a_par = round & 1;
-                            a_addr = sbase + L.a + r * CHUNK;
-                        } else {                                   // ... then the peer's r-th, in the order it pushes them
+        // ---- single-CTA issue: lane 0 ALONE runs the loop (no elect / warp votes / reconvergence on the critical
+        //      path).  Measured per-instruction cost on the issuing thread (tools/microbench/mma_rate.cu): MMA ~60,
+        //      wait on a complete barrier ~180, commit ~110, fence ~40 cycles; a 64-wide k-step (4 MMAs, one combined
+        //      wait, 1-2 commits) is ~600-700 cycles of issue work against 630 cycles of tensor-pipe time at N = 256.
+        //      (Two issuing threads in different warps -- own chunks / pushed chunks, accumulating into the same TMEM
+        //      columns -- were tried: tcgen05.commit arrivals got lost and results were corrupted, so one thread issues.)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0;
+            const uint16_t allmask = (uint16_t)((1u << d.nsplit) - 1);
+            for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++tiles_done) {
+                mbar_wait(in_ready, tiles_done & 1);
+                tc_fence_after();
+                int tk = tiles_done * 64;
+                GNB_TRACE(0, tk); ++tk;
+                for (int o = 0; o < nops; ++o) {
+                    const Op op = get_op(d, o);
+                    GNB_TRACE(0, tk); ++tk;
+                    const uint32_t idesc = umma_idesc(op.rows, BF16);
+                    const uint32_t dcol = tmem + op.d_col;
+                    for (int t = 0; t < op.kchunks; ++t) {
+                        uint32_t a_addr;
+                        int rslot = -1;                                // >= 0: this chunk sits in a remote slot
+                        if (op.a_kind == 0) {
+                            a_addr = sbase + L.a + t * CHUNK;
+                            mbar_wait(w_full(stage), phase);
+                        } else if (op.a_kind == 1) {
+                            a_addr = sbase + L.code + t * CHUNK;
+                            mbar_wait(w_full(stage), phase);
+                        } else if (t < own_chunks) {                   // own chunks first ...
+                            a_addr = sbase + L.a + t * CHUNK;
+                            mbar_wait2(a_ready(t), round & 1, w_full(stage), phase);
+                        } else {                                       // ... then the peer's, in the order it pushes them
                             rslot = (int)(rtotal % (uint32_t)d.RS);
-                            if (lane == 0) mbar_expect_tx(rready(rslot), CHUNK);
-                            __syncwarp();
-                            a_bar = rready(rslot), a_par = (rtotal / (uint32_t)d.RS) & 1;
                             a_addr = sbase + L.a + (d.AOWN + rslot) * CHUNK;
+                            mbar_expect_tx(rready(rslot), CHUNK);
+                            mbar_wait2(rready(rslot), (rtotal / (uint32_t)d.RS) & 1, w_full(stage), phase);
                             ++rtotal;
                         }
-                    }
-                    for (int nt = 0; nt < ntile;) {
-                        const int pair = (ntile - nt >= 2 && (stage & 1) == 0 && stage + 1 < d.nstage) ? 2 : 1;
-                        const long long c1 = GNB_TRACE_ON(p) ? clock64() : 0;
-                        if (a_bar && nt == 0) mbar_wait2_warp(a_bar, a_par, w_full(stage), phase);      // both queries in flight together
-                        else mbar_wait_warp(w_full(stage), phase);     // (a slot pair arrives as one copy on the first slot's barrier)
-                        if (GNB_TRACE_ON(p)) wait_w += clock64() - c1;
                         tc_fence_after();
-                        const int rows = min(128 * pair, op.rows - nt * 128);
-                        const uint64_t da = umma_desc(a_addr), db = umma_desc(sbase + L.ring + stage * CHUNK);
-                        const uint32_t first = (op.first_overwrites && t == 0) ? 0u : 1u;
-                        if constexpr (TWO) {
-                            // N = rows held by this CTA + the same number held by its partner; M = 256
-                            const uint32_t idesc = umma_idesc(2 * rows, BF16, 2 * BM);
-                            const uint32_t dcol = tmem + op.d_col;
-                            const uint16_t pairmask = (uint16_t)(3u << (half * 2)), othermask = (uint16_t)(3u << ((half ^ 1u) * 2));
-                            if (elect_one()) {
-                                umma_f16_2cta(dcol, da, db, idesc, first);
-                                umma_f16_2cta(dcol, da + 2, db + 2, idesc, 1u);
-                                umma_f16_2cta(dcol, da + 4, db + 4, idesc, 1u);
-                                umma_f16_2cta(dcol, da + 6, db + 6, idesc, 1u);
-                                umma_commit_mc_2cta(w_empty(stage), pairmask);     // both CTAs of the pair refill this slot
-                                if (rslot >= 0) umma_commit_mc_2cta(rfree(rslot), othermask);
-                            }
-                        } else {
-                            const uint32_t idesc = umma_idesc(rows, BF16);
-                            const uint32_t dcol = tmem + op.d_col + nt * 128;
-                            if (elect_one()) {
-                                umma_f16(dcol, da, db, idesc, first);
-                                umma_f16(dcol, da + 2, db + 2, idesc, 1u);
-                                umma_f16(dcol, da + 4, db + 4, idesc, 1u);
-                                umma_f16(dcol, da + 6, db + 6, idesc, 1u);
-                                umma_commit(w_empty(stage));          // frees the ring slot(s) when these MMAs retire
-                                if (pair == 2) umma_commit(w_empty(stage + 1));
-                                // last MMAs that read a remote slot: tell the PEER it may push into it again
-                                if (rslot >= 0 && nt + pair >= ntile) umma_commit_mc(rfree(rslot), (uint16_t)(1u << peer));
-                            }
-                        }
-                        __syncwarp();
-                        stage += pair;
-                        if (stage == d.nstage) { stage = 0; phase ^= 1; }
-                        nt += pair;
+                        const uint64_t da = umma_desc(a_addr), db = umma_desc(sbase + L.ring + stage * d.stage_bytes);
+                        umma_f16_x4(dcol, da, db, idesc, (op.first_overwrites && t == 0) ? 0u : 1u);
+                        umma_commit(w_empty(stage));              // frees the ring stage when these MMAs retire
+                        // MMAs that read a remote slot: tell the PEER it may push into it again
+                        if (rslot >= 0) umma_commit_mc(rfree(rslot), (uint16_t)(1u << peer));
+                        if (++stage == d.nstage) { stage = 0; phase ^= 1; }
                     }
-                }
-                if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
-                if (GNB_TRACE_ON(p) && lane == 0 && blockIdx.x == 0 && tiles_done < 8) {
-                    p.dbg[2 * 4096 + (tiles_done * 32 + o) * 2] = wait_a;
-                    p.dbg[2 * 4096 + (tiles_done * 32 + o) * 2 + 1] = wait_w;
-                }
-                if (op.a_kind == 2) ++round;
-                if (op.group_end) {
-                    if (elect_one()) {
-                        if constexpr (TWO) umma_commit_mc_2cta(acc_ready, (uint16_t)((1u << d.csize) - 1));
-                        else if (d.nsplit > 1) umma_commit_mc(acc_ready, (uint16_t)((1u << d.nsplit) - 1));
+                    GNB_TRACE(0, tk); ++tk;
+                    if (op.a_kind == 2) ++round;
+                    if (op.group_end) {
+                        if (d.nsplit > 1) umma_commit_mc(acc_ready, allmask);
                         else umma_commit(acc_ready);
                     }
-                    __syncwarp();
                 }
             }
         }
@@ -959,14 +976,19 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
     d.AOWN = d.KF > d.OWN ? d.KF : d.OWN;
     d.RS = d.nsplit > 1 ? (d.OWN >= 2 ? 2 : 1) : 0;
     d.ACH = d.AOWN + d.RS;
+    // ring stage: cta_group::2 = two k-chunks of WN <= 128 rows; otherwise one k-chunk of the widest op
+    {
+        const int rows = d.WN > d.NOUTC ? d.WN : d.NOUTC;
+        d.stage_bytes = d.two ? 2 * CHUNK : (rows * 128 + 1023) / 1024 * 1024;
+    }
     d.nstage = MAX_STAGES;
     while (d.nstage >= 2 && smem_layout(d).total + 1024 > 227 * 1024) --d.nstage;
-    if (d.two) d.nstage &= ~1;          // cta_group::2 stages are pairs of 16 KB slots
     if (d.nstage < 2) { set_error("%s: tile does not fit in shared memory", who); return GNB_E_UNSUPPORTED; }
     long long bytes = 0;
-    bytes += (long long)d.KF * d.WN * 128;
-    bytes += (long long)d.nb * ((long long)d.KZ * d.WN * 128 + 2LL * d.KH * d.WN * 128);
-    bytes += (long long)d.KH * d.NOUTC * 128;
+    for (int o = 0; o < num_ops(d); ++o) {
+        const Op op = get_op(d, o);
+        bytes += (long long)op.kchunks * op.rows * 128;
+    }
     d.packed_per_rank = bytes;
     return 0;
 }
@@ -1003,24 +1025,48 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
             return 0;
         };
         const int n0 = half * d.HN + mrow * d.WN;
-        PackOp op;
-        op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.WN, d.KF, -1, d.nsplit, d.OWN, d.two, 1.0f, w->lin_in_b, nullptr, 1, 0};
-        if ((rc = launch(op))) return rc;
-        for (int i = 0; i < d.nb; ++i) {
-            // x += alpha * (Wz code + bz)   [+ b1 of the previous block, folded here]
-            op = PackOp{w->lin_z_w[i], d.Hd, d.d_code, n0, d.WN, d.KZ, -1, d.nsplit, d.OWN, d.two, w->alpha, w->lin_z_b[i],
-                        i > 0 ? w->fc1_b[i - 1] : nullptr, 1, 0};
-            if ((rc = launch(op))) return rc;
-            op = PackOp{w->fc0_w[i], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
-            if ((rc = launch(op))) return rc;
-            op = PackOp{w->fc1_w[i], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
+        for (int o = 0; o < num_ops(d); ++o) {            // stream order == program order (get_op)
+            const Op g = get_op(d, o);
+            PackOp op;
+            switch (g.mat) {
+            case M_LIN_IN:
+                op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.WN, d.KF, -1, d.nsplit, d.OWN, d.two, 1.0f, w->lin_in_b, nullptr, 1, 0};
+                break;
+            case M_LIN_Z:
+                // x += alpha * (Wz code + bz)   [+ b1 of the previous block, folded here]
+                op = PackOp{w->lin_z_w[g.blk], d.Hd, d.d_code, n0, d.WN, d.KZ, -1, d.nsplit, d.OWN, d.two, w->alpha, w->lin_z_b[g.blk],
+                            g.blk > 0 ? w->fc1_b[g.blk - 1] : nullptr, 1, 0};
+                break;
+            case M_FC0:
+                op = PackOp{w->fc0_w[g.blk], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
+                break;
+            case M_FC1:
+                op = PackOp{w->fc1_w[g.blk], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
+                break;
+            default:
+                op = PackOp{w->lin_out_w, d.d_out, d.Hd, mrow * d.NOUTC, d.NOUTC, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
+                break;
+            }
             if ((rc = launch(op))) return rc;
         }
-        op = PackOp{w->lin_out_w, d.d_out, d.Hd, mrow * d.NOUTC, d.NOUTC, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
-        if ((rc = launch(op))) return rc;
         if (off != d.packed_per_rank) { set_error("gnb_decoder_pack_tc: internal size mismatch"); return GNB_E_INVALID; }
     }
     return 0;
+}
+
+// debugging aid (not part of the public header): returns a host pointer to 8 ints that a timed-out barrier wait fills
+// in before they trap (int[0] = number of reports, then from int[8] on {block, thread, source line, barrier address, parity, 0}
+// per report); readable after the launch failed
+extern "C" int* gnb_debug_hang_report() {
+    static int* host = nullptr;
+    if (!host) {
+        if (cudaHostAlloc((void**)&host, 4096, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 1024; ++i) host[i] = 0;
+        int* dev = nullptr;
+        if (cudaHostGetDevicePointer((void**)&dev, host, 0) != cudaSuccess) return nullptr;
+        if (cudaMemcpyToSymbol(gnb::tc::g_hang_report, &dev, sizeof(dev)) != cudaSuccess) return nullptr;
+    }
+    return host;
 }
 
 static long long* g_trace = nullptr;

@@ -128,6 +128,137 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(const unsigned char* buf, l
     }
 }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
+// The decoder's issue loop in isolation: a whole warp walks `ksteps` steps; per step `nwaits` waits on barriers that are
+// already complete, then one elected lane issues 4 MMAs (N columns) + `ncommits` commits.  mode 0: every lane polls
+// (try_wait loop), 1: lane 0 polls and a vote makes the result uniform, 2: single thread (lane 0) runs the whole loop.
+__global__ void __launch_bounds__(128, 1) issue_kernel(int N, int ksteps, int nwaits, int ncommits, int mode, long long* out) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bars[16];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x2c002c00u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 16; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (warp == 1 && (mode != 2 || lane == 0)) {
+        const uint32_t idesc = umma_idesc(N, 128);
+        const long long t0 = clock64();
+        uint32_t committed = 0, waited = 0;
+        for (int k = 0; k < ksteps; ++k) {
+            // waits on barriers 0..nwaits-1: never armed, so waiting for parity 1 ("previous phase") completes at once
+            for (int wv = 0; wv < nwaits; ++wv) {
+                const uint32_t bar = smem_u32(&bars[wv]);
+                if (mode == 0 || mode == 2) {
+                    while (!mbar_try(bar, 1)) { }
+                } else {
+                    uint32_t done = 0;
+                    do {
+                        if (lane == 0) done = mbar_try(bar, 1);
+                        done = __any_sync(0xffffffffu, done);
+                    } while (!done);
+                }
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t da = umma_desc(smem_u32(sm) + (k & 1) * 0), db = umma_desc(smem_u32(sm + 16 * 1024));
+            if (mode == 2 || elect_one()) {
+                umma_f16(tmem, da, db, idesc, k > 0);
+                umma_f16(tmem, da + 2, db + 2, idesc, 1u);
+                umma_f16(tmem, da + 4, db + 4, idesc, 1u);
+                umma_f16(tmem, da + 6, db + 6, idesc, 1u);
+                for (int c = 1; c < ncommits; ++c) umma_commit(smem_u32(&bars[12 + (c & 3)]));      // nobody waits on these
+                umma_commit(smem_u32(&bars[8 + (committed & 3)]));
+            }
+            if (mode != 2) __syncwarp();
+            ++committed;
+            if (committed - waited == 4) {
+                if (mode == 2 || lane == 0) mbar_wait(smem_u32(&bars[8 + (waited & 3)]), (waited >> 2) & 1);
+                if (mode != 2) __syncwarp();
+                ++waited;
+            }
+        }
+        if (mode == 2 || lane == 0) {
+            for (; waited < committed; ++waited) mbar_wait(smem_u32(&bars[8 + (waited & 3)]), (waited >> 2) & 1);
+            out[blockIdx.x * 4] = clock64() - t0;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 3) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// Per-instruction cost on the issuing thread: a single thread runs `ksteps` steps of
+//   [nwaits x try_wait on a complete barrier] [fence x tcgen05.fence::after_thread_sync] nmma x MMA [ncommits x commit]
+// and waits for the commits only every 8 steps (so the wait for completion is amortised away).
+__global__ void __launch_bounds__(128, 1) cost_kernel(int N, int ksteps, int nmma, int nwaits, int nfence, int ncommits, long long* out) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bars[16];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x2c002c00u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 16; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (warp == 1 && lane == 0) {
+        const uint32_t idesc = umma_idesc(N, 128);
+        const uint64_t da = umma_desc(smem_u32(sm)), db = umma_desc(smem_u32(sm + 16 * 1024));
+        const long long t0 = clock64();
+        uint32_t big = 0;
+        for (int k = 0; k < ksteps; ++k) {
+            for (int wv = 0; wv < nwaits; ++wv) while (!mbar_try(smem_u32(&bars[wv]), 1)) { }
+            for (int f = 0; f < nfence; ++f) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int m = 0; m < nmma; ++m) umma_f16(tmem, da + 2 * (m & 3), db + 2 * (m & 3), idesc, (k | m) > 0);
+            for (int c = 0; c < ncommits; ++c) umma_commit(smem_u32(&bars[12 + (c & 3)]));      // nobody waits on these
+            if ((k & 7) == 7) {
+                umma_commit(smem_u32(&bars[8]));
+                mbar_wait(smem_u32(&bars[8]), big & 1);
+                ++big;
+            }
+        }
+        out[blockIdx.x * 4] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 3) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
 int main() {
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
@@ -155,5 +286,41 @@ int main() {
             cyc /= sms, cp /= sms;
             printf("%4d %7d %8d %8d | %12.1f %10.3f %12.1f\n", N, ksteps, ckb, ncp, cyc / ksteps, 512.0 / (cyc / ksteps), cp / cyc);
         }
+    printf("\nper-instruction cost on the issuing thread (single thread; completion waited for every 8 steps)\n");
+    printf("%4s %5s %7s %7s %8s | %10s\n", "N", "nmma", "nwaits", "nfence", "commits", "cyc/step");
+    CK(cudaFuncSetAttribute(cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    {
+        const int cfg[][5] = {{32, 4, 0, 0, 0}, {32, 8, 0, 0, 0}, {32, 16, 0, 0, 0}, {32, 4, 1, 0, 0}, {32, 4, 2, 0, 0}, {32, 4, 0, 1, 0}, {32, 4, 0, 2, 0},
+                              {32, 4, 0, 0, 1}, {32, 4, 0, 0, 2}, {32, 4, 1, 0, 1}, {32, 4, 1, 1, 1}, {64, 4, 0, 0, 0}, {128, 4, 0, 0, 0}, {128, 8, 0, 0, 0},
+                              {128, 16, 0, 0, 0}, {256, 4, 0, 0, 0}, {256, 8, 0, 0, 0}, {256, 16, 0, 0, 0}, {256, 4, 1, 0, 1}, {256, 4, 2, 0, 2}, {128, 4, 1, 0, 1}};
+        for (auto& c : cfg) {
+            for (int rep = 0; rep < 2; ++rep) {
+                cost_kernel<<<sms, 128, 64 * 1024>>>(c[0], 2048, c[1], c[2], c[3], c[4], out);
+                CK(cudaDeviceSynchronize());
+            }
+            long long h[4 * 148];
+            CK(cudaMemcpy(h, out, sizeof(long long) * 4 * sms, cudaMemcpyDeviceToHost));
+            double cyc = 0;
+            for (int i = 0; i < sms; ++i) cyc += (double)h[i * 4];
+            printf("%4d %5d %7d %7d %8d | %10.1f\n", c[0], c[1], c[2], c[3], c[4], cyc / sms / 2048);
+        }
+    }
+    printf("\nissue loop: cycles per step (4 MMAs, nominal %d / %d cycles at N=128 / 256)\n", 256, 512);
+    printf("%4s %7s %8s %6s | %10s\n", "N", "nwaits", "commits", "mode", "cyc/step");
+    CK(cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    for (int N = 256; N <= 256; N *= 2)
+        for (int mode = 0; mode < 3; ++mode)
+            for (int nw = 0; nw <= 2; ++nw)
+                for (int nc = 1; nc <= 3; nc += 2) {
+                    for (int rep = 0; rep < 2; ++rep) {
+                        issue_kernel<<<sms, 128, 64 * 1024>>>(N, 2000, nw, nc, mode, out);
+                        CK(cudaDeviceSynchronize());
+                    }
+                    long long h[4 * 148];
+                    CK(cudaMemcpy(h, out, sizeof(long long) * 4 * sms, cudaMemcpyDeviceToHost));
+                    double cyc = 0;
+                    for (int i = 0; i < sms; ++i) cyc += (double)h[i * 4];
+                    printf("%4d %7d %8d %6d | %10.1f\n", N, nw, nc, mode, cyc / sms / 2000);
+                }
     return 0;
 }
