@@ -70,6 +70,16 @@ class GnbDecoderWeights(C.Structure):
     ]
 
 
+class GnbFusionParams(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
+        ("voxel_size", C.c_float), ("origin", C.c_float * 3), ("trunc_margin", C.c_float),
+        ("n_frames", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("h_projection", C.c_void_p), ("depth", C.c_void_p), ("color", C.c_void_p), ("label", C.c_void_p),
+        ("tsdf_vol", C.c_void_p), ("weight_vol", C.c_void_p), ("color_vol", C.c_void_p), ("label_vol", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/gennerf_b200.h declares
 SIGNATURES = {
     "gnb_version": (C.c_int, []),
@@ -100,6 +110,8 @@ SIGNATURES = {
     "gnb_get_3d_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gnb_farthest_point_sample": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]),
+    "gnb_tsdf_fusion_integrate": (C.c_int, [C.POINTER(GnbFusionParams), C.c_void_p]),
+    "gnb_tsdf_fusion_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_positional_encoding": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "gnb_tsdf_head": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
@@ -128,7 +140,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        for which, st in enumerate((GnbLiftParams, GnbSampleParams, GnbDecoderWeights)):
+        for which, st in enumerate((GnbLiftParams, GnbSampleParams, GnbDecoderWeights, GnbFusionParams)):
             if L.gnb_struct_size(which) != C.sizeof(st):
                 raise RuntimeError(f"gennerf_b200: ABI mismatch for {st.__name__}: library "
                                    f"{L.gnb_struct_size(which)} bytes, binding {C.sizeof(st)} bytes")

@@ -20,6 +20,7 @@ extern "C" int gnb_struct_size(int which) {
         case 0: return (int)sizeof(GnbLiftParams);
         case 1: return (int)sizeof(GnbSampleParams);
         case 2: return (int)sizeof(GnbDecoderWeights);
+        case 3: return (int)sizeof(GnbFusionParams);
         default: return -1;
     }
 }

@@ -8,6 +8,7 @@ unchanged.
     from gennerf_b200.dropin import LocalPoolPointnet      # was: src.models.components.pointnet
     from gennerf_b200.dropin import ResnetFC, PositionalEncoding, TSDFHeadSimple
     from gennerf_b200.dropin import GenNerf                # hot-path methods of src.models.model
+    from gennerf_b200.dropin import TSDFFusion             # was: src.data.tsdf
 
 CUDA tensors only.  Nothing here falls back to PyTorch arithmetic for the hot ops: the
 small per-point nn.Linear layers of the PointNet and the optional U-Net stay PyTorch, as
@@ -22,6 +23,62 @@ from . import ops
 
 PLANE_AXES = {"xz": [0, 2], "xy": [0, 1], "yz": [1, 2]}
 _PLANE_ID = {"xz": 0, "xy": 1, "yz": 2}
+
+
+# ------------------------------------------------------------------------------------------
+# src/data/tsdf.py: TSDFFusion (GT generation, evaluation re-fusion)
+# ------------------------------------------------------------------------------------------
+class TSDFFusion:
+    """Drop-in for the reference's TSDFFusion (src/data/tsdf.py:320-440): same constructor, `reset`, `integrate`
+    and the volumes `tsdf_vol`, `weight_vol`, `color_vol`, `label_vol` (flat, voxel id (x*ny + y)*nz + z).
+
+    `integrate(projection, depth, color, label)` takes one frame like the reference; `integrate_frames` takes T
+    frames at once (one launch per 64 frames, each voxel's running state in registers) and gives the same bits as T
+    calls.  `label_vol` is int32 here (the reference keeps int64); `get_volumes()` returns the normalised
+    (tsdf (nx,ny,nz), colour (3,nx,ny,nz) | None, label int64 (nx,ny,nz) | None) that `get_tsdf` wraps into its
+    TSDF container object (tsdf.py:420-440)."""
+
+    def __init__(self, voxel_dim=(128, 128, 128), voxel_size=.02, origin=(0, 0, 0), trunc_ratio=3,
+                 device=torch.device("cuda"), color=True, label=False):
+        nx, ny, nz = (int(d) for d in voxel_dim)
+        self.voxel_dim = (nx, ny, nz)
+        self.voxel_size = voxel_size
+        self.origin = torch.tensor(origin, dtype=torch.float, device=device).view(1, 3)
+        self._origin = [float(v) for v in torch.tensor(origin, dtype=torch.float).tolist()]
+        self.trunc_margin = voxel_size * trunc_ratio
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("gennerf_b200 TSDFFusion runs on CUDA devices only (there is no CPU fallback)")
+        V = nx * ny * nz
+        self.tsdf_vol = torch.ones(V, device=device)
+        self.weight_vol = torch.zeros(V, device=device)
+        self.color_vol = torch.zeros((3, V), device=device) if color else None
+        self.label_vol = -torch.ones(V, device=device, dtype=torch.int32) if label else None
+
+    def reset(self):
+        self.tsdf_vol.fill_(1)
+        self.weight_vol.fill_(0)
+        if self.color_vol is not None:
+            self.color_vol.fill_(0)
+        if self.label_vol is not None:
+            self.label_vol.fill_(-1)
+
+    def integrate_frames(self, projections, depths, colors=None, labels=None):
+        ops.tsdf_fusion_integrate(self.voxel_dim, self.voxel_size, self._origin, self.trunc_margin, projections, depths,
+                                  self.tsdf_vol, self.weight_vol,
+                                  colors if self.color_vol is not None else None, self.color_vol,
+                                  labels if self.label_vol is not None else None, self.label_vol)
+
+    def integrate(self, projection, depth, color=None, label=None):
+        self.integrate_frames(projection.reshape(1, 3, 4), depth.unsqueeze(0),
+                              color.unsqueeze(0) if color is not None else None,
+                              label.unsqueeze(0) if label is not None else None)
+
+    def get_volumes(self):
+        nx, ny, nz = self.voxel_dim
+        tsdf, color = ops.tsdf_fusion_finalize(self.tsdf_vol, self.weight_vol, self.color_vol)
+        label = self.label_vol.view(nx, ny, nz).long() if self.label_vol is not None else None
+        return tsdf.view(nx, ny, nz), (color.view(3, nx, ny, nz) if color is not None else None), label
 
 
 # ------------------------------------------------------------------------------------------

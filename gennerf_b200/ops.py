@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import GnbDecoderWeights, GnbLiftParams, GnbSampleParams, check, lib
+from ._lib import GNB_MAX_FRAMES, GnbDecoderWeights, GnbFusionParams, GnbLiftParams, GnbSampleParams, check, lib
 
 PLANES = ("xz", "xy", "yz")
 
@@ -563,3 +563,65 @@ def farthest_point_sample(xyz, npoint, start=None):
         check(lib().gnb_farthest_point_sample(x.data_ptr(), B, N, int(npoint), start.data_ptr(), scratch.data_ptr(),
                                               idx.data_ptr(), out.data_ptr(), _stream()), "gnb_farthest_point_sample")
     return out, idx
+
+
+# ------------------------------------------------------------------------------------------
+# TSDF fusion
+# ------------------------------------------------------------------------------------------
+def tsdf_fusion_integrate(voxel_dim, voxel_size, origin, trunc_margin, projections, depths, tsdf_vol, weight_vol,
+                          colors=None, color_vol=None, labels=None, label_vol=None):
+    """TSDFFusion.integrate (reference src/data/tsdf.py:369-418) for T frames in one launch per 64 frames.
+
+    projections (T,3,4); depths (T,H,W) CUDA fp32; colors (T,3,H,W) fp32 / labels (T,H,W) int32 optional.
+    tsdf_vol, weight_vol (V) fp32, color_vol (3,V) fp32, label_vol (V) int32 are updated IN PLACE, frames in
+    order: bit-identical to T sequential integrate() calls of the reference."""
+    nx, ny, nz = (int(d) for d in voxel_dim)
+    _need_cuda(depths, tsdf_vol, weight_vol, colors, color_vol, labels, label_vol)
+    V = nx * ny * nz
+    d = _f32(depths).contiguous()
+    T, H, W = d.shape
+    P = torch.as_tensor(projections).detach().to("cpu", torch.float32).reshape(T, 3, 4).contiguous()
+    for name, t, shape, dt in (("tsdf_vol", tsdf_vol, (V,), torch.float32), ("weight_vol", weight_vol, (V,), torch.float32),
+                               ("color_vol", color_vol, (3, V), torch.float32), ("label_vol", label_vol, (V,), torch.int32)):
+        if t is not None and (tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous()):
+            raise ValueError(f"tsdf_fusion_integrate: {name} must be a contiguous {dt} tensor of shape {shape}")
+    if (colors is None) != (color_vol is None) or (labels is None) != (label_vol is None):
+        raise ValueError("tsdf_fusion_integrate: colour / label frames and volumes go together")
+    c = _f32(colors).contiguous() if colors is not None else None
+    lb = labels.to(torch.int32).contiguous() if labels is not None else None
+    if c is not None and tuple(c.shape) != (T, 3, H, W):
+        raise ValueError("tsdf_fusion_integrate: colors must be (T,3,H,W)")
+    if lb is not None and tuple(lb.shape) != (T, H, W):
+        raise ValueError("tsdf_fusion_integrate: labels must be (T,H,W)")
+    org = _origin3(origin)
+    with torch.cuda.device(d.device):
+        for t0 in range(0, T, GNB_MAX_FRAMES):
+            n = min(GNB_MAX_FRAMES, T - t0)
+            q = GnbFusionParams()
+            q.nx, q.ny, q.nz = nx, ny, nz
+            q.voxel_size = float(voxel_size)
+            q.origin[0], q.origin[1], q.origin[2] = org
+            q.trunc_margin = float(trunc_margin)
+            q.n_frames, q.H, q.W = n, H, W
+            q.h_projection = P[t0:t0 + n].data_ptr()
+            q.depth = d[t0:t0 + n].data_ptr()
+            q.color = c[t0:t0 + n].data_ptr() if c is not None else None
+            q.label = lb[t0:t0 + n].data_ptr() if lb is not None else None
+            q.tsdf_vol, q.weight_vol = tsdf_vol.data_ptr(), weight_vol.data_ptr()
+            q.color_vol = color_vol.data_ptr() if color_vol is not None else None
+            q.label_vol = label_vol.data_ptr() if label_vol is not None else None
+            check(lib().gnb_tsdf_fusion_integrate(C.byref(q), _stream()), "gnb_tsdf_fusion_integrate")
+    return tsdf_vol, weight_vol
+
+
+def tsdf_fusion_finalize(tsdf_vol, weight_vol, color_vol=None):
+    """The normalisation of TSDFFusion.get_tsdf (reference tsdf.py:426-434): vol / weight where weight > 0."""
+    _need_cuda(tsdf_vol, weight_vol, color_vol)
+    V = weight_vol.numel()
+    out = torch.empty_like(tsdf_vol)
+    cout = torch.empty_like(color_vol) if color_vol is not None else None
+    with torch.cuda.device(tsdf_vol.device):
+        check(lib().gnb_tsdf_fusion_finalize(tsdf_vol.data_ptr(), weight_vol.data_ptr(),
+                                             color_vol.data_ptr() if color_vol is not None else None, V, out.data_ptr(),
+                                             cout.data_ptr() if cout is not None else None, _stream()), "gnb_tsdf_fusion_finalize")
+    return out, cout

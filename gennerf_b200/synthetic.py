@@ -111,3 +111,14 @@ def decoder_weights(g, d_feat, d_code, d_hidden=512, n_blocks=5, d_out=64, d_geo
     head_w = torch.randn(1, d_geo, generator=g) * (0.5 / math.sqrt(d_geo))
     head_b = 0.05 * torch.randn(1, generator=g)
     return w, head_w, head_b
+
+
+def surface_depth_maps(T, H, W, g, mean=0.9, holes=True):
+    """(T,H,W) smooth depth maps around `mean` metres (a wavy surface plus 2 cm of noise) with a regular pattern of
+    zero-depth pixels ("no measurement"), for the TSDF fusion path (reference src/data/tsdf.py:369-418)."""
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    d = torch.stack([mean + 0.4 * torch.sin(xx * (8.0 / W) + t) * torch.cos(yy * (6.0 / H))
+                     + 0.02 * torch.randn(H, W, generator=g) for t in range(T)])
+    if holes:
+        d[:, ::7, ::5] = 0.0
+    return d.contiguous()

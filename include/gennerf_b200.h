@@ -39,7 +39,7 @@ extern "C" {
 int gnb_version(void);
 const char* gnb_last_error(void);
 /* sizeof() of the parameter structs as compiled: 0 GnbLiftParams, 1 GnbSampleParams,
- * 2 GnbDecoderWeights.  Lets a foreign-language binding verify its struct layout. */
+ * 2 GnbDecoderWeights, 3 GnbFusionParams.  Lets a foreign-language binding verify its struct layout. */
 int gnb_struct_size(int which);
 
 /* -------------------------------------------------------------------------------------
@@ -212,6 +212,37 @@ int gnb_get_3d_points(const float* depth, const float* h_projection, int B, int 
                       void* stream);
 int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int npoint, const int64_t* start,
                               float* scratch, int64_t* out_idx, float* out_xyz, void* stream);
+
+/* -------------------------------------------------------------------------------------
+ * TSDF fusion of posed depth maps (SURVEY 8f "next" row 3): GT generation and evaluation re-fusion.
+ * gnb_tsdf_fusion_integrate replaces TSDFFusion.integrate() (src/data/tsdf.py:369-418) for n_frames frames
+ *   at once; frames are applied in order, so the volumes equal n_frames sequential integrate() calls bit
+ *   for bit.  The running volumes (the reference's tsdf_vol, weight_vol, color_vol, label_vol; flat voxel id
+ *   v = (x*ny + y)*nz + z) are read and updated in place; initialise them as TSDFFusion.reset() does
+ *   (tsdf 1, weight 0, colour 0, label -1).  trunc_margin = voxel_size * trunc_ratio (tsdf.py:341).
+ * gnb_tsdf_fusion_finalize replaces the normalisation of TSDFFusion.get_tsdf() (tsdf.py:426-434):
+ *   out = vol / weight where weight > 0, else vol.  tsdf_out / color_out may alias their inputs.
+ * ----------------------------------------------------------------------------------- */
+typedef struct GnbFusionParams {
+    int32_t nx, ny, nz;
+    float voxel_size;
+    float origin[3];
+    float trunc_margin;
+    int32_t n_frames;              /* <= GNB_MAX_FRAMES per call; call again for more        */
+    int32_t H, W;
+    const float* h_projection;     /* HOST (n_frames,3,4) world->pixel, row-major           */
+    const float* depth;            /* (n_frames,H,W)                                        */
+    const float* color;            /* (n_frames,3,H,W) or NULL                              */
+    const int32_t* label;          /* (n_frames,H,W) or NULL                                */
+    float* tsdf_vol;               /* (V)                                                   */
+    float* weight_vol;             /* (V)                                                   */
+    float* color_vol;              /* (3,V) or NULL (iff color == NULL)                     */
+    int32_t* label_vol;            /* (V) or NULL (iff label == NULL)                       */
+} GnbFusionParams;
+
+int gnb_tsdf_fusion_integrate(const GnbFusionParams* p, void* stream);
+int gnb_tsdf_fusion_finalize(const float* tsdf_vol, const float* weight_vol, const float* color_vol,
+                             int64_t n_voxels, float* tsdf_out, float* color_out, void* stream);
 
 /* -------------------------------------------------------------------------------------
  * Decoder.  Replaces

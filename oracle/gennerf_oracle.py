@@ -461,3 +461,125 @@ def farthest_point_sample(xyz, npoint, start):
         distance = torch.where(dist < distance, dist, distance)
         farthest = torch.max(distance, -1)[1]
     return xyz[bi[:, None], centroids], centroids
+
+
+# ----------------------------------------------------------------------------------------
+# f-3  TSDF fusion (GT generation / evaluation re-fusion)         src/data/tsdf.py:320-440
+# ----------------------------------------------------------------------------------------
+class TSDFFusion:
+    """CPU restatement of the reference's TSDFFusion (tsdf.py:320-440): running TSDF / weight
+    (/ colour / label) volumes over the flat voxel index v = (x*ny + y)*nz + z.
+
+    integrate() follows tsdf.py:369-418 op by op with the same ATen CPU kernels (2-D `@`,
+    true fp32 division by the Python-float truncation margin, masked assignments)."""
+
+    def __init__(self, voxel_dim, voxel_size, origin, trunc_ratio=3, color=True, label=False):
+        nx, ny, nz = (int(d) for d in voxel_dim)
+        self.voxel_dim = (nx, ny, nz)
+        self.voxel_size = voxel_size
+        self.origin = torch.tensor(origin, dtype=torch.float).view(1, 3)
+        self.trunc_margin = voxel_size * trunc_ratio                     # Python float (tsdf.py:341)
+        world = coordinates(voxel_dim).type(torch.float) * voxel_size + self.origin.T   # tsdf.py:344
+        self.world = torch.cat((world, torch.ones_like(world[:1])), dim=0)
+        V = nx * ny * nz
+        self.tsdf_vol = torch.ones(V)
+        self.weight_vol = torch.zeros(V)
+        self.color_vol = torch.zeros(3, V) if color else None
+        self.label_vol = -torch.ones(V, dtype=torch.long) if label else None
+
+    def reset(self):
+        self.tsdf_vol.fill_(1)
+        self.weight_vol.fill_(0)
+        if self.color_vol is not None:
+            self.color_vol.fill_(0)
+        if self.label_vol is not None:
+            self.label_vol.fill_(-1)
+
+    def integrate(self, projection, depth, color=None, label=None):
+        camera = projection @ self.world                                  # tsdf.py:380
+        px = (camera[0, :] / camera[2, :]).round().type(torch.long)
+        py = (camera[1, :] / camera[2, :]).round().type(torch.long)
+        pz = camera[2, :]
+        height, width = depth.size()
+        valid = (px >= 0) & (py >= 0) & (px < width) & (py < height) & (pz > 0)
+        valid_ = valid.clone()
+        valid[valid_] *= depth[py[valid_], px[valid_]] > 0                # tsdf.py:391
+        dist = pz[valid] - depth[py[valid], px[valid]]
+        dist = torch.clamp(dist / self.trunc_margin, min=-1)              # tsdf.py:395
+        valid1 = dist < 1
+        valid_ = valid.clone()
+        valid[valid_] *= valid1
+        dist = dist[valid1]
+        mask1 = self.weight_vol == 0
+        self.tsdf_vol[valid & mask1] = dist[mask1[valid]]                 # first observation: copy (tsdf.py:405)
+        mask2 = valid.clone()
+        valid2 = dist > -1
+        mask2[valid] *= valid2                                            # near surface
+        mask3 = ~mask1 & mask2
+        self.tsdf_vol[mask3] += dist[mask3[valid]]
+        self.weight_vol[mask2] += 1
+        if self.color_vol is not None:
+            self.color_vol[:, mask2] += color[:, py[mask2], px[mask2]]
+        if self.label_vol is not None:
+            self.label_vol[mask2] = label[py[mask2], px[mask2]]           # newest label wins
+
+    def get_volumes(self):
+        """The arithmetic of get_tsdf (tsdf.py:420-440) without the TSDF container object:
+        tsdf (nx,ny,nz), colour (3,nx,ny,nz) or None, label (nx,ny,nz) or None."""
+        nx, ny, nz = self.voxel_dim
+        seen = self.weight_vol > 0
+        tsdf = self.tsdf_vol.clone()
+        tsdf[seen] /= self.weight_vol[seen]
+        color = None
+        if self.color_vol is not None:
+            color = self.color_vol.clone()
+            color[:, seen] /= self.weight_vol[seen]
+            color = color.view(3, nx, ny, nz)
+        label = self.label_vol.view(nx, ny, nz).clone() if self.label_vol is not None else None
+        return tsdf.view(nx, ny, nz), color, label
+
+
+def tsdf_fusion_explicit(voxel_dim, voxel_size, origin, trunc_ratio, projections, depths, colors=None, labels=None):
+    """The same fusion written per voxel the way the CUDA kernel computes it: FMA-chain projection (as
+    project_indices_explicit), round-half-even pixel, then the running update in frame order.  Returns the raw
+    (tsdf_vol, weight_vol, color_vol, label_vol); must equal TSDFFusion.integrate called frame by frame."""
+    V = int(voxel_dim[0]) * int(voxel_dim[1]) * int(voxel_dim[2])
+    coords = coordinates(voxel_dim).float()
+    vs = torch.tensor(float(voxel_size), dtype=torch.float32)
+    org = torch.as_tensor(origin, dtype=torch.float32).reshape(3)
+    w = [coords[i] * vs + org[i] for i in range(3)]
+    one = torch.ones_like(w[0])
+    trunc = torch.tensor(voxel_size * trunc_ratio, dtype=torch.float32)    # the Python float, rounded to fp32 once
+    tsdf = torch.ones(V)
+    weight = torch.zeros(V)
+    color_vol = torch.zeros(3, V) if colors is not None else None
+    label_vol = -torch.ones(V, dtype=torch.long) if labels is not None else None
+    for f in range(projections.shape[0]):
+        P = projections[f]
+        H, W = depths[f].shape
+        cam = []
+        for r in range(3):
+            acc = P[r, 0] * w[0]
+            acc = _fma32(P[r, 1].expand_as(acc), w[1], acc)
+            acc = _fma32(P[r, 2].expand_as(acc), w[2], acc)
+            acc = _fma32(P[r, 3].expand_as(acc), one, acc)
+            cam.append(acc)
+        fx = (cam[0] / cam[2]).round()
+        fy = (cam[1] / cam[2]).round()
+        inb = (fx >= 0) & (fy >= 0) & (fx < W) & (fy < H) & (cam[2] > 0)
+        ix = torch.where(inb, fx, torch.zeros_like(fx)).long()
+        iy = torch.where(inb, fy, torch.zeros_like(fy)).long()
+        dpt = depths[f][iy, ix]
+        ok = inb & (dpt > 0)
+        dist = torch.clamp((cam[2] - dpt) / trunc, min=-1)
+        ok = ok & (dist < 1)
+        first = ok & (weight == 0)
+        near = ok & (dist > -1)
+        tsdf = torch.where(first, dist, tsdf)
+        tsdf = torch.where(near & ~first, tsdf + dist, tsdf)
+        weight = torch.where(near, weight + 1, weight)
+        if color_vol is not None:
+            color_vol = torch.where(near.unsqueeze(0), color_vol + colors[f][:, iy, ix], color_vol)
+        if label_vol is not None:
+            label_vol = torch.where(near, labels[f][iy, ix], label_vol)
+    return tsdf, weight, color_vol, label_vol

@@ -88,3 +88,23 @@ def test_gennerf_forward(golden_dir):
     assert torch.equal(out["feat"], o["feat"])
     for k in ("feat_geo", "feat_sem", "tsdf"):
         assert torch.allclose(out[k], o[k], rtol=1e-5, atol=1e-5), k
+
+
+def test_tsdf_fusion(golden_dir):
+    """the oracle's TSDFFusion and its per-voxel formulation against the real reference's volumes."""
+    G = load(golden_dir, "tsdf_fusion.pt")
+    i, o = G["in"], G["out"]
+    T = i["projection"].shape[0]
+    f = O.TSDFFusion(i["voxel_dim"], i["voxel_size"], i["origin"], trunc_ratio=i["trunc_ratio"], color=True, label=True)
+    for t in range(T):
+        f.integrate(i["projection"][t], i["depth"][t], i["color"][t], i["label"][t].long())
+        if t == 0:
+            assert torch.equal(f.tsdf_vol, o["frame0"]["tsdf_vol"]) and torch.equal(f.weight_vol, o["frame0"]["weight_vol"].float())
+    assert torch.equal(f.tsdf_vol, o["all"]["tsdf_vol"]) and torch.equal(f.weight_vol, o["all"]["weight_vol"].float())
+    assert torch.equal(f.color_vol, o["all"]["color_vol"]) and torch.equal(f.label_vol, o["all"]["label_vol"].long())
+    tsdf, color, _ = f.get_volumes()
+    assert torch.equal(tsdf.reshape(-1), o["normalised"]["tsdf"]) and torch.equal(color.reshape(3, -1), o["normalised"]["color"])
+    e = O.tsdf_fusion_explicit(i["voxel_dim"], i["voxel_size"], i["origin"], i["trunc_ratio"], i["projection"], i["depth"],
+                               i["color"], i["label"].long())
+    assert torch.equal(e[0], o["all"]["tsdf_vol"]) and torch.equal(e[1], o["all"]["weight_vol"].float())
+    assert torch.equal(e[2], o["all"]["color_vol"]) and torch.equal(e[3], o["all"]["label_vol"].long())

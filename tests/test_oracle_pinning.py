@@ -202,3 +202,37 @@ def test_next_rows(ref):
     s_ref, c_ref = ref.utils.farthest_point_sample(xyz, 16)
     s_o, c_o = O.farthest_point_sample(xyz, 16, c_ref[:, 0])
     assert torch.equal(c_ref, c_o) and torch.equal(s_ref, s_o)
+
+
+# ---- TSDF fusion (src/data/tsdf.py:320-440) -------------------------------------
+@pytest.mark.parametrize("color,label,trunc_ratio,origin", [(True, True, 3, (0.1, -0.2, 0.05)), (False, False, 3, (0, 0, 0)),
+                                                           (True, False, 8, (0.0, 0.0, 0.0)), (False, True, 1.5, (-0.3, 0.2, 0.0))])
+def test_tsdf_fusion(color, label, trunc_ratio, origin):
+    ref_shim.install()
+    from src.data.tsdf import TSDFFusion as RefFusion
+    g = S.gen(31)
+    vd, T, H, W = (40, 36, 20), 5, 48, 64
+    P = S.projections(T, H, W, vd, VS, g)
+    depths = S.surface_depth_maps(T, H, W, g)
+    colors = torch.rand(T, 3, H, W, generator=g)
+    labels = torch.randint(0, 40, (T, H, W), generator=g)
+    r = RefFusion(vd, VS, origin, trunc_ratio=trunc_ratio, device=torch.device("cpu"), color=color, label=label)
+    o = O.TSDFFusion(vd, VS, origin, trunc_ratio=trunc_ratio, color=color, label=label)
+    assert torch.equal(r.world, o.world)
+    for t in range(T):
+        r.integrate(P[t], depths[t], colors[t] if color else None, labels[t] if label else None)
+        o.integrate(P[t], depths[t], colors[t] if color else None, labels[t] if label else None)
+        assert torch.equal(r.tsdf_vol, o.tsdf_vol) and torch.equal(r.weight_vol, o.weight_vol)
+    if color:
+        assert torch.equal(r.color_vol, o.color_vol)
+    if label:
+        assert torch.equal(r.label_vol, o.label_vol)
+    # the per-voxel formulation the CUDA kernel follows (FMA-chain projection, running update in frame order)
+    e = O.tsdf_fusion_explicit(vd, VS, origin, trunc_ratio, P, depths, colors if color else None, labels if label else None)
+    assert torch.equal(r.tsdf_vol, e[0]) and torch.equal(r.weight_vol, e[1])
+    assert (not color) or torch.equal(r.color_vol, e[2])
+    assert (not label) or torch.equal(r.label_vol, e[3])
+    assert int((r.weight_vol > 0).sum()) > 100 and int(((r.weight_vol == 0) & (r.tsdf_vol == -1)).sum()) > 0
+    # reset (tsdf.py:359-367)
+    r.reset(), o.reset()
+    assert torch.equal(r.tsdf_vol, o.tsdf_vol) and torch.equal(r.weight_vol, o.weight_vol)
