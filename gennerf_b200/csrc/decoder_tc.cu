@@ -69,6 +69,8 @@ struct Dims {
     int nstage;                       // weight-ring stages
     int stage_bytes;                  // bytes of one stage: the weight rows of one step x 64 k (single-CTA issue: one k-chunk
                                       // of <= 256 rows; cta_group::2: two k-chunks of <= 128 rows)
+    int early;                        // 1: a dedicated warp stages the NEXT tile's lin_in / lin_z operands (sampling, encoding) while
+                                      // this tile's layers run; needs its own feature buffer (KF chunks) next to the code tile
     long long packed_per_rank;        // bytes
 };
 
@@ -322,17 +324,20 @@ struct TcKP {
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
 struct Smem {
-    uint32_t a, code, ring, bias, bars;     // byte offsets
+    uint32_t a, code, feat, ring, bias, bars;     // byte offsets
     uint32_t total;
 };
 __host__ __device__ inline Smem smem_layout(const Dims& d) {
     Smem s;
     s.a = 0;
     s.code = s.a + d.ACH * CHUNK;
-    s.ring = s.code + d.KZ * CHUNK;
+    s.feat = d.early ? s.code + d.KZ * CHUNK : s.a;          // lin_in operand: own buffer, or the first own chunk slots
+    s.ring = s.code + d.KZ * CHUNK + (d.early ? d.KF * CHUNK : 0);
     s.bias = s.ring + d.nstage * d.stage_bytes;
-    // fp32 table: b0[nb][HN] | b1_last[HN] | b_out[NOUT] | head_w[d_geo] | head_b
-    uint32_t nbias = (uint32_t)(d.nb * d.HN + d.HN + d.NOUT + d.d_geo + 1);
+    // fp32 table: bias[HN] | b_out[NOUT] | head_w[d_geo] | head_b.  bias[] is time-shared: the epilogue threads load
+    // fc_0's bias of block i into it during round 2i (which adds no bias) for round 2i+1, and the last fc_1 bias
+    // after round 2nb-1 -- a table of all blocks' biases (5 KB at d_hidden 512) is shared memory the operand buffers need
+    uint32_t nbias = (uint32_t)(d.HN + d.NOUT + d.d_geo + 1);
     s.bars = (s.bias + nbias * 4 + 15) & ~15u;
     // barriers: w_full[8] w_empty[8] a_ready[8] rready[4] rfree[4] acc_ready in_ready (12 spare) | tmem slot
     s.total = s.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2 + 12) * 8 + 16;
@@ -374,6 +379,90 @@ __host__ __device__ inline int act_kchunk(int nsplit, int own, int half, int t, 
     return (t & 1) ? ((half ^ 1) * own + r) : (half * own + r);
 }
 
+// Operand tiles of lin_in (features + bias columns) and lin_z (positional code + bias columns) of ONE query row:
+// writes the 16-byte units u0, u0+ustep, ... of the row into the swizzled code and feature chunks.  Features are
+// sampled here (fused query) or read from the feature tensor.
+template <bool BF16>
+__device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, const Smem& L, int half, int row, long long grow,
+                                             int u0, int ustep, int what = 3) {      // what: 1 = code tile, 2 = feature chunks
+    const Dims& d = p.d;
+    const GnbDecoderWeights& w = p.w;
+    const bool live = grow < p.n_rows;
+    float xyz3[3] = {0.f, 0.f, 0.f};
+    if (live && w.use_code != 2) xyz3[0] = __ldg(p.xyz + grow * 3), xyz3[1] = __ldg(p.xyz + grow * 3 + 1), xyz3[2] = __ldg(p.xyz + grow * 3 + 2);
+    if (what & 1) {
+    float code[64 * 4];                          // d_code + 2 <= 64*KZ (KZ <= 4)
+    const int kz = d.KZ * 64;
+    for (int k = 0; k < kz; ++k) code[k] = 0.0f;
+    if (live) {
+        if (w.use_code == 2) {
+            for (int k = 0; k < d.d_code; ++k) code[k] = __ldg(p.xyz + grow * d.d_code + k);
+        } else {
+            if (w.use_code == 0) { code[0] = xyz3[0], code[1] = xyz3[1], code[2] = xyz3[2]; }
+            else {
+                int o = 0;
+                if (w.include_input) { code[0] = xyz3[0], code[1] = xyz3[1], code[2] = xyz3[2]; o = 3; }
+                const float half_pi = (float)(3.14159265358979323846 * 0.5);
+                for (int f = 0; f < 2 * w.num_freqs; ++f) {
+                    const float freq = w.freq_factor * exp2f((float)(f >> 1));
+                    const float phase = (f & 1) ? half_pi : 0.0f;
+                    for (int dd = 0; dd < 3; ++dd) code[o + f * 3 + dd] = sinf(__fadd_rn(phase, __fmul_rn(xyz3[dd], freq)));
+                }
+            }
+        }
+    }
+    code[d.d_code] = 1.0f, code[d.d_code + 1] = 1.0f;      // bias hi / lo columns
+    for (int c = 0; c < d.KZ; ++c)
+        for (int u = u0; u < 8; u += ustep) {
+            const float* v = code + c * 64 + u * 8;
+            uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
+            *reinterpret_cast<uint4*>(sm + L.code + c * CHUNK + chunk_off(row, u)) = pk;
+        }
+    }
+    if (!(what & 2)) return;
+    TriCorners tcn;
+    BiCorners bc[3];
+    const int b = (p.fused && live) ? (int)(grow / p.s.Q) : 0;
+    if (p.fused && live) {
+        if (p.s.volume) trilinear_setup(p.s, xyz3[0], xyz3[1], xyz3[2], tcn);
+        if (p.s.Cp > 0) planes_setup(p.s, xyz3[0], xyz3[1], xyz3[2], bc);
+    }
+    for (int c = 0; c < d.KF; ++c)
+        for (int u = u0; u < 8; u += ustep) {
+            float v[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = c * 64 + u * 8 + h * 4;         // first of 4 feature columns
+                float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && k < d.d_feat) {
+                    if (!p.fused) {
+                        const float* src = p.feat + grow * d.d_feat + k;
+                        if ((d.d_feat & 3) == 0) f4 = ldg4(src);
+                        else {
+                            f4.x = __ldg(src);
+                            if (k + 1 < d.d_feat) f4.y = __ldg(src + 1);
+                            if (k + 2 < d.d_feat) f4.z = __ldg(src + 2);
+                            if (k + 3 < d.d_feat) f4.w = __ldg(src + 3);
+                        }
+                    } else {
+                        // (host guarantees C_p % 4 == 0, C % 4 == 0 and unit channel strides here)
+                        Vals<4> r = (k < p.s.Cp) ? sample_planes<4>(p.s, bc, b, k) : sample_volume<4>(p.s, tcn, b, k - p.s.Cp);
+                        f4 = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+                        if (p.s.out && half == 0) *reinterpret_cast<float4*>(p.s.out + grow * p.s.out_stride + k) = f4;
+                    }
+                }
+                v[h * 4 + 0] = f4.x, v[h * 4 + 1] = f4.y, v[h * 4 + 2] = f4.z, v[h * 4 + 3] = f4.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = c * 64 + u * 8 + e;
+                if (k == d.d_feat || k == d.d_feat + 1) v[e] = 1.0f;       // bias hi / lo columns
+            }
+            uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
+            *reinterpret_cast<uint4*>(sm + L.feat + c * CHUNK + chunk_off(row, u)) = pk;
+        }
+}
+
 // trace slot layout: dbg[role*4096 + k]; role 0 = MMA thread, 1 = epilogue warp 4 lane 0, 2 = producer
 // (compiled in only with -DGNB_TC_TRACE: even a predicated clock read per k-step costs the single-thread MMA
 //  issue loop ~10 %)
@@ -405,6 +494,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     auto rfree = [&](int sl) { return bar0 + 8u * (2 * MAX_STAGES + 12 + sl); };     // the PEER has consumed what I pushed into its slot sl
     const uint32_t acc_ready = bar0 + 8u * (2 * MAX_STAGES + MAX_CHUNKS);
     const uint32_t in_ready = acc_ready + 8;
+    const uint32_t in_free = in_ready + 8;                   // (early staging) the code tile may be overwritten: the tile's last lin_z has retired
+    const uint32_t feat_free = in_free + 8;                  // (early staging) the feature buffer may be overwritten: lin_in has retired
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2 + 12) * 8);
     float* bias_s = reinterpret_cast<float*>(sm + L.bias);
 
@@ -431,7 +522,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
         for (int t = 0; t < 8; ++t) mbar_init(a_ready(t), warps_in);
         for (int sl = 0; sl < 4; ++sl) { mbar_init(rready(sl), both); mbar_init(rfree(sl), 1); }
         mbar_init(acc_ready, d.nsplit);                   // every issuing CTA of the cluster commits to every CTA
-        mbar_init(in_ready, warps_in);
+        mbar_init(in_ready, d.early ? 1 : warps_in);
+        mbar_init(in_free, 1);
+        mbar_init(feat_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == ROLE_WARP0 + 2) {
@@ -445,11 +538,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     }
     {   // fp32 bias table
         const GnbDecoderWeights& w = p.w;
-        const int h0 = half * d.HN;
-        for (int i = threadIdx.x; i < d.nb * d.HN; i += NTHREADS) bias_s[i] = __ldg(w.fc0_b[i / d.HN] + h0 + i % d.HN);
-        float* b1 = bias_s + d.nb * d.HN;
-        for (int i = threadIdx.x; i < d.HN; i += NTHREADS) b1[i] = d.nb > 0 ? __ldg(w.fc1_b[d.nb - 1] + h0 + i) : 0.0f;
-        float* bo = b1 + d.HN;
+        float* bo = bias_s + d.HN;
         for (int i = threadIdx.x; i < d.NOUT; i += NTHREADS) bo[i] = i < d.d_out ? __ldg(w.lin_out_b + i) : 0.0f;
         float* hw = bo + d.NOUT;
         for (int i = threadIdx.x; i < d.d_geo; i += NTHREADS) hw[i] = __ldg(w.head_w + i);
@@ -564,7 +653,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         int rslot = -1;
                         for (int c = 0; c < nchunk; ++c) {
                             const int tt = t + c;
-                            if (op.a_kind == 0) a_addr[c] = sbase + L.a + tt * CHUNK;
+                            if (op.a_kind == 0) a_addr[c] = sbase + L.feat + tt * CHUNK;
                             else if (op.a_kind == 1) a_addr[c] = sbase + L.code + tt * CHUNK;
                             else {
                                 const bool own_chunk = d.nsplit == 1 || (tt & 1) == 0;
@@ -644,7 +733,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         uint32_t a_addr;
                         int rslot = -1;                                // >= 0: this chunk sits in a remote slot
                         if (op.a_kind == 0) {
-                            a_addr = sbase + L.a + t * CHUNK;
+                            a_addr = sbase + L.feat + t * CHUNK;
                             mbar_wait(w_full(stage), phase);
                         } else if (op.a_kind == 1) {
                             a_addr = sbase + L.code + t * CHUNK;
@@ -669,7 +758,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                     }
                     GNB_TRACE(0, tk); ++tk;
                     if (op.a_kind == 2) ++round;
+                    // (early staging) the last lin_z of the tile has been issued: when it retires, the staging warp may
+                    // overwrite the code tile and the feature buffer with the next tile's operands
+                    if (d.early && op.mat == M_LIN_Z && op.blk == d.nb - 1) umma_commit(in_free);
+                    if (d.early && o == 0) umma_commit(feat_free);
                     if (op.group_end) {
+                        // (early staging) this tile's first group may complete before the PEER has finished the previous
+                        // tile: its arrival must not count for the previous tile's last phase of acc_ready
+                        if (d.early && o == 1 && tiles_done > 0) mbar_wait(acc_ready, (tiles_done * (uint32_t)(2 * d.nb + 2) - 1) & 1);
                         if (d.nsplit > 1) umma_commit_mc(acc_ready, allmask);
                         else umma_commit(acc_ready);
                     }
@@ -677,6 +773,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
             }
         }
         }   // !TWO
+    } else if (!TWO && warp == ROLE_WARP0 + 3) {
+        // =============================== input staging (early mode) ============================
+        // One warp prepares the NEXT tile's lin_in / lin_z operands (xyz -> positional code, feature sampling or load,
+        // fp16/bf16 pack into the swizzled chunks) while the current tile's layers run, so the tensor pipe does not idle
+        // for a prologue between tiles.  Lane l stages rows l, l+32, l+64, l+96.
+        if (d.early) {
+            uint32_t it = 0;
+            for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++it) {
+                // features first (the slow part: gathers): their buffer is free as soon as the previous tile's lin_in has
+                // retired, almost a whole tile before they are needed; the code tile only after its last lin_z
+                if (it > 0) mbar_wait(feat_free, (it - 1) & 1);
+                for (int rr = 0; rr < BM / 32; ++rr) {
+                    const int row = rr * 32 + lane;
+                    stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 2);
+                }
+                if (it > 0) mbar_wait(in_free, (it - 1) & 1);
+                for (int rr = 0; rr < BM / 32; ++rr) {
+                    const int row = rr * 32 + lane;
+                    stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 1);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(in_ready);
+            }
+        }
     } else if (warp == ROLE_WARP0 + 2) {
         // =============================== A-chunk exchange (NSPLIT=2) ==========================
         // Pushes every own chunk into one of the peer's RS remote slots (cycled).  A slot is reused
@@ -711,78 +832,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
             int ek = (int)(grp / (2 * d.nb + 2)) * 64;
             if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             // ---------------- prologue: operand tiles of lin_in and lin_z -------------------
-            {
-                float code[64 * 4];                          // d_code + 2 <= 64*KZ (KZ <= 4)
-                const int kz = d.KZ * 64;
-                for (int k = 0; k < kz; ++k) code[k] = 0.0f;
-                float xyz3[3] = {0.f, 0.f, 0.f};
-                if (live) {
-                    if (w.use_code == 2) {
-                        for (int k = 0; k < d.d_code; ++k) code[k] = __ldg(p.xyz + grow * d.d_code + k);
-                    } else {
-                        xyz3[0] = __ldg(p.xyz + grow * 3), xyz3[1] = __ldg(p.xyz + grow * 3 + 1), xyz3[2] = __ldg(p.xyz + grow * 3 + 2);
-                        if (w.use_code == 0) { code[0] = xyz3[0], code[1] = xyz3[1], code[2] = xyz3[2]; }
-                        else {
-                            int o = 0;
-                            if (w.include_input) { code[0] = xyz3[0], code[1] = xyz3[1], code[2] = xyz3[2]; o = 3; }
-                            const float half_pi = (float)(3.14159265358979323846 * 0.5);
-                            for (int f = 0; f < 2 * w.num_freqs; ++f) {
-                                const float freq = w.freq_factor * exp2f((float)(f >> 1));
-                                const float phase = (f & 1) ? half_pi : 0.0f;
-                                for (int dd = 0; dd < 3; ++dd) code[o + f * 3 + dd] = sinf(__fadd_rn(phase, __fmul_rn(xyz3[dd], freq)));
-                            }
-                        }
-                    }
-                }
-                code[d.d_code] = 1.0f, code[d.d_code + 1] = 1.0f;      // bias hi / lo columns
-                for (int c = 0; c < d.KZ; ++c)
-                    for (int u = eg; u < 8; u += EPI_GROUPS) {           // the two groups write alternate units
-                        const float* v = code + c * 64 + u * 8;
-                        uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
-                        *reinterpret_cast<uint4*>(sm + L.code + c * CHUNK + chunk_off(row, u)) = pk;
-                    }
-                // features: sampled here (fused) or read from the feature tensor
-                TriCorners tcn;
-                BiCorners bc[3];
-                const int b = (p.fused && live) ? (int)(grow / p.s.Q) : 0;
-                if (p.fused && live) {
-                    if (p.s.volume) trilinear_setup(p.s, xyz3[0], xyz3[1], xyz3[2], tcn);
-                    if (p.s.Cp > 0) planes_setup(p.s, xyz3[0], xyz3[1], xyz3[2], bc);
-                }
-                for (int c = 0; c < d.KF; ++c)
-                    for (int u = eg; u < 8; u += EPI_GROUPS) {
-                        float v[8];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int k = c * 64 + u * 8 + h * 4;         // first of 4 feature columns
-                            float4 f4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (live && k < d.d_feat) {
-                                if (!p.fused) {
-                                    const float* src = p.feat + grow * d.d_feat + k;
-                                    if ((d.d_feat & 3) == 0) f4 = ldg4(src);
-                                    else {
-                                        f4.x = __ldg(src);
-                                        if (k + 1 < d.d_feat) f4.y = __ldg(src + 1);
-                                        if (k + 2 < d.d_feat) f4.z = __ldg(src + 2);
-                                        if (k + 3 < d.d_feat) f4.w = __ldg(src + 3);
-                                    }
-                                } else {
-                                    // (host guarantees C_p % 4 == 0, C % 4 == 0 and unit channel strides here)
-                                    Vals<4> r = (k < p.s.Cp) ? sample_planes<4>(p.s, bc, b, k) : sample_volume<4>(p.s, tcn, b, k - p.s.Cp);
-                                    f4 = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-                                    if (p.s.out && half == 0) *reinterpret_cast<float4*>(p.s.out + grow * p.s.out_stride + k) = f4;
-                                }
-                            }
-                            v[h * 4 + 0] = f4.x, v[h * 4 + 1] = f4.y, v[h * 4 + 2] = f4.z, v[h * 4 + 3] = f4.w;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int k = c * 64 + u * 8 + e;
-                            if (k == d.d_feat || k == d.d_feat + 1) v[e] = 1.0f;       // bias hi / lo columns
-                        }
-                        uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
-                        *reinterpret_cast<uint4*>(sm + L.a + c * CHUNK + chunk_off(row, u)) = pk;
-                    }
+            if (!d.early) {
+                stage_inputs<BF16>(p, sm, L, (int)half, row, grow, eg, EPI_GROUPS);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -790,17 +841,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                     else mbar_arrive_remote(map_to_cta(in_ready, lead_rank));      // the pair leader issues for both
                 }
                 if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
-            }
+            } else { ++ek; }
             // ---------------- epilogue rounds: accumulator -> next A operand -----------------
-            const float* b0 = bias_s;
-            const float* b1_last = bias_s + d.nb * d.HN;
+            const int et = threadIdx.x - EPI_WARP0 * 32;                 // 0..255: this thread's slot of the shared bias[] (HN <= 256)
             for (int r = 0; r < 2 * d.nb + 1; ++r) {
                 mbar_wait_park(acc_ready, grp & 1);
                 ++grp;
                 tc_fence_after();
                 if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
                 const bool from_net = (r & 1) == 1;                       // rounds: x, net, x, net, ..., x(last)
-                const float* bias = from_net ? (b0 + (r >> 1) * d.HN) : ((r == 2 * d.nb) ? b1_last : nullptr);
+                const float* bias = (from_net || r == 2 * d.nb) ? bias_s : nullptr;
+                // even round 2i, i < nb: nobody reads bias[] now (every thread finished round 2i-1 before this round's
+                // accumulator could be complete) -- load fc_0's bias of block i for the next round
+                float bnext = 0.0f;
+                const bool load_b0 = !from_net && r < 2 * d.nb && et < d.HN;
+                if (load_b0) bnext = __ldg(w.fc0_b[r >> 1] + half * d.HN + et);
                 const uint32_t src_col = from_net ? NET_COL : 0;
                 // both groups work on every chunk (group g converts its columns [32g, 32g+32)), so the
                 // first chunk -- which releases the MMAs of this layer -- is ready as early as possible
@@ -813,6 +868,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         if (t + h >= own_chunks) break;
                         tmem_ld_wait();
                         if (t + h + 1 < own_chunks) tmem_ld32(tlane + src_col + (t + h + 1) * 64 + eg * 32, v[(h + 1) & 1]);
+                        // (published to the other epilogue threads by the arrive below -> MMAs -> acc_ready chain)
+                        if (load_b0 && t + h == own_chunks - 1) bias_s[et] = bnext;
                         unsigned char* dst = sm + L.a + (t + h) * CHUNK;
                         const float* bch = bias ? bias + (t + h) * 64 + eg * 32 : nullptr;
 #pragma unroll
@@ -840,13 +897,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                     }
                 }
                 if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
+                if (r == 2 * d.nb - 1) {
+                    // the last round adds the last fc_1 bias: swap it into bias[] once every thread has read fc_0's
+                    const float b1v = et < d.HN ? __ldg(w.fc1_b[d.nb - 1] + half * d.HN + et) : 0.0f;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (et < d.HN) bias_s[et] = b1v;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
             }
             // ---------------- final epilogue: lin_out tile -> global, TSDF head -----------------
             {
                 mbar_wait_park(acc_ready, grp & 1);
                 ++grp;
                 tc_fence_after();
-                const float* bo = bias_s + d.nb * d.HN + d.HN;
+                const float* bo = bias_s + d.HN;
                 const float* hw = bo + d.NOUT;
                 float head = hw[d.d_geo];
                 for (int part = 0; part < (eg == 0 ? d.NOUT / 16 : 0); ++part) {
@@ -981,8 +1045,18 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
         const int rows = d.WN > d.NOUTC ? d.WN : d.NOUTC;
         d.stage_bytes = d.two ? 2 * CHUNK : (rows * 128 + 1023) / 1024 * 1024;
     }
+    d.early = 0;
     d.nstage = MAX_STAGES;
     while (d.nstage >= 2 && smem_layout(d).total + 1024 > 227 * 1024) --d.nstage;
+    if (!d.two && !getenv("GNB_TC_NO_EARLY")) {
+        // early input staging costs KF more chunks of shared memory: take it when the weight ring keeps its depth
+        Dims e = d;
+        e.early = 1;
+        e.AOWN = e.OWN, e.ACH = e.AOWN + e.RS;             // the lin_in operand no longer borrows the own chunk slots
+        e.nstage = MAX_STAGES;
+        while (e.nstage >= 2 && smem_layout(e).total + 1024 > 227 * 1024) --e.nstage;
+        if (e.nstage >= d.nstage || e.nstage >= 4) d = e;
+    }
     if (d.nstage < 2) { set_error("%s: tile does not fit in shared memory", who); return GNB_E_UNSUPPORTED; }
     long long bytes = 0;
     for (int o = 0; o < num_ops(d); ++o) {

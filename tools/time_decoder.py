@@ -8,6 +8,7 @@ VARIANTS = {
     "default": {},
     "two_cta": {"GNB_TC_TWO_CTA": "1"},
     "one_cta": {"GNB_TC_TWO_CTA": "0"},
+    "no_early": {"GNB_TC_NO_EARLY": "1"},   # inputs of a tile staged by the epilogue warps between tiles (no staging warp)
 }
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
@@ -22,14 +23,22 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=dev)
     xyz = S.query_points(n, (96, 96, 48), 0.04, g)[0].to(dev)
     feat = torch.randn(n, 32, generator=g).to(dev)
-    out, tsdf = ops.decode(dw, xyz, feat, "fp16")
+    fused = os.environ.get("TD_FUSED") == "1"       # sample the features from a volume inside the kernel (the bench's path)
+    if fused:
+        vd = (96, 96, 48)
+        vol = torch.randn(1, *vd, 32, generator=g).to(dev).permute(0, 4, 1, 2, 3)
+        xyz = xyz.unsqueeze(0)
+        run = lambda: ops.query_fused(dw, xyz, volume=vol, voxel_size=0.04, origin=torch.zeros(1, 3), want_feat=False)[:2]
+    else:
+        run = lambda: ops.decode(dw, xyz, feat, "fp16")
+    out, tsdf = run()
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ms = []
     for _ in range(7):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); ops.decode(dw, xyz, feat, "fp16"); b.record(); b.synchronize()
+        a.record(); run(); b.record(); b.synchronize()
         ms.append(a.elapsed_time(b))
     m = sorted(ms)[len(ms) // 2]
     flops = 2.0 * (32 * Hd + 5 * (15 * Hd + 2 * Hd * Hd) + Hd * 64 + 32) * n
