@@ -483,12 +483,15 @@ class GenNerf(nn.Module):
                 # reference model.py:131-136: unproject every frame, FPS to num_sparse_points, concatenate
                 if depth is None:
                     raise RuntimeError("gennerf_b200: encode() needs `depth` (or sparse_xyz=) for the triplane branch")
+                # (all B*T clouds in one unprojection launch and one FPS launch -- a cluster of CTAs per cloud; the first
+                # index of every cloud is drawn frame by frame, as the reference's T calls of torch.randint do)
                 B = projection.size(0)
-                parts = []
-                for t in range(T):
-                    pts = get_3d_points(depth[:, t], projection[:, t]).reshape(B, -1, 3)
-                    parts.append(farthest_point_sample(pts, self.cfg.encoder.pointnet.num_sparse_points)[0])
-                sparse_xyz = torch.cat(parts, dim=1)
+                npts = self.cfg.encoder.pointnet.num_sparse_points
+                d = depth[:, :T].reshape(B * T, *depth.shape[-2:])
+                pts = ops.get_3d_points(d, projection.reshape(B * T, 3, 4)).reshape(B * T, -1, 3)
+                N = pts.shape[1]
+                start = torch.stack([torch.randint(0, N, (B,), dtype=torch.long, device=pts.device) for _ in range(T)], dim=1)
+                sparse_xyz = ops.farthest_point_sample(pts, npts, start.reshape(-1))[0].reshape(B, T * npts, 3)
             c_plane_new = self.pointnet(sparse_xyz)
             self.c_plane = c_plane_new if self.c_plane is None else self.merger(c_plane_new, self.c_plane)
 

@@ -356,3 +356,20 @@ def test_get_3d_points_and_fps():
     s_o, c_o = O.farthest_point_sample(dup, 32, torch.tensor([1, 2, 3]))
     s, c = ops().farthest_point_sample(dup.to(DEV), 32, torch.tensor([1, 2, 3]).to(DEV))
     assert torch.equal(c.cpu(), c_o)
+
+
+@pytest.mark.parametrize("N,npoint,B", [(100003, 48, 2), (307200, 24, 1), (16385, 40, 3), (2049, 16, 2)])
+def test_fps_cluster_kernel_bit_identical(N, npoint, B, monkeypatch):
+    """The cluster FPS kernel (2..16 CTAs per cloud, slices in shared memory, candidates exchanged through DSMEM) selects
+    exactly the reference's indices: ragged slices, empty last slices, ties, several clouds per launch."""
+    g = S.gen(63)
+    xyz = torch.rand(B, N, 3, generator=g) * 4
+    xyz[:, N // 2:N // 2 + 50] = xyz[:, :50]                     # exact duplicates -> equal distances (tie rule)
+    start = torch.randint(0, N, (B,), generator=g)
+    s_o, c_o = O.farthest_point_sample(xyz, npoint, start)
+    s, c = ops().farthest_point_sample(xyz.to(DEV), npoint, start.to(DEV))
+    assert torch.equal(c.cpu(), c_o) and torch.equal(s.cpu(), s_o)
+    # the single-CTA kernel (clouds too large for a cluster fall back to it) agrees as well
+    monkeypatch.setenv("GNB_FPS_SINGLE_CTA", "1")
+    s1, c1 = ops().farthest_point_sample(xyz.to(DEV), npoint, start.to(DEV))
+    assert torch.equal(c1.cpu(), c_o) and torch.equal(s1.cpu(), s_o)

@@ -1,0 +1,143 @@
+"""BASELINE config 5: one training step (forward + L1 TSDF loss + backward + Adam) of the drop-in GenNerf on the B200
+path, one scene per GPU, data-parallel over N GPUs with an NCCL all-reduce of the gradients.
+
+Per scene: T = 8 frames of 480x640x32ch feature maps (requires_grad: they stand for the CNN output),
+160x160x64 grid @ 4 cm, triplane branch from the depth maps (unprojection + FPS 512 points per frame + PointNet ->
+3 x 128^2 x 32 planes), 2900 query points per frame, default MLP (d_hidden 512, 5 blocks).
+
+  python tools/bench_train.py [--steps K] [--warmup W]                 # one GPU
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_train.py
+
+Prints one JSON line (rank 0): scenes/s over all ranks, ms per step (max over ranks), the per-phase breakdown of rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gennerf_b200 import synthetic as S  # noqa: E402
+from gennerf_b200.dropin import GenNerf  # noqa: E402
+
+
+class Attr(dict):
+    __getattr__ = dict.get
+
+
+def attr(d):
+    return Attr({k: attr(v) if isinstance(d[k], dict) else v for k, v in d.items()}) if isinstance(d, dict) else d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = S.WORKLOADS["cfg5"]
+    VS, C, Cp = 0.04, 32, 32
+    T, H, W, vd, Q, R = wl["T"], wl["H"], wl["W"], wl["voxel_dim"], wl["Q"], wl["R"]
+    cfg = attr({
+        "voxel_size": VS, "voxel_dim_train": list(vd), "voxel_dim_val": list(vd),
+        "encoder": {"use_spatial": True, "spatial": {"num_layers": 1, "latent_size": C}, "use_pointnet": True, "use_auxiliary": False,
+                    "pointnet": {"num_sparse_points": 512, "c_dim": Cp, "dim": 3, "padding": 0.1, "hidden_dim": 32,
+                                 "scatter_type": "max", "plane_type": ["xz", "xy", "yz"], "plane_resolution": R,
+                                 "n_blocks": 5, "unet": False, "unet_kwargs": None, "sample_mode": "bilinear"},
+                    "plane_merger": {"strategy": "average", "alpha": 0.1}},
+        "mlp": {"d_out_sem": 32, "d_out_geo": 32, "n_blocks": 5, "d_hidden": 512, "combine_layer": 1000,
+                "combine_type": "average", "beta": 0.0, "use_spade": False, "use_layer_norm": False, "alpha": 1.0},
+        "use_code": True, "code": {"num_freqs": 2, "freq_factor": 0.5, "include_input": True},
+    })
+    torch.manual_seed(7)                                        # same initial weights on every rank
+    model = GenNerf(cfg, precision="fp16", fused=True).to(dev).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    g = S.gen(5000 + rank)                                      # a different scene per rank
+    P = S.projections(T, H, W, vd, VS, g).unsqueeze(0)
+    feats = torch.randn(1, T, C, H, W, generator=g).to(dev)
+    depth = S.surface_depth_maps(T, H, W, g, mean=1.5, holes=False).unsqueeze(0).to(dev)
+    xyz = S.query_points(Q, vd, VS, g).to(dev)
+    target = (torch.rand(1, Q, 1, generator=g) * 2 - 1).to(dev)
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)           # noqa: E731
+
+    def step(marks=None):
+        def mark(name):
+            if marks is not None:
+                e = ev()
+                e.record()
+                marks.append((name, e))
+        mark("start")
+        f = feats.detach().requires_grad_(True)
+        model.initialize_volume()
+        model.encode(P, f, depth, "train")
+        mark("encode")
+        out = model(xyz)
+        loss = (out["tsdf"] - target).abs().mean()
+        mark("query")
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        mark("backward")
+        if world > 1:                                           # data-parallel: average the gradients over the scenes
+            o = 0
+            for p_ in params:
+                n = p_.numel()
+                flat[o:o + n].copy_((p_.grad if p_.grad is not None else torch.zeros_like(p_)).reshape(-1))
+                o += n
+            dist.all_reduce(flat)
+            flat.div_(world)
+            o = 0
+            for p_ in params:
+                n = p_.numel()
+                if p_.grad is not None:
+                    p_.grad.copy_(flat[o:o + n].view_as(p_))
+                o += n
+            mark("allreduce")
+        opt.step()
+        mark("adam")
+        return loss, f.grad
+
+    for _ in range(max(args.warmup, 3)):
+        loss, gf = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(args.steps):
+        loss, gf = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    marks = []
+    step(marks)
+    torch.cuda.synchronize()
+    phases = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "training_scenes_per_s", "value": world / (t.item() * 1e-3), "unit": "scenes/s", "n_gpus": world,
+            "steps": args.steps, "ms_per_step": t.item(), "scaling": "weak",
+            "config": {"workload": "BASELINE config 5: fwd + L1 TSDF loss + bwd + Adam, one scene per GPU: 8 frames 480x640x32ch, "
+                                   "160x160x64 grid, FPS 512 pts/frame -> 3x128^2x32 planes, 23200 queries, MLP 512x5",
+                       "parallelism": f"dp{world} (NCCL all-reduce of {flat.numel()} gradient elements)"},
+            "phases_ms_rank0": phases, "loss": float(loss), "grad_feature_norm": float(gf.norm())}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
