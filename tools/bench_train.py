@@ -123,6 +123,13 @@ def main():
     step(marks)
     torch.cuda.synchronize()
     phases = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
+    if os.environ.get("TRAIN_PROFILE") and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70), file=sys.stderr)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.barrier()
