@@ -93,8 +93,9 @@ __global__ void __launch_bounds__(1024) fps_kernel(const float* __restrict__ xyz
 // Cluster version: CS CTAs (a thread-block cluster, up to 16) share one cloud.  CTA r keeps the coordinates of its
 // contiguous slice of the points in shared memory (SoA) and their running distances in registers, so an iteration
 // touches no global memory at all: distance update + local arg-max, one candidate (value, index, xyz) per CTA written
-// into every CTA's shared memory through DSMEM, ONE cluster barrier, then every warp reduces the CS candidates.
-// Candidates are double-buffered by iteration parity (a buffer is rewritten two barriers after it was read).  Same
+// into every CTA's shared memory through DSMEM followed by a remote mbarrier arrive (a hardware cluster barrier per
+// iteration cost ~2.5 us), then warp 0 of every CTA reduces the CS candidates.  Candidates and barriers are
+// double-buffered by iteration parity (a buffer is rewritten only after its reader has arrived for the next iteration).  Same
 // arithmetic and tie rule as above (lowest index among equal maxima, slices ascend with the CTA rank), so the selected
 // indices are bit-identical to the reference's.  307 200 points (480x640) x 512 samples: 30 ms -> ~0.3 ms per cloud,
 // and the clouds of a batch run in parallel (one cluster per GPC).
@@ -113,6 +114,8 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
                                                                      long long* __restrict__ out_idx, float* __restrict__ out_xyz) {
     extern __shared__ float fps_sm[];
     __shared__ FpsCand cand[2][16];
+    __shared__ FpsCand s_res;
+    __shared__ unsigned long long xbar[2];      // mbarriers: CS candidate arrivals per iteration parity
     __shared__ float s_val[32];
     __shared__ int s_idx[32];
     float* sx = fps_sm, *sy = fps_sm + chunk, *sz = fps_sm + 2 * chunk;
@@ -130,7 +133,13 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     for (int j = 0; j < FPS_PPT; ++j) dist[j] = 1e10f;
     int far = (int)start[b];
     float cx = __ldg(p + far * 3LL), cy = __ldg(p + far * 3LL + 1), cz = __ldg(p + far * 3LL + 2);
-    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 2; ++q)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&xbar[q])), "r"(cs) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // every CTA's barriers exist before any peer arrives on them
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     for (int it = 0; it < npoint; ++it) {
         if (rank == 0 && threadIdx.x == 0) {
             out_idx[(long long)b * npoint + it] = far;
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
                 const int oi = __shfl_xor_sync(FULL, besti, o);
                 if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
             }
-            // lane r hands this CTA's candidate to CTA r
+            // lane r hands this CTA's candidate to CTA r and arrives on that CTA's barrier (release: the stores first)
             if (lane < cs) {
                 FpsCand c;
                 c.val = best;
@@ -175,18 +184,26 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
                 const int li = besti == 0x7fffffff ? 0 : besti;
                 c.x = n_local > 0 ? sx[li] : 0.f, c.y = n_local > 0 ? sy[li] : 0.f, c.z = n_local > 0 ? sz[li] : 0.f;
                 const uint32_t local = (uint32_t)__cvta_generic_to_shared(&cand[it & 1][rank]);
-                uint32_t remote;
+                const uint32_t lbar = (uint32_t)__cvta_generic_to_shared(&xbar[it & 1]);
+                uint32_t remote, rbar;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(lane));
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(lbar), "r"(lane));
                 asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(c.val) : "memory");
                 asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + 4), "r"(c.idx) : "memory");
                 asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 8), "f"(c.x) : "memory");
                 asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 12), "f"(c.y) : "memory");
                 asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 16), "f"(c.z) : "memory");
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
             }
-        }
-        // one cluster-wide barrier per iteration (also orders s_val / s_idx reuse inside the CTA)
-        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-        {
+            // wait for the CS candidates of this iteration (this barrier is used every second iteration)
+            {
+                const uint32_t lbar = (uint32_t)__cvta_generic_to_shared(&xbar[it & 1]);
+                const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(lbar), "r"(parity) : "memory");
+            }
             FpsCand c;
             c.val = -2.0f, c.idx = 0x7fffffff, c.x = c.y = c.z = 0.f;
             if (lane < cs) c = cand[it & 1][lane];
@@ -197,9 +214,10 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
                 q.x = __shfl_xor_sync(FULL, c.x, o), q.y = __shfl_xor_sync(FULL, c.y, o), q.z = __shfl_xor_sync(FULL, c.z, o);
                 if (q.val > c.val || (q.val == c.val && q.idx < c.idx)) c = q;
             }
-            far = __shfl_sync(FULL, c.idx, 0);
-            cx = __shfl_sync(FULL, c.x, 0), cy = __shfl_sync(FULL, c.y, 0), cz = __shfl_sync(FULL, c.z, 0);
+            if (lane == 0) s_res = c;
         }
+        __syncthreads();
+        far = s_res.idx, cx = s_res.x, cy = s_res.y, cz = s_res.z;
     }
     // no CTA may exit while a peer can still write into its shared memory
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
