@@ -35,13 +35,21 @@ struct FuseKP {
 };
 static_assert(sizeof(FuseKP) <= 4096, "kernel parameter block must stay below 4 KB");
 
-__device__ __forceinline__ void fuse_project(const float* __restrict__ P, float wx, float wy, float wz, float& fx, float& fy,
-                                             float& cz) {
+// EARLY: reject before the two IEEE divisions when the voxel is behind the camera or the exact quotient lies more than
+// a quarter pixel outside the range that can round to a valid pixel (the rounded quotient is then outside as well)
+template <bool EARLY>
+__device__ __forceinline__ bool fuse_project(const float* __restrict__ P, float wx, float wy, float wz, float& fx, float& fy, float& cz,
+                                             int H = 0, int W = 0) {
     const float cx = __fadd_rn(__fmaf_rn(P[2], wz, __fmaf_rn(P[1], wy, __fmul_rn(P[0], wx))), P[3]);
     const float cy = __fadd_rn(__fmaf_rn(P[6], wz, __fmaf_rn(P[5], wy, __fmul_rn(P[4], wx))), P[7]);
     cz = __fadd_rn(__fmaf_rn(P[10], wz, __fmaf_rn(P[9], wy, __fmul_rn(P[8], wx))), P[11]);
+    if constexpr (EARLY) {
+        if (!(cz > 0.0f)) return false;
+        if (cx < -0.75f * cz || cx > ((float)W - 0.25f) * cz || cy < -0.75f * cz || cy > ((float)H - 0.25f) * cz) return false;
+    }
     fx = rintf(__fdiv_rn(cx, cz));
     fy = rintf(__fdiv_rn(cy, cz));
+    return true;
 }
 
 __global__ void __launch_bounds__(256) fuse_kernel(const __grid_constant__ FuseKP p) {
@@ -63,7 +71,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(const __grid_constant__ FuseK
             const float wy = __fadd_rn(__fmul_rn((float)((c & 2) ? y1 : y0), p.vs), p.oy);
             const float wz = __fadd_rn(__fmul_rn((float)((c & 4) ? z1 : z0), p.vs), p.oz);
             float fx, fy, cz;
-            fuse_project(P, wx, wy, wz, fx, fy, cz);
+            fuse_project<false>(P, wx, wy, wz, fx, fy, cz);
             const bool front = cz > 0.0f;
             behind = behind && !front;
             // one pixel of slack covers the rounding of the per-voxel arithmetic
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(const __grid_constant__ FuseK
     for (int k = 0; k < nk; ++k) {
         const int f = kept[k];
         float fx, fy, cz;
-        fuse_project(p.P[f], wx, wy, wz, fx, fy, cz);
+        if (!fuse_project<true>(p.P[f], wx, wy, wz, fx, fy, cz, p.H, p.W)) continue;
         // float comparisons == the reference's int64 comparisons for every finite value; NaN / inf compare false here
         // and convert to INT64_MIN (invalid) there                                        (tsdf.py:387)
         if (!((fx >= 0.0f) && (fy >= 0.0f) && (fx < (float)p.W) && (fy < (float)p.H) && (cz > 0.0f))) continue;

@@ -46,6 +46,13 @@ __device__ __forceinline__ int project_voxel(const float* __restrict__ P, float 
     float cx = __fadd_rn(__fmaf_rn(P[2], wz, __fmaf_rn(P[1], wy, __fmul_rn(P[0], wx))), P[3]);
     float cy = __fadd_rn(__fmaf_rn(P[6], wz, __fmaf_rn(P[5], wy, __fmul_rn(P[4], wx))), P[7]);
     float cz = __fadd_rn(__fmaf_rn(P[10], wz, __fmaf_rn(P[9], wy, __fmul_rn(P[8], wx))), P[11]);
+    // Cheap rejection before the two IEEE divisions (most projections that survive the brick culling still miss the
+    // image): behind the camera, or the exact quotient is more than a quarter pixel outside the range that can round
+    // to a valid pixel -- the correctly rounded quotient then rounds outside too, so the result is unchanged.
+    if (!fx_out) {
+        if (!(cz > 0.0f)) return -1;
+        if (cx < -0.75f * cz || cx > ((float)W - 0.25f) * cz || cy < -0.75f * cz || cy > ((float)H - 0.25f) * cz) return -1;
+    }
     float fx = rintf(__fdiv_rn(cx, cz));
     float fy = rintf(__fdiv_rn(cy, cz));
     if (fx_out) { *fx_out = fx; *fy_out = fy; }
