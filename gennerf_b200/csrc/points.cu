@@ -223,6 +223,54 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Training-time ray sampler: sample_points_on_rays(), reference src/models/utils.py:458-540 (iSDF).
+// One thread per (camera, ray, sample k): z = depth (k = 0) | linspace(min_dist, depth + delta, N)[k-1] | the k-th
+// gaussian depth (drawn by the caller, utils.py:496-498); camera point ((w-cx)/fx*z, (h-cy)/fy*z, z); world point =
+// pose . [x y z 1] as the FMA chain ATen's bmm computes for K = 4, divided by the homogeneous coordinate.  The
+// reference builds the stratified depths with one torch.linspace call per ray in a Python double loop.
+struct RayKP {
+    const long long* h_idx;    // (B,S)
+    const long long* w_idx;    // (B,S)
+    const float* depth;        // (B,S)
+    const float* intr;         // (B,3,3)
+    const float* pose;         // (B,4,4)
+    const float* gauss;        // (B,S,M)
+    int B, S, N, M;
+    float delta, min_dist;
+    float* xyz;                // (B,S,1+N+M,3)
+    float* z;                  // (B,S,1+N+M)
+};
+__global__ void ray_points_kernel(const RayKP p) {
+    const int K = 1 + p.N + p.M;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)p.B * p.S * K) return;
+    const int k = (int)(i % K);
+    const long long bs = i / K;
+    const int b = (int)(bs / p.S);
+    const float D = p.depth[bs];
+    float zz;
+    if (k == 0) zz = D;
+    else if (k <= p.N) {
+        // torch.linspace(min_dist, D + delta, N): step = (end - start) / (N - 1); symmetric evaluation about the midpoint
+        const float end = __fadd_rn(D, p.delta), start = p.min_dist;
+        const float step = __fdiv_rn(__fsub_rn(end, start), (float)(p.N - 1));
+        const int j = k - 1;
+        zz = j < p.N / 2 ? __fadd_rn(start, __fmul_rn(step, (float)j)) : __fsub_rn(end, __fmul_rn(step, (float)(p.N - 1 - j)));
+    } else zz = p.gauss[bs * p.M + (k - 1 - p.N)];
+    const float* Kc = p.intr + (long long)b * 9;
+    const float wn = __fdiv_rn(__fsub_rn((float)p.w_idx[bs], Kc[2]), Kc[0]);
+    const float hn = __fdiv_rn(__fsub_rn((float)p.h_idx[bs], Kc[5]), Kc[4]);
+    const float x = __fmul_rn(wn, zz), y = __fmul_rn(hn, zz);
+    const float* T = p.pose + (long long)b * 16;
+    float o[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) o[r] = __fadd_rn(__fmaf_rn(T[r * 4 + 2], zz, __fmaf_rn(T[r * 4 + 1], y, __fmul_rn(T[r * 4 + 0], x))), T[r * 4 + 3]);
+    p.xyz[i * 3 + 0] = __fdiv_rn(o[0], o[3]);
+    p.xyz[i * 3 + 1] = __fdiv_rn(o[1], o[3]);
+    p.xyz[i * 3 + 2] = __fdiv_rn(o[2], o[3]);
+    p.z[i] = zz;
+}
+
 // 4x4 inverse of [P; 0 0 0 1] in double precision (Gauss-Jordan with partial pivoting); returns the first 3 rows
 static bool inverse_rows(const float* P12, float* M12) {
     double a[4][8];
@@ -300,6 +348,23 @@ extern "C" int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int
         (void)cudaGetLastError();
     }
     fps_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(xyz, N, npoint, (const long long*)start, scratch, (long long*)out_idx, out_xyz);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_sample_points_on_rays(const int64_t* h_idxs, const int64_t* w_idxs, const float* depths, const float* intrinsics,
+                                         const float* poses, const float* gaussian_depths, int B, int S, int N, int M, float delta,
+                                         float min_dist, float* xyz_world, float* z, void* stream) {
+    GNB_CHECK_ARG(B >= 0 && S >= 0 && N >= 2 && M >= 0, "gnb_sample_points_on_rays: bad shape (N >= 2 stratified samples)");
+    if (B == 0 || S == 0) return 0;
+    GNB_CHECK_ARG(h_idxs && w_idxs && depths && intrinsics && poses && xyz_world && z && (M == 0 || gaussian_depths),
+                  "gnb_sample_points_on_rays: null pointer");
+    RayKP kp;
+    kp.h_idx = (const long long*)h_idxs, kp.w_idx = (const long long*)w_idxs, kp.depth = depths, kp.intr = intrinsics, kp.pose = poses;
+    kp.gauss = gaussian_depths, kp.B = B, kp.S = S, kp.N = N, kp.M = M, kp.delta = delta, kp.min_dist = min_dist;
+    kp.xyz = xyz_world, kp.z = z;
+    const long long n = (long long)B * S * (1 + N + M);
+    ray_points_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(kp);
     GNB_LAUNCH_CHECK();
     return 0;
 }

@@ -120,6 +120,12 @@ def farthest_point_sample(xyz, npoint, start=None):
     return ops.farthest_point_sample(xyz, npoint, start)
 
 
+def sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta, min_dist, sigma):
+    """utils.py:458-540 (iSDF ray sampling of the training step): one launch instead of a Python double loop of
+    torch.linspace calls.  Returns xyz_world (B,S,1+N+M,3), z (B,S,1+N+M)."""
+    return ops.sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta, min_dist, sigma)
+
+
 def normalize_coordinate(p, padding=0.1, plane="xz", encode=True):
     """reference src/models/utils.py:75-98: (B,N,3) -> (B,N,2) in [0, 1-1e-5]."""
     coord, _ = ops.plane_coords(p, padding, 1)

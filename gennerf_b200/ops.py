@@ -625,3 +625,32 @@ def tsdf_fusion_finalize(tsdf_vol, weight_vol, color_vol=None):
                                              color_vol.data_ptr() if color_vol is not None else None, V, out.data_ptr(),
                                              cout.data_ptr() if cout is not None else None, _stream()), "gnb_tsdf_fusion_finalize")
     return out, cout
+
+
+# ------------------------------------------------------------------------------------------
+# training-time ray sampler
+# ------------------------------------------------------------------------------------------
+def sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta, min_dist, sigma, gaussian_depths=None):
+    """sample_points_on_rays (reference utils.py:458-540) in one launch: xyz_world (B,S,1+N+M,3), z (B,S,1+N+M).
+    The M gaussian depths per ray are drawn here exactly as the reference draws them on its device (one
+    torch.normal(D, sigma) call per camera, utils.py:496-498) unless `gaussian_depths` (B,S,M) is given."""
+    _need_cuda(h_idxs, w_idxs, depths, intrinsics, poses, gaussian_depths)
+    dev = depths.device
+    B, S = depths.shape
+    d = _f32(depths).contiguous()
+    if gaussian_depths is None:
+        gaussian_depths = torch.stack([torch.normal(d[b].unsqueeze(-1).expand(S, M), sigma * torch.ones((S, M), device=dev))
+                                       for b in range(B)]) if B > 0 else torch.empty((0, S, M), device=dev)
+    gd = _f32(gaussian_depths).contiguous()
+    K = 1 + int(N) + int(M)
+    xyz = torch.empty((B, S, K, 3), device=dev, dtype=torch.float32)
+    z = torch.empty((B, S, K), device=dev, dtype=torch.float32)
+    h = h_idxs.to(torch.long).contiguous()
+    w = w_idxs.to(torch.long).contiguous()
+    ki = _f32(intrinsics).contiguous()
+    po = _f32(poses).contiguous()
+    with torch.cuda.device(dev):
+        check(lib().gnb_sample_points_on_rays(h.data_ptr(), w.data_ptr(), d.data_ptr(), ki.data_ptr(), po.data_ptr(), gd.data_ptr(),
+                                              B, S, int(N), int(M), float(delta), float(min_dist), xyz.data_ptr(), z.data_ptr(),
+                                              _stream()), "gnb_sample_points_on_rays")
+    return xyz, z

@@ -214,6 +214,19 @@ int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int npoint, co
                               float* scratch, int64_t* out_idx, float* out_xyz, void* stream);
 
 /* -------------------------------------------------------------------------------------
+ * Training-time ray sampler (SURVEY 8f "next" row 4).  Replaces sample_points_on_rays()
+ * (src/models/utils.py:458-540): per camera b and sampled pixel s, 1+N+M depths along the ray
+ * [depth | linspace(min_dist, depth+delta, N) | the M gaussian depths the caller drew with
+ * normal(depth, sigma)], unprojected with intrinsics (B,3,3) and transformed by poses (B,4,4).
+ * h_idxs, w_idxs int64 (B,S); depths (B,S); gaussian_depths (B,S,M);
+ * xyz_world (B,S,1+N+M,3); z (B,S,1+N+M).  Everything on the device.
+ * ----------------------------------------------------------------------------------- */
+int gnb_sample_points_on_rays(const int64_t* h_idxs, const int64_t* w_idxs, const float* depths,
+                              const float* intrinsics, const float* poses, const float* gaussian_depths,
+                              int B, int S, int N, int M, float delta, float min_dist,
+                              float* xyz_world, float* z, void* stream);
+
+/* -------------------------------------------------------------------------------------
  * TSDF fusion of posed depth maps (SURVEY 8f "next" row 3): GT generation and evaluation re-fusion.
  * gnb_tsdf_fusion_integrate replaces TSDFFusion.integrate() (src/data/tsdf.py:369-418) for n_frames frames
  *   at once; frames are applied in order, so the volumes equal n_frames sequential integrate() calls bit

@@ -583,3 +583,39 @@ def tsdf_fusion_explicit(voxel_dim, voxel_size, origin, trunc_ratio, projections
         if label_vol is not None:
             label_vol = torch.where(near, labels[f][iy, ix], label_vol)
     return tsdf, weight, color_vol, label_vol
+
+
+# ----------------------------------------------------------------------------------------
+# f-4  training-time ray sampler                              src/models/utils.py:458-540
+# ----------------------------------------------------------------------------------------
+def sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta, min_dist, gaussian_depths):
+    """CPU restatement of sample_points_on_rays (utils.py:458-540, iSDF ray sampling) with the random draw handed in:
+    `gaussian_depths` (B,S,M) is what the reference draws per camera with torch.normal(D, sigma) (utils.py:496-498).
+
+    Returns xyz_world (B,S,1+N+M,3) and z (B,S,1+N+M) = [surface depth | N stratified depths in
+    [min_dist, D+delta] | M gaussian depths].  The stratified depths use torch.linspace's element formula
+    (start + step*i below the midpoint, end - step*(N-1-i) above; step = (end-start)/(N-1) in fp32): the formula
+    of ATen's CUDA kernel, which the reference runs in training.  ATen's vectorised CPU kernel evaluates the same
+    expression with a different association inside each SIMD chunk and differs from it in the last bit of some
+    elements (by an amount that depends on the host's vector width), so this function is pinned against the real
+    reference to 1e-6 relative, not bit for bit."""
+    B, S = depths.shape
+    D = depths.float()
+    start = torch.tensor(float(min_dist), dtype=torch.float32)
+    end = D + delta                                                      # fp32 tensor + python float (utils.py:493)
+    step = (end - start) / (N - 1)
+    i = torch.arange(N, dtype=torch.float32)
+    lo = start + step.unsqueeze(-1) * i
+    hi = end.unsqueeze(-1) - step.unsqueeze(-1) * (N - 1 - i)
+    strat = torch.where(torch.arange(N) < N // 2, lo, hi)                # (B,S,N)
+    z = torch.cat((D.unsqueeze(-1), strat, gaussian_depths.float()), dim=-1)          # (B,S,1+N+M)
+    w_norm = (w_idxs - intrinsics[:, 0, 2].unsqueeze(-1)) / intrinsics[:, 0, 0].unsqueeze(-1)
+    h_norm = (h_idxs - intrinsics[:, 1, 2].unsqueeze(-1)) / intrinsics[:, 1, 1].unsqueeze(-1)
+    x = w_norm.unsqueeze(-1) * z
+    y = h_norm.unsqueeze(-1) * z
+    P = z.shape[2] * S
+    cam = torch.stack((x.reshape(B, P), y.reshape(B, P), z.reshape(B, P)), dim=-1)
+    hom = torch.cat((cam, torch.ones(B, P, 1)), dim=-1)
+    world = torch.bmm(poses, hom.permute(0, 2, 1)).permute(0, 2, 1)
+    xyz = world[:, :, :3] / world[:, :, 3:]
+    return xyz.reshape(B, S, -1, 3), z

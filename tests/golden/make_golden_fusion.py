@@ -1,4 +1,5 @@
-"""Golden vectors of the TSDF fusion path, generated FROM THE REAL REFERENCE (src/data/tsdf.py TSDFFusion on the CPU).
+"""Golden vectors of the TSDF fusion path and of the training-time ray sampler, generated FROM THE REAL REFERENCE
+(src/data/tsdf.py TSDFFusion, src/models/utils.py sample_points_on_rays, on the CPU).
 
 Run in the build container (where /root/reference is mounted):
     python tests/golden/make_golden_fusion.py
@@ -56,5 +57,31 @@ def main():
     print(f"tsdf_fusion.pt: {os.path.getsize(path) / 1024:.0f} KiB; seen voxels {int(seen.sum())} of {seen.numel()}")
 
 
+
+
+def rays_main():
+    """sample_points_on_rays (src/models/utils.py:458-540) on the CPU reference; the gaussian draw is replayed from the seed."""
+    ref_shim.install()
+    from src.models.utils import sample_points_on_rays
+    g = S.gen(311)
+    B, Sn, N, M, H, W = 3, 100, 20, 8, 240, 320
+    h = torch.randint(0, H, (B, Sn), generator=g)
+    w = torch.randint(0, W, (B, Sn), generator=g)
+    D = torch.rand(B, Sn, generator=g) * 3 + 0.4
+    K = S.intrinsics(H, W).expand(B, 3, 3).contiguous()
+    poses = torch.stack(list(S.camera_poses(B, (96, 96, 48), 0.04, g)))
+    torch.manual_seed(11)
+    xyz, z = sample_points_on_rays(h, w, D, K, poses, N=N, M=M, delta=0.1, min_dist=0.07, sigma=0.1)
+    torch.manual_seed(11)
+    gd = torch.stack([torch.normal(D[b].unsqueeze(-1).expand(Sn, M), 0.1 * torch.ones(Sn, M)) for b in range(B)])
+    assert torch.equal(z[..., 1 + N:], gd)
+    path = os.path.join(HERE, "ray_points.pt")
+    torch.save({"in": {"h_idxs": h.to(torch.int16), "w_idxs": w.to(torch.int16), "depths": D, "intrinsics": K, "poses": poses, "N": N, "M": M,
+                       "delta": 0.1, "min_dist": 0.07, "sigma": 0.1, "gaussian_depths": gd},
+                "out": {"xyz_world": xyz, "z": z}}, path)
+    print(f"ray_points.pt: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     main()
+    rays_main()

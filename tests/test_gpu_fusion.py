@@ -100,3 +100,27 @@ def test_fusion_edge_cases():
         ops.tsdf_fusion_integrate(vd, VS, (0, 0, 0), 0.12, P, torch.ones(2, 24, 32), f.tsdf_vol, f.weight_vol)   # CPU depth
     with pytest.raises(ValueError):
         ops.tsdf_fusion_integrate(vd, VS, (0, 0, 0), 0.12, P, torch.ones(2, 24, 32, device=DEV), f.tsdf_vol[:-1], f.weight_vol)
+
+
+# ---- training-time ray sampler (reference src/models/utils.py:458-540) ------------------------------
+def test_sample_points_on_rays_golden(golden_dir):
+    from gennerf_b200 import ops
+    G = torch.load(os.path.join(golden_dir, "ray_points.pt"), weights_only=False)
+    i, o = G["in"], G["out"]
+    args = [i["h_idxs"].long().to(DEV), i["w_idxs"].long().to(DEV), i["depths"].to(DEV), i["intrinsics"].to(DEV), i["poses"].to(DEV)]
+    xyz, z = ops.sample_points_on_rays(*args, i["N"], i["M"], i["delta"], i["min_dist"], i["sigma"], gaussian_depths=i["gaussian_depths"].to(DEV))
+    assert ((z.cpu() - o["z"]).abs() <= 1e-6 * o["z"].abs().clamp_min(1.0)).all()                       # vs the real reference (CPU linspace)
+    assert ((xyz.cpu() - o["xyz_world"]).abs() <= 1e-6 * o["xyz_world"].abs().clamp_min(1.0)).all()
+    # vs the oracle (same element formula): bit-exact
+    xo, zo = O.sample_points_on_rays(i["h_idxs"].long(), i["w_idxs"].long(), i["depths"], i["intrinsics"], i["poses"], i["N"], i["M"],
+                                     i["delta"], i["min_dist"], i["gaussian_depths"])
+    assert torch.equal(z.cpu(), zo) and torch.equal(xyz.cpu(), xo)
+    # the drop-in signature draws the gaussian depths itself: shapes, surface sample, spread
+    from gennerf_b200.dropin import sample_points_on_rays
+    x2, z2 = sample_points_on_rays(*args, N=i["N"], M=i["M"], delta=i["delta"], min_dist=i["min_dist"], sigma=i["sigma"])
+    assert x2.shape == xyz.shape and torch.equal(z2[..., :1 + i["N"]], z[..., :1 + i["N"]])
+    spread = (z2[..., 1 + i["N"]:] - z2[..., :1]).std().item()
+    assert 0.08 < spread < 0.12
+    # empty batch
+    e = ops.sample_points_on_rays(args[0][:0], args[1][:0], args[2][:0], args[3][:0], args[4][:0], 20, 8, 0.1, 0.07, 0.1)
+    assert e[0].shape == (0, 100, 29, 3)

@@ -108,3 +108,14 @@ def test_tsdf_fusion(golden_dir):
                                i["color"], i["label"].long())
     assert torch.equal(e[0], o["all"]["tsdf_vol"]) and torch.equal(e[1], o["all"]["weight_vol"].float())
     assert torch.equal(e[2], o["all"]["color_vol"]) and torch.equal(e[3], o["all"]["label_vol"].long())
+
+
+def test_sample_points_on_rays(golden_dir):
+    """the oracle's ray sampler against the real reference's output (1e-6: ATen's CPU linspace is
+    vector-width dependent in the last bit, see the oracle's docstring)."""
+    G = load(golden_dir, "ray_points.pt")
+    i, o = G["in"], G["out"]
+    xyz, z = O.sample_points_on_rays(i["h_idxs"].long(), i["w_idxs"].long(), i["depths"], i["intrinsics"], i["poses"], i["N"], i["M"],
+                                     i["delta"], i["min_dist"], i["gaussian_depths"])
+    assert ((z - o["z"]).abs() <= 1e-6 * o["z"].abs().clamp_min(1.0)).all()
+    assert ((xyz - o["xyz_world"]).abs() <= 1e-6 * o["xyz_world"].abs().clamp_min(1.0)).all()

@@ -236,3 +236,28 @@ def test_tsdf_fusion(color, label, trunc_ratio, origin):
     # reset (tsdf.py:359-367)
     r.reset(), o.reset()
     assert torch.equal(r.tsdf_vol, o.tsdf_vol) and torch.equal(r.weight_vol, o.weight_vol)
+
+
+# ---- training-time ray sampler (src/models/utils.py:458-540) --------------------
+@pytest.mark.parametrize("N,M", [(20, 8), (5, 0), (33, 3)])
+def test_sample_points_on_rays(N, M):
+    ref_shim.install()
+    from src.models.utils import sample_points_on_rays as ref_fn
+    g = S.gen(37)
+    B, Sn, H, W = 2, 64, 120, 160
+    h = torch.randint(0, H, (B, Sn), generator=g)
+    w = torch.randint(0, W, (B, Sn), generator=g)
+    D = torch.rand(B, Sn, generator=g) * 3 + 0.4
+    K = S.intrinsics(H, W).expand(B, 3, 3).contiguous()
+    poses = torch.stack(list(S.camera_poses(B, (48, 48, 24), VS, g)))
+    torch.manual_seed(5)
+    xr, zr = ref_fn(h, w, D, K, poses, N=N, M=M, delta=0.1, min_dist=0.07, sigma=0.1)
+    torch.manual_seed(5)                                       # replay the reference's draw (utils.py:496-498)
+    gd = torch.stack([torch.normal(D[b].unsqueeze(-1).expand(Sn, M), 0.1 * torch.ones(Sn, M)) for b in range(B)])
+    xo, zo = O.sample_points_on_rays(h, w, D, K, poses, N, M, 0.1, 0.07, gd)
+    assert xo.shape == xr.shape and zo.shape == zr.shape
+    # surface and gaussian depths are copied: exact; the stratified depths differ from ATen's vectorised CPU linspace
+    # in the last bit of some elements (see the oracle's docstring): 1e-6 relative
+    assert torch.equal(zo[..., 0], zr[..., 0]) and torch.equal(zo[..., 1 + N:], zr[..., 1 + N:])
+    assert ((zo - zr).abs() <= 1e-6 * zr.abs().clamp_min(1.0)).all()
+    assert ((xo - xr).abs() <= 1e-6 * xr.abs().clamp_min(1.0)).all()
