@@ -191,8 +191,7 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout (one JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's version banner / debug lines: not on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     Q = 1 << 20
     wl, P, feats_h, xyz_h, (w, hw, hb) = make_inputs(rank, Q)

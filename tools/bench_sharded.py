@@ -26,6 +26,7 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")        # NCCL's version banner / debug lines: not on stdout
     dist.init_process_group("nccl", device_id=dev)
 VS, C = 0.04, 32
 wl = S.WORKLOADS[args.cfg]

@@ -42,8 +42,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep NCCL's version banner off stdout (one JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's version banner / debug lines: not on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     wl = S.WORKLOADS["cfg5"]
     VS, C, Cp = 0.04, 32, 32
