@@ -77,6 +77,7 @@ class GnbFusionParams(C.Structure):
         ("n_frames", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
         ("h_projection", C.c_void_p), ("depth", C.c_void_p), ("color", C.c_void_p), ("label", C.c_void_p),
         ("tsdf_vol", C.c_void_p), ("weight_vol", C.c_void_p), ("color_vol", C.c_void_p), ("label_vol", C.c_void_p),
+        ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64),
     ]
 
 
@@ -112,6 +113,7 @@ SIGNATURES = {
                                             C.c_void_p, C.c_void_p]),
     "gnb_sample_points_on_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnb_tsdf_fusion_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "gnb_tsdf_fusion_integrate": (C.c_int, [C.POINTER(GnbFusionParams), C.c_void_p]),
     "gnb_tsdf_fusion_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_positional_encoding": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),

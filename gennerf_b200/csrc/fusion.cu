@@ -12,7 +12,13 @@
 //
 // A block owns a 4 x 4 x 16 brick of voxels and first drops the frames that cannot see the brick (all 8 corner
 // voxels behind the camera or beyond the same image border; exact, because voxel centres are convex combinations of
-// the corners and x/z is linear-fractional) -- the same culling as the lift.
+// the corners and x/z is linear-fractional) -- the same culling as the lift.  With a scratch buffer it also culls by
+// DEPTH: a first kernel reduces every 16x16 pixel tile of every depth map to (min, max); per brick and frame the tiles
+// under the brick's pixel bounding box give a depth range, and
+//   * min corner depth - max measured depth >= trunc  ->  every voxel is beyond the truncation band: frame skipped;
+//   * the box has no zero-depth pixel, lies inside the image, and max corner depth - min measured depth <= -trunc
+//       ->  every voxel is free space (clamped distance -1): `if (weight == 0) tsdf = -1` without projecting;
+// both exact (the per-voxel tests could only come out that way; small margins cover the fp32 rounding).
 #include "common.cuh"
 
 namespace gnb {
@@ -32,6 +38,8 @@ struct FuseKP {
     float* weight;           // (V)
     float* color_vol;        // (3,V) or null
     int* label_vol;          // (V) or null
+    const float2* tiles;     // (T, tiles_y, tiles_x) (min, max) of every 16x16 depth tile, or null
+    int tiles_x, tiles_y;
 };
 static_assert(sizeof(FuseKP) <= 4096, "kernel parameter block must stay below 4 KB");
 
@@ -52,6 +60,30 @@ __device__ __forceinline__ bool fuse_project(const float* __restrict__ P, float 
     return true;
 }
 
+constexpr int FUSE_TILE = 16;
+constexpr int F_SKIP = 0, F_FULL = 1, F_FREE = 2;
+
+// (min, max) of every 16x16 tile of every depth map; zero-depth ("no measurement") pixels take part as zeros
+__global__ void __launch_bounds__(256) depth_tiles_kernel(const float* __restrict__ depth, int H, int W, int tiles_x, int tiles_y,
+                                                          float2* __restrict__ tiles) {
+    __shared__ float s_min[8], s_max[8];
+    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, f = blockIdx.y;
+    const int px = tx * FUSE_TILE + (threadIdx.x & 15), py = ty * FUSE_TILE + (threadIdx.x >> 4);
+    float lo = 3.0e38f, hi = -3.0e38f;
+    if (px < W && py < H) lo = hi = depth[((long long)f * H + py) * W + px];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(FULL, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) { lo = fminf(lo, s_min[i]); hi = fmaxf(hi, s_max[i]); }
+        tiles[((long long)f * tiles_y + ty) * tiles_x + tx] = make_float2(lo, hi);
+    }
+}
+
 __global__ void __launch_bounds__(256) fuse_kernel(const __grid_constant__ FuseKP p) {
     __shared__ unsigned char keep[GNB_MAX_FRAMES];
     __shared__ int kept[GNB_MAX_FRAMES];
@@ -60,33 +92,65 @@ __global__ void __launch_bounds__(256) fuse_kernel(const __grid_constant__ FuseK
     const int bz = blockIdx.x % gbz, by = (blockIdx.x / gbz) % gby, bx = blockIdx.x / (gbz * gby);
     const int x0 = bx * FUSE_BX, y0 = by * FUSE_BY, z0 = bz * FUSE_BZ;
 
-    // ---- frame culling: thread f tests frame f against the brick's 8 corner voxels ----
-    if (threadIdx.x < p.T) {
-        const float* P = p.P[threadIdx.x];
+    // ---- frame culling: 8 lanes per frame, one brick corner each (all 256 threads busy for 32 frames) ----
+    {
         const int x1 = min(x0 + FUSE_BX, p.nx) - 1, y1 = min(y0 + FUSE_BY, p.ny) - 1, z1 = min(z0 + FUSE_BZ, p.nz) - 1;
-        bool behind = true, left = true, right = true, above = true, below = true;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        const int lane = threadIdx.x & 31;
+        const unsigned sh = lane & ~7u;
+        for (int base = 0; base < p.T * 8; base += 256) {
+            const int task = base + threadIdx.x;
+            const bool active = task < p.T * 8;                 // whole 8-lane groups are active or not
+            const int t = active ? (task >> 3) : 0, c = task & 7;
+            const float* P = p.P[t];
             const float wx = __fadd_rn(__fmul_rn((float)((c & 1) ? x1 : x0), p.vs), p.ox);
             const float wy = __fadd_rn(__fmul_rn((float)((c & 2) ? y1 : y0), p.vs), p.oy);
             const float wz = __fadd_rn(__fmul_rn((float)((c & 4) ? z1 : z0), p.vs), p.oz);
             float fx, fy, cz;
             fuse_project<false>(P, wx, wy, wz, fx, fy, cz);
             const bool front = cz > 0.0f;
-            behind = behind && !front;
+            auto all8 = [&](bool v) { return ((__ballot_sync(FULL, v) >> sh) & 0xffu) == 0xffu; };
             // one pixel of slack covers the rounding of the per-voxel arithmetic
-            left = left && front && fx < -1.0f;
-            right = right && front && fx > (float)p.W;
-            above = above && front && fy < -1.0f;
-            below = below && front && fy > (float)p.H;
+            const bool behind = all8(!front), left = all8(front && fx < -1.0f), right = all8(front && fx > (float)p.W);
+            const bool above = all8(front && fy < -1.0f), below = all8(front && fy > (float)p.H);
+            const bool all_front = all8(cz > 1e-3f);
+            float cz_min = cz, cz_max = cz, fx_min = fx, fx_max = fx, fy_min = fy, fy_max = fy;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                cz_min = fminf(cz_min, __shfl_xor_sync(FULL, cz_min, o)), cz_max = fmaxf(cz_max, __shfl_xor_sync(FULL, cz_max, o));
+                fx_min = fminf(fx_min, __shfl_xor_sync(FULL, fx_min, o)), fx_max = fmaxf(fx_max, __shfl_xor_sync(FULL, fx_max, o));
+                fy_min = fminf(fy_min, __shfl_xor_sync(FULL, fy_min, o)), fy_max = fmaxf(fy_max, __shfl_xor_sync(FULL, fy_max, o));
+            }
+            if (!active || c != 0) continue;
+            int cls = (behind || left || right || above || below) ? F_SKIP : F_FULL;
+            if (cls == F_FULL && p.tiles && all_front && fx_min > -1.0e6f && fx_max < 1.0e6f && fy_min > -1.0e6f && fy_max < 1.0e6f) {
+                // pixel bounding box of the brick (every voxel centre projects inside the corners' box; +-1 px for rounding),
+                // clipped to the image: voxels that project outside the image are not updated anyway
+                const bool inside = fx_min >= 1.0f && fy_min >= 1.0f && fx_max <= (float)(p.W - 2) && fy_max <= (float)(p.H - 2);
+                const int bx0 = max(0, (int)fx_min - 1), bx1 = min(p.W - 1, (int)fx_max + 1);
+                const int by0 = max(0, (int)fy_min - 1), by1 = min(p.H - 1, (int)fy_max + 1);
+                const int tx0 = bx0 / FUSE_TILE, tx1 = bx1 / FUSE_TILE, ty0 = by0 / FUSE_TILE, ty1 = by1 / FUSE_TILE;
+                if (bx0 <= bx1 && by0 <= by1 && (tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 64) {
+                    float dmin = 3.0e38f, dmax = -3.0e38f;
+                    const float2* tl = p.tiles + (long long)t * p.tiles_y * p.tiles_x;
+                    for (int ty = ty0; ty <= ty1; ++ty)
+                        for (int tx = tx0; tx <= tx1; ++tx) {
+                            const float2 mm = __ldg(tl + ty * p.tiles_x + tx);
+                            dmin = fminf(dmin, mm.x), dmax = fmaxf(dmax, mm.y);
+                        }
+                    const float band = p.trunc * 1.0001f + 1.0e-5f;
+                    if (!(dmax > 0.0f)) cls = F_SKIP;                                  // no measurement under the brick
+                    else if (cz_min - dmax >= band) cls = F_SKIP;                       // dist >= 1 for every voxel (tsdf.py:398)
+                    else if (inside && dmin > 0.0f && cz_max - dmin <= -band) cls = F_FREE;    // dist clamps to -1 for every voxel
+                }
+            }
+            keep[t] = (unsigned char)cls;
         }
-        keep[threadIdx.x] = !(behind || left || right || above || below);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int n = 0;
         for (int f = 0; f < p.T; ++f)
-            if (keep[f]) kept[n++] = f;                  // ascending: the reference's frame order
+            if (keep[f] != F_SKIP) kept[n++] = f | ((int)keep[f] << 8);      // ascending: the reference's frame order
         n_kept = n;
     }
     __syncthreads();
@@ -112,7 +176,13 @@ __global__ void __launch_bounds__(256) fuse_kernel(const __grid_constant__ FuseK
     const long long HW = (long long)p.H * p.W;
 
     for (int k = 0; k < nk; ++k) {
-        const int f = kept[k];
+        const int f = kept[k] & 0xff;
+        if ((kept[k] >> 8) == F_FREE) {
+            // free space for the whole brick: valid pixel, depth > 0, distance clamped to -1 -> only the first-observation
+            // copy of tsdf.py:405 can happen
+            if (weight == 0.0f) { tsdf = -1.0f; touched = true; }
+            continue;
+        }
         float fx, fy, cz;
         if (!fuse_project<true>(p.P[f], wx, wy, wz, fx, fy, cz, p.H, p.W)) continue;
         // float comparisons == the reference's int64 comparisons for every finite value; NaN / inf compare false here
@@ -163,6 +233,10 @@ __global__ void fuse_finalize_kernel(const float* __restrict__ tsdf, const float
 
 using namespace gnb;
 
+extern "C" int64_t gnb_tsdf_fusion_scratch_bytes(int n_frames, int H, int W) {
+    return (int64_t)n_frames * ceil_div(H, FUSE_TILE) * ceil_div(W, FUSE_TILE) * (int64_t)sizeof(float2);
+}
+
 extern "C" int gnb_tsdf_fusion_integrate(const GnbFusionParams* q, void* stream) {
     GNB_CHECK_ARG(q, "gnb_tsdf_fusion_integrate: null parameters");
     GNB_CHECK_ARG(q->nx > 0 && q->ny > 0 && q->nz > 0 && q->voxel_size > 0.0f, "gnb_tsdf_fusion_integrate: bad grid");
@@ -185,6 +259,13 @@ extern "C" int gnb_tsdf_fusion_integrate(const GnbFusionParams* q, void* stream)
     kp.tsdf = q->tsdf_vol, kp.weight = q->weight_vol, kp.color_vol = q->color_vol, kp.label_vol = q->label_vol;
     const long long bricks = (long long)ceil_div(q->nx, FUSE_BX) * ceil_div(q->ny, FUSE_BY) * ceil_div(q->nz, FUSE_BZ);
     GNB_CHECK_ARG(bricks < (1ll << 31), "gnb_tsdf_fusion_integrate: grid too large");
+    kp.tiles = nullptr, kp.tiles_x = ceil_div(q->W, FUSE_TILE), kp.tiles_y = ceil_div(q->H, FUSE_TILE);
+    if (q->scratch && q->scratch_bytes >= gnb_tsdf_fusion_scratch_bytes(q->n_frames, q->H, q->W)) {
+        kp.tiles = (const float2*)q->scratch;
+        depth_tiles_kernel<<<dim3((unsigned)(kp.tiles_x * kp.tiles_y), (unsigned)q->n_frames), 256, 0, (cudaStream_t)stream>>>(
+            q->depth, q->H, q->W, kp.tiles_x, kp.tiles_y, (float2*)q->scratch);
+        GNB_LAUNCH_CHECK();
+    }
     fuse_kernel<<<(unsigned)bricks, 256, 0, (cudaStream_t)stream>>>(kp);
     GNB_LAUNCH_CHECK();
     return 0;

@@ -569,7 +569,7 @@ def farthest_point_sample(xyz, npoint, start=None):
 # TSDF fusion
 # ------------------------------------------------------------------------------------------
 def tsdf_fusion_integrate(voxel_dim, voxel_size, origin, trunc_margin, projections, depths, tsdf_vol, weight_vol,
-                          colors=None, color_vol=None, labels=None, label_vol=None):
+                          colors=None, color_vol=None, labels=None, label_vol=None, depth_culling=True):
     """TSDFFusion.integrate (reference src/data/tsdf.py:369-418) for T frames in one launch per 64 frames.
 
     projections (T,3,4); depths (T,H,W) CUDA fp32; colors (T,3,H,W) fp32 / labels (T,H,W) int32 optional.
@@ -610,6 +610,10 @@ def tsdf_fusion_integrate(voxel_dim, voxel_size, origin, trunc_margin, projectio
             q.tsdf_vol, q.weight_vol = tsdf_vol.data_ptr(), weight_vol.data_ptr()
             q.color_vol = color_vol.data_ptr() if color_vol is not None else None
             q.label_vol = label_vol.data_ptr() if label_vol is not None else None
+            if depth_culling:
+                nbytes = lib().gnb_tsdf_fusion_scratch_bytes(n, H, W)
+                scratch = torch.empty(nbytes, dtype=torch.uint8, device=d.device)
+                q.scratch, q.scratch_bytes = scratch.data_ptr(), nbytes
             check(lib().gnb_tsdf_fusion_integrate(C.byref(q), _stream()), "gnb_tsdf_fusion_integrate")
     return tsdf_vol, weight_vol
 

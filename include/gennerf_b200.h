@@ -251,8 +251,11 @@ typedef struct GnbFusionParams {
     float* weight_vol;             /* (V)                                                   */
     float* color_vol;              /* (3,V) or NULL (iff color == NULL)                     */
     int32_t* label_vol;            /* (V) or NULL (iff label == NULL)                       */
+    void* scratch;                 /* optional, >= gnb_tsdf_fusion_scratch_bytes(): enables  */
+    int64_t scratch_bytes;         /*   the depth-band culling (same results, fewer projections) */
 } GnbFusionParams;
 
+int64_t gnb_tsdf_fusion_scratch_bytes(int n_frames, int H, int W);
 int gnb_tsdf_fusion_integrate(const GnbFusionParams* p, void* stream);
 int gnb_tsdf_fusion_finalize(const float* tsdf_vol, const float* weight_vol, const float* color_vol,
                              int64_t n_voxels, float* tsdf_out, float* color_out, void* stream);

@@ -65,6 +65,11 @@ def test_fusion_vs_oracle(vd, T, H, W, trunc_ratio, color, label, origin):
         assert torch.equal(f.color_vol.cpu(), o.color_vol)
     if label:
         assert torch.equal(f.label_vol.cpu().long(), o.label_vol)
+    # the depth-band culling (16x16 min/max tiles of the depth maps) must not change a single bit
+    from gennerf_b200 import ops
+    t2, w2 = torch.ones_like(f.tsdf_vol), torch.zeros_like(f.weight_vol)
+    ops.tsdf_fusion_integrate(vd, VS, origin, VS * trunc_ratio, P, depths.to(DEV), t2, w2, depth_culling=False)
+    assert torch.equal(t2, f.tsdf_vol) and torch.equal(w2, f.weight_vol)
     to, co, lo = o.get_volumes()
     tf, cf, lf = f.get_volumes()
     assert torch.equal(tf.cpu(), to) and (co is None or torch.equal(cf.cpu(), co)) and (lo is None or torch.equal(lf.cpu(), lo))
