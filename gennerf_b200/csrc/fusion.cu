@@ -63,24 +63,38 @@ __device__ __forceinline__ bool fuse_project(const float* __restrict__ P, float 
 constexpr int FUSE_TILE = 16;
 constexpr int F_SKIP = 0, F_FULL = 1, F_FREE = 2;
 
-// (min, max) of every 16x16 tile of every depth map; zero-depth ("no measurement") pixels take part as zeros
+// (min, max) of every 16x16 tile of every depth map; zero-depth ("no measurement") pixels take part as zeros.
+// A block reduces a 64x16 pixel strip (four tiles): 16 threads x float4 per image row.
 __global__ void __launch_bounds__(256) depth_tiles_kernel(const float* __restrict__ depth, int H, int W, int tiles_x, int tiles_y,
                                                           float2* __restrict__ tiles) {
-    __shared__ float s_min[8], s_max[8];
-    const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, f = blockIdx.y;
-    const int px = tx * FUSE_TILE + (threadIdx.x & 15), py = ty * FUSE_TILE + (threadIdx.x >> 4);
+    __shared__ float s_min[16][4], s_max[16][4];
+    const int strips_x = (tiles_x + 3) / 4;
+    const int sx = blockIdx.x % strips_x, ty = blockIdx.x / strips_x, f = blockIdx.y;
+    const int r = threadIdx.x >> 4, q = threadIdx.x & 15;             // image row inside the tile, float4 inside the strip
+    const int py = ty * FUSE_TILE + r, px = sx * 64 + q * 4;
     float lo = 3.0e38f, hi = -3.0e38f;
-    if (px < W && py < H) lo = hi = depth[((long long)f * H + py) * W + px];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = fminf(lo, __shfl_xor_sync(FULL, lo, o));
-        hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, o));
+    if (py < H) {
+        const float* row = depth + ((long long)f * H + py) * W;
+        if ((W & 3) == 0 && px + 3 < W) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row + px));
+            lo = fminf(fminf(v.x, v.y), fminf(v.z, v.w)), hi = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+        } else {
+            for (int k = 0; k < 4; ++k)
+                if (px + k < W) { const float v = __ldg(row + px + k); lo = fminf(lo, v), hi = fmaxf(hi, v); }
+        }
     }
-    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+    // the 4 threads of one tile in this row
+    lo = fminf(lo, __shfl_xor_sync(FULL, lo, 1)), hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, 1));
+    lo = fminf(lo, __shfl_xor_sync(FULL, lo, 2)), hi = fmaxf(hi, __shfl_xor_sync(FULL, hi, 2));
+    if ((q & 3) == 0) { s_min[r][q >> 2] = lo; s_max[r][q >> 2] = hi; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) { lo = fminf(lo, s_min[i]); hi = fmaxf(hi, s_max[i]); }
-        tiles[((long long)f * tiles_y + ty) * tiles_x + tx] = make_float2(lo, hi);
+    if (threadIdx.x < 4) {
+        const int tx = sx * 4 + threadIdx.x;
+        if (tx < tiles_x) {
+            lo = s_min[0][threadIdx.x], hi = s_max[0][threadIdx.x];
+            for (int i = 1; i < 16; ++i) { lo = fminf(lo, s_min[i][threadIdx.x]); hi = fmaxf(hi, s_max[i][threadIdx.x]); }
+            tiles[((long long)f * tiles_y + ty) * tiles_x + tx] = make_float2(lo, hi);
+        }
     }
 }
 
@@ -262,7 +276,7 @@ extern "C" int gnb_tsdf_fusion_integrate(const GnbFusionParams* q, void* stream)
     kp.tiles = nullptr, kp.tiles_x = ceil_div(q->W, FUSE_TILE), kp.tiles_y = ceil_div(q->H, FUSE_TILE);
     if (q->scratch && q->scratch_bytes >= gnb_tsdf_fusion_scratch_bytes(q->n_frames, q->H, q->W)) {
         kp.tiles = (const float2*)q->scratch;
-        depth_tiles_kernel<<<dim3((unsigned)(kp.tiles_x * kp.tiles_y), (unsigned)q->n_frames), 256, 0, (cudaStream_t)stream>>>(
+        depth_tiles_kernel<<<dim3((unsigned)(((kp.tiles_x + 3) / 4) * kp.tiles_y), (unsigned)q->n_frames), 256, 0, (cudaStream_t)stream>>>(
             q->depth, q->H, q->W, kp.tiles_x, kp.tiles_y, (float2*)q->scratch);
         GNB_LAUNCH_CHECK();
     }
