@@ -92,6 +92,8 @@ SIGNATURES = {
     "gnb_project_indices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, c_float_p, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_sample_features": (C.c_int, [C.POINTER(GnbSampleParams), C.c_void_p]),
+    "gnb_sample_binned_scratch_bytes": (C.c_int64, [C.POINTER(GnbSampleParams)]),
+    "gnb_sample_features_binned": (C.c_int, [C.POINTER(GnbSampleParams), C.c_void_p, C.c_int64, C.c_void_p]),
     "gnb_plane_coords": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_scatter_scratch_bytes": (C.c_int64, [C.c_int, C.c_int64, C.c_int, C.c_int]),
     "gnb_scatter_mean_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,

@@ -195,14 +195,29 @@ def _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding):
     return s, keep, B, Q, Cp, Cv
 
 
-def sample_features(xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1):
+def sample_features(xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1, binned="auto"):
     """GenNerf.map_features (reference model.py:163-204): (B,Q,3) -> (B,Q,C_p + C), plane
-    features first.  `volume` is the accumulated (already normalised == summed) volume."""
+    features first.  `volume` is the accumulated (already normalised == summed) volume.
+
+    binned: "auto" sorts the queries into voxel bricks and gathers from shared-memory tiles
+    (gnb_sample_features_binned, same bits) when there is at least about one query per two voxels
+    and the volume is channels-last; True forces it (raises when it does not apply); False never."""
     s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
     out = torch.empty((B, Q, Cp + Cv), device=xyz.device, dtype=torch.float32)
     s.out, s.out_stride = out.data_ptr(), Cp + Cv
     with torch.cuda.device(out.device):
-        check(lib().gnb_sample_features(C.byref(s), _stream()), "gnb_sample_features")
+        use = False
+        if binned and volume is not None and Q > 0:
+            dense = binned is True or (B * Q >= (1 << 16) and 2 * Q >= volume.shape[2] * volume.shape[3] * volume.shape[4])
+            nbytes = lib().gnb_sample_binned_scratch_bytes(C.byref(s)) if dense else 0
+            if binned is True and nbytes == 0:
+                raise RuntimeError("gennerf_b200: the binned sampler needs a channels-last fp32 volume with C % 4 == 0")
+            use = nbytes > 0
+        if use:
+            scratch = torch.empty(nbytes, device=out.device, dtype=torch.uint8)
+            check(lib().gnb_sample_features_binned(C.byref(s), scratch.data_ptr(), nbytes, _stream()), "gnb_sample_features_binned")
+        else:
+            check(lib().gnb_sample_features(C.byref(s), _stream()), "gnb_sample_features")
     return out
 
 

@@ -135,6 +135,16 @@ typedef struct GnbSampleParams {
 
 int gnb_sample_features(const GnbSampleParams* p, void* stream);
 
+/* Brick-binned variant of gnb_sample_features for MANY random queries per voxel (dense extraction of
+ * trilinear_interpolation() / GenNerf.map_features over ~V or more points): the queries are counting-sorted by the
+ * brick of voxels holding their base cell, each brick's corner voxels are staged in shared memory with bulk copies and
+ * gathered from there.  Same results, bit for bit, as gnb_sample_features.  Needs a channels-last fp32 volume
+ * (vol_stride_c == 1, vol_stride_z == C, C % 4 == 0) and caller-provided scratch:
+ * gnb_sample_binned_scratch_bytes() returns the size for these parameters (out may still be NULL), or 0 when the
+ * binned path does not apply to them -- call gnb_sample_features then. */
+int64_t gnb_sample_binned_scratch_bytes(const GnbSampleParams* p);
+int gnb_sample_features_binned(const GnbSampleParams* p, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* Backward of gnb_sample_features (ATen grid_sampler_{3d,2d}_backward chained through the
  * reference's coordinate normalisations).  grad_out: (B,Q,grad_out_stride) = [planes | volume].
  * grad_volume / grad_planes (HOST array of 3 device pointers) use the forward strides and must be
