@@ -46,70 +46,118 @@ __global__ void plane_coords_kernel(const float* __restrict__ p, long long n, fl
 
 // ---------------------------------------------------------------------------------------
 // Atomic mode.  One warp takes 32 consecutive points of one scene; lane i computes the three
-// cell indices of point i.  The features of the 32 points are then streamed with lanes =
-// channels (coalesced C_p*4-byte rows).  Consecutive points that fall into the same cell are
-// summed in registers first (run-length warp aggregation) and leave as ONE vector of
-// reductions: in the reference's real usage (metric coordinates, SURVEY trap T6) most points
-// clamp into the last row/column, and this removes the hot-address serialisation.
+// cell indices of point i.  The 32 feature rows are loaded ONCE into registers with lanes =
+// channels (coalesced C_p*4-byte rows, all loads in flight together) and serve the three planes.
+// Consecutive points that fall into the same cell are summed in registers first (run-length
+// warp aggregation) and leave as ONE vector of reductions.  In the reference's real usage
+// (metric coordinates, SURVEY trap T6) most points clamp into the last row / column and, above
+// all, into the corner cell (R-1, R-1): that cell has its own register accumulator per warp,
+// is combined across the block in shared memory and reaches global memory once per block.
 // ---------------------------------------------------------------------------------------
-template <int NCH>   // channels per lane = ceil(C_p / 32)
+template <int NCH>   // 32-channel groups = ceil(C_p / 32)
 __global__ void __launch_bounds__(256) scatter_atomic_kernel(const float* __restrict__ p, const float* __restrict__ c,
                                                              int B, long long N, int Cp, int R, float den,
                                                              float* __restrict__ planes, int* __restrict__ count) {
+    __shared__ float s_corner[NCH * 32];
+    __shared__ int s_corner_n;
     const int lane = threadIdx.x & 31;
-    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long warps_per_scene = (N + 31) / 32;
-    if (warp >= warps_per_scene * B) return;
-    const int b = (int)(warp / warps_per_scene);
-    const long long n0 = (warp % warps_per_scene) * 32;
+    const int b = blockIdx.y, k = blockIdx.z;                   // scene, plane (the reductions of a warp are issued one after
+                                                                // the other, so the three planes go to different warps)
+    const long long group = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // 32-point group inside the scene
+    const long long n0 = group * 32;
     const long long RR = (long long)R * R;
-    int cell[3] = {-1, -1, -1};
-    if (n0 + lane < N) {
-        const float* pp = p + ((long long)b * N + n0 + lane) * 3;
-        plane_cells(pp[0], pp[1], pp[2], den, R, cell);
-    }
-    const int npts = (int)min((long long)32, N - n0);
-    const float* __restrict__ cb = c + ((long long)b * N + n0) * Cp;
+    const int corner = (R - 1) + R * (R - 1);
+    for (int i = threadIdx.x; i < NCH * 32; i += blockDim.x) s_corner[i] = 0.0f;
+    if (threadIdx.x == 0) s_corner_n = 0;
+    __syncthreads();
+    float* __restrict__ pl = planes + ((long long)k * B + b) * RR * Cp;
+    int* __restrict__ cn = count + ((long long)k * B + b) * RR;
+    if (n0 < N) {
+        int cellk = -1;
+        if (n0 + lane < N) {
+            const float* pp = p + ((long long)b * N + n0 + lane) * 3;
+            int cell[3];
+            plane_cells(pp[0], pp[1], pp[2], den, R, cell);
+            cellk = k == 0 ? cell[0] : (k == 1 ? cell[1] : cell[2]);
+        }
+        const int npts = (int)min((long long)32, N - n0);
+        const float* __restrict__ cb = c + ((long long)b * N + n0) * Cp;
+#pragma unroll 1
+        for (int h = 0; h < NCH; ++h) {
+            const int ch = h * 32 + lane;
+            const bool has = ch < Cp;
+            float cr[32];                                   // this lane's channel of the 32 points
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float* __restrict__ pl = planes + ((long long)k * B + b) * RR * Cp;
-        int* __restrict__ cn = count + ((long long)k * B + b) * RR;
-        int run_cell = -1, run_n = 0;
-        float acc[NCH];
+            for (int j = 0; j < 32; ++j) cr[j] = (has && j < npts) ? __ldg(cb + (long long)j * Cp + ch) : 0.0f;
+            int run_cell = -1, run_n = 0, corner_n = 0;
+            float acc = 0.0f, corner_acc = 0.0f;
 #pragma unroll
-        for (int h = 0; h < NCH; ++h) acc[h] = 0.0f;
-        for (int j = 0; j <= npts; ++j) {
-            int cj = (j < npts) ? __shfl_sync(FULL, cell[k], j) : -2;
-            if (cj != run_cell) {
-                if (run_cell >= 0) {
-#pragma unroll
-                    for (int h = 0; h < NCH; ++h) {
-                        int ch = h * 32 + lane;
-                        if (ch < Cp) atomicAdd(pl + (long long)run_cell * Cp + ch, acc[h]);
-                        acc[h] = 0.0f;
+            for (int j = 0; j < 32; ++j) {
+                const int cj = __shfl_sync(FULL, cellk, j);
+                if (j < npts) {
+                    if (cj == corner) {
+                        corner_acc += cr[j], ++corner_n;
+                    } else {
+                        if (cj != run_cell) {
+                            if (run_cell >= 0) {
+                                if (has) atomicAdd(pl + (long long)run_cell * Cp + ch, acc);
+                                if (lane == 0 && h == 0) atomicAdd(cn + run_cell, run_n);
+                            }
+                            run_cell = cj, run_n = 0, acc = 0.0f;
+                        }
+                        acc += cr[j], ++run_n;
                     }
-                    if (lane == 0) atomicAdd(cn + run_cell, run_n);
                 }
-                run_cell = cj, run_n = 0;
             }
-            if (j < npts) {
-#pragma unroll
-                for (int h = 0; h < NCH; ++h) {
-                    int ch = h * 32 + lane;
-                    if (ch < Cp) acc[h] += __ldg(cb + (long long)j * Cp + ch);
-                }
-                ++run_n;
+            if (run_cell >= 0) {
+                if (has) atomicAdd(pl + (long long)run_cell * Cp + ch, acc);
+                if (lane == 0 && h == 0) atomicAdd(cn + run_cell, run_n);
+            }
+            if (corner_n) {
+                atomicAdd(&s_corner[h * 32 + lane], corner_acc);
+                if (lane == 0 && h == 0) atomicAdd(&s_corner_n, corner_n);
             }
         }
     }
+    __syncthreads();
+    if (s_corner_n > 0) {
+        for (int ch = threadIdx.x; ch < Cp; ch += blockDim.x) atomicAdd(pl + (long long)corner * Cp + ch, s_corner[ch]);
+        if (threadIdx.x == 0) atomicAdd(cn + corner, s_corner_n);
+    }
 }
 
-// mean = sum / max(count, 1) (torch_scatter.scatter_mean), in place over (3*B*R*R, C_p)
-__global__ void scatter_finalize_kernel(float* __restrict__ planes, const int* __restrict__ count, long long cells, int Cp) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cells * Cp) return;
-    int n = count[i / Cp];
-    if (n > 1) planes[i] = __fdiv_rn(planes[i], (float)n);
+// mean = sum / max(count, 1) (torch_scatter.scatter_mean), in place over (3*B*R*R, C_p).  Cells with at most one point are
+// left alone (not even read).  VEC = 4: one thread per float4 of a cell, lanes_per_cell = C_p / 4.
+template <int VEC>
+__global__ void __launch_bounds__(256) scatter_finalize_kernel(float* __restrict__ planes, const int* __restrict__ count, long long cells,
+                                                               int Cp, int lanes_per_cell, int lg_lanes) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cells * lanes_per_cell) return;
+    const long long cell = lg_lanes >= 0 ? (i >> lg_lanes) : i / lanes_per_cell;
+    const int n = __ldg(count + cell);
+    if (n <= 1) return;
+    const float d = (float)n;
+    if constexpr (VEC == 4) {
+        float4* q = reinterpret_cast<float4*>(planes) + i;
+        float4 v = *q;
+        v.x = __fdiv_rn(v.x, d), v.y = __fdiv_rn(v.y, d), v.z = __fdiv_rn(v.z, d), v.w = __fdiv_rn(v.w, d);
+        *q = v;
+    } else {
+        planes[i] = __fdiv_rn(planes[i], d);
+    }
+}
+
+static int launch_finalize(float* planes, const int* count, long long cells, int Cp, cudaStream_t st) {
+    const bool vec = Cp % 4 == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0;
+    const int lanes = vec ? Cp / 4 : Cp;
+    int lg = 0;
+    while ((1 << lg) < lanes) ++lg;
+    if ((1 << lg) != lanes) lg = -1;
+    const unsigned blocks = (unsigned)((cells * lanes + 255) / 256);
+    if (vec) scatter_finalize_kernel<4><<<blocks, 256, 0, st>>>(planes, count, cells, Cp, lanes, lg);
+    else scatter_finalize_kernel<1><<<blocks, 256, 0, st>>>(planes, count, cells, Cp, lanes, lg);
+    GNB_LAUNCH_CHECK();
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -120,20 +168,19 @@ __global__ void scatter_finalize_kernel(float* __restrict__ planes, const int* _
 constexpr int SORT_TILE = 2048;    // items per block and radix pass (256 threads x 8)
 
 __global__ void det_keys_kernel(const float* __restrict__ p, int B, long long N, int R, float den,
-                                unsigned* __restrict__ keys, unsigned* __restrict__ vals, int* __restrict__ count) {
+                                unsigned* __restrict__ keys, unsigned* __restrict__ vals, unsigned* __restrict__ long_count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *long_count = 0u;
     if (i >= (long long)B * N) return;
     int b = (int)(i / N);
     long long n = i % N;
     int cell[3];
     plane_cells(p[i * 3], p[i * 3 + 1], p[i * 3 + 2], den, R, cell);
-    const long long RR = (long long)R * R;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         long long seg = (long long)k * B + b;
         keys[seg * N + n] = (unsigned)cell[k];
         vals[seg * N + n] = (unsigned)n;
-        atomicAdd(count + seg * RR + cell[k], 1);
     }
 }
 
@@ -232,32 +279,132 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const unsigned* __re
     }
 }
 
-// start[cell] = first sorted position of the cell (per segment)
-__global__ void det_starts_kernel(const unsigned* __restrict__ keys, long long N, long long RR, unsigned* __restrict__ start) {
+// start[cell] = first sorted position of the cell, count[cell] = one past its last (per segment; count is zero-filled before,
+// so it stays 0 for cells without points).  det_reduce turns count into the number of points.  No atomics: the counts are
+// exact by construction.
+__global__ void det_starts_kernel(const unsigned* __restrict__ keys, long long N, long long RR, unsigned* __restrict__ start,
+                                  int* __restrict__ count) {
     const int seg = blockIdx.y;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const unsigned* k = keys + (long long)seg * N;
-    if (i == 0 || k[i - 1] != k[i]) start[(long long)seg * RR + k[i]] = (unsigned)i;
+    const unsigned ki = k[i];
+    if (i == 0 || k[i - 1] != ki) start[(long long)seg * RR + ki] = (unsigned)i;
+    if (i == N - 1 || k[i + 1] != ki) count[(long long)seg * RR + ki] = (int)(i + 1);
 }
+
+constexpr int DET_LONG = 1024;     // cells with at least this many points go to det_reduce_long_kernel
 
 // one warp per cell: sequential fp32 sum over the cell's points in ascending point index
 __global__ void __launch_bounds__(256) det_reduce_kernel(const float* __restrict__ c, const unsigned* __restrict__ vals,
-                                                         const unsigned* __restrict__ start, const int* __restrict__ count,
-                                                         int B, long long N, int Cp, long long RR, float* __restrict__ planes) {
+                                                         const unsigned* __restrict__ start, int* __restrict__ count,
+                                                         int B, long long N, int Cp, long long RR, float* __restrict__ planes,
+                                                         unsigned* __restrict__ long_list, unsigned* __restrict__ long_count) {
     const int lane = threadIdx.x & 31;
     const long long cell_g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // over 3*B*RR
     if (cell_g >= 3LL * B * RR) return;
     const long long seg = cell_g / RR;
     const int b = (int)(seg % B);
-    const int n = count[cell_g];
+    const int end = count[cell_g];
+    const int n = end > 0 ? end - (int)start[cell_g] : 0;
+    __syncwarp();
+    if (lane == 0 && end > 0) count[cell_g] = n;
+    if (n >= DET_LONG) {
+        if (lane == 0) long_list[atomicAdd(long_count, 1u)] = (unsigned)cell_g;
+        return;
+    }
     const unsigned* v = vals + seg * N + (n > 0 ? start[cell_g] : 0u);
     const float* __restrict__ cb = c + (long long)b * N * Cp;
     for (int ch = lane; ch < Cp; ch += 32) {
         float acc = 0.0f;
-        for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, __ldg(cb + (long long)v[i] * Cp + ch));
+        int i = 0;
+        for (; i + 8 <= n; i += 8) {                        // 8 gathers in flight, added in ascending point order
+            float r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] = __ldg(cb + (long long)__ldg(v + i + u) * Cp + ch);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = __fadd_rn(acc, r[u]);
+        }
+        for (; i < n; ++i) acc = __fadd_rn(acc, __ldg(cb + (long long)v[i] * Cp + ch));
         if (n > 1) acc = __fdiv_rn(acc, (float)n);
         planes[cell_g * Cp + ch] = acc;
+    }
+}
+
+// Cells with very many points (the clamped border cells of SURVEY trap T6): the sum stays ONE sequential fp32 chain per
+// channel (that is what makes it bit-identical to the CPU scatter_add_), but the gathers are taken off the chain: all 8
+// warps of a block stage the next batch of feature rows in shared memory (double buffered) while warp 0 adds the current one.
+constexpr int DET_LONG_SMEM = 64 * 1024;           // bytes per batch buffer
+template <int NH>   // 32-channel groups = ceil(C_p / 32)
+__global__ void __launch_bounds__(256) det_reduce_long_kernel(const float* __restrict__ c, const unsigned* __restrict__ vals,
+                                                              const unsigned* __restrict__ start, const int* __restrict__ count,
+                                                              int B, long long N, int Cp, long long RR, float* __restrict__ planes,
+                                                              const unsigned* __restrict__ long_list, const unsigned* __restrict__ long_count) {
+    extern __shared__ __align__(16) float s_rows[];             // [2][rows_per_batch][Cp]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows = DET_LONG_SMEM / (Cp * 4);
+    const unsigned n_long = *long_count;
+    for (unsigned e = blockIdx.x; e < n_long; e += gridDim.x) {
+        const long long cell_g = long_list[e];
+        const long long seg = cell_g / RR;
+        const int b = (int)(seg % B), n = count[cell_g];
+        const unsigned* v = vals + seg * N + start[cell_g];
+        const float* __restrict__ cb = c + (long long)b * N * Cp;
+        const int batches = (n + rows - 1) / rows;
+        float acc[NH];                                         // warp 0: channel lane + 32*h
+#pragma unroll
+        for (int h = 0; h < NH; ++h) acc[h] = 0.0f;
+        auto stage = [&](int bt, int tid, int nthr) {                             // every thread: 8 gathers in flight, coalesced along the channels
+            float* dst = s_rows + (size_t)(bt & 1) * rows * Cp;
+            const int r0 = bt * rows, nr = min(rows, n - r0);
+            if ((Cp & 3) == 0) {
+                const int c4 = Cp >> 2, total = nr * c4;
+                for (int base = 0; base < total; base += 8 * nthr) {
+                    float4 t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int idx = base + u * nthr + tid;
+                        if (idx < total) {
+                            const int r = idx / c4, q = idx - r * c4;
+                            t[u] = ldg4(cb + (long long)__ldg(v + r0 + r) * Cp + q * 4);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int idx = base + u * nthr + tid;
+                        if (idx < total) reinterpret_cast<float4*>(dst)[idx] = t[u];
+                    }
+                }
+            } else {
+                for (int idx = tid; idx < nr * Cp; idx += nthr) {
+                    const int r = idx / Cp, ch = idx - r * Cp;
+                    dst[idx] = __ldg(cb + (long long)__ldg(v + r0 + r) * Cp + ch);
+                }
+            }
+        };
+        stage(0, threadIdx.x, blockDim.x);
+        __syncthreads();
+        for (int bt = 0; bt < batches; ++bt) {
+            if (warp != 0) {
+                if (bt + 1 < batches) stage(bt + 1, threadIdx.x - 32, blockDim.x - 32);      // warp 0 is adding
+            } else {
+                const float* src = s_rows + (size_t)(bt & 1) * rows * Cp;
+                const int nr = min(rows, n - bt * rows);
+#pragma unroll 8
+                for (int r = 0; r < nr; ++r) {
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+                        if (NH == 1 || h * 32 + lane < Cp) acc[h] = __fadd_rn(acc[h], src[r * Cp + h * 32 + (NH == 1 ? min(lane, Cp - 1) : lane)]);
+                }
+            }
+            __syncthreads();
+        }
+        if (warp == 0) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h)
+                if (h * 32 + lane < Cp) planes[cell_g * Cp + h * 32 + lane] = __fdiv_rn(acc[h], (float)n);
+        }
+        __syncthreads();
     }
 }
 
@@ -381,7 +528,7 @@ static int radix_bits(long long RR) {
 }
 
 struct DetScratch {
-    unsigned *keys[2], *vals[2], *hist, *start;
+    unsigned *keys[2], *vals[2], *hist, *start, *long_list, *long_count;
     long long bytes;
 };
 
@@ -395,6 +542,8 @@ static DetScratch det_layout(void* base, int B, long long N, int R) {
     s.vals[0] = take(items), s.vals[1] = take(items);
     s.hist = take(segs * 256 * (tiles > 0 ? tiles : 1));
     s.start = take(segs * RR);
+    s.long_list = take(items / DET_LONG + 1);
+    s.long_count = take(1);
     s.bytes = q - (char*)base;
     return s;
 }
@@ -431,16 +580,15 @@ extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, in
         GNB_CHECK_ARG(Cp <= 256, "gnb_scatter_mean_planes: C_p %d > 256 not supported", Cp);
         GNB_CUDA(cudaMemsetAsync(planes, 0, cells * Cp * sizeof(float), st));
         if (N > 0) {
-            long long warps = (N + 31) / 32 * B;
-            unsigned blocks = (unsigned)((warps + 7) / 8);
+            const dim3 blocks((unsigned)(((N + 31) / 32 + 7) / 8), (unsigned)B, 3);       // 8 groups of 32 points per block; grid rows = scenes, layers = planes
             if (Cp <= 32) scatter_atomic_kernel<1><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
             else if (Cp <= 64) scatter_atomic_kernel<2><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
             else if (Cp <= 128) scatter_atomic_kernel<4><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
             else scatter_atomic_kernel<8><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
             GNB_LAUNCH_CHECK();
             if (mode == GNB_SCATTER_ATOMIC) {
-                scatter_finalize_kernel<<<ceil_div(cells * Cp, 256), 256, 0, st>>>(planes, count, cells, Cp);
-                GNB_LAUNCH_CHECK();
+                int rc = launch_finalize(planes, count, cells, Cp, st);
+                if (rc) return rc;
             }
         }
         return 0;
@@ -452,7 +600,7 @@ extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, in
     const int segs = 3 * B;
     int cur = 0;
     if (N > 0) {
-        det_keys_kernel<<<ceil_div((long long)B * N, 256), 256, 0, st>>>(p, B, N, R, den, s.keys[0], s.vals[0], count);
+        det_keys_kernel<<<ceil_div((long long)B * N, 256), 256, 0, st>>>(p, B, N, R, den, s.keys[0], s.vals[0], s.long_count);
         GNB_LAUNCH_CHECK();
         const int tiles = (int)((N + SORT_TILE - 1) / SORT_TILE);
         const int bits = radix_bits(RR);
@@ -466,20 +614,36 @@ extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, in
             GNB_LAUNCH_CHECK();
             cur ^= 1;
         }
-        det_starts_kernel<<<dim3(ceil_div(N, 256), segs), 256, 0, st>>>(s.keys[cur], N, RR, s.start);
+        det_starts_kernel<<<dim3(ceil_div(N, 256), segs), 256, 0, st>>>(s.keys[cur], N, RR, s.start, count);
         GNB_LAUNCH_CHECK();
     }
-    det_reduce_kernel<<<ceil_div(cells, 8), 256, 0, st>>>(c, s.vals[cur], s.start, count, B, N, Cp, RR, planes);
+    if (N == 0) GNB_CUDA(cudaMemsetAsync(s.long_count, 0, 4, st));
+    det_reduce_kernel<<<ceil_div(cells, 8), 256, 0, st>>>(c, s.vals[cur], s.start, count, B, N, Cp, RR, planes, s.long_list, s.long_count);
     GNB_LAUNCH_CHECK();
+    if (N >= DET_LONG) {
+        GNB_CHECK_ARG(Cp <= 256, "gnb_scatter_mean_planes: C_p %d > 256 not supported", Cp);
+        const long long cap = (long long)segs * N / DET_LONG + 1;
+        const unsigned grid = (unsigned)(cap < 296 ? cap : 296);
+#define GNB_DET_LONG(NH)                                                                                                               \
+    do {                                                                                                                               \
+        GNB_CUDA(cudaFuncSetAttribute(det_reduce_long_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * DET_LONG_SMEM));    \
+        det_reduce_long_kernel<NH><<<grid, 256, 2 * DET_LONG_SMEM, st>>>(c, s.vals[cur], s.start, count, B, N, Cp, RR, planes,         \
+                                                                         s.long_list, s.long_count);                                   \
+    } while (0)
+        if (Cp <= 32) GNB_DET_LONG(1);
+        else if (Cp <= 64) GNB_DET_LONG(2);
+        else if (Cp <= 128) GNB_DET_LONG(4);
+        else GNB_DET_LONG(8);
+#undef GNB_DET_LONG
+        GNB_LAUNCH_CHECK();
+    }
     return 0;
 }
 
 extern "C" int gnb_scatter_finalize(float* planes, const int32_t* count, int64_t n_cells, int Cp, void* stream) {
     GNB_CHECK_ARG(planes && count && n_cells >= 0 && Cp >= 1, "gnb_scatter_finalize: bad arguments");
     if (n_cells == 0) return 0;
-    scatter_finalize_kernel<<<ceil_div(n_cells * Cp, 256), 256, 0, (cudaStream_t)stream>>>(planes, count, n_cells, Cp);
-    GNB_LAUNCH_CHECK();
-    return 0;
+    return launch_finalize(planes, count, n_cells, Cp, (cudaStream_t)stream);
 }
 
 extern "C" int64_t gnb_pool_scratch_bytes(int B, int64_t N, int Hd, int R) {
