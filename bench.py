@@ -180,6 +180,46 @@ def config_dict(Q):
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
+def side_kernels(ops, S, dev, vol, xyz, flush, pk):
+    """The other HBM-bound kernels of the path, timed alone on rank 0 after the timed step (not part of `value`):
+    the gather-only sampler on the step's own volume and queries, and BASELINE config 3's triplane scatter
+    (3 x 256^2 planes, C_p = 32; 4 096 reference-faithful points and all 614 400 pixels of 8 frames).
+    Algorithmic bytes as SURVEY 8d.  CUDA-graph replays, L2 flushed between replays, median of 10."""
+    def timed(fn):
+        fn()
+        g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(g, stream=st):
+                fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(10):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record(); b.synchronize()
+            ms.append(a.elapsed_time(b))
+        return sorted(ms)[len(ms) // 2]
+
+    def roof(byt, ms):
+        gbs = byt / (ms * 1e-3) / 1e9
+        return {"ms": ms, "algorithmic_bytes": byt, "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}}
+
+    out = {}
+    Q, C = xyz.shape[1], vol.shape[1]
+    byt = Q * (12 + 4 * C) + min(vol.numel() * 4, 8 * Q * C * 4)
+    for name, binned in (("sampler_binned", True), ("sampler_staged", False)):
+        out[name] = roof(byt, timed(lambda: ops.sample_features(xyz, volume=vol, voxel_size=VS, binned=binned)))
+        out[name]["queries"] = Q
+    g = S.gen(1003)
+    R, Cp = 256, 32
+    for N in (4096, 614400):
+        p = S.plane_points(N, g, "unit").to(dev)
+        c = torch.randn(1, N, Cp, generator=g).to(dev)
+        byt = N * (12 + 4 * Cp) + 3 * R * R * (4 * Cp + 4)
+        out[f"scatter_mean_planes_N{N}"] = roof(byt, timed(lambda: ops.scatter_mean_planes(p, c, R, 0.1, "atomic")))
+    return out
+
+
 def run_native(args):
     import torch.distributed as dist
     from gennerf_b200 import ops
@@ -394,6 +434,11 @@ def run_native(args):
             "clocks": clocks.summary(),
             "wall_s_timed_region": t_wall,
         }
+        try:
+            from gennerf_b200 import synthetic as S
+            line["hbm_kernels"] = side_kernels(ops, S, dev, vol_l, xyz, flush, pk)
+        except Exception as e:                              # a side measurement must not take the bench line down
+            line["hbm_kernels"] = {"error": repr(e)}
         if not args.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
             sample_q = 20000
