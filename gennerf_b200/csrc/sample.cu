@@ -212,9 +212,14 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (bc[k].w[j] == 0.0f) continue;
+                        if (s.psc == 1 && (c + 3 < s.Cp) && ((reinterpret_cast<uintptr_t>(gb + bc[k].off[j]) & 15) == 0)) {
+                            atomicAdd(reinterpret_cast<float4*>(gb + bc[k].off[j]),        // one 16-byte reduction
+                                      make_float4(bc[k].w[j] * g4[0], bc[k].w[j] * g4[1], bc[k].w[j] * g4[2], bc[k].w[j] * g4[3]));
+                        } else {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (c + e < s.Cp) atomicAdd(gb + bc[k].off[j] + e * s.psc, bc[k].w[j] * g4[e]);
+                            for (int e = 0; e < 4; ++e)
+                                if (c + e < s.Cp) atomicAdd(gb + bc[k].off[j] + e * s.psc, bc[k].w[j] * g4[e]);
+                        }
                     }
                 }
                 if (p.gxyz) {
