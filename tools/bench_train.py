@@ -35,7 +35,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--matmul-precision", default="high", choices=["highest", "high"],
+                    help="torch.set_float32_matmul_precision for the PyTorch part (the MLP's dgrad/wgrad): 'high' (TF32) is what "
+                         "the reference's training sets (src/utils/utils.py:48); 'highest' = fp32 SIMT GEMMs")
     args = ap.parse_args()
+    torch.set_float32_matmul_precision(args.matmul_precision)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -141,7 +145,8 @@ def main():
             "steps": args.steps, "ms_per_step": t.item(), "scaling": "weak",
             "config": {"workload": "BASELINE config 5: fwd + L1 TSDF loss + bwd + Adam, one scene per GPU: 8 frames 480x640x32ch, "
                                    "160x160x64 grid, FPS 512 pts/frame -> 3x128^2x32 planes, 23200 queries, MLP 512x5",
-                       "parallelism": f"dp{world} (NCCL all-reduce of {flat.numel()} gradient elements)"},
+                       "parallelism": f"dp{world} (NCCL all-reduce of {flat.numel()} gradient elements)",
+                       "float32_matmul_precision": args.matmul_precision},
             "phases_ms_rank0": phases, "loss": float(loss), "grad_feature_norm": float(gf.norm())}))
     if world > 1:
         dist.destroy_process_group()
