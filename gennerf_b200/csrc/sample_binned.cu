@@ -169,7 +169,8 @@ __device__ __forceinline__ Unit decode_unit(const BinKP& p, int brick, int part)
 }
 
 // Volume part of up to 32 staged queries (tab): G lanes per query, NV float4s of channels per lane.
-// TILE: corners come from the shared-memory tile (LDS.128), else from global memory.
+// TILE: corners come from the shared-memory tile (LDS.128) with the tile's constant corner steps (dx, dy, dz; the halo is
+// replicated, so no border cases); else from global memory with the per-query steps of the table (0 at the border).
 template <int NV, bool TILE>
 __device__ __forceinline__ void gather_volume(const SampleKP& s, const float* __restrict__ src, const float* __restrict__ tab, int nq, int lane,
                                               int lgG, int dx, int dy, int dz) {
@@ -182,7 +183,7 @@ __device__ __forceinline__ void gather_volume(const SampleKP& s, const float* __
         const float* e = tab + ql * BIN_TAB;
         const int4 hd = *reinterpret_cast<const int4*>(e);                   // base, x / y / z step (0 at the border)
         const float4 wa = *reinterpret_cast<const float4*>(e + 4), wb = *reinterpret_cast<const float4*>(e + 8);
-        const int ox = hd.y, oy = hd.z, oz = hd.w;
+        const int ox = TILE ? dx : hd.y, oy = TILE ? dy : hd.z, oz = TILE ? dz : hd.w;
         const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
         float* out = s.out + *reinterpret_cast<const long long*>(e + 12);
         const float* base = src + hd.x;
@@ -211,6 +212,36 @@ __device__ __forceinline__ void gather_volume(const SampleKP& s, const float* __
                 }
             }
         }
+    }
+}
+
+// The tile path at C = 32 (9 x 9 x 9 voxels of 128 B): 4 lanes per query, two float4 each, every corner step a compile-time
+// immediate of the LDS.128.
+constexpr int T32_Z = 32, T32_Y = 9 * 32, T32_X = 81 * 32;
+__device__ __forceinline__ void gather_tile_c32(const SampleKP& s, const float* __restrict__ tile, const float* __restrict__ tab, int nq, int lane) {
+    const int sub = lane & 3, grp = lane >> 2;
+    const int fa = (sub + ((grp & 1) ? 4 : 0)) * 4, fb = fa ^ 16;       // odd queries start with the other half row (bank halves)
+#pragma unroll 1
+    for (int vit = 0; vit < 4; ++vit) {
+        const int ql = vit * 8 + grp;
+        if (ql >= nq) continue;
+        const float* e = tab + ql * BIN_TAB;
+        const int base = *reinterpret_cast<const int*>(e);
+        const float4 wa = *reinterpret_cast<const float4*>(e + 4), wb = *reinterpret_cast<const float4*>(e + 8);
+        const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        float* out = s.out + *reinterpret_cast<const long long*>(e + 12);
+        const float* pa = tile + base + fa;
+        const float* pb = tile + base + fb;
+        float4 va[8], vb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            constexpr int dummy = 0;
+            const int o = ((k & 1) ? T32_X : dummy) + ((k & 2) ? T32_Y : dummy) + ((k & 4) ? T32_Z : dummy);
+            va[k] = *reinterpret_cast<const float4*>(pa + o);
+            vb[k] = *reinterpret_cast<const float4*>(pb + o);
+        }
+        *reinterpret_cast<float4*>(out + fa) = corners8(va, w);
+        *reinterpret_cast<float4*>(out + fb) = corners8(vb, w);
     }
 }
 
@@ -255,15 +286,22 @@ __global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(
                 if (lane == 0) bar_arrive(full);
                 continue;
             }
+            // the tile always holds (bx+1) x (by+1) x (bz+1) corner voxels: where the grid ends inside it, the last voxel of
+            // the axis is replicated, which is exactly the clamped corner (weight 0) the reference-order sum reads there
             const int tx = min(p.bx + 1, s.nx - un.x0), ty = min(p.by + 1, s.ny - un.y0), tz = min(p.bz + 1, s.nz - un.z0);
-            const uint32_t row_bytes = (uint32_t)(tz * s.C * 4);
-            if (lane == 0) bar_expect_tx(full, row_bytes * (uint32_t)(tx * ty));
+            const int txr = min(p.bx + 1, tx + 1), tyr = min(p.by + 1, ty + 1);
+            const bool zrep = tz < p.bz + 1;
+            const uint32_t row_bytes = (uint32_t)(tz * s.C * 4), vox_bytes = (uint32_t)(s.C * 4);
+            if (lane == 0) bar_expect_tx(full, (row_bytes + (zrep ? vox_bytes : 0u)) * (uint32_t)(txr * tyr));
             __syncwarp();
             float* tile = reinterpret_cast<float*>(smem_raw + st * BIN_TILE_BYTES);
             const float* src = s.volume + (long long)un.b * s.vsb + un.x0 * s.vsx + un.y0 * s.vsy + un.z0 * s.vsz;
-            for (int r = lane; r < tx * ty; r += 32) {
-                const int xi = r / ty, yi = r - xi * ty;
-                bulk_g2s(smem_u32(tile + xi * p.lsx + yi * p.lsy), src + xi * s.vsx + yi * s.vsy, row_bytes, full);
+            for (int r = lane; r < txr * tyr; r += 32) {
+                const int xi = r / tyr, yi = r - xi * tyr;
+                const float* row = src + min(xi, tx - 1) * s.vsx + min(yi, ty - 1) * s.vsy;
+                float* dst = tile + xi * p.lsx + yi * p.lsy;
+                bulk_g2s(smem_u32(dst), row, row_bytes, full);
+                if (zrep) bulk_g2s(smem_u32(dst + tz * s.C), row + (tz - 1) * s.vsz, vox_bytes, full);
             }
         }
         return;
@@ -354,8 +392,12 @@ __global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(
                 for (int k = 0; k < 8; ++k) e[4 + k] = tc.w[k];
             }
             __syncwarp();
-            if (use_tile) gather_volume<NV, true>(s, tile, tab, nq, lane, lgGv, dx, dy, dz);
-            else gather_volume<NV, false>(s, vol, tab, nq, lane, lgGv, dx, dy, dz);
+            if (use_tile) {
+                if (NV == 2 && s.C == 32 && dx == T32_X && dy == T32_Y) gather_tile_c32(s, tile, tab, nq, lane);
+                else gather_volume<NV, true>(s, tile, tab, nq, lane, lgGv, dx, dy, dz);
+            } else {
+                gather_volume<NV, false>(s, vol, tab, nq, lane, lgGv, dx, dy, dz);
+            }
             __syncwarp();
         }
         __syncwarp();
