@@ -99,9 +99,6 @@ SIGNATURES = {
     "gnb_scatter_mean_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gnb_scatter_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
-    "gnb_scatter_tiled_scratch_bytes": (C.c_int64, [C.c_int, C.c_int64, C.c_int, C.c_int]),
-    "gnb_scatter_mean_planes_tiled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double,
-                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gnb_backproject_frames_bwd": (C.c_int, [C.POINTER(GnbLiftParams), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "gnb_sample_features_bwd": (C.c_int, [C.POINTER(GnbSampleParams), C.c_void_p, C.c_int64, C.c_void_p,
                                           C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),

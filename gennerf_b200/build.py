@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgennerf_b200.so")
-SOURCES = ["error.cu", "lift.cu", "sample.cu", "sample_binned.cu", "planes.cu", "planes_tiled.cu", "points.cu", "fusion.cu", "decoder_simt.cu", "decoder_tc.cu"]
+SOURCES = ["error.cu", "lift.cu", "sample.cu", "sample_binned.cu", "planes.cu", "points.cu", "fusion.cu", "decoder_simt.cu", "decoder_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

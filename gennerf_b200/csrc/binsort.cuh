@@ -1,5 +1,5 @@
-// Pieces of the block-histogram counting sort shared by the brick-binned sampler (sample_binned.cu) and the tiled
-// triplane scatter (planes_tiled.cu): every block of a count kernel leaves its histogram in hmat[bin][block]; the kernels
+// Pieces of the block-histogram counting sort of the brick-binned sampler (sample_binned.cu; also used by the tiled
+// triplane scatter experiment, tools/experiments/planes_tiled_scatter.cu.txt): every block of a count kernel leaves its histogram in hmat[bin][block]; the kernels
 // below turn that into per-block write offsets, bin sizes / starts and the list of work units -- without a single atomic,
 // so the sorted order is the same in every run.
 #pragma once

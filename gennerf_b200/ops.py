@@ -242,10 +242,8 @@ def scatter_mean_planes(p, c, reso, padding=0.1, mode="atomic"):
     """LocalPoolPointnet.generate_plane_features for xz, xy, yz at once (reference
     pointnet.py:72-89, without the U-Net).  p (B,N,3), c (B,N,C_p) ->
     planes (3,B,C_p,R,R) logical (channels-last storage), count (3,B,R,R) int32.
-    mode 'atomic' (global reductions, the default and currently the fastest at every measured size), 'tiled'
-    (experimental: points sorted by plane tile, every cell summed by the warp that owns it, no global floating-point
-    atomics, no zero-fill / finalize pass), 'auto' (= atomic for now), 'deterministic' (bit-identical to the CPU scatter
-    order), 'sum' (atomic, sums left undivided for an all-reduce)."""
+    mode 'atomic' (16-byte vector reductions; fast), 'auto' (= atomic), 'deterministic' (bit-identical to the CPU
+    scatter order), 'sum' (atomic, sums left undivided for an all-reduce)."""
     _need_cuda(p, c)
     p, c = _f32(p).contiguous(), _f32(c).contiguous()
     B, N, _ = p.shape
@@ -254,18 +252,7 @@ def scatter_mean_planes(p, c, reso, padding=0.1, mode="atomic"):
     store = torch.empty((3, B, R, R, Cp), device=p.device, dtype=torch.float32)
     count = torch.empty((3, B, R, R), device=p.device, dtype=torch.int32)
     if mode == "auto":
-        mode = "atomic"            # the tiled path does not beat it yet (tools/scatter_bench.py)
-    if mode == "tiled":
-        nbytes = lib().gnb_scatter_tiled_scratch_bytes(B, N, Cp, R) if N > 0 else 0
-        if nbytes == 0:
-            mode = "atomic"                                # empty input or a shape the tiled path does not take
-        else:
-            scratch = torch.empty(nbytes, device=p.device, dtype=torch.uint8)
-            with torch.cuda.device(p.device):
-                check(lib().gnb_scatter_mean_planes_tiled(p.data_ptr(), c.data_ptr(), B, N, Cp, R, float(padding), store.data_ptr(),
-                                                          count.data_ptr(), scratch.data_ptr(), nbytes, _stream()),
-                      "gnb_scatter_mean_planes_tiled")
-            return store.permute(0, 1, 4, 2, 3), count
+        mode = "atomic"
     m = {"atomic": _lib.SCATTER_ATOMIC, "deterministic": _lib.SCATTER_DETERMINISTIC, "sum": _lib.SCATTER_ATOMIC_SUM}[mode]
     nbytes = lib().gnb_scatter_scratch_bytes(B, N, R, m)
     scratch = torch.empty(max(nbytes, 1), device=p.device, dtype=torch.uint8)

@@ -185,16 +185,6 @@ int gnb_scatter_mean_planes(const float* p, const float* c, int B, int64_t N, in
  * GNB_SCATTER_ATOMIC_SUM partial sums and counts). */
 int gnb_scatter_finalize(float* planes, const int32_t* count, int64_t n_cells, int Cp, void* stream);
 
-/* Tiled scatter-mean for MANY points (the same reference code, pointnet.py:72-89, all three planes): the (point, plane)
- * pairs are counting-sorted by plane tile and every tile is accumulated in shared memory and written once -- no global
- * floating-point atomics, no zero-fill, no finalize pass; robust against the clamped border cells of metric coordinates.
- * planes (3,B,R,R,C_p) and count (3,B,R,R) are fully overwritten with MEANS and counts (counts exact, sums within fp32
- * rounding of the reference order, as in GNB_SCATTER_ATOMIC).  gnb_scatter_tiled_scratch_bytes() gives the scratch size,
- * or 0 when the shape is not supported (then use gnb_scatter_mean_planes). */
-int64_t gnb_scatter_tiled_scratch_bytes(int B, int64_t N, int Cp, int R);
-int gnb_scatter_mean_planes_tiled(const float* p, const float* c, int B, int64_t N, int Cp, int R, double padding,
-                                  float* planes, int32_t* count, void* scratch, int64_t scratch_bytes, void* stream);
-
 /* -------------------------------------------------------------------------------------
  * Local pooling.  Replaces LocalPoolPointnet.pool_local()
  * (src/models/components/pointnet.py:105-121): for each plane scatter-(max|mean) the point

@@ -39,7 +39,7 @@ for N in (4096, 614400):
         p = S.plane_points(N, g, domain, voxel_dim=(96, 96, 48)).to(dev)
         c = torch.randn(1, N, Cp, generator=g).to(dev)
         byt = N * (12 + 4 * Cp) + 3 * R * R * (4 * Cp + 4)
-        for mode in ("atomic", "tiled", "deterministic"):
+        for mode in ("atomic", "deterministic"):
             m = timed(lambda: ops.scatter_mean_planes(p, c, R, 0.1, mode))
             print(f"scatter_mean N={N} {domain:6s} {mode:13s}: {m*1e3:8.1f} us  alg {byt/1e6:.1f} MB -> {byt/m/1e6:.0f} GB/s ({byt/m/1e6/PEAK:.2f} of HBM)", flush=True)
         for st in ("max", "mean"):
