@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256) depth_tiles_kernel(const float* __restric
     }
 }
 
-__global__ void __launch_bounds__(256) fuse_kernel(const __grid_constant__ FuseKP p) {
+// (8 resident blocks per SM = 32 registers: the kernel is issue / latency bound, full occupancy is worth ~11 %)
+__global__ void __launch_bounds__(256, 8) fuse_kernel(const __grid_constant__ FuseKP p) {
     __shared__ unsigned char keep[GNB_MAX_FRAMES];
     __shared__ int kept[GNB_MAX_FRAMES];
     __shared__ int n_kept;

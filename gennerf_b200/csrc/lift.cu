@@ -83,8 +83,10 @@ __device__ __forceinline__ void voxel_world(long long v, int ny, int nz, float v
 // than a pixel outside the same image border, cannot see any voxel of the brick (voxel centres
 // are convex combinations of the corner centres and x/z is linear-fractional), so it is skipped
 // for the whole block.  Frames are still visited in ascending order, so the sum order is kept.
+// Resident blocks per SM: the kernel is latency / issue bound, so occupancy pays more than registers -- 6 blocks (40 registers, a
+// few spilled words) for up to 8 lanes per voxel (C <= 32: config 4 514 -> 414 us), 5 blocks (48 registers) above (C = 128: 80 -> 70 us).
 template <int G, int VEC, bool CL, int NVW>
-__global__ void __launch_bounds__(256) lift_kernel(const __grid_constant__ LiftKP p) {
+__global__ void __launch_bounds__(256, (G <= 8 ? 6 : 5)) lift_kernel(const __grid_constant__ LiftKP p) {
     // NVW = voxels per warp (power of two, 32/G <= NVW <= 32)
     constexpr int ITER = NVW * G / 32;                     // gathers per lane per frame
     constexpr int VPI = 32 / G;                            // voxels per gather instruction
