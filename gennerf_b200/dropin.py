@@ -468,10 +468,10 @@ class GenNerf(nn.Module):
         kernel; repeated calls keep accumulating, as in the reference."""
         T = projection.size(1)
         if self.cfg.encoder.use_spatial:
-            feats = []
-            for t in range(T):
-                img = image[:, t]
-                feats.append(self.spatial(img) if self.spatial is not None else img)
+            # the reference indexes image[:, t] per frame (model.py:116); unbind gives the same views with ONE backward node
+            # (a stack) instead of T select-backwards that each zero-fill and accumulate a tensor of the whole batch
+            frames = image.unbind(1)
+            feats = [self.spatial(frames[t]) if self.spatial is not None else frames[t] for t in range(T)]
             voxel_dim = self.cfg.voxel_dim_train if self.training else self.cfg.voxel_dim_val
             if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
                 # training: differentiable lift (gradients scatter-add back into the feature maps)
