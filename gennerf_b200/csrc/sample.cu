@@ -94,11 +94,15 @@ __device__ __forceinline__ float4 staged_plane(const SampleKP& p, const float* _
     return r;
 }
 
-__global__ void __launch_bounds__(32 * ST_WARPS) sample_staged_kernel(const __grid_constant__ SampleKP p, int Gv, int Gp) {
-    __shared__ __align__(16) float s_tab[ST_WARPS][32 * ST_WORDS];      // per warp: volume corner table
-    __shared__ __align__(16) float s_ptab[ST_WARPS][32 * PT_WORDS];     // per warp: plane corner tables
+// 9 resident blocks per SM = 56 registers: measured sweet spot (1 Mi queries, config-2 volume: 9 -> 108 us; 10 blocks /
+// 48 registers split the 8 corner loads into two batches -> 160 us; 5 blocks / 93 registers -> 125 us).
+__global__ void __launch_bounds__(32 * ST_WARPS, 9) sample_staged_kernel(const __grid_constant__ SampleKP p, int Gv, int Gp) {
+    // per warp: volume corner table, then (only when there are planes) the plane corner tables -- dynamic shared memory, so
+    // that a volume-only launch is not limited to 8 blocks per SM by 24.5 KB of tables it does not use
+    extern __shared__ __align__(16) float s_staged[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tv = s_tab[warp];
+    float* tv = s_staged + warp * 32 * ST_WORDS;
+    float* tp = s_staged + ST_WARPS * 32 * ST_WORDS + warp * 32 * PT_WORDS;
     const long long ngroups = (p.total + 31) / 32;
     for (long long grp = (long long)blockIdx.x * ST_WARPS + warp; grp < ngroups; grp += (long long)gridDim.x * ST_WARPS) {
         const long long q0 = grp * 32, q = q0 + lane;
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS) sample_staged_kernel(const __gr
                 planes_setup(p, x, y, z, bc);
 #pragma unroll
                 for (int pl = 0; pl < 3; ++pl) {
-                    float* e = s_ptab[warp] + lane * PT_WORDS + pl * 8;
+                    float* e = tp + lane * PT_WORDS + pl * 8;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         reinterpret_cast<int*>(e)[k] = (int)bc[pl].off[k];
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(32 * ST_WARPS) sample_staged_kernel(const __gr
 #pragma unroll
                     for (int pl = 0; pl < 3; ++pl) {
                         if (p.plane[pl] == nullptr) continue;
-                        const float4 a = staged_plane(p, s_ptab[warp] + ql * PT_WORDS + pl * 8, p.plane[pl] + b * p.psb + c);
+                        const float4 a = staged_plane(p, tp + ql * PT_WORDS + pl * 8, p.plane[pl] + b * p.psb + c);
                         r.x = __fadd_rn(r.x, a.x), r.y = __fadd_rn(r.y, a.y), r.z = __fadd_rn(r.z, a.z), r.w = __fadd_rn(r.w, a.w);
                     }
                     *reinterpret_cast<float4*>(out + c) = r;
@@ -390,7 +394,8 @@ extern "C" int gnb_sample_features(const GnbSampleParams* s, void* stream) {
         long long groups = (kp.total + 31) / 32;
         long long want = (groups + ST_WARPS - 1) / ST_WARPS;
         unsigned blocks = (unsigned)(want < (long long)sms * 16 ? want : (long long)sms * 16);
-        sample_staged_kernel<<<blocks, 32 * ST_WARPS, 0, (cudaStream_t)stream>>>(kp, pow2_lanes(kp.C / 4 > 0 ? kp.C / 4 : 1),
+        const size_t smem = (size_t)ST_WARPS * 32 * (ST_WORDS + (kp.Cp > 0 ? PT_WORDS : 0)) * sizeof(float);
+        sample_staged_kernel<<<blocks, 32 * ST_WARPS, smem, (cudaStream_t)stream>>>(kp, pow2_lanes(kp.C / 4 > 0 ? kp.C / 4 : 1),
                                                                         pow2_lanes(kp.Cp / 4 > 0 ? kp.Cp / 4 : 1));
         GNB_LAUNCH_CHECK();
         return 0;
