@@ -137,7 +137,7 @@ template <int LPP>
 __global__ void __launch_bounds__(256) scatter_atomic_v4_kernel(const float* __restrict__ p, const float* __restrict__ c,
                                                                 int B, long long N, int R, float den,
                                                                 float* __restrict__ planes, int* __restrict__ count) {
-    constexpr int Cp = LPP * 4, SLOTS = 32 / LPP, PPS = LPP;     // points per slot = 32 / SLOTS
+    constexpr int Cp = LPP * 4, PPS = LPP;                      // 32 / LPP slots of LPP points each
     __shared__ float s_corner[8][Cp];                           // per warp
     __shared__ int s_corner_n[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
