@@ -33,7 +33,7 @@ def test_header_symbols_exported(library):
 def test_struct_layout_matches(library):
     import ctypes as C
     L = library.lib()
-    for which, st in enumerate((library.GnbLiftParams, library.GnbSampleParams, library.GnbDecoderWeights)):
+    for which, st in enumerate((library.GnbLiftParams, library.GnbSampleParams, library.GnbDecoderWeights, library.GnbFusionParams)):
         assert L.gnb_struct_size(which) == C.sizeof(st)
 
 
@@ -49,6 +49,39 @@ def test_argument_errors_do_not_touch_the_gpu(library):
     assert L.gnb_backproject_frames(C.byref(p), None) == -1
     assert b"voxel grid" in L.gnb_last_error()
     assert L.gnb_plane_coords(None, 10, 0.1, 8, None, None, None) == -1
+
+
+def test_binned_sampler_plan_is_host_only(library):
+    """gnb_sample_binned_scratch_bytes decides on the host whether the brick-binned path applies (channels-last fp32
+    volume, C % 4 == 0, z-rows contiguous) and how much scratch it needs; 0 sends the caller to gnb_sample_features."""
+    import ctypes as C
+    L = library.lib()
+
+    def params(nx, ny, nz, ch, Q, channels_last=True, B=1):
+        s = library.GnbSampleParams()
+        s.batch, s.n_query, s.xyz = B, Q, 0x10000
+        s.volume = 0x20000
+        s.nx, s.ny, s.nz, s.C = nx, ny, nz, ch
+        if channels_last:
+            s.vol_stride_c, s.vol_stride_z, s.vol_stride_y, s.vol_stride_x = 1, ch, nz * ch, ny * nz * ch
+        else:
+            s.vol_stride_z, s.vol_stride_y, s.vol_stride_x, s.vol_stride_c = 1, nz, ny * nz, nx * ny * nz
+        s.vol_stride_b = nx * ny * nz * ch
+        s.voxel_size = 0.04
+        return s
+
+    Q = 1 << 20
+    n = L.gnb_sample_binned_scratch_bytes(C.byref(params(96, 96, 48, 32, Q)))
+    assert n >= Q * 20                                   # 16-byte sorted records + 4-byte bin ids per query, plus the tables
+    assert n < Q * 20 + (64 << 20)
+    assert L.gnb_sample_binned_scratch_bytes(C.byref(params(96, 96, 48, 32, Q, channels_last=False))) == 0
+    assert L.gnb_sample_binned_scratch_bytes(C.byref(params(96, 96, 48, 30, Q))) == 0        # C % 4 != 0
+    assert L.gnb_sample_binned_scratch_bytes(C.byref(params(96, 96, 48, 1, Q))) == 0
+    more = L.gnb_sample_binned_scratch_bytes(C.byref(params(96, 96, 48, 32, 2 * Q)))
+    assert more > n
+    assert L.gnb_sample_binned_scratch_bytes(C.byref(params(256, 256, 96, 32, Q, B=2))) > 0
+    s = params(96, 96, 48, 32, Q)
+    assert L.gnb_sample_features_binned(C.byref(s), None, 0, None) != 0 and b"binned" in L.gnb_last_error()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
