@@ -512,7 +512,7 @@ extern "C" int gnb_sample_features_binned(const GnbSampleParams* sp, void* scrat
     long long blocks = (k.s.total + 2047) / 2048;
     const long long max_blocks = 2LL * sms < BIN_MAXB ? 2LL * sms : BIN_MAXB;
     if (blocks > max_blocks) blocks = max_blocks;
-    k.chunk = ((k.s.total + blocks - 1) / blocks + 1023) / 1024 * 1024;
+    k.chunk = ((k.s.total + blocks - 1) / blocks + 31) / 32 * 32;          // equal chunks: every SM gets the same number of blocks
     blocks = (k.s.total + k.chunk - 1) / k.chunk;
     if (pl.smem_hist) {
         GNB_CUDA(cudaFuncSetAttribute(bin_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.hist_bytes));
