@@ -133,85 +133,95 @@ __global__ void __launch_bounds__(256) scatter_atomic_kernel(const float* __rest
 // (sm_90+): the L2 retires a quarter of the operations.  Slot g of the warp owns the LPP consecutive points
 // [g * LPP, (g + 1) * LPP) of the warp's 32 and run-length-aggregates them like the scalar kernel; the corner cell is
 // collected per lane and combined across the block.
+// gridDim.z = 3: one plane per warp (few points: the reductions a warp issues one after the other are what takes time);
+// gridDim.z = 1: a warp serves all three planes from the feature rows it loaded once (many points: the rows are not read
+// three times through the L2 that is busy with the reductions).
 template <int LPP>
 __global__ void __launch_bounds__(256) scatter_atomic_v4_kernel(const float* __restrict__ p, const float* __restrict__ c,
                                                                 int B, long long N, int R, float den,
                                                                 float* __restrict__ planes, int* __restrict__ count) {
     constexpr int Cp = LPP * 4, PPS = LPP;                      // 32 / LPP slots of LPP points each
-    __shared__ float s_corner[8][Cp];                           // per warp
-    __shared__ int s_corner_n[8];
+    __shared__ float s_corner[3][8][Cp];                        // per plane and warp
+    __shared__ int s_corner_n[3][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = lane / LPP, sub = lane % LPP;
-    const int b = blockIdx.y, k = blockIdx.z;
+    const int b = blockIdx.y;
+    const int k0 = gridDim.z == 3 ? (int)blockIdx.z : 0, k1 = gridDim.z == 3 ? k0 + 1 : 3;
     const long long group = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     const long long n0 = group * 32;
     const long long RR = (long long)R * R;
     const int corner = (R - 1) + R * (R - 1);
-    float* __restrict__ pl = planes + ((long long)k * B + b) * RR * Cp;
-    int* __restrict__ cn = count + ((long long)k * B + b) * RR;
-    float4 corner_acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int corner_n = 0;
-    if (n0 < N) {
-        int cellk = -1;
+    int cell[3] = {-1, -1, -1};
+    const int npts = n0 < N ? (int)min((long long)32, N - n0) : 0;
+    float4 cr[PPS];                                             // this lane's float4 of the slot's points
+    if (npts > 0) {
         if (n0 + lane < N) {
             const float* pp = p + ((long long)b * N + n0 + lane) * 3;
-            int cell[3];
             plane_cells(pp[0], pp[1], pp[2], den, R, cell);
-            cellk = k == 0 ? cell[0] : (k == 1 ? cell[1] : cell[2]);
         }
-        const int npts = (int)min((long long)32, N - n0);
         const float* __restrict__ cb = c + ((long long)b * N + n0) * Cp;
-        float4 cr[PPS];                                     // this lane's float4 of the slot's points
 #pragma unroll
         for (int j = 0; j < PPS; ++j) {
             const int pt = slot * PPS + j;
             cr[j] = pt < npts ? ldg4(cb + (long long)pt * Cp + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        int run_cell = -1, run_n = 0;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto flush = [&]() {
-            if (run_cell >= 0) {
-                atomicAdd(reinterpret_cast<float4*>(pl + (long long)run_cell * Cp + sub * 4), acc);
-                if (sub == 0) atomicAdd(cn + run_cell, run_n);
-            }
-        };
+    }
 #pragma unroll
-        for (int j = 0; j < PPS; ++j) {
-            const int pt = slot * PPS + j;
-            const int cj = __shfl_sync(FULL, cellk, pt);
-            if (pt < npts) {
-                if (cj == corner) {
-                    corner_acc.x += cr[j].x, corner_acc.y += cr[j].y, corner_acc.z += cr[j].z, corner_acc.w += cr[j].w;
-                    ++corner_n;
-                } else {
-                    if (cj != run_cell) {
-                        flush();
-                        run_cell = cj, run_n = 0, acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 3; ++k) {
+        if (k < k0 || k >= k1) continue;
+        float* __restrict__ pl = planes + ((long long)k * B + b) * RR * Cp;
+        int* __restrict__ cn = count + ((long long)k * B + b) * RR;
+        float4 corner_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int corner_n = 0;
+        if (npts > 0) {
+            int run_cell = -1, run_n = 0;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto flush = [&]() {
+                if (run_cell >= 0) {
+                    atomicAdd(reinterpret_cast<float4*>(pl + (long long)run_cell * Cp + sub * 4), acc);
+                    if (sub == 0) atomicAdd(cn + run_cell, run_n);
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < PPS; ++j) {
+                const int pt = slot * PPS + j;
+                const int cj = __shfl_sync(FULL, cell[k], pt);
+                if (pt < npts) {
+                    if (cj == corner) {
+                        corner_acc.x += cr[j].x, corner_acc.y += cr[j].y, corner_acc.z += cr[j].z, corner_acc.w += cr[j].w;
+                        ++corner_n;
+                    } else {
+                        if (cj != run_cell) {
+                            flush();
+                            run_cell = cj, run_n = 0, acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        acc.x += cr[j].x, acc.y += cr[j].y, acc.z += cr[j].z, acc.w += cr[j].w;
+                        ++run_n;
                     }
-                    acc.x += cr[j].x, acc.y += cr[j].y, acc.z += cr[j].z, acc.w += cr[j].w;
-                    ++run_n;
                 }
             }
+            flush();
         }
-        flush();
-    }
-    // corner cell: slots of the warp by shuffles, warps of the block through shared memory, one reduction per block
+        // corner cell: slots of the warp by shuffles, warps of the block through shared memory, one reduction per block
 #pragma unroll
-    for (int o = LPP; o < 32; o <<= 1) {
-        corner_acc.x += __shfl_xor_sync(FULL, corner_acc.x, o), corner_acc.y += __shfl_xor_sync(FULL, corner_acc.y, o);
-        corner_acc.z += __shfl_xor_sync(FULL, corner_acc.z, o), corner_acc.w += __shfl_xor_sync(FULL, corner_acc.w, o);
-        corner_n += __shfl_xor_sync(FULL, corner_n, o);
+        for (int o = LPP; o < 32; o <<= 1) {
+            corner_acc.x += __shfl_xor_sync(FULL, corner_acc.x, o), corner_acc.y += __shfl_xor_sync(FULL, corner_acc.y, o);
+            corner_acc.z += __shfl_xor_sync(FULL, corner_acc.z, o), corner_acc.w += __shfl_xor_sync(FULL, corner_acc.w, o);
+            corner_n += __shfl_xor_sync(FULL, corner_n, o);
+        }
+        if (slot == 0) *reinterpret_cast<float4*>(&s_corner[k][warp][sub * 4]) = corner_acc;
+        if (lane == 0) s_corner_n[k][warp] = corner_n;
     }
-    if (slot == 0) *reinterpret_cast<float4*>(&s_corner[warp][sub * 4]) = corner_acc;
-    if (lane == 0) s_corner_n[warp] = corner_n;
     __syncthreads();
-    if (threadIdx.x < Cp) {
-        float t = 0.0f;
-        int nn = 0;
-        for (int w = 0; w < 8; ++w) t += s_corner[w][threadIdx.x], nn += s_corner_n[w];
-        if (nn > 0) {
-            atomicAdd(pl + (long long)corner * Cp + threadIdx.x, t);
-            if (threadIdx.x == 0) atomicAdd(cn + corner, nn);
+    for (int k = k0; k < k1; ++k) {
+        if (threadIdx.x < Cp) {
+            float t = 0.0f;
+            int nn = 0;
+            for (int w = 0; w < 8; ++w) t += s_corner[k][w][threadIdx.x], nn += s_corner_n[k][w];
+            if (nn > 0) {
+                atomicAdd(planes + (((long long)k * B + b) * RR + corner) * Cp + threadIdx.x, t);
+                if (threadIdx.x == 0) atomicAdd(count + ((long long)k * B + b) * RR + corner, nn);
+            }
         }
     }
 }
@@ -671,13 +681,14 @@ extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, in
         GNB_CUDA(cudaMemsetAsync(planes, 0, cells * Cp * sizeof(float), st));
         if (N > 0) {
             const dim3 blocks((unsigned)(((N + 31) / 32 + 7) / 8), (unsigned)B, 3);       // 8 groups of 32 points per block; grid rows = scenes, layers = planes
+            const dim3 blocks4(blocks.x, blocks.y, N >= 32768 ? 1 : 3);                      // v4 kernels: see the kernel comment
             const bool v4 = (reinterpret_cast<uintptr_t>(c) & 15) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0 && !getenv("GNB_SCATTER_SCALAR");
-            if (v4 && Cp == 4) scatter_atomic_v4_kernel<1><<<blocks, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
-            else if (v4 && Cp == 8) scatter_atomic_v4_kernel<2><<<blocks, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
-            else if (v4 && Cp == 16) scatter_atomic_v4_kernel<4><<<blocks, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
-            else if (v4 && Cp == 32) scatter_atomic_v4_kernel<8><<<blocks, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
-            else if (v4 && Cp == 64) scatter_atomic_v4_kernel<16><<<blocks, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
-            else if (v4 && Cp == 128) scatter_atomic_v4_kernel<32><<<blocks, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
+            if (v4 && Cp == 4) scatter_atomic_v4_kernel<1><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
+            else if (v4 && Cp == 8) scatter_atomic_v4_kernel<2><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
+            else if (v4 && Cp == 16) scatter_atomic_v4_kernel<4><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
+            else if (v4 && Cp == 32) scatter_atomic_v4_kernel<8><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
+            else if (v4 && Cp == 64) scatter_atomic_v4_kernel<16><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
+            else if (v4 && Cp == 128) scatter_atomic_v4_kernel<32><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
             else if (Cp <= 32) scatter_atomic_kernel<1><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
             else if (Cp <= 64) scatter_atomic_kernel<2><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
             else if (Cp <= 128) scatter_atomic_kernel<4><<<blocks, 256, 0, st>>>(p, c, B, N, Cp, R, den, planes, count);
