@@ -8,8 +8,8 @@
 // kernel moves ~1 KB of L2->SM sectors per query and is bound by L2 (160 us per Mi queries at C = 32, 0.19 of the
 // HBM roofline on algorithmic bytes).  Here the queries are first counting-sorted by the brick of voxels that holds
 // their base cell (order inside a bin is irrelevant: queries are independent); then a CTA stages a brick's corner
-// voxels ((bx+1)(by+1)(bz+1) x C floats, <= 93 KB) into shared memory with 1-D bulk copies (one per contiguous z-row,
-// all completing on one mbarrier) and serves the brick's queries with LDS.128 gathers.  HBM/L2 see every voxel ~1.4x
+// voxels ((bx+1)(by+1)(bz+1) x C floats, <= 93 KB) into shared memory with ONE tensor-map TMA copy (a 5-D box of the
+// channels-last volume; fallback: a 1-D bulk copy per contiguous z-row) and serves the brick's queries with LDS.128 gathers.  HBM/L2 see every voxel ~1.4x
 // (halo) instead of every query 8x.  Bricks with few queries are gathered straight from global memory.
 //
 //   bin_count_kernel   -> bid[q], count[brick]    (shared-memory histogram per block, one global add per non-empty bin)
@@ -17,7 +17,9 @@
 //   bin_scatter_kernel -> sorted[rank] = (x,y,z,q)(ranges reserved per block and bin, ranks by shared-memory atomics)
 //   sample_binned_kernel                          (one persistent CTA per SM: a producer warp claims bricks from an atomic
 //                                                  counter and keeps two tile buffers filled; 15 consumer warps gather)
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "binsort.cuh"
 #include "sample.cuh"
@@ -37,6 +39,7 @@ struct BinKP {
     int nbricks;                             // batch * nb
     int lsx, lsy;                            // tile strides in floats (z stride = C)
     int tile_min;                            // bins with fewer queries gather from global memory
+    int use_tmap;                            // tiles arrive as ONE tensor-map copy (else: a bulk copy per z-row)
     unsigned* count;                         // [nbricks]   } zeroed by the launcher
     unsigned* cursor;                        // [nbricks]   }
     unsigned* work;                          // [1]         }
@@ -247,7 +250,7 @@ __device__ __forceinline__ void gather_tile_c32(const SampleKP& s, const float* 
 
 // NV = float4s of channels per lane in the volume gather (2: C = 32 takes 4 lanes per query, 8 queries per trip)
 template <int NV>
-__global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(const __grid_constant__ BinKP p, int lgGv, int Gp) {
+__global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(const __grid_constant__ BinKP p, const __grid_constant__ CUtensorMap tmap, int lgGv, int Gp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_full[2], s_empty[2];
     __shared__ Unit s_unit[2];               // the producer's decoded claim per stage (b < 0: no more work)
@@ -286,6 +289,20 @@ __global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(
                 if (lane == 0) bar_arrive(full);
                 continue;
             }
+            if (p.use_tmap) {
+                // the whole (bx+1) x (by+1) x (bz+1) x C box in one request; what lies beyond the grid arrives as zeros and
+                // is never read (border bricks take the gather with per-query corner steps, 0 at the border)
+                if (lane == 0) {
+                    const uint32_t box_bytes = (uint32_t)((p.bx + 1) * (p.by + 1) * (p.bz + 1) * s.C * 4);
+                    bar_expect_tx(full, box_bytes);
+                    asm volatile(
+                        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+                            smem_u32(smem_raw + st * BIN_TILE_BYTES)),
+                        "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(un.z0), "r"(un.y0), "r"(un.x0), "r"(un.b), "r"(full)
+                        : "memory");
+                }
+                continue;
+            }
             // the tile always holds (bx+1) x (by+1) x (bz+1) corner voxels: where the grid ends inside it, the last voxel of
             // the axis is replicated, which is exactly the clamped corner (weight 0) the reference-order sum reads there
             const int tx = min(p.bx + 1, s.nx - un.x0), ty = min(p.by + 1, s.ny - un.y0), tz = min(p.bz + 1, s.nz - un.z0);
@@ -317,6 +334,7 @@ __global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(
         const float* vol = s.volume + (long long)b * s.vsb;
         const float* tile = reinterpret_cast<const float*>(smem_raw + st * BIN_TILE_BYTES);
         const bool use_tile = un.use_tile;
+        const bool interior = un.x0 + p.bx + 1 <= s.nx && un.y0 + p.by + 1 <= s.ny && un.z0 + p.bz + 1 <= s.nz;   // no replicated / zero halo
         const int dx = use_tile ? p.lsx : (int)s.vsx, dy = use_tile ? p.lsy : (int)s.vsy, dz = use_tile ? s.C : (int)s.vsz;   // gather strides
         const long long origin_off = use_tile ? (long long)un.x0 * dx + (long long)un.y0 * dy + (long long)un.z0 * dz : 0;
         float4 pt_next = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -393,7 +411,7 @@ __global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(
             }
             __syncwarp();
             if (use_tile) {
-                if (NV == 2 && s.C == 32 && dx == T32_X && dy == T32_Y) gather_tile_c32(s, tile, tab, nq, lane);
+                if (NV == 2 && s.C == 32 && dx == T32_X && dy == T32_Y && (!p.use_tmap || interior)) gather_tile_c32(s, tile, tab, nq, lane);
                 else gather_volume<NV, true>(s, tile, tab, nq, lane, lgGv, dx, dy, dz);
             } else {
                 gather_volume<NV, false>(s, vol, tab, nq, lane, lgGv, dx, dy, dz);
@@ -530,14 +548,39 @@ extern "C" int gnb_sample_features_binned(const GnbSampleParams* sp, void* scrat
     if (pl.smem_hist) bin_scatter_kernel<true><<<(unsigned)blocks, 1024, pl.hist_bytes, stream>>>(k);
     else bin_scatter_kernel<false><<<(unsigned)blocks, 1024, 0, stream>>>(k);
     GNB_LAUNCH_CHECK();
+    // tensor map of the channels-last volume (C, z, y, x, scene): a brick's tile is one TMA box
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    k.use_tmap = 0;
+    if (k.s.C <= 256 && !getenv("GNB_BIN_ROWCOPY")) {
+        const int e = k.bx + 1, ez = k.bz + 1;
+        cuuint64_t gdim[5] = {(cuuint64_t)k.s.C, (cuuint64_t)k.s.nz, (cuuint64_t)k.s.ny, (cuuint64_t)k.s.nx, (cuuint64_t)sp->batch};
+        cuuint64_t gstr[4] = {(cuuint64_t)k.s.vsz * 4, (cuuint64_t)k.s.vsy * 4, (cuuint64_t)k.s.vsx * 4, (cuuint64_t)k.s.vsb * 4};
+        cuuint32_t box[5] = {(cuuint32_t)k.s.C, (cuuint32_t)ez, (cuuint32_t)e, (cuuint32_t)e, 1u};
+        cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+        if (sp->batch == 1) gstr[3] = gstr[2] * (cuuint64_t)k.s.nx;        // unused extent-1 dimension: any valid stride
+        // the driver entry point comes through the runtime, so the library does not link against libcuda
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn && qres == cudaDriverEntryPointSuccess) {
+            const CUresult r = reinterpret_cast<EncodeTiled>(fn)(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(k.s.volume), gdim, gstr, box,
+                                                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            k.use_tmap = r == CUDA_SUCCESS ? 1 : 0;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
     const size_t smem = 2 * (size_t)BIN_TILE_BYTES + (size_t)BIN_WARPS * 32 * BIN_TAB * 4;
     const unsigned grid = (unsigned)(sms < k.nbricks ? sms : k.nbricks), threads = 32 * (BIN_WARPS + 1);
     if (pl.NV == 2) {
         GNB_CUDA(cudaFuncSetAttribute(sample_binned_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sample_binned_kernel<2><<<grid, threads, smem, stream>>>(k, pl.lgGv, pl.Gp);
+        sample_binned_kernel<2><<<grid, threads, smem, stream>>>(k, tmap, pl.lgGv, pl.Gp);
     } else {
         GNB_CUDA(cudaFuncSetAttribute(sample_binned_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sample_binned_kernel<1><<<grid, threads, smem, stream>>>(k, pl.lgGv, pl.Gp);
+        sample_binned_kernel<1><<<grid, threads, smem, stream>>>(k, tmap, pl.lgGv, pl.Gp);
     }
     GNB_LAUNCH_CHECK();
     return 0;

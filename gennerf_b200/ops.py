@@ -200,7 +200,7 @@ def sample_features(xyz, volume=None, planes=None, *, voxel_size=0.04, origin=No
     features first.  `volume` is the accumulated (already normalised == summed) volume.
 
     binned: "auto" sorts the queries into voxel bricks and gathers from shared-memory tiles
-    (gnb_sample_features_binned, same bits) when there is at least one query per voxel
+    (gnb_sample_features_binned, same bits) when there is at least one query per three voxels
     and the volume is channels-last; True forces it (raises when it does not apply); False never."""
     s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
     out = torch.empty((B, Q, Cp + Cv), device=xyz.device, dtype=torch.float32)
@@ -208,7 +208,7 @@ def sample_features(xyz, volume=None, planes=None, *, voxel_size=0.04, origin=No
     with torch.cuda.device(out.device):
         use = False
         if binned and volume is not None and Q > 0:
-            dense = binned is True or (B * Q >= (1 << 16) and Q >= volume.shape[2] * volume.shape[3] * volume.shape[4])
+            dense = binned is True or (B * Q >= (1 << 16) and 3 * Q >= volume.shape[2] * volume.shape[3] * volume.shape[4])
             nbytes = lib().gnb_sample_binned_scratch_bytes(C.byref(s)) if dense else 0
             if binned is True and nbytes == 0:
                 raise RuntimeError("gennerf_b200: the binned sampler needs a channels-last fp32 volume with C % 4 == 0")
