@@ -67,6 +67,7 @@ class GnbDecoderWeights(C.Structure):
         ("lin_out_w", C.c_void_p), ("lin_out_b", C.c_void_p),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p),
         ("tc_dtype", C.c_int32),
+        ("status", C.c_void_p),
     ]
 
 
@@ -86,6 +87,8 @@ SIGNATURES = {
     "gnb_version": (C.c_int, []),
     "gnb_last_error": (C.c_char_p, []),
     "gnb_struct_size": (C.c_int, [C.c_int]),
+    "gnb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "gnb_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "gnb_nchw_to_nhwc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p]),
     "gnb_backproject_frames": (C.c_int, [C.POINTER(GnbLiftParams), C.c_void_p]),
@@ -115,6 +118,9 @@ SIGNATURES = {
                                             C.c_void_p, C.c_void_p]),
     "gnb_sample_points_on_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnb_valid_pixel_count": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnb_valid_pixel_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_tsdf_fusion_scratch_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "gnb_tsdf_fusion_integrate": (C.c_int, [C.POINTER(GnbFusionParams), C.c_void_p]),
     "gnb_tsdf_fusion_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -129,6 +135,8 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_query_fused_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(GnbDecoderWeights), C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnb_query_grid_fused_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(C.c_int32), C.c_void_p,
+                                            C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -158,3 +166,11 @@ def check(rc, what):
     if rc != 0:
         msg = lib().gnb_last_error().decode(errors="replace")
         raise RuntimeError(f"gennerf_b200: {what} failed (code {rc}): {msg}")
+
+
+def set_option(name, value):
+    """Tuning / debugging switch of the library (see gnb_set_option in include/gennerf_b200.h); returns the old value."""
+    old = C.c_int(0)
+    check(lib().gnb_get_option(name.encode(), C.byref(old)), "gnb_get_option")
+    check(lib().gnb_set_option(name.encode(), int(value)), "gnb_set_option")
+    return old.value

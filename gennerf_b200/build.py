@@ -58,7 +58,7 @@ def build(force=False, verbose=False, trace=False):
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+        cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout)

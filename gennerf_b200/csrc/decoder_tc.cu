@@ -301,6 +301,11 @@ __device__ __forceinline__ float round16(float a) {
     if constexpr (BF16) return __bfloat162float(__float2bfloat16_rn(a));
     else return __half2float(__float2half_rn(fminf(fmaxf(a, -65504.0f), 65504.0f)));
 }
+// fp16 saturation probe on packed operands: a half is +-65504 (0x7BFF / 0xFBFF) exactly when satfinite clipped it (or the
+// value was that number, which is as good as clipped); |h| + 0x0401 then carries into bit 15.  2 integer ops per 4 halves.
+__device__ __forceinline__ uint32_t sat_probe(uint32_t a, uint32_t b) {
+    return (((a & 0x7FFF7FFFu) + 0x04010401u) | ((b & 0x7FFF7FFFu) + 0x04010401u)) & 0x80008000u;
+}
 // byte offset of the 16-byte unit u (8 columns) of row r inside a swizzled chunk
 __device__ __forceinline__ uint32_t chunk_off(int r, int u) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((u ^ (r & 7)) << 4)); }
 
@@ -312,6 +317,8 @@ struct TcKP {
     GnbDecoderWeights w;          // fp32 biases, head, encoding options (matrices are read from `packed`)
     const unsigned char* packed;
     const float* xyz;             // (n_rows,3), or (n_rows,d_code) codes when w.use_code == 2
+    const float* gaxes;           // dense-grid mode (xyz == null): the gnx + gny + gnz axis coordinates; query row r of a
+    int gnx, gny, gnz;            //   scene is the grid point (x[i], y[j], z[k]), r = (i*gny + j)*gnz + k  (utils.py:926-935)
     const float* feat;            // (n_rows,d_feat) when !fused
     int fused;
     SampleKP s;                   // sampler (fused); s.out = optional fp32 feature output
@@ -384,12 +391,20 @@ __host__ __device__ inline int act_kchunk(int nsplit, int own, int half, int t, 
 // sampled here (fused query) or read from the feature tensor.
 template <bool BF16>
 __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, const Smem& L, int half, int row, long long grow,
-                                             int u0, int ustep, int what = 3) {      // what: 1 = code tile, 2 = feature chunks
+                                             int u0, int ustep, int what, uint32_t& ovf) {      // what: 1 = code tile, 2 = feature chunks
     const Dims& d = p.d;
     const GnbDecoderWeights& w = p.w;
     const bool live = grow < p.n_rows;
     float xyz3[3] = {0.f, 0.f, 0.f};
-    if (live && w.use_code != 2) xyz3[0] = __ldg(p.xyz + grow * 3), xyz3[1] = __ldg(p.xyz + grow * 3 + 1), xyz3[2] = __ldg(p.xyz + grow * 3 + 2);
+    if (live && w.use_code != 2) {
+        if (p.gaxes) {            // the query grid is never materialised: derive the point from the row index
+            const long long r = grow % ((long long)p.gnx * p.gny * p.gnz);
+            const int k = (int)(r % p.gnz), j = (int)((r / p.gnz) % p.gny), i = (int)(r / ((long long)p.gnz * p.gny));
+            xyz3[0] = __ldg(p.gaxes + i), xyz3[1] = __ldg(p.gaxes + p.gnx + j), xyz3[2] = __ldg(p.gaxes + p.gnx + p.gny + k);
+        } else {
+            xyz3[0] = __ldg(p.xyz + grow * 3), xyz3[1] = __ldg(p.xyz + grow * 3 + 1), xyz3[2] = __ldg(p.xyz + grow * 3 + 2);
+        }
+    }
     if (what & 1) {
     float code[64 * 4];                          // d_code + 2 <= 64*KZ (KZ <= 4)
     const int kz = d.KZ * 64;
@@ -416,6 +431,7 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
         for (int u = u0; u < 8; u += ustep) {
             const float* v = code + c * 64 + u * 8;
             uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
+            if constexpr (!BF16) ovf |= sat_probe(pk.x, pk.y) | sat_probe(pk.z, pk.w);
             *reinterpret_cast<uint4*>(sm + L.code + c * CHUNK + chunk_off(row, u)) = pk;
         }
     }
@@ -459,6 +475,7 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
                 if (k == d.d_feat || k == d.d_feat + 1) v[e] = 1.0f;       // bias hi / lo columns
             }
             uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
+            if constexpr (!BF16) ovf |= sat_probe(pk.x, pk.y) | sat_probe(pk.z, pk.w);
             *reinterpret_cast<uint4*>(sm + L.feat + c * CHUNK + chunk_off(row, u)) = pk;
         }
 }
@@ -779,24 +796,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
         // fp16/bf16 pack into the swizzled chunks) while the current tile's layers run, so the tensor pipe does not idle
         // for a prologue between tiles.  Lane l stages rows l, l+32, l+64, l+96.
         if (d.early) {
-            uint32_t it = 0;
+            uint32_t it = 0, ovf = 0;
             for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++it) {
                 // features first (the slow part: gathers): their buffer is free as soon as the previous tile's lin_in has
                 // retired, almost a whole tile before they are needed; the code tile only after its last lin_z
                 if (it > 0) mbar_wait(feat_free, (it - 1) & 1);
                 for (int rr = 0; rr < BM / 32; ++rr) {
                     const int row = rr * 32 + lane;
-                    stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 2);
+                    stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 2, ovf);
                 }
                 if (it > 0) mbar_wait(in_free, (it - 1) & 1);
                 for (int rr = 0; rr < BM / 32; ++rr) {
                     const int row = rr * 32 + lane;
-                    stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 1);
+                    stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 1, ovf);
                 }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(in_ready);
             }
+            if (ovf && p.w.status) atomicOr(p.w.status, 1);
         }
     } else if (warp == ROLE_WARP0 + 2) {
         // =============================== A-chunk exchange (NSPLIT=2) ==========================
@@ -826,6 +844,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const GnbDecoderWeights& w = p.w;
         uint32_t grp = 0;                                    // acc_ready uses so far
+        uint32_t ovf = 0;                                    // fp16 operands that saturated (reported through w.status)
         for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
             const long long grow = (long long)tile * rows_per_cluster + mrow * BM + row;
             const bool live = grow < p.n_rows;
@@ -833,7 +852,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
             if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             // ---------------- prologue: operand tiles of lin_in and lin_z -------------------
             if (!d.early) {
-                stage_inputs<BF16>(p, sm, L, (int)half, row, grow, eg, EPI_GROUPS);
+                stage_inputs<BF16>(p, sm, L, (int)half, row, grow, eg, EPI_GROUPS, 3, ovf);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -885,6 +904,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                             }
                             uint4 pk = make_uint4(pack16_relu<BF16>(f[0], f[1]), pack16_relu<BF16>(f[2], f[3]),
                                                   pack16_relu<BF16>(f[4], f[5]), pack16_relu<BF16>(f[6], f[7]));
+                            if constexpr (!BF16) ovf |= sat_probe(pk.x, pk.y) | sat_probe(pk.z, pk.w);
                             *reinterpret_cast<uint4*>(dst + chunk_off(row, eg * 4 + u)) = pk;
                         }
                         tc_fence_before();
@@ -938,6 +958,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                     }
                 }
                 if (live && half == 0 && eg == 0 && p.tsdf) p.tsdf[grow] = tanhf(head);
+                if (ovf && live && p.w.status) atomicOr(p.w.status, 1);
+                ovf = 0;
                 tc_fence_before();
                 if (threadIdx.x == EPI_WARP0 * 32) { GNB_TRACE(1, ek); } ++ek;
             }
@@ -1023,7 +1045,7 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
     // cta_group::2 pairs (each CTA streams half of B, 256 rows per cluster) are built and parity-tested but opt-in:
     // measured this round they run at 0.91x of the single-CTA issue because a cluster of 4 leaves 16 SMs idle
     // and the per-layer epilogue -> exchange -> MMA latency chain, not the weight ingest, then bounds a layer
-    d.two = getenv("GNB_TC_TWO_CTA") ? 1 : 0;
+    d.two = opt(OPT_TC_TWO_CTA) ? 1 : 0;
     if (d.HN % 32 != 0) d.two = 0;
     d.csize = d.nsplit * (d.two ? 2 : 1);
     d.WN = d.two ? d.HN / 2 : d.HN;
@@ -1048,7 +1070,7 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
     d.early = 0;
     d.nstage = MAX_STAGES;
     while (d.nstage >= 2 && smem_layout(d).total + 1024 > 227 * 1024) --d.nstage;
-    if (!d.two && !getenv("GNB_TC_NO_EARLY")) {
+    if (!d.two && !opt(OPT_TC_NO_EARLY)) {
         // early input staging costs KF more chunks of shared memory: take it when the weight ring keeps its depth
         Dims e = d;
         e.early = 1;
@@ -1165,8 +1187,7 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
     const int rows_per_cluster = d.two ? 2 * BM : BM;
     kp.n_tiles = (int)((kp.n_rows + rows_per_cluster - 1) / rows_per_cluster);
     kp.n_clusters = sms / d.csize;
-    if (const char* e = getenv("GNB_DEBUG_MAX_CLUSTERS")) {   // profiling aid: fewer resident clusters
-        int m = atoi(e);
+    if (const int m = opt(OPT_DEBUG_MAX_CLUSTERS)) {          // profiling aid: fewer resident clusters
         if (m > 0 && m < kp.n_clusters) kp.n_clusters = m;
     }
     if (kp.n_clusters > kp.n_tiles) kp.n_clusters = kp.n_tiles;
@@ -1189,7 +1210,7 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
         int max_clusters = 0;
         cfg.gridDim = dim3(sms / d.csize * d.csize);
         GNB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
-        if (getenv("GNB_DEBUG_PRINT")) fprintf(stderr, "[gnb] decoder: cluster size %d, max co-resident clusters %d\n", d.csize, max_clusters);
+        if (opt(OPT_DEBUG_PRINT)) fprintf(stderr, "[gnb] decoder: cluster size %d, max co-resident clusters %d\n", d.csize, max_clusters);
         if (max_clusters > 0 && kp.n_clusters > max_clusters) kp.n_clusters = max_clusters;
         cfg.gridDim = dim3(kp.n_clusters * d.csize);
     }
@@ -1207,9 +1228,8 @@ extern "C" int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, con
     return launch_tc(w, packed, kp, stream);
 }
 
-extern "C" int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed, float* out,
-                                    float* tsdf, void* stream) {
-    TcKP kp = {};
+static int query_fused_common(const GnbSampleParams* s, const GnbDecoderWeights* w, TcKP& kp, float* out, float* tsdf, const char* who) {
+    (void)who;
     int rc = fill_sample_kp(s, kp.s);
     if (rc) return rc;
     GNB_CHECK_ARG(w && w->use_code != 2, "gnb_query_fused_tc: the fused query encodes xyz itself (use_code 0 or 1)");
@@ -1218,13 +1238,38 @@ extern "C" int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeig
     GNB_CHECK_ARG(out || tsdf, "gnb_query_fused_tc: no output requested");
     GNB_CHECK_ARG(!s->out || (s->out_stride >= w->d_feat && s->out_stride % 4 == 0), "gnb_query_fused_tc: bad feature output stride");
     bool ok = true;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    // float4 loads / stores: base pointers must be 16-byte aligned too (a sliced view may not be)
+    ok = ok && al16(kp.s.volume) && al16(kp.s.plane[0]) && al16(kp.s.plane[1]) && al16(kp.s.plane[2]) && al16(s->out);
     if (kp.s.volume) ok = ok && kp.s.vsc == 1 && kp.s.C % 4 == 0 && kp.s.vsb % 4 == 0 && kp.s.vsx % 4 == 0 && kp.s.vsy % 4 == 0 && kp.s.vsz % 4 == 0;
     if (kp.s.Cp > 0) ok = ok && kp.s.psc == 1 && kp.s.Cp % 4 == 0 && kp.s.psb % 4 == 0 && kp.s.psh % 4 == 0 && kp.s.psw % 4 == 0;
     if (!ok) {
-        set_error("gnb_query_fused_tc: the fused path needs channels-last volume / planes with channel counts % 4 == 0 "
+        set_error("gnb_query_fused_tc: the fused path needs 16-byte aligned channels-last volume / planes with channel counts % 4 == 0 "
                   "(use gnb_sample_features + gnb_decode_tc otherwise)");
         return GNB_E_UNSUPPORTED;
     }
     kp.xyz = s->xyz, kp.feat = nullptr, kp.fused = 1, kp.n_rows = kp.s.total, kp.out = out, kp.tsdf = tsdf;
+    return 0;
+}
+
+extern "C" int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed, float* out,
+                                    float* tsdf, void* stream) {
+    TcKP kp = {};
+    int rc = query_fused_common(s, w, kp, out, tsdf, "gnb_query_fused_tc");
+    if (rc || kp.s.total == 0) return rc;
+    return launch_tc(w, packed, kp, stream);
+}
+
+extern "C" int gnb_query_grid_fused_tc(const GnbSampleParams* s, const int32_t* h_grid3, const float* axes, const GnbDecoderWeights* w,
+                                         const void* packed, float* out, float* tsdf, void* stream) {
+    GNB_CHECK_ARG(s && h_grid3 && axes, "gnb_query_grid_fused_tc: null argument");
+    GNB_CHECK_ARG(h_grid3[0] > 0 && h_grid3[1] > 0 && h_grid3[2] > 0, "gnb_query_grid_fused_tc: bad grid");
+    GnbSampleParams sg = *s;
+    sg.n_query = (int64_t)h_grid3[0] * h_grid3[1] * h_grid3[2];
+    sg.xyz = axes;                                     // (only so that the shared argument checks see a non-null pointer)
+    TcKP kp = {};
+    int rc = query_fused_common(&sg, w, kp, out, tsdf, "gnb_query_grid_fused_tc");
+    if (rc || kp.s.total == 0) return rc;
+    kp.xyz = nullptr, kp.gaxes = axes, kp.gnx = h_grid3[0], kp.gny = h_grid3[1], kp.gnz = h_grid3[2];
     return launch_tc(w, packed, kp, stream);
 }

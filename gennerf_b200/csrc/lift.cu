@@ -508,7 +508,7 @@ static int launch_lift(const LiftKP& kp, int C, cudaStream_t st) {
     constexpr int NVMAX = (256 / G) < 32 ? (256 / G) : 32;
     constexpr int NVMIN = (32 / G) > 4 ? (32 / G) : 4;      // bricks are at least 2 x 2 x 8
     int nvw = NVMAX >= 16 ? 16 : NVMAX;
-    if (const char* e = getenv("GNB_LIFT_NVW")) nvw = atoi(e);
+    if (const int e = opt(OPT_LIFT_NVW)) nvw = e;
     if (nvw <= NVMIN) return launch_lift_nvw<G, VEC, NVMIN>(kp, C, st);
     if constexpr (NVMAX >= 2 * NVMIN) { if (nvw <= 2 * NVMIN || NVMAX == 2 * NVMIN) return launch_lift_nvw<G, VEC, 2 * NVMIN>(kp, C, st); }
     if constexpr (NVMAX >= 4 * NVMIN) { if (nvw <= 4 * NVMIN || NVMAX == 4 * NVMIN) return launch_lift_nvw<G, VEC, 4 * NVMIN>(kp, C, st); }

@@ -682,7 +682,7 @@ extern "C" int gnb_scatter_mean_planes(const float* p, const float* c, int B, in
         if (N > 0) {
             const dim3 blocks((unsigned)(((N + 31) / 32 + 7) / 8), (unsigned)B, 3);       // 8 groups of 32 points per block; grid rows = scenes, layers = planes
             const dim3 blocks4(blocks.x, blocks.y, N >= 32768 ? 1 : 3);                      // v4 kernels: see the kernel comment
-            const bool v4 = (reinterpret_cast<uintptr_t>(c) & 15) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0 && !getenv("GNB_SCATTER_SCALAR");
+            const bool v4 = (reinterpret_cast<uintptr_t>(c) & 15) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0 && !opt(OPT_SCATTER_SCALAR);
             if (v4 && Cp == 4) scatter_atomic_v4_kernel<1><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
             else if (v4 && Cp == 8) scatter_atomic_v4_kernel<2><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);
             else if (v4 && Cp == 16) scatter_atomic_v4_kernel<4><<<blocks4, 256, 0, st>>>(p, c, B, N, R, den, planes, count);

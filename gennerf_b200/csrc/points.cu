@@ -326,7 +326,7 @@ extern "C" int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int
     // Cluster size: the iteration time is ~2.1 us of exchange / reduction latency + ~0.063 ns per point of a CTA's slice
     // (measured: 2.41 us at 4 800, 3.32 us at 19 200 points per CTA), and only a few 16-CTA clusters are co-resident
     // (~6 on a B200), so with many clouds a smaller cluster that lets every cloud run in the first wave wins.
-    if (!getenv("GNB_FPS_SINGLE_CTA")) {
+    if (!opt(OPT_FPS_SINGLE_CTA)) {
         GNB_CUDA(cudaFuncSetAttribute(fps_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         int best_cs = 0;
         double best_t = 1e30;
@@ -350,7 +350,7 @@ extern "C" int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int
             const double t = waves * (2.1 + 0.063e-3 * (double)chunk);
             if (t < best_t * 0.97) best_t = t, best_cs = cs;           // ties go to the smaller cluster
         }
-        if (const char* e = getenv("GNB_FPS_CLUSTER")) best_cs = atoi(e);    // tuning aid
+        if (const int e = opt(OPT_FPS_CLUSTER)) best_cs = e;    // tuning aid
         if (best_cs > 1 && N > 2048) {
             const int cs = best_cs;
             const long long chunk = (N + cs - 1) / cs;
@@ -389,6 +389,121 @@ extern "C" int gnb_sample_points_on_rays(const int64_t* h_idxs, const int64_t* w
     kp.xyz = xyz_world, kp.z = z;
     const long long n = (long long)B * S * (1 + N + M);
     ray_points_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(kp);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sample_valid_depth_pixels (reference src/models/utils.py:340-363): per depth map, `argwhere(depth != 0)` (row-major
+// list of the valid pixels, 16 bytes each), `randperm(n_valid)[:S]`, gather.  Here the list is never built: a count
+// pass gives every image row's number of valid pixels and their exclusive prefix (and n_valid, which the caller needs
+// on the host for the reference's randperm call -- the same synchronisation the reference has in argwhere); the select
+// pass finds the k-th valid pixel of the map for each of the S drawn ranks k: binary search over the row prefix, then
+// one warp walks the row 32 pixels at a time with ballot / popc.  Same (h, w) as the reference for the same ranks.
+// ---------------------------------------------------------------------------------------------------------------
+namespace gnb {
+
+// grid (H, B): block = one image row; row_count[b][h]
+__global__ void valid_row_count_kernel(const float* __restrict__ depth, int H, int W, int* __restrict__ row_count) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    const float* row = depth + ((long long)b * H + h) * W;
+    int n = 0;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) n += (__ldg(row + w) != 0.0f) ? 1 : 0;
+    n = __reduce_add_sync(FULL, n);
+    __shared__ int s[8];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s[i];
+        row_count[b * H + h] = t;
+    }
+}
+
+// one block per map: exclusive prefix over the H rows (in place), total to n_valid[b]
+__global__ void valid_row_scan_kernel(int* __restrict__ row_count, int H, int* __restrict__ n_valid) {
+    const int b = blockIdx.x;
+    int* rc = row_count + (long long)b * H;
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int h0 = 0; h0 < H; h0 += blockDim.x) {
+        const int h = h0 + threadIdx.x;
+        const int v = h < H ? rc[h] : 0;
+        // block-wide inclusive scan (blockDim.x = 256: warp scans + scan of the 8 warp totals)
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(FULL, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        __shared__ int wt[8];
+        if ((threadIdx.x & 31) == 31) wt[threadIdx.x >> 5] = x;
+        __syncthreads();
+        int base = carry;
+        for (int i = 0; i < (int)(threadIdx.x >> 5); ++i) base += wt[i];
+        if (h < H) rc[h] = base + x - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = base + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_valid[b] = carry;
+}
+
+// one warp per (map, sample): rank k -> (h, w) of the k-th valid pixel in row-major order
+__global__ void valid_select_kernel(const float* __restrict__ depth, int B, int H, int W, const int* __restrict__ row_prefix,
+                                    const int* __restrict__ n_valid, const long long* __restrict__ rank, int S,
+                                    long long* __restrict__ h_out, long long* __restrict__ w_out) {
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (long long)B * S) return;
+    const int b = (int)(wid / S);
+    const long long k = rank[wid];
+    const int* rp = row_prefix + (long long)b * H;
+    if (k < 0 || k >= n_valid[b]) {                       // caller error (rank outside the valid list)
+        if (lane == 0) h_out[wid] = -1, w_out[wid] = -1;
+        return;
+    }
+    int lo = 0, hi = H - 1;                                // last row whose prefix <= k
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (rp[mid] <= k) lo = mid; else hi = mid - 1;
+    }
+    int need = (int)(k - rp[lo]);                          // the need-th valid pixel of row lo
+    const float* row = depth + ((long long)b * H + lo) * W;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+        const int w = w0 + lane;
+        const unsigned m = __ballot_sync(FULL, w < W && __ldg(row + w) != 0.0f);
+        const int c = __popc(m);
+        if (need < c) {
+            // position of the need-th set bit
+            unsigned mm = m;
+            for (int i = 0; i < need; ++i) mm &= mm - 1;
+            if (lane == 0) h_out[wid] = lo, w_out[wid] = w0 + (__ffs(mm) - 1);
+            return;
+        }
+        need -= c;
+    }
+}
+
+}  // namespace gnb
+
+extern "C" int gnb_valid_pixel_count(const float* depth, int B, int H, int W, int32_t* row_prefix, int32_t* n_valid, void* stream) {
+    GNB_CHECK_ARG(B >= 0 && H > 0 && W > 0, "gnb_valid_pixel_count: bad shape");
+    if (B == 0) return 0;
+    GNB_CHECK_ARG(depth && row_prefix && n_valid, "gnb_valid_pixel_count: null pointer");
+    gnb::valid_row_count_kernel<<<dim3((unsigned)H, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(depth, H, W, row_prefix);
+    GNB_LAUNCH_CHECK();
+    gnb::valid_row_scan_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(row_prefix, H, n_valid);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_valid_pixel_select(const float* depth, int B, int H, int W, const int32_t* row_prefix, const int32_t* n_valid,
+                                      const int64_t* rank, int S, int64_t* h_idxs, int64_t* w_idxs, void* stream) {
+    GNB_CHECK_ARG(B >= 0 && H > 0 && W > 0 && S >= 0, "gnb_valid_pixel_select: bad shape");
+    if (B == 0 || S == 0) return 0;
+    GNB_CHECK_ARG(depth && row_prefix && n_valid && rank && h_idxs && w_idxs, "gnb_valid_pixel_select: null pointer");
+    const long long threads = (long long)B * S * 32;
+    gnb::valid_select_kernel<<<gnb::ceil_div(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+        depth, B, H, W, row_prefix, n_valid, (const long long*)rank, S, (long long*)h_idxs, (long long*)w_idxs);
     GNB_LAUNCH_CHECK();
     return 0;
 }

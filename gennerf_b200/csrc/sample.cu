@@ -387,7 +387,7 @@ extern "C" int gnb_sample_features(const GnbSampleParams* s, void* stream) {
     bool small = true;
     if (kp.volume) small = small && ((long long)kp.nx * kp.vsx + (long long)kp.ny * kp.vsy + (long long)kp.nz * kp.vsz < 0x7fffffffLL);
     if (kp.Cp > 0) small = small && ((long long)kp.R * kp.psh + (long long)kp.R * kp.psw < 0x7fffffffLL);
-    if (vec && small && !getenv("GNB_SAMPLE_GENERIC")) {
+    if (vec && small && !opt(OPT_SAMPLE_GENERIC)) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

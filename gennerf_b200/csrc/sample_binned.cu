@@ -478,7 +478,7 @@ static bool plan_binned(const GnbSampleParams* sp, BinPlan& pl) {
     pl.zero_bytes = o_work + 256;
     const size_t o_start = pl.zero_bytes, o_ustart = o_start + up(((size_t)k.nbricks + 1) * 4);
     k.unit_max = 1536;
-    if (const char* e = getenv("GNB_BIN_UNIT")) k.unit_max = atoi(e) > 31 ? atoi(e) : 1536;       // tuning aid
+    if (const int e = opt(OPT_BIN_UNIT)) k.unit_max = e > 31 ? e : 1536;       // tuning aid
     const size_t max_units = (size_t)k.nbricks + (size_t)(s.total / k.unit_max) + 1;
     const size_t o_units = o_ustart + up(((size_t)k.nbricks + 1) * 4), o_bid = o_units + up(max_units * 8), o_sorted = o_bid + up((size_t)s.total * 4);
     k.units = reinterpret_cast<uint2*>(o_units);
@@ -552,7 +552,7 @@ extern "C" int gnb_sample_features_binned(const GnbSampleParams* sp, void* scrat
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     k.use_tmap = 0;
-    if (k.s.C <= 256 && !getenv("GNB_BIN_ROWCOPY")) {
+    if (k.s.C <= 256 && !opt(OPT_BIN_ROWCOPY)) {
         const int e = k.bx + 1, ez = k.bz + 1;
         cuuint64_t gdim[5] = {(cuuint64_t)k.s.C, (cuuint64_t)k.s.nz, (cuuint64_t)k.s.ny, (cuuint64_t)k.s.nx, (cuuint64_t)sp->batch};
         cuuint64_t gstr[4] = {(cuuint64_t)k.s.vsz * 4, (cuuint64_t)k.s.vsy * 4, (cuuint64_t)k.s.vsx * 4, (cuuint64_t)k.s.vsb * 4};

@@ -126,6 +126,12 @@ def sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta
     return ops.sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta, min_dist, sigma)
 
 
+def sample_valid_depth_pixels(depth, num_samples):
+    """reference src/models/utils.py:340-363: b_idxs (B,1), h_idxs (B,S), w_idxs (B,S) of randomly chosen pixels with
+    depth != 0 (same torch.randperm draws as the reference, no argwhere list)."""
+    return ops.sample_valid_depth_pixels(depth, num_samples)
+
+
 def normalize_coordinate(p, padding=0.1, plane="xz", encode=True):
     """reference src/models/utils.py:75-98: (B,N,3) -> (B,N,2) in [0, 1-1e-5]."""
     coord, _ = ops.plane_coords(p, padding, 1)
@@ -329,23 +335,37 @@ class LocalPoolPointnet(nn.Module):
     scatter-max/gather local pooling run on the sm_100a kernels; `unet` (a user-supplied
     nn.Module applied to every plane, reference pointnet.py:85-87) stays PyTorch."""
 
-    def __init__(self, c_dim=128, dim=3, hidden_dim=128, scatter_type="max", unet=None, unet_kwargs=None,
+    def __init__(self, c_dim=128, dim=3, hidden_dim=128, scatter_type="max", unet=False, unet_kwargs=None,
                  unet3d=False, unet3d_kwargs=None, plane_resolution=None, grid_resolution=None, plane_type="xz",
                  padding=0.1, n_blocks=5, scatter_mode="atomic"):
         super().__init__()
         if scatter_type not in ("max", "mean"):
             raise ValueError("incorrect scatter type")
-        if "grid" in plane_type:
-            raise NotImplementedError("gennerf_b200: 'grid' features are not on the path")
+        if "grid" in plane_type or unet3d:
+            raise NotImplementedError("gennerf_b200: 'grid' features / unet3d are not on the path "
+                                      "(dead code in the reference: pointnet.py:182)")
+        self.plane_type = [plane_type] if isinstance(plane_type, str) else list(plane_type)
+        if sorted(self.plane_type) != ["xy", "xz", "yz"]:
+            # pool_local (reference pointnet.py:105-121) sums over the planes of plane_type; the kernel pools over all three
+            raise NotImplementedError("gennerf_b200: LocalPoolPointnet is built for plane_type ['xz', 'xy', 'yz'] "
+                                      f"(the reference config); got {plane_type!r}")
         self.c_dim, self.hidden_dim = c_dim, hidden_dim
         self.fc_pos = nn.Linear(dim, 2 * hidden_dim)
         self.blocks = nn.ModuleList([_PointBlockFC(2 * hidden_dim, hidden_dim) for _ in range(n_blocks)])
         self.fc_c = nn.Linear(hidden_dim, c_dim)
         self.actvn = nn.ReLU()
-        self.unet = unet if isinstance(unet, nn.Module) else None
+        # `unet`: the reference's bool (pointnet.py:51-54 builds UNet(c_dim, in_channels=c_dim, **unet_kwargs)) or a ready
+        # nn.Module.  The U-Net is cuDNN convolutions between scatter and query (SURVEY section 2: stays PyTorch), so
+        # the reference's own class is used -- it must be importable (the drop-in lives inside the reference tree);
+        # a config that asks for it is never silently run without it.
+        if isinstance(unet, nn.Module):
+            self.unet = unet
+        elif unet:
+            self.unet = _reference_unet(c_dim, unet_kwargs)
+        else:
+            self.unet = None
         self.unet3d = None
         self.reso_plane, self.reso_grid = plane_resolution, grid_resolution
-        self.plane_type = [plane_type] if isinstance(plane_type, str) else list(plane_type)
         self.padding = padding
         self.scatter_type = scatter_type
         self.scatter_mode = scatter_mode            # 'atomic' | 'deterministic' (extra knob, default = fast)
@@ -380,9 +400,23 @@ class LocalPoolPointnet(nn.Module):
 
     @classmethod
     def from_conf(cls, cfg, unet=None):
-        return cls(c_dim=cfg.c_dim, dim=cfg.dim, hidden_dim=cfg.hidden_dim, scatter_type=cfg.scatter_type, unet=unet,
+        """reference pointnet.py:173-189.  `unet=` (an nn.Module) overrides cfg.unet / cfg.unet_kwargs."""
+        return cls(c_dim=cfg.c_dim, dim=cfg.dim, hidden_dim=cfg.hidden_dim, scatter_type=cfg.scatter_type,
+                   unet=unet if unet is not None else cfg.unet, unet_kwargs=getattr(cfg, "unet_kwargs", None),
                    plane_resolution=cfg.plane_resolution, plane_type=cfg.plane_type, padding=cfg.padding,
                    n_blocks=cfg.n_blocks)
+
+
+def _reference_unet(c_dim, unet_kwargs):
+    """UNet(c_dim, in_channels=c_dim, **unet_kwargs) of the reference tree (src/models/components/unet.py:114-236)."""
+    try:
+        from src.models.components.unet import UNet
+    except Exception as e:                                   # noqa: BLE001 -- whatever keeps the import from working
+        raise RuntimeError(
+            "gennerf_b200: the config asks for the plane U-Net (pointnet.unet: True) but the reference's "
+            "src.models.components.unet.UNet cannot be imported; run inside the reference tree, pass unet=<nn.Module>, "
+            f"or set pointnet.unet: False ({type(e).__name__}: {e})") from e
+    return UNet(c_dim, in_channels=c_dim, **dict(unet_kwargs or {}))
 
 
 class FeaturePlaneMerger(nn.Module):
@@ -442,6 +476,7 @@ class GenNerf(nn.Module):
         self.origin = torch.tensor([0, 0, 0]).view(1, 3)
         self.voxel_sizes = [int(cfg.voxel_size * 100)]
         self._dw = None
+        self._dw_key = None
         self.initialize_volume()
 
     @property
@@ -454,13 +489,45 @@ class GenNerf(nn.Module):
         self.count = None
         self.c_plane = None
 
+    def _weights_key(self):
+        """Identity + version of every decoder parameter: an optimiser step, load_state_dict, .to() or .half() changes it."""
+        ps = list(self.mlp.parameters()) + list(self.head_geo.parameters())
+        return (self.precision,) + tuple((p.data_ptr(), p._version, p.device, p.dtype) for p in ps)
+
     def refresh_weights(self):
-        """Re-read the decoder parameters (call after an optimiser step / load_state_dict)."""
+        """Re-read the decoder parameters: device views of the fp32 tensors, `alpha`, and (fp16 / bf16) the packed
+        tensor-core image.  forward() calls this by itself whenever a parameter has changed since the last call."""
         self._dw = self.mlp.device_weights(head=self.head_geo, code=self.code if self.cfg.use_code else None,
                                            precision=self.precision)
         if not self.cfg.use_code:
             self._dw.w.use_code, self._dw.w.d_code = 0, 3
+        self._dw_key = self._weights_key()
         return self._dw
+
+    def decoder_weights(self):
+        """The cached ops.DecoderWeights, rebuilt when any mlp / head parameter changed (optimiser step in between two
+        eval forwards, load_state_dict, .to(device)): a stale packed image would decode with old weights silently."""
+        if self._dw is None or getattr(self, "_dw_key", None) != self._weights_key():
+            self.refresh_weights()
+        return self._dw
+
+    def fp16_overflowed(self):
+        """True when a tensor-core forward since the last call saturated an fp16 operand (|value| >= 65504): such outputs
+        are outside the 1e-2 TSDF contract; rebuild the model with precision='fp32' for that checkpoint / input scale.
+        One 4-byte device-to-host read."""
+        return self._dw is not None and self._dw.overflowed()
+
+    def _planes_for_kernels(self):
+        """self.c_plane as the kernels want it: channels-last fp32 (a U-Net or the 'learn' merger hands over NCHW planes);
+        converted once per encode and cached by tensor identity."""
+        if not self.cfg.encoder.use_pointnet or self.c_plane is None:
+            return None
+        key = tuple((k, v.data_ptr(), v._version) for k, v in self.c_plane.items())
+        if getattr(self, "_pl_key", None) != key:
+            self._pl_cl = {k: (v if v.is_contiguous(memory_format=torch.channels_last) else
+                               v.detach().contiguous(memory_format=torch.channels_last)) for k, v in self.c_plane.items()}
+            self._pl_key = key
+        return self._pl_cl
 
     def encode(self, projection, image, depth=None, mode="val", sparse_xyz=None):
         """reference model.py:77-150.  projection (B,T,3,4), image (B,T,3,H,W) (or (B,T,C,H,W)
@@ -519,26 +586,50 @@ class GenNerf(nn.Module):
         d_geo, d_sem = self.cfg.mlp.d_out_geo, self.cfg.mlp.d_out_sem
         if torch.is_grad_enabled() and (self.training or xyz.requires_grad):
             return self._forward_train(xyz)
-        dw = self._dw if (self._dw is not None and not self.training) else self.refresh_weights()
-        if self.precision in ("fp16", "bf16") and self.fused:
+        dw = self.decoder_weights()
+        volume = self.volume if self.cfg.encoder.use_spatial else None
+        planes = self._planes_for_kernels()
+        fusable = self.precision in ("fp16", "bf16") and self.fused and ops.fused_query_applies(volume, planes)
+        if fusable:
             out, tsdf, feat = ops.query_fused(
-                dw, xyz, volume=self.volume if self.cfg.encoder.use_spatial else None,
-                planes=self.c_plane if self.cfg.encoder.use_pointnet else None,
-                voxel_size=self.cfg.voxel_size, origin=self.origin,
+                dw, xyz, volume=volume, planes=planes, voxel_size=self.cfg.voxel_size, origin=self.origin,
                 padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1,
                 precision=self.precision)
         else:
+            # layouts the fused prologue cannot read with float4 (reference-layout volume, odd channel counts):
+            # the strided sampler kernel + the decoder kernel -- still no PyTorch arithmetic
             feat = self.map_features(xyz)
             out, tsdf = ops.decode(dw, xyz, feat, self.precision)
         return {"feat_geo": out[..., :d_geo], "feat_sem": out[..., d_geo:d_geo + d_sem], "tsdf": tsdf, "feat": feat}
 
     @torch.no_grad()
-    def predict_tsdf(self, nx, ny, nz, volume_size=None):
+    def predict_tsdf(self, nx, ny=None, nz=None, volume_size=None):
         """reference model.py:752-790 without its 10 000-point chunk loop, per-chunk volume
         re-normalisation and per-chunk D2H copies: the whole (nx,ny,nz) grid is decoded by one fused
-        kernel launch.  Returns tsdf (1,nx,ny,nz) on the device."""
+        kernel launch.
+
+        Two call forms: `predict_tsdf(batch, b_idx)` -- the reference's signature: grid dimensions from
+        batch['vol_%02d_tsdf'], extent voxel_size * voxel_dim_test, result (1,nx,ny,nz) on the CPU like the
+        reference's concatenated chunks (ONE device-to-host copy) -- and `predict_tsdf(nx, ny, nz, volume_size=None)`,
+        which returns the (1,nx,ny,nz) TSDF on the device."""
+        if isinstance(nx, dict):
+            batch, b_idx = nx, int(ny or 0)
+            trgt = batch["vol_%02d_tsdf" % self.voxel_sizes[0]]
+            gx, gy, gz = (int(d) for d in trgt.shape[-3:])
+            return self.predict_tsdf(gx, gy, gz).cpu()
         if volume_size is None:
             volume_size = [self.cfg.voxel_size * d for d in self.cfg.voxel_dim_test]
+        volume = self.volume if self.cfg.encoder.use_spatial else None
+        planes = self._planes_for_kernels()
+        if self.precision in ("fp16", "bf16") and self.fused and ops.fused_query_applies(volume, planes):
+            # the (V,3) query grid is derived in the kernel from the row index and the three linspace axes (generated on
+            # the CPU like the reference's, so the coordinates are bit-identical): 12 B/point less to write and read
+            axes = [torch.linspace(0, float(volume_size[i]), n) for i, n in enumerate((nx, ny, nz))]
+            tsdf, _ = ops.query_grid_fused(self.decoder_weights(), (nx, ny, nz), [a.to(self.device) for a in axes],
+                                           volume=volume, planes=planes, voxel_size=self.cfg.voxel_size, origin=self.origin,
+                                           padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1,
+                                           precision=self.precision)
+            return tsdf[:1] if tsdf.shape[0] > 1 else tsdf
         grid = get_grid_coordinates(nx, ny, nz, volume_size, self.origin, device=self.device).reshape(1, -1, 3)
         was_training = self.training
         self.eval()
@@ -570,3 +661,60 @@ class GenNerf(nn.Module):
         feat_geo, feat_sem = out[..., :d_geo], out[..., d_geo:d_geo + d_sem]
         tsdf = torch.tanh(torch.nn.functional.linear(feat_geo, self.head_geo.fc.weight, self.head_geo.fc.bias))
         return {"feat_geo": feat_geo, "feat_sem": feat_sem, "tsdf": tsdf, "feat": feat}
+
+
+# ------------------------------------------------------------------------------------------
+# src/models/voxel_net.py -- the lift half of VoxelNet (Atlas clone)
+# ------------------------------------------------------------------------------------------
+class VoxelNet(nn.Module):
+    """The hot-path half of the reference's VoxelNet (src/models/voxel_net.py:27-175): `encode` (per-frame 2D CNN ->
+    backproject -> accumulate, :76-144) and the volume normalisation that opens `forward` (:162-168) on the fused lift
+    kernel.  The 2D CNN (`spatial`), the 3D encoder-decoder (`backbone3d`) and the multi-scale TSDF heads (`heads3d`)
+    are dense cuDNN convolutions outside the path: pass the reference's own modules in; attribute
+    names, `cfg` keys (voxel_size, voxel_dim_{train,val}, encoder.use_spatial) and `.volume` / `.valid` are unchanged."""
+
+    def __init__(self, cfg, spatial=None, backbone3d=None, heads3d=None):
+        super().__init__()
+        self.cfg = cfg
+        self.spatial, self.backbone3d, self.heads3d = spatial, backbone3d, heads3d
+        self.origin = torch.tensor([0, 0, 0]).view(1, 3)
+        self.initialize_volume()
+
+    def initialize_volume(self):
+        self.volume = None
+        self.valid = None
+        self.count = None
+        self.c_plane = None
+
+    def encode(self, projection, image, depth=None):
+        """reference voxel_net.py:76-144: projection (B,T,3,4), image (B,T,3,H,W) -> accumulates self.volume (the SUM over
+        the frames that see a voxel, bit-identical to the reference's frame-by-frame adds) and self.valid (bool OR).
+        All T frames go through ONE lift launch; repeated calls keep accumulating."""
+        if not self.cfg.encoder.use_spatial:
+            return
+        T = projection.size(1)
+        frames = image.unbind(1)
+        feats = [self.spatial(frames[t]) if self.spatial is not None else frames[t] for t in range(T)]
+        voxel_dim = self.cfg.voxel_dim_train if self.training else self.cfg.voxel_dim_val
+        if torch.is_grad_enabled() and any(f.requires_grad for f in feats):
+            vol, cnt, val = ag.backproject_frames(voxel_dim, self.cfg.voxel_size, self.origin, projection, feats)
+            if self.volume is None:
+                self.volume, self.count, self.valid = vol, cnt, val
+            else:
+                self.volume, self.count, self.valid = self.volume + vol, self.count + cnt, self.valid + val
+        else:
+            out = None if self.volume is None else (self.volume, self.count, self.valid)
+            self.volume, self.count, self.valid = ops.backproject_frames(
+                voxel_dim, self.cfg.voxel_size, self.origin, projection, feats, out=out)
+
+    def normalized_volume(self):
+        """reference voxel_net.py:163-168: `volume / valid` with NaN -> 0.  `valid` is boolean (trap T2), so this is the
+        accumulated sum where a frame saw the voxel and 0 elsewhere -- exactly what the lift kernel wrote: no pass."""
+        return self.volume
+
+    def forward(self, targets=None):
+        """reference voxel_net.py:147-175: normalise, 3D CNN, heads (the latter two are the caller's modules)."""
+        if self.backbone3d is None or self.heads3d is None:
+            raise RuntimeError("gennerf_b200: VoxelNet.forward needs the reference's backbone3d and heads3d modules "
+                               "(dense 3D convolutions are outside the path); encode() / normalized_volume() do not")
+        return self.heads3d(self.backbone3d(self.normalized_volume()), targets)

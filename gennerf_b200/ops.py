@@ -326,6 +326,9 @@ class DecoderWeights:
             w.fc1_w[i], w.fc1_b[i] = self.t[f"blocks.{i}.fc_1.weight"].data_ptr(), self.t[f"blocks.{i}.fc_1.bias"].data_ptr()
         w.lin_out_w, w.lin_out_b = self.t["lin_out.weight"].data_ptr(), self.t["lin_out.bias"].data_ptr()
         w.head_w, w.head_b = self.head_w.data_ptr(), self.head_b.data_ptr()
+        # device status word: the tensor-core kernels set bit 0 when an fp16 operand saturated (see overflowed())
+        self.status = torch.zeros(1, device=device, dtype=torch.int32)
+        w.status = self.status.data_ptr()
         self.w = w
         self.device = torch.device(device)
         self.packed = None
@@ -343,6 +346,15 @@ class DecoderWeights:
             check(lib().gnb_decoder_pack_tc(C.byref(self.w), self.packed.data_ptr(), _stream()), "gnb_decoder_pack_tc")
         self.packed_dtype = dtype
         return self.packed
+
+    def overflowed(self, reset=True):
+        """True when a tensor-core launch since the last reset saturated an fp16 operand at +-65504 (input feature,
+        positional code or hidden activation): that result is outside the 1e-2 TSDF contract -- decode with
+        precision='fp32'.  Costs one 4-byte device-to-host read (a stream sync)."""
+        hit = bool(self.status.item())
+        if hit and reset:
+            self.status.zero_()
+        return hit
 
     def tc_image(self, dtype):
         if self.packed is None or getattr(self, "packed_dtype", None) != dtype:
@@ -390,6 +402,47 @@ def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
         check(lib().gnb_query_fused_tc(C.byref(s), C.byref(weights.w), packed.data_ptr(), out.data_ptr(),
                                          tsdf.data_ptr(), _stream()), "gnb_query_fused_tc")
     return out, tsdf, feat
+
+
+def query_grid_fused(weights, grid_dim, axes, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
+                     want_out=False, precision="fp16"):
+    """GenNerf.predict_tsdf's query (reference model.py:752-790) in one kernel without a materialised query grid:
+    `axes` = (ax (nx,), ay (ny,), az (nz,)) CUDA fp32 coordinate axes (torch.linspace of get_grid_coordinates,
+    utils.py:926-935).  Returns tsdf (B,nx,ny,nz) and, with want_out, out (B,nx*ny*nz,d_out)."""
+    nx, ny, nz = (int(d) for d in grid_dim)
+    ref = volume if volume is not None else next(p for p in planes.values() if p is not None)
+    B, dev = ref.shape[0], ref.device
+    ax = torch.cat([_f32(a).reshape(-1) for a in axes]).to(dev).contiguous()
+    if ax.numel() != nx + ny + nz:
+        raise RuntimeError("query_grid_fused: axes must hold nx, ny and nz coordinates")
+    dummy = torch.empty((B, 0, 3), device=dev, dtype=torch.float32)
+    s, keep, _, _, Cp, Cv = _fill_sample_params(dummy, volume, planes, voxel_size, origin, padding)
+    Q = nx * ny * nz
+    out = torch.empty((B, Q, weights.w.d_out), device=dev, dtype=torch.float32) if want_out else None
+    tsdf = torch.empty((B, nx, ny, nz), device=dev, dtype=torch.float32)
+    packed = weights.tc_image(precision)
+    g3 = (C.c_int32 * 3)(nx, ny, nz)
+    with torch.cuda.device(dev):
+        check(lib().gnb_query_grid_fused_tc(C.byref(s), g3, ax.data_ptr(), C.byref(weights.w), packed.data_ptr(),
+                                              out.data_ptr() if out is not None else None, tsdf.data_ptr(), _stream()),
+              "gnb_query_grid_fused_tc")
+    return tsdf, out
+
+
+def fused_query_applies(volume=None, planes=None):
+    """True when gnb_query_fused_tc can read these tensors (16-byte aligned channels-last fp32 storage with channel
+    counts % 4 == 0); otherwise callers use sample_features + decode."""
+    ts = ([volume] if volume is not None else []) + [p for p in (planes or {}).values() if p is not None]
+    for t in ts:
+        if t.dtype != torch.float32 or t.shape[1] % 4 or t.stride(1) != 1 or t.data_ptr() % 16:
+            return False
+        if any(st % 4 for i, st in enumerate(t.stride()) if i != 1):
+            return False
+    if planes:
+        ps = [p for p in planes.values() if p is not None]
+        if any(p.stride() != ps[0].stride() or p.shape != ps[0].shape for p in ps):
+            return False
+    return True
 
 
 def positional_encoding(x, num_freqs, freq_factor, include_input=True):
@@ -676,3 +729,28 @@ def sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta
                                               B, S, int(N), int(M), float(delta), float(min_dist), xyz.data_ptr(), z.data_ptr(),
                                               _stream()), "gnb_sample_points_on_rays")
     return xyz, z
+
+
+def sample_valid_depth_pixels(depth, num_samples):
+    """sample_valid_depth_pixels (reference utils.py:340-363): depth (B,H,W) -> b_idxs (B,1), h_idxs, w_idxs (B,S) int64.
+    The ranks are drawn as the reference draws them (one torch.randperm(n_valid[b], device)[:S] per map, in map order, so
+    the same generator state selects the same pixels); the argwhere list itself is never materialised."""
+    _need_cuda(depth)
+    d = _f32(depth).contiguous()
+    B, H, W = d.shape
+    dev = d.device
+    prefix = torch.empty((B, H), device=dev, dtype=torch.int32)
+    nvalid = torch.empty((B,), device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        check(lib().gnb_valid_pixel_count(d.data_ptr(), B, H, W, prefix.data_ptr(), nvalid.data_ptr(), _stream()),
+              "gnb_valid_pixel_count")
+        counts = nvalid.tolist()                             # host sync, as torch.argwhere has in the reference
+        if any(c < num_samples for c in counts):
+            raise ValueError("Not enough non-zero depth pixels to sample from.")
+        rank = torch.stack([torch.randperm(c, device=dev)[:num_samples] for c in counts]) if B > 0 else \
+            torch.empty((0, num_samples), device=dev, dtype=torch.long)
+        h = torch.empty((B, num_samples), device=dev, dtype=torch.long)
+        w = torch.empty((B, num_samples), device=dev, dtype=torch.long)
+        check(lib().gnb_valid_pixel_select(d.data_ptr(), B, H, W, prefix.data_ptr(), nvalid.data_ptr(), rank.contiguous().data_ptr(),
+                                           int(num_samples), h.data_ptr(), w.data_ptr(), _stream()), "gnb_valid_pixel_select")
+    return torch.arange(B, device=dev).unsqueeze(1), h, w

@@ -41,6 +41,13 @@ const char* gnb_last_error(void);
 /* sizeof() of the parameter structs as compiled: 0 GnbLiftParams, 1 GnbSampleParams,
  * 2 GnbDecoderWeights, 3 GnbFusionParams.  Lets a foreign-language binding verify its struct layout. */
 int gnb_struct_size(int which);
+/* Tuning / debugging switches (GNB_TC_TWO_CTA, GNB_TC_NO_EARLY, GNB_DEBUG_MAX_CLUSTERS, GNB_DEBUG_PRINT, GNB_LIFT_NVW,
+ * GNB_SCATTER_SCALAR, GNB_FPS_SINGLE_CTA, GNB_FPS_CLUSTER, GNB_SAMPLE_GENERIC, GNB_BIN_UNIT, GNB_BIN_ROWCOPY,
+ * GNB_SCATTER_TILED, GNB_BIN_PRESORTED).  Every option takes its default from the environment variable of the same name,
+ * read ONCE per process (never on a hot-path call); these two calls read / change it afterwards.  None of them changes
+ * results beyond floating-point summation order. */
+int gnb_set_option(const char* name, int value);
+int gnb_get_option(const char* name, int* value);
 
 /* -------------------------------------------------------------------------------------
  * Layout helper: (T frames) NCHW -> NHWC, one launch.  src[t] is (B,C,H,W); dst is
@@ -236,6 +243,15 @@ int gnb_sample_points_on_rays(const int64_t* h_idxs, const int64_t* w_idxs, cons
                               int B, int S, int N, int M, float delta, float min_dist,
                               float* xyz_world, float* z, void* stream);
 
+/* sample_valid_depth_pixels (src/models/utils.py:340-363) without materialising argwhere(depth != 0): gnb_valid_pixel_count
+ * writes, per depth map (B,H,W), the exclusive prefix of the valid-pixel count of every image row (row_prefix (B,H)) and
+ * the total n_valid (B); gnb_valid_pixel_select maps S ranks per map (rank (B,S) int64, each in [0, n_valid[b]) -- the
+ * caller draws them exactly like the reference: torch.randperm(n_valid[b])[:S]) to the (h, w) of the rank-th valid pixel
+ * in row-major order, i.e. argwhere(depth[b] != 0)[rank].  h_idxs / w_idxs (B,S) int64; -1 for a rank out of range. */
+int gnb_valid_pixel_count(const float* depth, int B, int H, int W, int32_t* row_prefix, int32_t* n_valid, void* stream);
+int gnb_valid_pixel_select(const float* depth, int B, int H, int W, const int32_t* row_prefix, const int32_t* n_valid,
+                           const int64_t* rank, int S, int64_t* h_idxs, int64_t* w_idxs, void* stream);
+
 /* -------------------------------------------------------------------------------------
  * TSDF fusion of posed depth maps (SURVEY 8f "next" row 3): GT generation and evaluation re-fusion.
  * gnb_tsdf_fusion_integrate replaces TSDFFusion.integrate() (src/data/tsdf.py:369-418) for n_frames frames
@@ -304,6 +320,9 @@ typedef struct GnbDecoderWeights {
     const float* lin_out_w; const float* lin_out_b;
     const float* head_w;    const float* head_b;
     int32_t tc_dtype;              /* tensor-core operand type: GNB_TC_FP16 (default) or GNB_TC_BF16 */
+    int32_t* status;               /* optional device int32 (NULL = off): the tensor-core kernels OR bit 0 into it when an  */
+                                   /* fp16 operand (input feature, code or activation) saturated at +-65504, i.e. the      */
+                                   /* result is outside the 1e-2 contract and the fp32 decoder should be used instead      */
 } GnbDecoderWeights;
 
 /* Stand-alone pieces (the reference's modules called on their own). */
@@ -329,6 +348,14 @@ int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, const float* x
  * (optional output), out (feat_geo|feat_sem), tsdf, in one kernel. */
 int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed,
                        float* out, float* tsdf, void* stream);
+
+/* Dense-grid extraction (GenNerf.predict_tsdf, model.py:752-790 with get_grid_coordinates, utils.py:926-935): the same
+ * fused kernel, but the (nx*ny*nz, 3) query grid is never materialised -- query row r of a scene is the grid point
+ * (axes[i], axes[nx + j], axes[nx + ny + k]) with r = (i*ny + j)*nz + k.  `axes` (device, nx + ny + nz floats) holds the
+ * three torch.linspace axes; s->xyz and s->n_query are ignored (n_query = nx*ny*nz), h_grid3 = {nx, ny, nz} on the host.
+ * No 10 000-point chunk loop, no per-chunk re-normalisation or D2H copy, and 12 B/query less HBM traffic. */
+int gnb_query_grid_fused_tc(const GnbSampleParams* s, const int32_t* h_grid3, const float* axes,
+                            const GnbDecoderWeights* w, const void* packed, float* out, float* tsdf, void* stream);
 
 #ifdef __cplusplus
 }

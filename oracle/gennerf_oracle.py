@@ -619,3 +619,16 @@ def sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta
     world = torch.bmm(poses, hom.permute(0, 2, 1)).permute(0, 2, 1)
     xyz = world[:, :, :3] / world[:, :, 3:]
     return xyz.reshape(B, S, -1, 3), z
+
+
+def select_valid_depth_pixels(depth, ranks):
+    """The deterministic part of sample_valid_depth_pixels (reference src/models/utils.py:340-363):
+    idxs[b] = argwhere(depth[b] != 0)[ranks[b]] -> h_idxs (B,S), w_idxs (B,S).  The reference draws
+    ranks[b] = randperm(n_valid_b)[:S]; the draw itself is RNG-defined and stays torch's."""
+    hs, ws = [], []
+    for b in range(depth.shape[0]):
+        valid_indices = torch.argwhere(depth[b] != 0)
+        sel = valid_indices[ranks[b]]
+        hs.append(sel[:, 0])
+        ws.append(sel[:, 1])
+    return torch.stack(hs), torch.stack(ws)

@@ -168,7 +168,7 @@ def test_predict_tsdf_dense_grid(golden_dir):
     assert (tsdf.cpu().reshape(-1) - ref["tsdf"].reshape(-1)).abs().max().item() <= 1e-2
 
 
-def test_decode_tc_cta_group2_variant(monkeypatch):
+def test_decode_tc_cta_group2_variant():
     """The opt-in cta_group::2 variant (256 rows per cluster of 4, each CTA streams half of B) against the
     default single-CTA issue: same numerics up to accumulation order."""
     from gennerf_b200 import ops
@@ -179,10 +179,14 @@ def test_decode_tc_cta_group2_variant(monkeypatch):
     feat = torch.randn(n, 32, generator=g).to(DEV)
     dw1 = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
     a, ta = ops.decode(dw1, xyz, feat, "fp16")
-    monkeypatch.setenv("GNB_TC_TWO_CTA", "1")
-    dw2 = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
-    b, tb = ops.decode(dw2, xyz, feat, "fp16")
-    torch.cuda.synchronize()
+    from gennerf_b200 import _lib
+    old = _lib.set_option("GNB_TC_TWO_CTA", 1)
+    try:
+        dw2 = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+        b, tb = ops.decode(dw2, xyz, feat, "fp16")
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("GNB_TC_TWO_CTA", old)
     assert dw2.packed.numel() == dw1.packed.numel()
     assert ((a - b).abs().max() / a.abs().max()).item() < 2e-3
     assert (ta - tb).abs().max().item() < 5e-3

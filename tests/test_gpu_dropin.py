@@ -1,0 +1,259 @@
+"""Drop-in boundary on the GPU: a reference-built checkpoint loaded into the drop-in GenNerf gives
+the reference's outputs; cached decoder weights follow the parameters; plane layouts a U-Net produces are accepted; the
+backward formulas refuse a double backward; dense extraction generates its query grid in the kernel; the fp16 decoder
+reports saturation instead of returning clipped results silently."""
+import os
+
+import pytest
+import torch
+from torch import nn
+
+from gennerf_b200 import synthetic as S
+from oracle import gennerf_oracle as O
+from oracle.ref_shim import to_attr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+PLANES = ("xz", "xy", "yz")
+
+
+@pytest.fixture(scope="module")
+def SD(golden_dir):
+    return torch.load(os.path.join(golden_dir, "state_dict.pt"), map_location="cpu")
+
+
+def _small_model(SD, precision, fused=True, unet=None):
+    from gennerf_b200.dropin import GenNerf
+    small = SD["small"]
+    model = GenNerf(to_attr(small["cfg"]), precision=precision, fused=fused, unet=unet).eval()
+    model.load_state_dict(small["state_dict"], strict=unet is None)
+    model = model.to(DEV)
+    i = small["in"]
+    # the reference normalises volume / valid inside forward (model.py:195-199): sum where valid, 0 elsewhere
+    vol = (i["volume"] * i["valid"]).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    model.volume, model.valid = vol, i["valid"].to(DEV)
+    model.c_plane = {k: v.to(DEV) for k, v in i["planes"].items()}
+    return model
+
+
+def rel(a, b):
+    b = b.float()
+    return ((a.detach().cpu().float() - b).abs().max() / b.abs().max()).item()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_reference_checkpoint_gives_reference_outputs(SD, precision):
+    model = _small_model(SD, precision)
+    o = SD["small"]["out"]
+    with torch.no_grad():
+        out = model(SD["small"]["in"]["xyz"].to(DEV))
+    assert rel(out["feat"], o["feat"]) <= 1e-5
+    if precision == "fp32":
+        for k in ("feat_geo", "feat_sem", "tsdf"):
+            assert rel(out[k], o[k]) <= 2e-5, k
+    else:
+        assert (out["tsdf"].cpu() - o["tsdf"]).abs().max().item() <= 1e-2
+        assert not model.fp16_overflowed()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_cached_decoder_weights_follow_the_parameters(SD, precision):
+    """eval forward -> optimiser step -> eval forward: the second forward must use the NEW weights and alpha
+    (the packed fp16 image and alpha were snapshots nothing invalidated)."""
+    model = _small_model(SD, precision)
+    xyz = SD["small"]["in"]["xyz"].to(DEV)
+    with torch.no_grad():
+        before = model(xyz)["tsdf"].clone()
+    opt = torch.optim.SGD(list(model.mlp.parameters()) + list(model.head_geo.parameters()), lr=0.05)
+    model.train()
+    loss = model(xyz)["tsdf"].abs().mean()
+    loss.backward()
+    opt.step()
+    model.eval()
+    with torch.no_grad():
+        after = model(xyz)["tsdf"].clone()
+    assert (after - before).abs().max().item() > 1e-4, "stale decoder weights: the optimiser step changed nothing"
+    # a model freshly built from the updated parameters agrees
+    from gennerf_b200.dropin import GenNerf
+    fresh = GenNerf(to_attr(SD["small"]["cfg"]), precision=precision).eval().to(DEV)
+    fresh.load_state_dict(model.state_dict())
+    fresh.volume, fresh.valid, fresh.c_plane = model.volume, model.valid, model.c_plane
+    with torch.no_grad():
+        want = fresh(xyz)["tsdf"]
+    assert torch.equal(after, want)
+    # load_state_dict (in place) is noticed as well
+    model.load_state_dict(SD["small"]["state_dict"])
+    with torch.no_grad():
+        again = model(xyz)["tsdf"]
+    assert torch.equal(again, before)
+
+
+def test_unet_style_nchw_planes_run_fused(SD):
+    """A U-Net after the scatter hands over contiguous NCHW planes (reference pointnet.py:85-87, the default yaml has
+    unet: True): the fused fp16 path must take them (converted once), not raise."""
+    class TinyUNet(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.Conv2d(8, 8, 3, padding=1)
+
+        def forward(self, x):
+            return self.conv(x)
+    g = S.gen(71)
+    model = _small_model(SD, "fp16", unet=TinyUNet().to(DEV))
+    xyz = SD["small"]["in"]["xyz"].to(DEV)
+    p = S.plane_points(600, g, "unit").to(DEV)
+    with torch.no_grad():
+        model.c_plane = model.pointnet(p)                       # scatter kernels -> U-Net -> NCHW planes
+        assert all(v.is_contiguous() for v in model.c_plane.values())
+        out = model(xyz)
+        ref_model = _small_model(SD, "fp32", fused=False)
+        ref_model.c_plane = model.c_plane
+        ref = ref_model(xyz)
+    assert torch.equal(out["feat"], ref["feat"])
+    assert (out["tsdf"] - ref["tsdf"]).abs().max().item() <= 1e-2
+
+
+def test_double_backward_raises(SD):
+    """The reference's eikonal / gradient losses differentiate d(tsdf)/d(xyz) again (utils.py:636-649, create_graph=True).
+    The sampler's backward kernel is once-differentiable: that must fail loudly, not drop the second-order term."""
+    model = _small_model(SD, "fp32").train()
+    xyz = SD["small"]["in"]["xyz"].to(DEV).requires_grad_(True)
+    tsdf = model(xyz)["tsdf"]
+    (grad,) = torch.autograd.grad(tsdf.sum(), xyz, create_graph=True)
+    with pytest.raises(RuntimeError):
+        grad.pow(2).sum().backward()
+
+
+def test_predict_tsdf_grid_is_generated_in_kernel(SD):
+    """SURVEY f-2: predict_tsdf's (V,3) grid (utils.py:926-935) is never materialised; same TSDF as answering the
+    materialised grid, and the reference's (batch, b_idx) signature returns it on the CPU."""
+    from gennerf_b200.dropin import get_grid_coordinates
+    model = _small_model(SD, "fp16")
+    nx, ny, nz = 21, 17, 9
+    size = [model.cfg.voxel_size * d for d in model.cfg.voxel_dim_test]
+    a = model.predict_tsdf(nx, ny, nz)
+    grid = get_grid_coordinates(nx, ny, nz, size, device=DEV).reshape(1, -1, 3)
+    with torch.no_grad():
+        b = model(grid)["tsdf"].reshape(1, nx, ny, nz)
+    assert torch.equal(a, b)
+    batch = {"vol_%02d_tsdf" % model.voxel_sizes[0]: torch.zeros(2, 1, nx, ny, nz)}
+    c = model.predict_tsdf(batch, 0)
+    assert c.device.type == "cpu" and torch.equal(c, a.cpu())
+    # and against the oracle answering the same grid
+    i = SD["small"]["in"]
+    sd = SD["small"]["state_dict"]
+    w = {k[4:]: v for k, v in sd.items() if k.startswith("mlp.")}
+    ref = O.gennerf_forward(O.get_grid_coordinates(nx, ny, nz, size).reshape(1, -1, 3), w, sd["head_geo.fc.weight"],
+                            sd["head_geo.fc.bias"], volume=i["volume"], valid=i["valid"], planes=i["planes"],
+                            voxel_size=model.cfg.voxel_size, padding=0.1, num_freqs=model.cfg.code.num_freqs,
+                            freq_factor=model.cfg.code.freq_factor)
+    assert (a.cpu().reshape(-1) - ref["tsdf"].reshape(-1)).abs().max().item() <= 1e-2
+
+
+def test_fp16_saturation_is_reported():
+    """Activations above fp16's 65504 saturate in the tensor-core decoder (cvt.satfinite): the kernel must say so.
+    Realistic magnitudes (|activation| of a few hundred) stay inside the 1e-2 bar and raise no flag."""
+    from gennerf_b200 import ops
+    g = S.gen(72)
+    n, d_feat = 3000, 32
+    w, hw, hb = S.decoder_weights(g, d_feat, 15, 512, 5, 64, 32)
+    xyz = S.query_points(n, (96, 96, 48), 0.04, g)[0]
+
+    def run(scale):
+        feat = torch.randn(n, d_feat, generator=S.gen(73)) * scale
+        dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+        out, tsdf = ops.decode(dw, xyz.to(DEV), feat.to(DEV), "fp16")
+        code = O.positional_encoding(xyz, 2, 0.5, True)
+        ref = O.resnetfc_forward(torch.cat((code, feat), -1), w, 5, 15)
+        return dw.overflowed(), out.cpu(), ref
+    hit, out, ref = run(30.0)                      # hidden activations ~1e2 .. 1e3
+    assert ref.abs().max() > 100 and not hit
+    assert ((out - ref).abs().max() / ref.abs().max()).item() < 4e-3
+    hit, out, ref = run(3.0e4)                     # hidden activations far above 6e4
+    assert ref.abs().max() > 6.0e4
+    assert hit, "fp16 operands saturated but the status word stayed clear"
+    # the exact mode has no such limit
+    feat = torch.randn(n, d_feat, generator=S.gen(73)) * 3.0e4
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    out32, _ = ops.decode(dw, xyz.to(DEV), feat.to(DEV), "fp32")
+    assert ((out32.cpu() - ref).abs().max() / ref.abs().max()).item() < 2e-5 and not dw.overflowed()
+
+
+def test_custom_op_opcheck():
+    """torch.library.opcheck: schema, fake implementation and autograd registration of the sampler op agree with the
+    CUDA implementation."""
+    from gennerf_b200 import torch_ops as T
+    g = S.gen(74)
+    vol = torch.randn(1, 8, 6, 5, 4, generator=g).to(DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    planes = [torch.randn(1, 4, 8, 8, generator=g).to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for _ in range(3)]
+    xyz = S.query_points(50, (6, 5, 4), 0.04, g).to(DEV).requires_grad_(True)
+    torch.library.opcheck(T.sample_features, (xyz, vol, *planes, 0.04, [0.0, 0.0, 0.0], 0.1),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    p = S.plane_points(300, g, "unit").to(DEV)
+    c = torch.randn(1, 300, 4, generator=g).to(DEV).requires_grad_(True)
+    torch.library.opcheck(T.scatter_mean_planes, (p, c, 8, 0.1, "atomic"),
+                          test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+def test_sample_valid_depth_pixels():
+    """SURVEY f-4: valid-pixel sampling without the argwhere list.  Deterministic part against the oracle on given ranks;
+    the whole function against the reference's own lines run with the same CUDA generator state."""
+    import ctypes as C
+    from gennerf_b200 import ops
+    from gennerf_b200._lib import check, lib
+    g = S.gen(75)
+    B, H, W, Sn = 3, 37, 53, 200
+    depth = S.surface_depth_maps(B, H, W, g)
+    depth[1, :5] = 0.0                                   # empty rows
+    depth[2, :, ::2] = 0.0
+    d = depth.to(DEV)
+    nvalid = [(depth[b] != 0).sum().item() for b in range(B)]
+    ranks = torch.stack([torch.randint(0, n, (Sn,), generator=g) for n in nvalid])
+    ranks[:, 0] = 0
+    ranks[:, 1] = torch.tensor(nvalid) - 1
+    prefix = torch.empty((B, H), device=DEV, dtype=torch.int32)
+    nv = torch.empty((B,), device=DEV, dtype=torch.int32)
+    h = torch.empty((B, Sn), device=DEV, dtype=torch.long)
+    w = torch.empty((B, Sn), device=DEV, dtype=torch.long)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    check(lib().gnb_valid_pixel_count(d.data_ptr(), B, H, W, prefix.data_ptr(), nv.data_ptr(), st), "count")
+    check(lib().gnb_valid_pixel_select(d.data_ptr(), B, H, W, prefix.data_ptr(), nv.data_ptr(), ranks.to(DEV).data_ptr(), Sn,
+                                       h.data_ptr(), w.data_ptr(), st), "select")
+    assert nv.tolist() == nvalid
+    h_o, w_o = O.select_valid_depth_pixels(depth, ranks)
+    assert torch.equal(h.cpu(), h_o) and torch.equal(w.cpu(), w_o)
+    # whole function == the reference's code path on the same device with the same generator state
+    torch.cuda.manual_seed(1234)
+    b_idx, hh, ww = ops.sample_valid_depth_pixels(d, Sn)
+    torch.cuda.manual_seed(1234)
+    want = []
+    for b in range(B):
+        vi = torch.argwhere(d[b] != 0)
+        want.append(vi[torch.randperm(vi.shape[0], device=DEV)[:Sn]])
+    want = torch.stack(want)
+    assert torch.equal(hh, want[..., 0]) and torch.equal(ww, want[..., 1]) and b_idx.shape == (B, 1)
+    assert (d[b_idx, hh, ww] != 0).all()
+    with pytest.raises(ValueError):
+        ops.sample_valid_depth_pixels(torch.zeros(1, 8, 8, device=DEV), 4)
+
+
+def test_voxelnet_encode_dropin():
+    """VoxelNet.encode (reference voxel_net.py:76-144) + the normalisation of forward (:163-168): bit-exact volume and
+    validity, also when encode is called twice (accumulation)."""
+    from gennerf_b200.dropin import VoxelNet
+    wl = S.WORKLOADS["small"]
+    g = S.gen(76)
+    C_ = 32
+    cfg = to_attr({"voxel_size": 0.04, "voxel_dim_train": list(wl["voxel_dim"]), "voxel_dim_val": list(wl["voxel_dim"]),
+                   "encoder": {"use_spatial": True}})
+    P = S.projections(wl["T"], wl["H"], wl["W"], wl["voxel_dim"], 0.04, g, pull_back=0.8).unsqueeze(0)
+    feats = S.frame_features(wl["T"], C_, wl["H"], wl["W"], g)
+    image = torch.stack(feats, dim=1).to(DEV)                     # (B,T,C,H,W): the CNN is outside the path
+    net = VoxelNet(cfg).eval()
+    net.encode(P[:, :2], image[:, :2])
+    net.encode(P[:, 2:], image[:, 2:])
+    vol_o, valid_o, _ = O.encode_volume(wl["voxel_dim"], 0.04, torch.tensor([0, 0, 0]).view(1, 3), P, feats)
+    assert torch.equal(net.valid.cpu(), valid_o)
+    assert torch.equal(net.normalized_volume().cpu(), O.normalize_volume(vol_o, valid_o))
+    with pytest.raises(RuntimeError):
+        net.forward()

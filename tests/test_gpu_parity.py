@@ -359,7 +359,7 @@ def test_get_3d_points_and_fps():
 
 
 @pytest.mark.parametrize("N,npoint,B", [(100003, 48, 2), (307200, 24, 1), (16385, 40, 3), (2049, 16, 2)])
-def test_fps_cluster_kernel_bit_identical(N, npoint, B, monkeypatch):
+def test_fps_cluster_kernel_bit_identical(N, npoint, B):
     """The cluster FPS kernel (2..16 CTAs per cloud, slices in shared memory, candidates exchanged through DSMEM) selects
     exactly the reference's indices: ragged slices, empty last slices, ties, several clouds per launch."""
     g = S.gen(63)
@@ -370,6 +370,10 @@ def test_fps_cluster_kernel_bit_identical(N, npoint, B, monkeypatch):
     s, c = ops().farthest_point_sample(xyz.to(DEV), npoint, start.to(DEV))
     assert torch.equal(c.cpu(), c_o) and torch.equal(s.cpu(), s_o)
     # the single-CTA kernel (clouds too large for a cluster fall back to it) agrees as well
-    monkeypatch.setenv("GNB_FPS_SINGLE_CTA", "1")
-    s1, c1 = ops().farthest_point_sample(xyz.to(DEV), npoint, start.to(DEV))
+    from gennerf_b200 import _lib
+    old = _lib.set_option("GNB_FPS_SINGLE_CTA", 1)
+    try:
+        s1, c1 = ops().farthest_point_sample(xyz.to(DEV), npoint, start.to(DEV))
+    finally:
+        _lib.set_option("GNB_FPS_SINGLE_CTA", old)
     assert torch.equal(c1.cpu(), c_o) and torch.equal(s1.cpu(), s_o)

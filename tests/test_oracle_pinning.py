@@ -261,3 +261,19 @@ def test_sample_points_on_rays(N, M):
     assert torch.equal(zo[..., 0], zr[..., 0]) and torch.equal(zo[..., 1 + N:], zr[..., 1 + N:])
     assert ((zo - zr).abs() <= 1e-6 * zr.abs().clamp_min(1.0)).all()
     assert ((xo - xr).abs() <= 1e-6 * xr.abs().clamp_min(1.0)).all()
+
+
+def test_sample_valid_depth_pixels():
+    """utils.py:340-363: the oracle's deterministic half on the reference's own randperm draws == the reference."""
+    ref_shim.install()
+    from src.models.utils import sample_valid_depth_pixels as ref_fn
+    g = S.gen(38)
+    depth = S.surface_depth_maps(3, 31, 45, g)
+    depth[1, :4] = 0.0
+    Sn = 150
+    torch.manual_seed(9)
+    b_r, h_r, w_r = ref_fn(depth, Sn)
+    torch.manual_seed(9)                                       # replay the reference's draws
+    ranks = torch.stack([torch.randperm(int((depth[b] != 0).sum()))[:Sn] for b in range(3)])
+    h_o, w_o = O.select_valid_depth_pixels(depth, ranks)
+    assert torch.equal(h_r, h_o) and torch.equal(w_r, w_o) and b_r.shape == (3, 1)
