@@ -1,14 +1,21 @@
 #!/usr/bin/env python
-"""Benchmark of the lift-and-query hot path (BASELINE.json metric).
+"""Benchmark of the lift-and-query hot path (BASELINE.json metric: voxel.frames/s back-projection; TSDF query points/s).
 
-One "step" = one pass of the hot path over one batch of synthetic input of BASELINE config 2:
-  lift   8 frames of 240x320x32ch features into a 96x96x48 grid @ 4 cm  (voxel.frames/s)
-  query  1 Mi TSDF query points: trilinear sampler + ResNet-MLP decoder + TSDF head (points/s)
-`value` = TSDF query points per second over the whole step (lift included), inputs resident in
-HBM in the REFERENCE's layouts (NCHW feature maps: the NCHW->NHWC pass is inside the step).
-`e2e` = the same through the drop-in API with pinned HOST buffers (H2D of features/xyz and D2H
-of the TSDF of every step inside the timed region; steps double-buffered over two streams, and also one at a time).  `--impl reference` times the reference's CPU algorithm
-(the oracle port: same ATen CPU kernels the reference calls) on the host cores.
+One "step" = ONE SCENE of BASELINE config 4 through the whole path, on N GPUs of one box (strong scaling: the scene is
+fixed, the GPUs share it as north_star partitions it):
+  features  32 frames of 480x640x32 feature maps in the reference's NCHW layout, T/N frames per rank (the rank that ran
+            the 2D CNN on them): NCHW->NHWC into the rank's slot of ONE flat buffer, then ONE NCCL all-gather (N > 1)
+  lift      every rank lifts the whole 256x256x96 grid itself (cheaper than moving the 805 MB volume; --lift slab
+            measures the x-slab + all-gather alternative)
+  planes    3 x 256^2 x 32 triplanes: each rank scatters ITS frames' points (32 x 512 in total), partial sums and counts
+            are all-reduced with NCCL, divided locally
+  query     16 Mi TSDF queries in contiguous ranges of Q/N per rank: trilinear + 3 x bilinear sampler fused into the
+            tcgen05 ResNet-MLP decoder; no collective on this path
+`value` = 16 Mi / (time of the whole step), device-timed, max over ranks; inputs resident in HBM (1.26 GB of features and
+an 805 MB volume: larger than the 126 MB L2, so no flush is needed between steps).  `e2e` = the same scene through the
+drop-in `GenNerf.shard_scene / encode / forward` with pinned HOST buffers: H2D of the rank's frames and query range and
+D2H of its TSDF range inside the timed region.  `--impl reference` times the reference's CPU algorithm (oracle port: the
+same ATen CPU kernels the reference calls) on the host cores on a bounded sample of the same scene.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
 """
@@ -28,8 +35,11 @@ sys.path.insert(0, ROOT)
 from gennerf_b200 import synthetic as S   # noqa: E402
 
 VS = 0.04
-C_FEAT = 32
+C_FEAT, C_PLANE, R_PLANE, PTS_PER_FRAME = 32, 32, 256, 512
 MLP = dict(d_hidden=512, n_blocks=5, d_out=64, d_geo=32, num_freqs=2, freq_factor=0.5)
+D_CODE = 3 + 6 * MLP["num_freqs"]
+WL = S.WORKLOADS["cfg4"]
+SEED = 1004
 
 
 def peaks():
@@ -37,19 +47,9 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             p = json.load(f)
-        return dict(hbm=p["hbm_gbs"], bf16=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
-    return dict(hbm=6650.0, bf16=1400.0, source="fallback")
-
-
-def measured_traffic(kernel):
-    """dram__bytes_read + dram__bytes_write of the kernel's bench launch, from the committed ncu capture."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    try:
-        with open(path) as f:
-            t = json.load(f)[kernel]
-        return {"dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
-    except Exception:
-        return None
+        return dict(hbm=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
 def flops_per_query(d_feat, d_code, d_hidden, n_blocks, d_out, d_geo):
@@ -59,6 +59,16 @@ def flops_per_query(d_feat, d_code, d_hidden, n_blocks, d_out, d_geo):
 def lift_bytes(T, C, H, W, V, n_valid):
     """every input element once (or only the gathered ones if fewer), every output once."""
     return min(T * C * H * W * 4, n_valid * C * 4) + V * C * 4 + V * 5 + T * 48
+
+
+def config_dict():
+    return {"workload": "BASELINE config 4 as ONE scene: combined volume + triplane, 32 synthetic frames 480x640 x 32 ch -> "
+                        "256x256x96 grid @4cm + 3x256^2x32 planes from 32x512 points, 16 Mi TSDF queries through the fused "
+                        "sampler + ResNet-MLP decoder (d_hidden 512, 5 blocks, d_out 32+32); frames, points and queries sharded "
+                        "over the GPUs",
+            "frames": WL["T"], "image": [WL["H"], WL["W"]], "channels": C_FEAT, "grid": list(WL["voxel_dim"]),
+            "planes": [3, R_PLANE, R_PLANE, C_PLANE], "plane_points": WL["T"] * PTS_PER_FRAME, "queries": WL["Q"],
+            "l2": "inputs larger than L2 (1.26 GB features, 805 MB volume, 201 MB queries vs 126 MB L2): no flush between steps"}
 
 
 class ClockSampler:
@@ -108,40 +118,68 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_inputs(rank, Q):
-    wl = S.WORKLOADS["cfg2"]
-    g = S.gen(1002 + rank)
-    P = S.projections(wl["T"], wl["H"], wl["W"], wl["voxel_dim"], VS, g).unsqueeze(0)
-    feats = S.frame_features(wl["T"], C_FEAT, wl["H"], wl["W"], g)
-    xyz = S.query_points(Q, wl["voxel_dim"], VS, g)
-    d_code = 3 + 6 * MLP["num_freqs"]
-    w, hw, hb = S.decoder_weights(g, C_FEAT, d_code, MLP["d_hidden"], MLP["n_blocks"], MLP["d_out"], MLP["d_geo"])
-    return wl, P, feats, xyz, (w, hw, hb)
+# ------------------------------------------------------------------------------------------------
+# synthetic scene (identical bits on every rank and in both arms: everything from one seeded CPU generator)
+# ------------------------------------------------------------------------------------------------
+def scene_small_parts():
+    """Everything but the frames and the queries (cheap): projections, plane points + features, decoder weights."""
+    g = S.gen(SEED)
+    P = S.projections(WL["T"], WL["H"], WL["W"], WL["voxel_dim"], VS, g).unsqueeze(0)
+    N = WL["T"] * PTS_PER_FRAME
+    pts = S.plane_points(N, g, "metric", voxel_dim=WL["voxel_dim"])        # metres, as GenNerf.encode really feeds them (trap T6)
+    cpt = torch.randn(1, N, C_PLANE, generator=g)
+    w, hw, hb = S.decoder_weights(g, C_FEAT + C_PLANE, D_CODE, MLP["d_hidden"], MLP["n_blocks"], MLP["d_out"], MLP["d_geo"])
+    return P, pts, cpt, (w, hw, hb)
+
+
+def frame(t):
+    """Frame t's (1,C,H,W) feature map, NCHW like the reference's CNN output; per-frame seed so that a rank can make its own."""
+    return torch.randn(1, C_FEAT, WL["H"], WL["W"], generator=S.gen(SEED * 1000 + t))
+
+
+def queries(q0, q1, chunk=1 << 20):
+    """Queries [q0, q1) of the scene's Q: generated in 1 Mi blocks with per-block seeds (any rank can make any range)."""
+    out = []
+    for b0 in range(q0 - q0 % chunk, q1, chunk):
+        blk = S.query_points(chunk, WL["voxel_dim"], VS, S.gen(SEED * 7919 + b0 // chunk))
+        out.append(blk[:, max(q0 - b0, 0):min(q1 - b0, chunk)])
+    return torch.cat(out, dim=1).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm (oracle port) on the host cores
+# reference arm: the reference's CPU algorithm (oracle port) on the host cores, bounded sample of the same scene
 # ------------------------------------------------------------------------------------------------
-def cpu_step_time(wl, P, feats, xyz, weights, sample_q, reps=1):
-    """seconds for lift (full size) and for `sample_q` queries, best of `reps`."""
+def cpu_scene_time(n_frames, n_queries, P, pts, cpt, weights):
+    """Seconds of the oracle for: lift of `n_frames` frames into the full grid, the full triplane scatter, and
+    `n_queries` queries in the reference's 10 000-point chunks (model.py:769-777, volume re-normalised per chunk)."""
     from oracle import gennerf_oracle as O
     w, hw, hb = weights
     origin = torch.tensor([0, 0, 0]).view(1, 3)
-    t_lift = t_query = float("inf")
     with torch.no_grad():
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            vol, valid, _ = O.encode_volume(wl["voxel_dim"], VS, origin, P, feats)
-            t1 = time.perf_counter()
-            # the reference answers a query list in chunks of 10 000 (model.py:769-777), re-normalising
-            # the volume inside every forward call (model.py:195-199)
-            for q0 in range(0, sample_q, 10000):
-                O.gennerf_forward(xyz[:, q0:min(sample_q, q0 + 10000)], w, hw, hb, volume=vol, valid=valid, voxel_size=VS,
-                                  num_freqs=MLP["num_freqs"], freq_factor=MLP["freq_factor"], n_blocks=MLP["n_blocks"],
-                                  d_out_geo=MLP["d_geo"], d_out_sem=MLP["d_out"] - MLP["d_geo"])
-            t2 = time.perf_counter()
-            t_lift, t_query = min(t_lift, t1 - t0), min(t_query, t2 - t1)
-    return t_lift, t_query
+        feats = [frame(t) for t in range(n_frames)]
+        t0 = time.perf_counter()
+        vol, valid, _ = O.encode_volume(WL["voxel_dim"], VS, origin, P[:, :n_frames], feats)
+        t1 = time.perf_counter()
+        planes = {k: O.generate_plane_features(pts, cpt, k, R_PLANE, 0.1) for k in O.PLANES}
+        t2 = time.perf_counter()
+        xyz = queries(0, n_queries)
+        t3 = time.perf_counter()
+        for q0 in range(0, n_queries, 10000):
+            O.gennerf_forward(xyz[:, q0:q0 + 10000], w, hw, hb, volume=vol, valid=valid, planes=planes, voxel_size=VS, padding=0.1,
+                              num_freqs=MLP["num_freqs"], freq_factor=MLP["freq_factor"], n_blocks=MLP["n_blocks"],
+                              d_out_geo=MLP["d_geo"], d_out_sem=MLP["d_out"] - MLP["d_geo"])
+        t4 = time.perf_counter()
+    return t1 - t0, t2 - t1, t4 - t3
+
+
+def cpu_estimate(n_frames, n_queries, parts):
+    P, pts, cpt, weights = parts
+    tl, tp, tq = cpu_scene_time(n_frames, n_queries, P, pts, cpt, weights)
+    Q, T = WL["Q"], WL["T"]
+    total = tl * (T / n_frames) + tp + tq * (Q / n_queries)
+    V = WL["voxel_dim"][0] * WL["voxel_dim"][1] * WL["voxel_dim"][2]
+    return total, {"lift_s_per_frame": tl / n_frames, "planes_s": tp, "query_s_per_10k": tq / (n_queries / 10000),
+                   "lift_voxel_frames_per_s": V * n_frames / tl}
 
 
 def run_reference(args):
@@ -149,42 +187,37 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    Q = 1 << 20
-    wl, P, feats, xyz, weights = make_inputs(0, Q)
-    sample_q = 20000
-    times = []
+    parts = scene_small_parts()
+    n_frames, n_queries = 2, 10000
+    times, detail = [], None
     for i in range(args.warmup + args.steps):
-        tl, tq = cpu_step_time(wl, P, feats, xyz, weights, sample_q)
+        t, detail = cpu_estimate(n_frames, n_queries, parts)
         if i >= args.warmup:
-            times.append(tl + tq * (Q / sample_q))
+            times.append(t)
     t = sum(times) / len(times)
-    val = Q / t
+    val = WL["Q"] / t
+    sample = (f"per step: lift of {n_frames} of {WL['T']} frames into the full grid (scaled x{WL['T'] // n_frames}), the full triplane "
+              f"scatter, {n_queries} of {WL['Q']} queries as one of the reference's 10k chunks incl. its per-chunk volume "
+              f"re-normalisation (scaled x{WL['Q'] // n_queries})")
     line = {"impl": "reference", "metric": "tsdf_query_points_per_s", "value": val, "unit": "points/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(Q),
-            "cpu_baseline": {"value": val, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"lift at full size + {sample_q} of {Q} queries in the reference's 10k chunks, "
-                                       "query time scaled linearly to 1 Mi"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(),
+            "cpu_baseline": {"value": val, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                             "detail": detail},
             "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
-
-
-def config_dict(Q):
-    wl = S.WORKLOADS["cfg2"]
-    return {"workload": "BASELINE config 2: volumetric encoder, 8 synthetic 240x320 frames x 32 ch -> 96x96x48 grid @4cm, "
-                        f"{Q} TSDF queries, sampler + ResNet-MLP decoder (d_hidden 512, 5 blocks, d_out 32+32)",
-            "frames": wl["T"], "image": [wl["H"], wl["W"]], "channels": C_FEAT, "grid": list(wl["voxel_dim"]),
-            "queries_per_gpu": Q, "l2": "256 MiB scratch written between timed steps (L2 flush)"}
 
 
 # ------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------
-def side_kernels(ops, S, dev, vol, xyz, flush, pk):
-    """The other HBM-bound kernels of the path, timed alone on rank 0 after the timed step (not part of `value`):
-    the gather-only sampler on the step's own volume and queries, and BASELINE config 3's triplane scatter
-    (3 x 256^2 planes, C_p = 32; 4 096 reference-faithful points and all 614 400 pixels of 8 frames).
-    Algorithmic bytes as SURVEY 8d.  CUDA-graph replays, L2 flushed between replays, median of 10."""
+def hbm_side_kernels(ops, dev, pk):
+    """The HBM-bound kernels of the path timed alone on rank 0 (not part of `value`), BASELINE config 2 / 3 shapes:
+    the lift (NCHW and channels-last input), the gather-only sampler on that volume with 1 Mi queries, config 3's
+    triplane scatter.  Algorithmic bytes as SURVEY 8d; CUDA-graph replays, L2 flushed between replays, median of 10."""
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    origin = torch.tensor([0, 0, 0]).view(1, 3)
+
     def timed(fn):
         fn()
         g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
@@ -205,25 +238,106 @@ def side_kernels(ops, S, dev, vol, xyz, flush, pk):
         return {"ms": ms, "algorithmic_bytes": byt, "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}}
 
     out = {}
+    wl = S.WORKLOADS["cfg2"]
+    g = S.gen(1002)
+    P = S.projections(wl["T"], wl["H"], wl["W"], wl["voxel_dim"], VS, g).unsqueeze(0)
+    feats = [f.to(dev) for f in S.frame_features(wl["T"], C_FEAT, wl["H"], wl["W"], g)]
+    feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    xyz = S.query_points(1 << 20, wl["voxel_dim"], VS, g).to(dev)
+    vol, cnt, _ = ops.backproject_frames(wl["voxel_dim"], VS, origin, P, feats_cl)
+    V = cnt.numel()
+    lb = lift_bytes(wl["T"], C_FEAT, wl["H"], wl["W"], V, int(cnt.sum().item()))
+    out["lift_cfg2_nchw_input"] = dict(roof(lb, timed(lambda: ops.backproject_frames(wl["voxel_dim"], VS, origin, P, feats))),
+                                       includes="NCHW->NHWC pass + lift kernel", voxel_frames=V * wl["T"])
+    out["lift_cfg2_channels_last_input"] = dict(roof(lb, timed(lambda: ops.backproject_frames(wl["voxel_dim"], VS, origin, P, feats_cl))),
+                                                includes="lift kernel only", voxel_frames=V * wl["T"])
     Q, C = xyz.shape[1], vol.shape[1]
     byt = Q * (12 + 4 * C) + min(vol.numel() * 4, 8 * Q * C * 4)
     for name, binned in (("sampler_binned", True), ("sampler_staged", False)):
-        out[name] = roof(byt, timed(lambda: ops.sample_features(xyz, volume=vol, voxel_size=VS, binned=binned)))
-        out[name]["queries"] = Q
+        out[name] = dict(roof(byt, timed(lambda: ops.sample_features(xyz, volume=vol, voxel_size=VS, binned=binned))), queries=Q)
     g = S.gen(1003)
-    R, Cp = 256, 32
     for N in (4096, 614400):
         p = S.plane_points(N, g, "unit").to(dev)
-        c = torch.randn(1, N, Cp, generator=g).to(dev)
-        byt = N * (12 + 4 * Cp) + 3 * R * R * (4 * Cp + 4)
-        out[f"scatter_mean_planes_N{N}"] = roof(byt, timed(lambda: ops.scatter_mean_planes(p, c, R, 0.1, "atomic")))
+        c = torch.randn(1, N, C_PLANE, generator=g).to(dev)
+        byt = N * (12 + 4 * C_PLANE) + 3 * R_PLANE * R_PLANE * (4 * C_PLANE + 4)
+        out[f"scatter_mean_planes_N{N}"] = roof(byt, timed(lambda: ops.scatter_mean_planes(p, c, R_PLANE, 0.1, "atomic")))
     return out
+
+
+def gpu_eager_baseline(dev, P, pts, cpt, weights, n_frames=4, n_chunks=50):
+    """Informational: the reference's own ATen CUDA path on this B200 (bmm / index_put_ / grid_sample / TF32 F.linear as
+    src/utils/utils.py:48 sets it, 10 000-point chunks with .cpu() per chunk, model.py:769-777), bounded sample, scaled."""
+    from oracle import eager_gpu as E
+    w, hw, hb = weights
+    old = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
+    try:
+        origin = torch.tensor([0, 0, 0]).view(1, 3)
+        wd = {k: v.to(dev) for k, v in w.items()}
+        hwd, hbd = hw.to(dev), hb.to(dev)
+        feats = [frame(t).to(dev) for t in range(n_frames)]
+        Pd = P.to(dev)
+        with torch.no_grad():
+            E.encode_volume(WL["voxel_dim"], VS, origin, Pd[:, :1], feats[:1])       # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            vol, valid = E.encode_volume(WL["voxel_dim"], VS, origin, Pd[:, :n_frames], feats)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            planes = {k: E.generate_plane_features(pts.to(dev), cpt.to(dev), k, R_PLANE, 0.1) for k in E.PLANES}
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            xyz = queries(0, n_chunks * 10000).to(dev)
+            E.predict_chunks(xyz[:, :20000], 10000, wd, hwd, hbd, vol, valid, planes, VS, 0.1, MLP["num_freqs"], MLP["freq_factor"],
+                             MLP["n_blocks"], MLP["d_geo"])
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            E.predict_chunks(xyz, 10000, wd, hwd, hbd, vol, valid, planes, VS, 0.1, MLP["num_freqs"], MLP["freq_factor"],
+                             MLP["n_blocks"], MLP["d_geo"])
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+        tl, tp, tq = t1 - t0, t2 - t1, t4 - t3
+        Q, T = WL["Q"], WL["T"]
+        total = tl * T / n_frames + tp + tq * Q / (n_chunks * 10000)
+        V = WL["voxel_dim"][0] * WL["voxel_dim"][1] * WL["voxel_dim"][2]
+        return {"value": Q / total, "unit": "points/s", "ms_per_step_scaled": total * 1e3,
+                "what": "the reference's own PyTorch code path (ATen CUDA kernels, TF32 matmul, 10k-query chunks with a D2H copy "
+                        "and a volume re-normalisation per chunk) on the same B200, one GPU",
+                "sample": f"lift of {n_frames} of {T} frames (scaled), full triplane scatter, {n_chunks} of {Q // 10000} query chunks (scaled)",
+                "lift_voxel_frames_per_s": V * n_frames / tl, "query_points_per_s": n_chunks * 10000 / tq}
+    finally:
+        torch.set_float32_matmul_precision(old)
+
+
+def parity_check(ops, dev, P, feats_all, vol, planes, tsdf, xyz_h, weights, n_check=2000):
+    """Bench-time parity (rank 0): (1) the lift of the scene's first two frames into the full grid == the CPU oracle,
+    bit for bit; (2) `n_check` of the TSDFs this run produced, against the fp32 oracle answering the same points on the
+    volume / planes this run built (copied to the host): |dTSDF| <= 1e-2."""
+    from oracle import gennerf_oracle as O
+    origin = torch.tensor([0, 0, 0]).view(1, 3)
+    w, hw, hb = weights
+    with torch.no_grad():
+        v2, c2, m2 = ops.backproject_frames(WL["voxel_dim"], VS, origin, P[:, :2], feats_all[:2])
+        vo, mo, co = O.encode_volume(WL["voxel_dim"], VS, origin, P[:, :2], [frame(0), frame(1)])
+        lift_ok = bool(torch.equal(v2.cpu(), vo) and torch.equal(c2.cpu(), co) and torch.equal(m2.cpu(), mo))
+        del v2, vo
+        g = S.gen(99)
+        idx = torch.randperm(xyz_h.shape[1], generator=g)[:n_check]
+        vol_h = vol.cpu()
+        valid_h = torch.ones((1, 1) + tuple(vol_h.shape[2:]), dtype=torch.bool)       # the lift zeroes unseen voxels itself
+        pl_h = {k: planes[i].cpu() for i, k in enumerate(O.PLANES)}
+        ref = O.gennerf_forward(xyz_h[:, idx], w, hw, hb, volume=vol_h, valid=valid_h, planes=pl_h, voxel_size=VS, padding=0.1,
+                                num_freqs=MLP["num_freqs"], freq_factor=MLP["freq_factor"])
+        err = (tsdf.reshape(1, -1, 1)[:, idx.to(dev)].cpu() - ref["tsdf"]).abs().max().item()
+    return {"parity_checked": True, "lift_2_frames_full_grid_bit_exact": lift_ok, "tsdf_samples": n_check,
+            "tsdf_max_abs_err_vs_fp32_oracle": err, "tsdf_bar": 1e-2, "ok": bool(lift_ok and err <= 1e-2)}
 
 
 def run_native(args):
     import torch.distributed as dist
-    from gennerf_b200 import ops
-    from gennerf_b200._lib import lib
+    from gennerf_b200 import ops, parallel
+    from gennerf_b200.dropin import GenNerf
+    from oracle.ref_shim import to_attr
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -231,237 +345,249 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's version banner / debug lines: not on stdout (one JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # NCCL's banner / debug lines: not on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
-    Q = 1 << 20
-    wl, P, feats_h, xyz_h, (w, hw, hb) = make_inputs(rank, Q)
+    T, H, W = WL["T"], WL["H"], WL["W"]
+    nx, ny, nz = WL["voxel_dim"]
+    V, Q = nx * ny * nz, WL["Q"]
     origin = torch.tensor([0, 0, 0]).view(1, 3)
-    T, H, W = wl["T"], wl["H"], wl["W"]
-    V = wl["voxel_dim"][0] * wl["voxel_dim"][1] * wl["voxel_dim"][2]
-
-    feats = [f.to(dev) for f in feats_h]                    # reference layout: NCHW contiguous
-    xyz = xyz_h.to(dev)
-    dw = ops.DecoderWeights(w, hw, hb, n_blocks=MLP["n_blocks"], d_geo=MLP["d_geo"], use_code=True,
-                            num_freqs=MLP["num_freqs"], freq_factor=MLP["freq_factor"], device=dev)
     precision = args.precision
+
+    P, pts_h, cpt_h, (w, hw, hb) = scene_small_parts()
+    t0, t1 = parallel.shard_range(T, rank, world)
+    q0, q1 = parallel.shard_range(Q, rank, world)
+    n0, n1 = parallel.shard_range(pts_h.shape[1], rank, world)
+    frames_h = [frame(t) for t in range(t0, t1)]                   # this rank's frames (its share of the CNN's output), NCHW
+    xyz_h = queries(q0, q1)
+    frames_d = [f.to(dev) for f in frames_h]
+    xyz = xyz_h.to(dev)
+    pts, cpt = pts_h[:, n0:n1].to(dev), cpt_h[:, n0:n1].to(dev)
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=MLP["n_blocks"], d_geo=MLP["d_geo"], use_code=True, num_freqs=MLP["num_freqs"],
+                            freq_factor=MLP["freq_factor"], device=dev)
     if precision != "fp32":
-        dw.pack(precision)                                  # raises if the tcgen05 path is unavailable: no fallback
-    fused = precision != "fp32" and not args.unfused
-    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
-
-    def lift():
-        return ops.backproject_frames(wl["voxel_dim"], VS, origin, P, feats)
-
-    def query(vol, x):
-        if fused:
-            out, tsdf, _ = ops.query_fused(dw, x, volume=vol, voxel_size=VS, origin=origin, want_feat=False, precision=precision)
-            return tsdf
-        feat = ops.sample_features(x, volume=vol, voxel_size=VS, origin=origin)
-        return ops.decode(dw, x, feat, precision)[1]
+        dw.pack(precision)                                          # raises if the tcgen05 path is unavailable: no fallback
+    fb = parallel.FrameBuffer(T, 1, C_FEAT, H, W, dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)               # noqa: E731
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # eager warm-up (also JIT-free first-touch of every kernel), then capture the step as CUDA graphs:
-    # the launch-bound part of the path (3 short kernels before the decoder) replays without host gaps
-    for _ in range(max(args.warmup, 3)):
-        vol, cnt, valid = lift()
-        tsdf = query(vol, xyz)
-        flush.fill_(1)
-    n_valid = int(cnt.sum().item())
-    barrier()
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        g_step, g_lift, g_query = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_lift, stream=side):
-            vol_l, cnt_l, valid_l = lift()
-        with torch.cuda.graph(g_query, stream=side):
-            tsdf_q = query(vol_l, xyz)
-        with torch.cuda.graph(g_step, stream=side):
-            vol_s, cnt_s, valid_s = lift()
-            tsdf_s = query(vol_s, xyz)
-    barrier()
+    class Step:
+        """One pass of the path; `marks` = events at the phase boundaries."""
 
-    def timed(graph, n):
-        ms = []
-        for _ in range(n):
-            flush.fill_(1)                                  # L2 flush, outside the event pair
-            a, b = ev(), ev()
-            a.record()
-            graph.replay()
-            b.record()
-            ms.append((a, b))
-        torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in ms) / len(ms)
+        def __call__(self, marks=None):
+            def mark():
+                if marks is not None:
+                    e = ev()
+                    e.record()
+                    marks.append(e)
+            mark()
+            # ---- features: own frames NCHW -> NHWC into the flat buffer, all ranks' frames gathered over NVLink
+            if frames_d:
+                ops.nchw_to_nhwc(frames_d, out=fb.flat[t0:t1])
+            if args.features == "broadcast" and world > 1:
+                # (alternative: rank 0 ran the CNN alone -- only its buffer is meaningful; one broadcast of 1.26 GB)
+                fb.broadcast(src=0)
+            else:
+                fb.all_gather()
+            mark()
+            # ---- lift
+            if args.lift == "slab" and world > 1:
+                vol, cnt, valid = parallel.lift_sharded(ops, WL["voxel_dim"], VS, origin, P, fb.frames, gather=True)
+            else:
+                vol, cnt, valid = ops.backproject_frames(WL["voxel_dim"], VS, origin, P, fb.frames)
+            mark()
+            # ---- triplanes: own points -> partial sums -> all-reduce -> divide
+            planes, pcnt = parallel.scatter_planes_sharded(ops, pts, cpt, R_PLANE, 0.1)
+            pl = {k: planes[i] for i, k in enumerate(ops.PLANES)}
+            mark()
+            # ---- queries of this rank's range
+            if precision == "fp32" or args.unfused:
+                feat = ops.sample_features(xyz, volume=vol, planes=pl, voxel_size=VS, origin=origin, padding=0.1)
+                tsdf = ops.decode(dw, xyz, feat, precision)[1]
+            else:
+                tsdf = ops.query_fused(dw, xyz, volume=vol, planes=pl, voxel_size=VS, origin=origin, padding=0.1, want_feat=False,
+                                       precision=precision)[1]
+            mark()
+            self.out = (vol, cnt, planes, tsdf)
+            return tsdf
+
+    step = Step()
+    if args.features == "broadcast" and world > 1 and rank == 0:    # rank 0 "ran the CNN": it holds every frame
+        frames_all = [frame(t).to(dev) for t in range(T)]
+        ops.nchw_to_nhwc(frames_all, out=fb.flat)
+        del frames_all
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
 
     clocks = ClockSampler(local)
-    clocks.__enter__()                                      # sampled over every timed region below (closed after e2e)
-    for _ in range(3):
-        g_step.replay()
+    clocks.__enter__()                                              # sampled over every timed region below
+    marks_all = []
+    a, b = ev(), ev()
     barrier()
     t_wall0 = time.perf_counter()
-    ms_step = timed(g_step, args.steps)
+    a.record()
+    for _ in range(args.steps):
+        m = []
+        step(m)
+        marks_all.append(m)
+    b.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    ms_lift = timed(g_lift, max(args.steps, 10))
-    ms_query = timed(g_query, max(3, args.steps // 2))
-    # the lift kernel alone, features already channels-last (what a channels_last CNN hands over)
-    feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
-    g_lcl = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(side):
-        ops.backproject_frames(wl["voxel_dim"], VS, origin, P, feats_cl)
-        with torch.cuda.graph(g_lcl, stream=side):
-            ops.backproject_frames(wl["voxel_dim"], VS, origin, P, feats_cl)
-    barrier()
-    ms_lift_cl = timed(g_lcl, max(args.steps, 10))
-    ms_samp, ms_dec = ms_query, 0.0
+    ms_step = a.elapsed_time(b) / args.steps
+    ph = torch.tensor([[m[i].elapsed_time(m[i + 1]) for i in range(4)] for m in marks_all], dtype=torch.float64).mean(0)
+    vol, cnt, planes, tsdf = step.out
+    n_valid = int(cnt.sum().item())
+    overflow = dw.overflowed() if precision == "fp16" else False
 
-    # ---- end to end through the drop-in API with pinned host buffers ----------------------
-    feats_pin = [f.pin_memory() for f in feats_h]
+    # ---- end to end through the drop-in API with pinned host buffers -----------------------------------------------
+    cfg = to_attr({
+        "voxel_size": VS, "voxel_dim_train": list(WL["voxel_dim"]), "voxel_dim_val": list(WL["voxel_dim"]),
+        "voxel_dim_test": list(WL["voxel_dim"]),
+        "encoder": {"use_spatial": True, "spatial": {"num_layers": 0, "latent_size": C_FEAT}, "use_pointnet": True, "use_auxiliary": False,
+                    "pointnet": {"num_sparse_points": PTS_PER_FRAME, "c_dim": C_PLANE, "dim": 3, "padding": 0.1, "hidden_dim": 32,
+                                 "scatter_type": "max", "plane_type": ["xz", "xy", "yz"], "plane_resolution": R_PLANE,
+                                 "n_blocks": 5, "unet": False, "unet_kwargs": None, "sample_mode": "bilinear"},
+                    "plane_merger": {"strategy": "average", "alpha": 0.1}},
+        "mlp": {"d_out_sem": MLP["d_out"] - MLP["d_geo"], "d_out_geo": MLP["d_geo"], "n_blocks": MLP["n_blocks"],
+                "d_hidden": MLP["d_hidden"], "combine_layer": 1000, "combine_type": "average", "beta": 0.0, "use_spade": False,
+                "use_layer_norm": False, "alpha": 1.0},
+        "use_code": True, "code": {"num_freqs": MLP["num_freqs"], "freq_factor": MLP["freq_factor"], "include_input": True}})
+    torch.manual_seed(7)
+    model = GenNerf(cfg, precision=precision if precision != "bf16" else "fp16").eval()
+    model.mlp.load_state_dict(w)
+    model.head_geo.load_state_dict({"fc.weight": hw, "fc.bias": hb})
+    model = model.to(dev)
+    if world > 1:
+        model.shard_scene()
+    img_pin = torch.stack(frames_h, dim=1).pin_memory() if frames_h else torch.empty(1, 0, C_FEAT, H, W).pin_memory()
     xyz_pin = xyz_h.pin_memory()
-    tsdf_pin = torch.empty((1, Q, 1), dtype=torch.float32).pin_memory()
+    pts_pin = pts_h.pin_memory()
+    tsdf_pin = torch.empty((1, q1 - q0, 1), dtype=torch.float32).pin_memory()
+    Pd = P.to(dev)
 
     def e2e_step():
-        fd = [f.to(dev, non_blocking=True) for f in feats_pin]
+        model.initialize_volume()
+        img = img_pin.to(dev, non_blocking=True)
         xd = xyz_pin.to(dev, non_blocking=True)
-        vol, cnt, valid = ops.backproject_frames(wl["voxel_dim"], VS, origin, P, fd)
-        tsdf_pin.copy_(query(vol, xd), non_blocking=True)
+        sp = pts_pin.to(dev, non_blocking=True)
+        with torch.no_grad():
+            model.encode(Pd, img, None, "val", sparse_xyz=sp)
+            out = model(xd)
+        tsdf_pin.copy_(out["tsdf"], non_blocking=True)
 
     for _ in range(2):
         e2e_step()
     barrier()
-    e2e_ms = []
+    a2, b2 = ev(), ev()
+    a2.record()
     for _ in range(args.steps):
-        flush.fill_(1)
-        a, b = ev(), ev()
-        a.record()
         e2e_step()
-        b.record()
-        b.synchronize()
-        e2e_ms.append(a.elapsed_time(b))
+    b2.record()
     barrier()
-    ms_e2e_sync = sum(e2e_ms) / len(e2e_ms)                 # one step at a time: upload, lift, query, download
-
-    # The same steps as a double-buffered pipeline, the way a serving loop runs them: a copy stream uploads step k+1's
-    # inputs (its own H2D from the pinned buffers, every step) while the compute stream works on step k; the TSDF of
-    # every step is read back to pinned host memory.  Timed as ONE region over all K steps (L2 flushed between steps
-    # inside the region), so pipeline fill and drain are included.
-    copy_s, comp_s = torch.cuda.Stream(), torch.cuda.Stream()
-    bufs = [([torch.empty_like(f, device=dev) for f in feats_pin], torch.empty_like(xyz_pin, device=dev)) for _ in range(2)]
-    tsdf_pins = [torch.empty((1, Q, 1), dtype=torch.float32).pin_memory() for _ in range(2)]
-    ev_up = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-
-    def e2e_pipeline(n):
-        for k in range(n):
-            i = k & 1
-            with torch.cuda.stream(copy_s):
-                if k >= 2:
-                    copy_s.wait_event(ev_free[i])           # step k-2 no longer reads this buffer pair
-                for dst, src in zip(bufs[i][0], feats_pin):
-                    dst.copy_(src, non_blocking=True)
-                bufs[i][1].copy_(xyz_pin, non_blocking=True)
-                ev_up[i].record(copy_s)
-            with torch.cuda.stream(comp_s):
-                comp_s.wait_event(ev_up[i])
-                flush.fill_(1)
-                vol, cnt, valid = ops.backproject_frames(wl["voxel_dim"], VS, origin, P, bufs[i][0])
-                tsdf_pins[i].copy_(query(vol, bufs[i][1]), non_blocking=True)
-                ev_free[i].record(comp_s)
-
-    torch.cuda.synchronize()
-    e2e_pipeline(3)
-    torch.cuda.synchronize()
-    barrier()
-    a, b = ev(), ev()
-    comp_s.wait_stream(torch.cuda.current_stream())
-    copy_s.wait_stream(torch.cuda.current_stream())
-    a.record(copy_s)
-    e2e_pipeline(args.steps)
-    torch.cuda.current_stream().wait_stream(comp_s)
-    torch.cuda.current_stream().wait_stream(copy_s)
-    b.record()
-    b.synchronize()
-    ms_e2e = a.elapsed_time(b) / args.steps
-    barrier()
+    ms_e2e = a2.elapsed_time(b2) / args.steps
     clocks.__exit__(None, None, None)
 
-    t = torch.tensor([ms_step, ms_e2e, ms_lift, ms_query, ms_lift_cl, ms_e2e_sync], device=dev, dtype=torch.float64)
+    tt = torch.tensor([ms_step, ms_e2e] + ph.tolist(), device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_e2e, ms_lift, ms_query, ms_lift_cl, ms_e2e_sync = t.tolist()
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e, ms_feat, ms_lift, ms_planes, ms_query = tt.tolist()
 
     if rank == 0:
         pk = peaks()
-        d_code = 3 + 6 * MLP["num_freqs"]
-        fl = flops_per_query(C_FEAT, d_code, MLP["d_hidden"], MLP["n_blocks"], MLP["d_out"], MLP["d_geo"]) * Q
-        dec_ms = ms_query
-        tf = fl / (dec_ms * 1e-3) / 1e12
+        d_feat = C_FEAT + C_PLANE
+        fl = flops_per_query(d_feat, D_CODE, MLP["d_hidden"], MLP["n_blocks"], MLP["d_out"], MLP["d_geo"]) * (q1 - q0)
+        tf = fl / (ms_query * 1e-3) / 1e12
         lb = lift_bytes(T, C_FEAT, H, W, V, n_valid)
         lift_gbs = lb / (ms_lift * 1e-3) / 1e9
-        lift_cl_gbs = lb / (ms_lift_cl * 1e-3) / 1e9
+        feat_bytes = T * C_FEAT * H * W * 4
+        fused = precision != "fp32" and not args.unfused
         line = {
-            "metric": "tsdf_query_points_per_s", "value": world * Q / (ms_step * 1e-3), "unit": "points/s", "n_gpus": world,
+            "metric": "tsdf_query_points_per_s", "value": Q / (ms_step * 1e-3), "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[precision], "data": "synthetic",
-            "config": dict(config_dict(Q), parallelism=f"replicas x{world} (queries and scenes sharded, no data-path collective)",
-                           decoder=f"{precision} tcgen05 fused sampler+MLP" if fused else f"{precision} sampler + decoder kernels"),
-            "roofline": {"kernel": "decoder_tc_kernel (fused sampler + MLP)" if fused else "sampler + decoder", "bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": tf / pk["bf16"], "traffic": measured_traffic("decoder_tc_kernel") if fused else None, "peak_source": pk["source"] + " bf16 cuBLAS sustained (fp16 and bf16 share the tensor-core rate)",
-                         "flops_per_launch": fl, "ms_per_launch": dec_ms},
-            "backprojection": {"metric": "voxel_frames_per_s", "value": world * V * T / (ms_lift * 1e-3), "ms": ms_lift,
-                               "includes": "NCHW->NHWC pass + fused lift kernel",
+            "scaling": "strong", "vs_baseline": None, "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[precision],
+            "data": "synthetic", "config": config_dict(),
+            "parallelism": {"gpus": world, "frames_per_rank": t1 - t0, "queries_per_rank": q1 - q0,
+                            "features": args.features if world > 1 else "local", "lift": args.lift if world > 1 else "single GPU",
+                            "planes": "points sharded, NCCL all-reduce of sums + counts", "queries": "contiguous ranges, no collective"},
+            "decoder": f"{precision} tcgen05 fused sampler+MLP" if fused else f"{precision} sampler + decoder kernels",
+            "phases_ms": {"features_transpose_and_gather": ms_feat, "lift": ms_lift, "planes_scatter_allreduce": ms_planes,
+                          "query_range": ms_query, "step": ms_step},
+            "collectives": {"feature_gather": {"bytes_total": feat_bytes, "bytes_received_per_gpu": feat_bytes * (world - 1) // world,
+                                               "ms_incl_local_transpose": ms_feat,
+                                               "gbs_received_per_gpu": (feat_bytes * (world - 1) / world) / (ms_feat * 1e-3) / 1e9 if world > 1 else None,
+                                               "nvlink_reference_gbs": 770.0},
+                            "plane_allreduce_bytes": 3 * R_PLANE * R_PLANE * (C_PLANE + 1) * 4},
+            "roofline": {"kernel": "decoder_tc_kernel (fused sampler + MLP, one launch = this rank's query range)" if fused else "sampler + decoder",
+                         "bound": "tensor", "achieved": tf, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": tf / pk["bf16_burst"],
+                         "frac_of_sustained": tf / pk["bf16_sustained"], "traffic": None,
+                         "peak_source": pk["source"] + ": bf16 cuBLAS burst (fp16 and bf16 share the tensor-core rate)",
+                         "flops_per_launch": fl, "ms_per_launch": ms_query},
+            "backprojection": {"metric": "voxel_frames_per_s", "value": V * T / (ms_lift * 1e-3), "ms": ms_lift,
+                               "includes": "lift kernel on the gathered channels-last frames (every rank lifts the whole grid)",
                                "roofline": {"bound": "hbm", "achieved": lift_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                             "frac": lift_gbs / pk["hbm"], "algorithmic_bytes": lb},
-                               "channels_last_input": {"value": world * V * T / (ms_lift_cl * 1e-3), "ms": ms_lift_cl,
-                                                       "includes": "fused lift kernel only (features handed over NHWC)",
-                                                       "roofline": {"bound": "hbm", "achieved": lift_cl_gbs, "peak": pk["hbm"],
-                                                                    "unit": "GB/s", "frac": lift_cl_gbs / pk["hbm"]}},
                                "valid_voxel_frames": n_valid},
-            "breakdown_ms": {"lift": ms_lift, "query": ms_query, "step": ms_step},
-            "timing": "CUDA-graph replays of the step, CUDA events around each replay, L2 flushed between replays",
-            "e2e": {"value": world * Q / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": sum(f.numel() for f in feats_h) * 4 + xyz_h.numel() * 4,
-                    "d2h_bytes_per_step": Q * 4,
-                    "how": "double-buffered pipeline over all timed steps (copy stream uploads step k+1 from pinned host memory while "
-                           "step k computes; TSDF read back every step; L2 flush between steps inside the region)",
-                    "one_step_at_a_time": {"value": world * Q / (ms_e2e_sync * 1e-3), "ms_per_step": ms_e2e_sync}},
-            "gpu_launches": args.steps * (3 if fused else 4),
+            "timing": "K steps back to back between barriers, CUDA events, max over ranks; phases from events inside the steps",
+            "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": (img_pin.numel() + xyz_pin.numel() + pts_pin.numel()) * 4, "d2h_bytes_per_step": (q1 - q0) * 4,
+                    "bytes_are": "per rank (every rank uploads its frames, its query range and the sparse points, downloads its TSDF range)",
+                    "how": "drop-in GenNerf.shard_scene / encode(projection, image, sparse_xyz=) / forward(xyz) from pinned host "
+                           "buffers: H2D, NCHW->NHWC, feature all-gather, lift, PointNet + scatter, fused query, D2H of the TSDF"},
+            "gpu_launches": args.steps * (5 + (1 if args.lift == "slab" and world > 1 else 0)),
+            "fp16_saturated": overflow,
             "clocks": clocks.summary(),
             "wall_s_timed_region": t_wall,
         }
-        try:
-            from gennerf_b200 import synthetic as S
-            line["hbm_kernels"] = side_kernels(ops, S, dev, vol_l, xyz, flush, pk)
-        except Exception as e:                              # a side measurement must not take the bench line down
-            line["hbm_kernels"] = {"error": repr(e)}
+        if not args.no_parity:
+            try:
+                line["parity"] = parity_check(ops, dev, P, fb.frames, vol, planes, tsdf, xyz_h, (w, hw, hb))
+                line["parity_checked"] = line["parity"]["ok"]
+            except Exception as e:                                  # noqa: BLE001
+                line["parity"] = {"parity_checked": False, "error": repr(e)}
+                line["parity_checked"] = False
+        if world == 1 and not args.no_side:
+            del step.out, vol, planes, tsdf
+            try:
+                line["hbm_kernels"] = hbm_side_kernels(ops, dev, pk)
+            except Exception as e:                                  # a side measurement must not take the bench line down
+                line["hbm_kernels"] = {"error": repr(e)}
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(dev, P, pts_h, cpt_h, (w, hw, hb))
+            except Exception as e:                                  # noqa: BLE001
+                line["gpu_eager_baseline"] = {"error": repr(e)}
         if not args.no_cpu:
             torch.set_num_threads(os.cpu_count() or 1)
-            sample_q = 20000
-            tl, tq = cpu_step_time(wl, P, feats_h, xyz_h, (w, hw, hb), sample_q)
-            line["cpu_baseline"] = {"value": Q / (tl + tq * (Q / sample_q)), "unit": "points/s", "cores": torch.get_num_threads(),
-                                    "kind": "port", "lift_voxel_frames_per_s": V * T / tl,
-                                    "sample": f"lift at full size + {sample_q} of {Q} queries in the reference's 10k chunks, "
-                                              "query time scaled linearly"}
+            t, detail = cpu_estimate(1, 10000, (P, pts_h, cpt_h, (w, hw, hb)))
+            line["cpu_baseline"] = {"value": Q / t, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": "lift of 1 of 32 frames into the full grid (scaled x32), the full triplane scatter, "
+                                              "10 000 of 16 Mi queries as one reference chunk (scaled)", "detail": detail}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
-                    help="decoder operands: fp16/bf16 = tcgen05 tensor cores (fp32 accumulate), fp32 = CUDA cores")
+                    help="decoder operands: fp16 = tcgen05 tensor cores (fp32 accumulate; the 1e-2 TSDF mode), fp32 = CUDA cores "
+                         "(1e-5 mode); bf16 = tcgen05 with 8-bit significands (range-safe but ~3e-2 TSDF: outside the bar)")
+    ap.add_argument("--features", default="allgather", choices=["allgather", "broadcast"],
+                    help="N > 1: every rank owns T/N frames and they are all-gathered (default), or rank 0 owns all and broadcasts")
+    ap.add_argument("--lift", default="replicated", choices=["replicated", "slab"],
+                    help="N > 1: every rank lifts the whole grid (default), or x-slabs + all-gather of the volume")
     ap.add_argument("--unfused", action="store_true", help="separate sampler and decoder kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-side", action="store_true", help="skip the side measurements (HBM kernels, eager-GPU baseline)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the bench-time parity check")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -29,8 +29,8 @@
 // chunk; each chunk has its own mbarrier, so the MMA of a layer starts as soon as its first
 // chunk is ready.  With NSPLIT=2 each CTA produces half of the chunks and pushes them to its
 // peer with a bulk shared::cta -> shared::cluster copy that completes on the peer's barrier.
-// lin_in / lin_z biases (and fc_1's, folded into the next lin_z) ride in two extra K columns
-// as a bf16 hi+lo pair; fc_0 / lin_out / last fc_1 biases are added in fp32 by the epilogue.
+// lin_z biases (with lin_in's folded into lin_z_0's and fc_1's into the next lin_z) ride in two extra K columns of the
+// code tile as a 16-bit hi+lo pair; fc_0 / lin_out / last fc_1 biases are added in fp32 by the epilogue.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <cuda_fp16.h>
@@ -468,11 +468,6 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
                     }
                 }
                 v[h * 4 + 0] = f4.x, v[h * 4 + 1] = f4.y, v[h * 4 + 2] = f4.z, v[h * 4 + 3] = f4.w;
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int k = c * 64 + u * 8 + e;
-                if (k == d.d_feat || k == d.d_feat + 1) v[e] = 1.0f;       // bias hi / lo columns
             }
             uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
             if constexpr (!BF16) ovf |= sat_probe(pk.x, pk.y) | sat_probe(pk.z, pk.w);
@@ -1049,7 +1044,7 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
     if (d.HN % 32 != 0) d.two = 0;
     d.csize = d.nsplit * (d.two ? 2 : 1);
     d.WN = d.two ? d.HN / 2 : d.HN;
-    d.KF = (d.d_feat + 2 + 63) / 64;
+    d.KF = (d.d_feat + 63) / 64;             // no bias columns: lin_in's bias rides with lin_z_0's (same accumulation group)
     d.KZ = (d.d_code + 2 + 63) / 64;
     d.KH = d.Hd / 64;
     d.NOUT = d.two ? (d.d_out + 31) / 32 * 32 : (d.d_out + 15) / 16 * 16;     // each CTA of a pair holds NOUT/2 rows
@@ -1126,12 +1121,14 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
             PackOp op;
             switch (g.mat) {
             case M_LIN_IN:
-                op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.WN, d.KF, -1, d.nsplit, d.OWN, d.two, 1.0f, w->lin_in_b, nullptr, 1, 0};
+                op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.WN, d.KF, -1, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
                 break;
             case M_LIN_Z:
-                // x += alpha * (Wz code + bz)   [+ b1 of the previous block, folded here]
+                // x += alpha * (Wz code + bz)   [+ b1 of the previous block, or lin_in's bias for block 0: lin_in and lin_z_0
+                // accumulate into x in the same group, so one pair of bias columns serves both and a 64-wide feature vector
+                // (volume 32 + planes 32) stays ONE k-chunk]
                 op = PackOp{w->lin_z_w[g.blk], d.Hd, d.d_code, n0, d.WN, d.KZ, -1, d.nsplit, d.OWN, d.two, w->alpha, w->lin_z_b[g.blk],
-                            g.blk > 0 ? w->fc1_b[g.blk - 1] : nullptr, 1, 0};
+                            g.blk > 0 ? w->fc1_b[g.blk - 1] : w->lin_in_b, 1, 0};
                 break;
             case M_FC0:
                 op = PackOp{w->fc0_w[g.blk], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};

@@ -529,10 +529,74 @@ class GenNerf(nn.Module):
             self._pl_key = key
         return self._pl_cl
 
+    def shard_scene(self, group=None, enabled=True):
+        """ONE scene over the ranks of `group` (torch.distributed; SURVEY 8e, BASELINE config 4).  Afterwards
+        `encode(projection, image, depth)` takes ALL T projections but only THIS rank's frames
+        (parallel.shard_range(T, rank, world) of them, in frame order): every rank runs the 2D CNN and the farthest-point
+        sampling on its own frames, the channels-last feature maps are all-gathered in one NCCL call over NVLink, the
+        sampled points (a few KB) likewise, and every rank lifts the whole grid and builds the planes itself -- cheaper
+        than moving the volume.  `forward(xyz)` then answers whatever range of the queries the caller hands to this rank
+        (parallel.shard_range(Q, ...)); no collective on the query path.  Inference only."""
+        self._scene_group = (group if group is not None else True) if enabled else None
+
+    def _encode_sharded(self, projection, image, depth, sparse_xyz):
+        import torch.distributed as dist
+
+        from . import parallel
+        group = None if self._scene_group is True else self._scene_group
+        rank, world = parallel._ws(group)
+        if torch.is_grad_enabled() and image.requires_grad:
+            raise RuntimeError("gennerf_b200: scene sharding is an inference path (training is data-parallel, one scene per GPU)")
+        T = projection.size(1)
+        t0, t1 = parallel.shard_range(T, rank, world)
+        if image.size(1) != t1 - t0:
+            raise RuntimeError(f"shard_scene: rank {rank} of {world} owns frames [{t0},{t1}) of {T} but got {image.size(1)}")
+        voxel_dim = self.cfg.voxel_dim_train if self.training else self.cfg.voxel_dim_val
+        if self.cfg.encoder.use_spatial:
+            frames = image.unbind(1)
+            mine = [self.spatial(f) if self.spatial is not None else f for f in frames]
+            B, C, H, W = mine[0].shape if mine else (image.size(0), image.size(2), image.size(3), image.size(4))
+            fb = parallel.FrameBuffer(T, B, C, H, W, image.device, group)
+            nchw = [i for i, f in enumerate(mine) if f.is_contiguous()]
+            if len(nchw) == len(mine) and mine:
+                ops.nchw_to_nhwc(mine, out=fb.flat[t0:t1])                  # reference layout: transposed straight into the slot
+            else:
+                for i, f in enumerate(mine):
+                    fb.frames[t0 + i].copy_(f)
+            fb.all_gather()
+            out = None if self.volume is None else (self.volume, self.count, self.valid)
+            self.volume, self.count, self.valid = ops.backproject_frames(
+                voxel_dim, self.cfg.voxel_size, self.origin, projection, fb.frames, out=out)
+        if self.cfg.encoder.use_pointnet:
+            if sparse_xyz is None:
+                if depth is None:
+                    raise RuntimeError("gennerf_b200: encode() needs `depth` (or sparse_xyz=) for the triplane branch")
+                B = projection.size(0)
+                npts = self.cfg.encoder.pointnet.num_sparse_points
+                Tl = t1 - t0
+                d = depth.reshape(B * Tl, *depth.shape[-2:])
+                pts = ops.get_3d_points(d, projection[:, t0:t1].reshape(B * Tl, 3, 4)).reshape(B * Tl, -1, 3)
+                start = torch.stack([torch.randint(0, pts.shape[1], (B,), dtype=torch.long, device=pts.device) for _ in range(Tl)], dim=1)
+                local = ops.farthest_point_sample(pts, npts, start.reshape(-1))[0].reshape(B, Tl, npts, 3)
+                if world > 1 and T % world == 0:
+                    allp = torch.empty((world, B, Tl, npts, 3), device=local.device, dtype=local.dtype)
+                    dist.all_gather_into_tensor(allp, local.contiguous(), group=group)
+                    sparse_xyz = allp.permute(1, 0, 2, 3, 4).reshape(B, T * npts, 3)          # frame order
+                elif world > 1:
+                    parts = parallel._all_gather_ragged(local.transpose(0, 1).contiguous(),
+                                                        [b - a for a, b in (parallel.shard_range(T, r, world) for r in range(world))], group)
+                    sparse_xyz = torch.cat(parts, dim=0).transpose(0, 1).reshape(B, T * npts, 3)
+                else:
+                    sparse_xyz = local.reshape(B, T * npts, 3)
+            c_plane_new = self.pointnet(sparse_xyz)
+            self.c_plane = c_plane_new if self.c_plane is None else self.merger(c_plane_new, self.c_plane)
+
     def encode(self, projection, image, depth=None, mode="val", sparse_xyz=None):
         """reference model.py:77-150.  projection (B,T,3,4), image (B,T,3,H,W) (or (B,T,C,H,W)
         feature maps when no `spatial` CNN is attached).  All T frames are lifted by ONE fused
         kernel; repeated calls keep accumulating, as in the reference."""
+        if getattr(self, "_scene_group", None) is not None:
+            return self._encode_sharded(projection, image, depth, sparse_xyz)
         T = projection.size(1)
         if self.cfg.encoder.use_spatial:
             # the reference indexes image[:, t] per frame (model.py:116); unbind gives the same views with ONE backward node
@@ -649,18 +713,27 @@ class GenNerf(nn.Module):
             planes=self.c_plane if self.cfg.encoder.use_pointnet else None,
             voxel_size=self.cfg.voxel_size, origin=self.origin,
             padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1)
-        code = xyz
-        if self.cfg.use_code:
-            # positional encoding with torch ops so that d/dxyz flows (eikonal / gradient losses)
-            f = self.code._freqs.to(xyz.device)
-            ph = self.code._phases.to(xyz.device)
-            x2 = xyz.reshape(-1, 3)
-            emb = torch.sin(torch.addcmul(ph, x2.unsqueeze(1).repeat(1, self.code.num_freqs * 2, 1), f)).view(x2.shape[0], -1)
-            code = (torch.cat((x2, emb), dim=-1) if self.code.include_input else emb).reshape(B, N, -1)
-        out = self.mlp.forward_torch(torch.cat((code, feat), dim=-1))
+        out, tsdf = decode_train(self.mlp, self.head_geo, self.code if self.cfg.use_code else None, xyz, feat)
         feat_geo, feat_sem = out[..., :d_geo], out[..., d_geo:d_geo + d_sem]
-        tsdf = torch.tanh(torch.nn.functional.linear(feat_geo, self.head_geo.fc.weight, self.head_geo.fc.bias))
         return {"feat_geo": feat_geo, "feat_sem": feat_sem, "tsdf": tsdf, "feat": feat}
+
+
+def decode_train(mlp, head, code, xyz, feat):
+    """Differentiable decoder of a training step (reference model.py:226-246 under autograd): positional encoding with
+    torch ops so that d/dxyz flows, ResnetFC.forward_torch, tanh head.  xyz (B,N,3), feat (B,N,C_lat) ->
+    out (B,N,d_out), tsdf (B,N,1).  `code`: the PositionalEncoding module or None (cfg.use_code False)."""
+    B, N, _ = xyz.shape
+    z = xyz
+    if code is not None:
+        f = code._freqs.to(xyz.device)
+        ph = code._phases.to(xyz.device)
+        x2 = xyz.reshape(-1, 3)
+        emb = torch.sin(torch.addcmul(ph, x2.unsqueeze(1).repeat(1, code.num_freqs * 2, 1), f)).view(x2.shape[0], -1)
+        z = (torch.cat((x2, emb), dim=-1) if code.include_input else emb).reshape(B, N, -1)
+    out = mlp.forward_torch(torch.cat((z, feat), dim=-1))
+    d_geo = head.fc.weight.shape[1]
+    tsdf = torch.tanh(torch.nn.functional.linear(out[..., :d_geo], head.fc.weight, head.fc.bias))
+    return out, tsdf
 
 
 # ------------------------------------------------------------------------------------------

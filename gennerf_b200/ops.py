@@ -14,6 +14,22 @@ from ._lib import GNB_MAX_FRAMES, GnbDecoderWeights, GnbFusionParams, GnbLiftPar
 PLANES = ("xz", "xy", "yz")
 
 
+def _nvtx(fn):
+    """NVTX range `gnb.<op>` around the op (Nsight timelines).  A push / pop pair costs ~1 us with no
+    profiler attached."""
+    import functools
+    name = "gnb." + fn.__name__
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        torch.cuda.nvtx.range_push(name)
+        try:
+            return fn(*a, **k)
+        finally:
+            torch.cuda.nvtx.range_pop()
+    return wrapped
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -39,6 +55,7 @@ def _origin3(origin):
 # ------------------------------------------------------------------------------------------
 # lift
 # ------------------------------------------------------------------------------------------
+@_nvtx
 def backproject_frames(voxel_dim, voxel_size, origin, projections, features, *, mean=False,
                        volume_layout="channels_last", out=None, x_range=None, accumulate=None):
     """Fused back-projection of T frames (reference utils.py:948 + model.py:121-127,195-199).
@@ -132,12 +149,19 @@ def project_indices(voxel_dim, voxel_size, origin, projection, H, W, device="cud
     return px, py, valid
 
 
-def nchw_to_nhwc(frames):
-    """T tensors (B,C,H,W) contiguous -> one (T,B,H,W,C) tensor (layout helper)."""
+@_nvtx
+def nchw_to_nhwc(frames, out=None):
+    """T tensors (B,C,H,W) contiguous -> one (T,B,H,W,C) tensor (layout helper); `out` = a contiguous (T,B,H,W,C) buffer
+    (e.g. a rank's slice of parallel.FrameBuffer.flat) to write into."""
     frames = [_f32(f).contiguous() for f in frames]
     _need_cuda(*frames)
     B, Cc, H, W = frames[0].shape
-    dst = torch.empty((len(frames), B, H, W, Cc), device=frames[0].device, dtype=torch.float32)
+    if out is None:
+        dst = torch.empty((len(frames), B, H, W, Cc), device=frames[0].device, dtype=torch.float32)
+    else:
+        dst = out
+        if tuple(dst.shape) != (len(frames), B, H, W, Cc) or not dst.is_contiguous() or dst.dtype != torch.float32:
+            raise RuntimeError("nchw_to_nhwc: out must be a contiguous fp32 (T,B,H,W,C) tensor")
     ptrs = (C.c_void_p * len(frames))(*[f.data_ptr() for f in frames])
     with torch.cuda.device(dst.device):
         check(lib().gnb_nchw_to_nhwc(ptrs, len(frames), dst.data_ptr(), B, Cc, H, W, _stream()), "gnb_nchw_to_nhwc")
@@ -195,6 +219,7 @@ def _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding):
     return s, keep, B, Q, Cp, Cv
 
 
+@_nvtx
 def sample_features(xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1, binned="auto"):
     """GenNerf.map_features (reference model.py:163-204): (B,Q,3) -> (B,Q,C_p + C), plane
     features first.  `volume` is the accumulated (already normalised == summed) volume.
@@ -224,6 +249,7 @@ def sample_features(xyz, volume=None, planes=None, *, voxel_size=0.04, origin=No
 # ------------------------------------------------------------------------------------------
 # triplane projection
 # ------------------------------------------------------------------------------------------
+@_nvtx
 def plane_coords(p, padding, reso):
     """normalize_coordinate + coordinate2index for the three planes (reference utils.py:57-98).
     p (B,N,3) -> coord (3,B,N,2) fp32, index (3,B,N) int64; plane order xz, xy, yz."""
@@ -238,6 +264,7 @@ def plane_coords(p, padding, reso):
     return coord, index
 
 
+@_nvtx
 def scatter_mean_planes(p, c, reso, padding=0.1, mode="atomic"):
     """LocalPoolPointnet.generate_plane_features for xz, xy, yz at once (reference
     pointnet.py:72-89, without the U-Net).  p (B,N,3), c (B,N,C_p) ->
@@ -263,6 +290,7 @@ def scatter_mean_planes(p, c, reso, padding=0.1, mode="atomic"):
     return store.permute(0, 1, 4, 2, 3), count
 
 
+@_nvtx
 def scatter_finalize(planes, count):
     """sums (3,B,C_p,R,R) [channels-last storage] / max(count,1) in place (after an all-reduce)."""
     store = planes.permute(0, 1, 3, 4, 2)
@@ -274,6 +302,7 @@ def scatter_finalize(planes, count):
     return planes
 
 
+@_nvtx
 def pool_local(p, c, reso, padding=0.1, scatter_type="max"):
     """LocalPoolPointnet.pool_local (reference pointnet.py:105-121): c (B,N,Hd) -> (B,N,Hd)."""
     _need_cuda(p, c)
@@ -362,6 +391,7 @@ class DecoderWeights:
         return self.packed
 
 
+@_nvtx
 def decode(weights, xyz, feat, precision="fp32"):
     """PositionalEncoding -> ResnetFC -> TSDFHeadSimple (reference model.py:226-246).
     precision: 'fp32' (CUDA cores, exact mode) | 'fp16' | 'bf16' (tcgen05, 16-bit operands).
@@ -386,6 +416,7 @@ def decode(weights, xyz, feat, precision="fp32"):
     return out.reshape(*lead, weights.w.d_out), tsdf.reshape(*lead, 1)
 
 
+@_nvtx
 def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
                 want_feat=True, precision="fp16"):
     """GenNerf.forward in one kernel (sampler fused into the tcgen05 decoder).
@@ -404,6 +435,7 @@ def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
     return out, tsdf, feat
 
 
+@_nvtx
 def query_grid_fused(weights, grid_dim, axes, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
                      want_out=False, precision="fp16"):
     """GenNerf.predict_tsdf's query (reference model.py:752-790) in one kernel without a materialised query grid:
@@ -486,6 +518,7 @@ def tsdf_head(feat_geo, weight, bias):
 # ------------------------------------------------------------------------------------------
 # backward passes -- raw ops; gennerf_b200.autograd wires them into torch.autograd
 # ------------------------------------------------------------------------------------------
+@_nvtx
 def backproject_frames_bwd(voxel_dim, voxel_size, origin, projections, grad_volume, feat_shape, n_frames, *,
                            nhwc=False, mean=False, count=None, x_range=None):
     """grad_volume (B,C,nx,ny,nz) logical (any dense strides) -> list of T gradient maps (B,C,H,W) logical, in
@@ -532,6 +565,7 @@ def backproject_frames_bwd(voxel_dim, voxel_size, origin, projections, grad_volu
     return grads
 
 
+@_nvtx
 def sample_features_bwd(grad_out, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
                         need_volume=True, need_planes=True, need_xyz=True):
     """Backward of sample_features: returns (grad_xyz | None, grad_volume | None, {plane: grad} | None) with the
@@ -558,6 +592,7 @@ def sample_features_bwd(grad_out, xyz, volume=None, planes=None, *, voxel_size=0
     return gxyz, gvol, gpl
 
 
+@_nvtx
 def scatter_mean_planes_bwd(p, grad_planes, count, padding=0.1):
     """grad_planes (3,B,C_p,R,R) logical -> grad_c (B,N,C_p)."""
     _need_cuda(p, grad_planes, count)
@@ -572,6 +607,7 @@ def scatter_mean_planes_bwd(p, grad_planes, count, padding=0.1):
     return gc
 
 
+@_nvtx
 def pool_local_fwd_keep(p, c, reso, padding=0.1, scatter_type="max"):
     """pool_local that also returns the scratch buffer the backward needs."""
     _need_cuda(p, c)
@@ -588,6 +624,7 @@ def pool_local_fwd_keep(p, c, reso, padding=0.1, scatter_type="max"):
     return out, scratch
 
 
+@_nvtx
 def pool_local_bwd(p, c, grad_out, fwd_scratch, reso, padding=0.1, scatter_type="max"):
     p, c, go = _f32(p).contiguous(), _f32(c).contiguous(), _f32(grad_out).contiguous()
     B, N, _ = p.shape
@@ -606,6 +643,7 @@ def pool_local_bwd(p, c, grad_out, fwd_scratch, reso, padding=0.1, scatter_type=
 # ------------------------------------------------------------------------------------------
 # front end of the triplane branch
 # ------------------------------------------------------------------------------------------
+@_nvtx
 def get_3d_points(depth_map, projection):
     """get_3d_points (reference utils.py:120-175): depth (B,H,W), projection (B,3,4) -> (B,H,W,3)."""
     _need_cuda(depth_map)
@@ -618,6 +656,7 @@ def get_3d_points(depth_map, projection):
     return out
 
 
+@_nvtx
 def farthest_point_sample(xyz, npoint, start=None):
     """farthest_point_sample (reference utils.py:178-202): xyz (B,N,3) -> sampled (B,npoint,3), indices (B,npoint).
     `start` (B,) int64 is the first index; the reference draws it with torch.randint(0, N, (B,))."""
@@ -639,6 +678,7 @@ def farthest_point_sample(xyz, npoint, start=None):
 # ------------------------------------------------------------------------------------------
 # TSDF fusion
 # ------------------------------------------------------------------------------------------
+@_nvtx
 def tsdf_fusion_integrate(voxel_dim, voxel_size, origin, trunc_margin, projections, depths, tsdf_vol, weight_vol,
                           colors=None, color_vol=None, labels=None, label_vol=None, depth_culling=True):
     """TSDFFusion.integrate (reference src/data/tsdf.py:369-418) for T frames in one launch per 64 frames.
@@ -689,6 +729,7 @@ def tsdf_fusion_integrate(voxel_dim, voxel_size, origin, trunc_margin, projectio
     return tsdf_vol, weight_vol
 
 
+@_nvtx
 def tsdf_fusion_finalize(tsdf_vol, weight_vol, color_vol=None):
     """The normalisation of TSDFFusion.get_tsdf (reference tsdf.py:426-434): vol / weight where weight > 0."""
     _need_cuda(tsdf_vol, weight_vol, color_vol)
@@ -705,6 +746,7 @@ def tsdf_fusion_finalize(tsdf_vol, weight_vol, color_vol=None):
 # ------------------------------------------------------------------------------------------
 # training-time ray sampler
 # ------------------------------------------------------------------------------------------
+@_nvtx
 def sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta, min_dist, sigma, gaussian_depths=None):
     """sample_points_on_rays (reference utils.py:458-540) in one launch: xyz_world (B,S,1+N+M,3), z (B,S,1+N+M).
     The M gaussian depths per ray are drawn here exactly as the reference draws them on its device (one
@@ -731,6 +773,7 @@ def sample_points_on_rays(h_idxs, w_idxs, depths, intrinsics, poses, N, M, delta
     return xyz, z
 
 
+@_nvtx
 def sample_valid_depth_pixels(depth, num_samples):
     """sample_valid_depth_pixels (reference utils.py:340-363): depth (B,H,W) -> b_idxs (B,1), h_idxs, w_idxs (B,S) int64.
     The ranks are drawn as the reference draws them (one torch.randperm(n_valid[b], device)[:S] per map, in map order, so

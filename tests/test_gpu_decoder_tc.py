@@ -34,9 +34,9 @@ def emulate_tc(code, feat, w, n_blocks, alpha, dtype):
             hi = bf(b_cols)
             y = y + hi + bf(b_cols - hi)
         return y
-    x = lin(feat, w["lin_in.weight"], w["lin_in.bias"])
+    x = lin(feat, w["lin_in.weight"])
     for i in range(n_blocks):
-        bz = alpha * w[f"lin_z.{i}.bias"] + (w[f"blocks.{i - 1}.fc_1.bias"] if i > 0 else 0)
+        bz = alpha * w[f"lin_z.{i}.bias"] + (w[f"blocks.{i - 1}.fc_1.bias"] if i > 0 else w["lin_in.bias"])
         x = x + lin(code, w[f"lin_z.{i}.weight"], bz, alpha)
         net = lin(F.relu(x), w[f"blocks.{i}.fc_0.weight"]) + w[f"blocks.{i}.fc_0.bias"]
         x = x + lin(F.relu(net), w[f"blocks.{i}.fc_1.weight"])

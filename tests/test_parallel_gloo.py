@@ -74,6 +74,23 @@ def _worker(rank, world, port, nx, result_dir):
         vol_o, valid_o, cnt_o = O.encode_volume(vd, VS, ORIGIN, P, feats)
         assert torch.equal(vol, vol_o) and torch.equal(cnt, cnt_o) and torch.equal(valid, valid_o)
 
+        # frames owned per rank (the CNN ran on T/N frames each) -> one flat all-gather (equal and ragged ownership)
+        for Tn in (4, 3):
+            fr = S.frame_features(Tn, 4, 6, 8, S.gen(8))
+            fb = parallel.FrameBuffer(Tn, 1, 4, 6, 8, "cpu")
+            fb.flat.fill_(float("nan"))
+            for t in range(*fb.owned):
+                fb.frames[t].copy_(fr[t])
+            fb.all_gather()
+            for t in range(Tn):
+                assert torch.equal(fb.frames[t], fr[t]) and fb.frames[t].shape == fr[t].shape
+            fb2 = parallel.FrameBuffer(Tn, 1, 4, 6, 8, "cpu")
+            if rank == 0:
+                for t in range(Tn):
+                    fb2.frames[t].copy_(fr[t])
+            fb2.broadcast(src=0)
+            assert all(torch.equal(fb2.frames[t], fr[t]) for t in range(Tn))
+
         # triplane: each rank scatters its share of the points; the all-reduced result equals the full scatter
         N, Cp, R = 1001, 4, 8
         p = S.plane_points(N, g, "unit")
