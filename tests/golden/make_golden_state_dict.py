@@ -54,10 +54,14 @@ def main():
     m = GenNerf(copy.deepcopy(small)).eval()
     g = S.gen(109)
     with torch.no_grad():
-        for p in m.parameters():                      # fc_1 of every block is zero-initialised (trap T9): randomise
+        for p in m.pointnet.parameters():             # (the PointNet's fc_1 are zero-initialised too)
             p.copy_(torch.randn(p.shape, generator=g) * (0.3 if p.dim() > 1 else 0.05))
-        m.mlp.alpha.fill_(0.9)
+        # decoder: fc_1 of every block is zero-initialised (trap T9) -> kaiming-scale random weights, small biases, and a
+        # head scaled so that |pre-tanh| stays O(1) (tanh saturation hides errors) -- gennerf_b200.synthetic
         C = 64
+        w, hw, hb = S.decoder_weights(g, C + 8, 15, 64, 5, 64, 32, alpha=0.9)
+        m.mlp.load_state_dict(w)
+        m.head_geo.load_state_dict({"fc.weight": hw, "fc.bias": hb})
         xyz = S.query_points(300, wl["voxel_dim"], VS, g)
         m.volume = torch.randn(1, C, *wl["voxel_dim"], generator=g)
         m.valid = torch.rand(1, 1, *wl["voxel_dim"], generator=g) > 0.3

@@ -187,6 +187,5 @@ def test_decode_tc_cta_group2_variant():
         torch.cuda.synchronize()
     finally:
         _lib.set_option("GNB_TC_TWO_CTA", old)
-    assert dw2.packed.numel() == dw1.packed.numel()
     assert ((a - b).abs().max() / a.abs().max()).item() < 2e-3
     assert (ta - tb).abs().max().item() < 5e-3

@@ -63,7 +63,7 @@ def test_cached_decoder_weights_follow_the_parameters(SD, precision):
     model = _small_model(SD, precision)
     xyz = SD["small"]["in"]["xyz"].to(DEV)
     with torch.no_grad():
-        before = model(xyz)["tsdf"].clone()
+        before = model(xyz)["feat_geo"].clone()            # (pre-tanh: the golden model's TSDF saturates at +-1, trap T9)
     opt = torch.optim.SGD(list(model.mlp.parameters()) + list(model.head_geo.parameters()), lr=0.05)
     model.train()
     loss = model(xyz)["tsdf"].abs().mean()
@@ -71,7 +71,7 @@ def test_cached_decoder_weights_follow_the_parameters(SD, precision):
     opt.step()
     model.eval()
     with torch.no_grad():
-        after = model(xyz)["tsdf"].clone()
+        after = model(xyz)["feat_geo"].clone()
     assert (after - before).abs().max().item() > 1e-4, "stale decoder weights: the optimiser step changed nothing"
     # a model freshly built from the updated parameters agrees
     from gennerf_b200.dropin import GenNerf
@@ -79,12 +79,12 @@ def test_cached_decoder_weights_follow_the_parameters(SD, precision):
     fresh.load_state_dict(model.state_dict())
     fresh.volume, fresh.valid, fresh.c_plane = model.volume, model.valid, model.c_plane
     with torch.no_grad():
-        want = fresh(xyz)["tsdf"]
+        want = fresh(xyz)["feat_geo"]
     assert torch.equal(after, want)
     # load_state_dict (in place) is noticed as well
     model.load_state_dict(SD["small"]["state_dict"])
     with torch.no_grad():
-        again = model(xyz)["tsdf"]
+        again = model(xyz)["feat_geo"]
     assert torch.equal(again, before)
 
 
@@ -97,7 +97,7 @@ def test_unet_style_nchw_planes_run_fused(SD):
             self.conv = nn.Conv2d(8, 8, 3, padding=1)
 
         def forward(self, x):
-            return self.conv(x)
+            return self.conv(x).contiguous()                    # NCHW, as the reference U-Net's cat / upsample path returns
     g = S.gen(71)
     model = _small_model(SD, "fp16", unet=TinyUNet().to(DEV))
     xyz = SD["small"]["in"]["xyz"].to(DEV)
