@@ -234,6 +234,55 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
                  "h"(mask)
                  : "memory");
 }
+// Warp-converged issue.  tcgen05.mma / tcgen05.commit are uniform-datapath instructions (UTCHMMA / UTCBAR take uniform
+// registers and issue once per warp).  Inside a divergent `if (lane == 0)` region ptxas cannot prove that the operands are
+// warp-uniform and wraps EVERY such instruction in an "ELECT ... R2UR ... BRA.U.ANY" serialisation loop (~80 cycles per MMA
+// on the issuing thread: tools/microbench/umma_pair_test.cu measures 775 cycles for 8 MMAs + commit issued by one thread
+// against 512 -- the tensor pipe's own time -- from a converged warp).  So the issuing warp stays converged, computes its
+// operands with all 32 lanes and elects the issuing lane inside the asm block.
+__device__ __forceinline__ void umma_f16_x4_u(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+        "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+        "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, 1;\n\t}" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_u(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_u(uint32_t bar, uint16_t mask) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bulk copies from a converged warp (UBLKCP is a uniform-datapath instruction as well): expect_tx + copy by one elected lane
+__device__ __forceinline__ void bulk_g2s_u(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+                 "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2peer_u(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(dst_cluster),
+                 "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
 // 2-CTA variants: one instruction drives the tensor cores of both SMs of the pair (M = 256: 128 rows from
 // each CTA's A tile, each CTA supplies half of the N rows of B); commits can signal any set of CTAs
 __device__ __forceinline__ void umma_f16_2cta(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
@@ -568,7 +617,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
 
     if (warp == ROLE_WARP0) {
         // =============================== weight producer ======================================
-        if (lane == 0) {
+        if (TWO ? (lane == 0) : true) {
             int stage = 0;
             uint32_t phase = 0;
             if constexpr (TWO) {
@@ -598,10 +647,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                     for (int o = 0; o < nops; ++o) {
                         const Op op = get_op(d, o);
                         const uint32_t bytes = (uint32_t)op.rows * 128u;
-                        for (int kc = 0; kc < op.kchunks; ++kc) {
+                        for (int kc = 0; kc < op.kchunks; ++kc) {       // (the whole warp, converged: see umma_f16_x4_u)
                             mbar_wait(w_empty(stage), phase ^ 1);
-                            mbar_expect_tx(w_full(stage), bytes);
-                            bulk_g2s(sbase + L.ring + stage * d.stage_bytes, src, bytes, w_full(stage));
+                            bulk_g2s_u(sbase + L.ring + stage * d.stage_bytes, src, bytes, w_full(stage));
                             src += bytes;
                             if (++stage == d.nstage) { stage = 0; phase ^= 1; }
                         }
@@ -721,13 +769,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 }
             }
         } else {
-        // ---- single-CTA issue: lane 0 ALONE runs the loop (no elect / warp votes / reconvergence on the critical
-        //      path).  Measured per-instruction cost on the issuing thread (tools/microbench/mma_rate.cu): MMA ~60,
-        //      wait on a complete barrier ~180, commit ~110, fence ~40 cycles; a 64-wide k-step (4 MMAs, one combined
-        //      wait, 1-2 commits) is ~600-700 cycles of issue work against 630 cycles of tensor-pipe time at N = 256.
-        //      (Two issuing threads in different warps -- own chunks / pushed chunks, accumulating into the same TMEM
-        //      columns -- were tried: tcgen05.commit arrivals got lost and results were corrupted, so one thread issues.)
-        if (lane == 0) {
+        // ---- single-CTA issue: the WHOLE warp walks the program, converged (see umma_f16_x4_u); every lane polls the
+        //      barriers (uniform addresses: ~110 cycles per wait on a complete barrier, against ~230 for one polling lane plus a
+        //      broadcast).  (Two issuing threads in different warps -- own chunks / pushed chunks, accumulating into the same
+        //      TMEM columns -- were tried in round 1: tcgen05.commit arrivals got lost and results were corrupted.)
+        {
             int stage = 0;
             uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0;
             const uint16_t allmask = (uint16_t)((1u << d.nsplit) - 1);
@@ -735,10 +781,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 mbar_wait(in_ready, tiles_done & 1);
                 tc_fence_after();
                 int tk = tiles_done * 64;
-                GNB_TRACE(0, tk); ++tk;
+                if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
                 for (int o = 0; o < nops; ++o) {
                     const Op op = get_op(d, o);
-                    GNB_TRACE(0, tk); ++tk;
+                    if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
                     const uint32_t idesc = umma_idesc(op.rows, BF16);
                     const uint32_t dcol = tmem + op.d_col;
                     for (int t = 0; t < op.kchunks; ++t) {
@@ -756,30 +802,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         } else {                                       // ... then the peer's, in the order it pushes them
                             rslot = (int)(rtotal % (uint32_t)d.RS);
                             a_addr = sbase + L.a + (d.AOWN + rslot) * CHUNK;
-                            mbar_expect_tx(rready(rslot), CHUNK);
+                            mbar_expect_tx_u(rready(rslot), CHUNK);
                             mbar_wait2(rready(rslot), (rtotal / (uint32_t)d.RS) & 1, w_full(stage), phase);
                             ++rtotal;
                         }
                         tc_fence_after();
                         const uint64_t da = umma_desc(a_addr), db = umma_desc(sbase + L.ring + stage * d.stage_bytes);
-                        umma_f16_x4(dcol, da, db, idesc, (op.first_overwrites && t == 0) ? 0u : 1u);
-                        umma_commit(w_empty(stage));              // frees the ring stage when these MMAs retire
+                        umma_f16_x4_u(dcol, da, db, idesc, (op.first_overwrites && t == 0) ? 0u : 1u);
+                        umma_commit_u(w_empty(stage));            // frees the ring stage when these MMAs retire
                         // MMAs that read a remote slot: tell the PEER it may push into it again
-                        if (rslot >= 0) umma_commit_mc(rfree(rslot), (uint16_t)(1u << peer));
+                        if (rslot >= 0) umma_commit_mc_u(rfree(rslot), (uint16_t)(1u << peer));
                         if (++stage == d.nstage) { stage = 0; phase ^= 1; }
                     }
-                    GNB_TRACE(0, tk); ++tk;
+                    if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
                     if (op.a_kind == 2) ++round;
                     // (early staging) the last lin_z of the tile has been issued: when it retires, the staging warp may
                     // overwrite the code tile and the feature buffer with the next tile's operands
-                    if (d.early && op.mat == M_LIN_Z && op.blk == d.nb - 1) umma_commit(in_free);
-                    if (d.early && o == 0) umma_commit(feat_free);
+                    if (d.early && op.mat == M_LIN_Z && op.blk == d.nb - 1) umma_commit_u(in_free);
+                    if (d.early && o == 0) umma_commit_u(feat_free);
                     if (op.group_end) {
                         // (early staging) this tile's first group may complete before the PEER has finished the previous
                         // tile: its arrival must not count for the previous tile's last phase of acc_ready
                         if (d.early && o == 1 && tiles_done > 0) mbar_wait(acc_ready, (tiles_done * (uint32_t)(2 * d.nb + 2) - 1) & 1);
-                        if (d.nsplit > 1) umma_commit_mc(acc_ready, allmask);
-                        else umma_commit(acc_ready);
+                        if (d.nsplit > 1) umma_commit_mc_u(acc_ready, allmask);
+                        else umma_commit_u(acc_ready);
                     }
                 }
             }
@@ -816,7 +862,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
         // Pushes every own chunk into one of the peer's RS remote slots (cycled).  A slot is reused
         // only after the peer's MMAs that read it have retired (rfree, signalled by the peer's
         // multicast tcgen05.commit).
-        if (lane == 0 && d.nsplit > 1) {
+        if (d.nsplit > 1) {                                   // (the whole warp, converged)
             uint32_t round = 0, ptotal = 0;
             for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters) {
                 for (int r = 0; r < 2 * d.nb + 1; ++r, ++round) {
@@ -826,7 +872,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         if (use > 0) mbar_wait(rfree(sl), (use - 1) & 1);
                         const uint32_t src = sbase + L.a + t * CHUNK;
                         const uint32_t dst = sbase + L.a + (d.AOWN + sl) * CHUNK;
-                        bulk_s2peer(map_to_cta(dst, peer), src, CHUNK, map_to_cta(rready(sl), peer));
+                        bulk_s2peer_u(map_to_cta(dst, peer), src, CHUNK, map_to_cta(rready(sl), peer));
                     }
                 }
             }
