@@ -135,6 +135,9 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_query_fused_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(GnbDecoderWeights), C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnb_query_fused_sorted_scratch_bytes": (C.c_int64, [C.POINTER(GnbSampleParams)]),
+    "gnb_query_fused_sorted_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(GnbDecoderWeights), C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gnb_query_grid_fused_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(C.c_int32), C.c_void_p,
                                             C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -366,6 +366,8 @@ struct TcKP {
     GnbDecoderWeights w;          // fp32 biases, head, encoding options (matrices are read from `packed`)
     const unsigned char* packed;
     const float* xyz;             // (n_rows,3), or (n_rows,d_code) codes when w.use_code == 2
+    const float4* sorted;         // brick-sorted mode (xyz == null): row r is the record (x, y, z, query index); outputs go to the
+                                  //   rows the indices name.  The staging warp then walks the volume brick by brick (L1 / L2 hits)
     const float* gaxes;           // dense-grid mode (xyz == null): the gnx + gny + gnz axis coordinates; query row r of a
     int gnx, gny, gnz;            //   scene is the grid point (x[i], y[j], z[k]), r = (i*gny + j)*gnz + k  (utils.py:926-935)
     const float* feat;            // (n_rows,d_feat) when !fused
@@ -445,8 +447,13 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
     const GnbDecoderWeights& w = p.w;
     const bool live = grow < p.n_rows;
     float xyz3[3] = {0.f, 0.f, 0.f};
+    long long orow = grow;                       // row of the outputs (differs from the processing row in sorted mode)
     if (live && w.use_code != 2) {
-        if (p.gaxes) {            // the query grid is never materialised: derive the point from the row index
+        if (p.sorted) {
+            const float4 rec = __ldg(p.sorted + grow);
+            xyz3[0] = rec.x, xyz3[1] = rec.y, xyz3[2] = rec.z;
+            orow = (long long)__float_as_int(rec.w);
+        } else if (p.gaxes) {            // the query grid is never materialised: derive the point from the row index
             const long long r = grow % ((long long)p.gnx * p.gny * p.gnz);
             const int k = (int)(r % p.gnz), j = (int)((r / p.gnz) % p.gny), i = (int)(r / ((long long)p.gnz * p.gny));
             xyz3[0] = __ldg(p.gaxes + i), xyz3[1] = __ldg(p.gaxes + p.gnx + j), xyz3[2] = __ldg(p.gaxes + p.gnx + p.gny + k);
@@ -487,7 +494,7 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
     if (!(what & 2)) return;
     TriCorners tcn;
     BiCorners bc[3];
-    const int b = (p.fused && live) ? (int)(grow / p.s.Q) : 0;
+    const int b = (p.fused && live) ? (int)(orow / p.s.Q) : 0;
     if (p.fused && live) {
         if (p.s.volume) trilinear_setup(p.s, xyz3[0], xyz3[1], xyz3[2], tcn);
         if (p.s.Cp > 0) planes_setup(p.s, xyz3[0], xyz3[1], xyz3[2], bc);
@@ -513,7 +520,7 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
                         // (host guarantees C_p % 4 == 0, C % 4 == 0 and unit channel strides here)
                         Vals<4> r = (k < p.s.Cp) ? sample_planes<4>(p.s, bc, b, k) : sample_volume<4>(p.s, tcn, b, k - p.s.Cp);
                         f4 = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-                        if (p.s.out && half == 0) *reinterpret_cast<float4*>(p.s.out + grow * p.s.out_stride + k) = f4;
+                        if (p.s.out && half == 0) *reinterpret_cast<float4*>(p.s.out + orow * p.s.out_stride + k) = f4;
                     }
                 }
                 v[h * 4 + 0] = f4.x, v[h * 4 + 1] = f4.y, v[h * 4 + 2] = f4.z, v[h * 4 + 3] = f4.w;
@@ -974,6 +981,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 const float* bo = bias_s + d.HN;
                 const float* hw = bo + d.NOUT;
                 float head = hw[d.d_geo];
+                const long long orow = (p.sorted && live) ? (long long)__float_as_int(__ldg(reinterpret_cast<const float*>(p.sorted + grow) + 3)) : grow;
                 for (int part = 0; part < (eg == 0 ? d.NOUT / 16 : 0); ++part) {
                     uint32_t v[16];
                     tmem_ld16(tlane + NET_COL + part * 16, v);
@@ -986,7 +994,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         if (n < d.d_geo) head = fmaf(f[e], hw[n], head);
                     }
                     if (live && half == 0 && p.out) {
-                        float* o = p.out + grow * d.d_out + part * 16;
+                        float* o = p.out + orow * d.d_out + part * 16;
                         if ((d.d_out & 3) == 0) {
 #pragma unroll
                             for (int e = 0; e < 16; e += 4)
@@ -998,7 +1006,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                         }
                     }
                 }
-                if (live && half == 0 && eg == 0 && p.tsdf) p.tsdf[grow] = tanhf(head);
+                if (live && half == 0 && eg == 0 && p.tsdf) p.tsdf[orow] = tanhf(head);
                 if (ovf && live && p.w.status) atomicOr(p.w.status, 1);
                 ovf = 0;
                 tc_fence_before();
@@ -1300,6 +1308,21 @@ extern "C" int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeig
     TcKP kp = {};
     int rc = query_fused_common(s, w, kp, out, tsdf, "gnb_query_fused_tc");
     if (rc || kp.s.total == 0) return rc;
+    return launch_tc(w, packed, kp, stream);
+}
+
+extern "C" int64_t gnb_query_fused_sorted_scratch_bytes(const GnbSampleParams* s) { return bin_sort_scratch_bytes(s); }
+
+extern "C" int gnb_query_fused_sorted_tc(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed, float* out,
+                                           float* tsdf, void* scratch, int64_t scratch_bytes, void* stream) {
+    TcKP kp = {};
+    int rc = query_fused_common(s, w, kp, out, tsdf, "gnb_query_fused_sorted_tc");
+    if (rc || kp.s.total == 0) return rc;
+    const float4* sorted = nullptr;
+    GnbSampleParams ss = *s;
+    ss.out = nullptr;                                  // (the sort plan only validates it)
+    if ((rc = bin_sort(&ss, scratch, scratch_bytes, stream, &sorted))) return rc;
+    kp.xyz = nullptr, kp.sorted = sorted;
     return launch_tc(w, packed, kp, stream);
 }
 

@@ -154,4 +154,8 @@ __device__ __forceinline__ void planes_setup(const SampleKP& p, float x, float y
 
 int fill_sample_kp(const GnbSampleParams* s, SampleKP& kp);
 
+// counting sort of the queries by voxel brick (sample_binned.cu); 0 bytes = the parameters do not allow it
+int64_t bin_sort_scratch_bytes(const GnbSampleParams* sp);
+int bin_sort(const GnbSampleParams* sp, void* scratch, int64_t scratch_bytes, void* stream, const float4** sorted);
+
 }  // namespace gnb

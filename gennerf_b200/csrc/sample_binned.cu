@@ -502,28 +502,14 @@ extern "C" int64_t gnb_sample_binned_scratch_bytes(const GnbSampleParams* sp) {
     return (int64_t)pl.total_bytes;
 }
 
-extern "C" int gnb_sample_features_binned(const GnbSampleParams* sp, void* scratch, int64_t scratch_bytes, void* stream_) {
-    BinPlan pl;
-    GNB_CHECK_ARG(sp, "sample_binned: null params");
-    {
-        SampleKP chk;
-        int rc = fill_sample_kp(sp, chk);
-        if (rc) return rc;
-        if (chk.total == 0) return 0;
-    }
-    GNB_CHECK_ARG(plan_binned(sp, pl), "sample_binned: needs a channels-last fp32 volume with C %% 4 == 0 (use gnb_sample_features)");
-    GNB_CHECK_ARG(sp->out && sp->out_stride >= pl.kp.s.C + pl.kp.s.Cp, "sample_binned: bad output");
-    GNB_CHECK_ARG(scratch && aligned16(scratch) && scratch_bytes >= (int64_t)pl.total_bytes, "sample_binned: scratch too small (gnb_sample_binned_scratch_bytes)");
-    cudaStream_t stream = (cudaStream_t)stream_;
+// The counting sort of the queries by brick (count -> reduce -> scan -> scatter): fills k.sorted / k.start / k.units in `scratch`.
+static int launch_bin_sort(BinPlan& pl, void* scratch, cudaStream_t stream, int sms) {
     BinKP& k = pl.kp;
     unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
     k.count = reinterpret_cast<unsigned*>(base + (size_t)k.count), k.cursor = reinterpret_cast<unsigned*>(base + (size_t)k.cursor);
     k.work = reinterpret_cast<unsigned*>(base + (size_t)k.work), k.start = reinterpret_cast<unsigned*>(base + (size_t)k.start);
     k.sorted = reinterpret_cast<float4*>(base + (size_t)k.sorted), k.bid = reinterpret_cast<unsigned*>(base + (size_t)k.bid);
     k.ustart = reinterpret_cast<unsigned*>(base + (size_t)k.ustart), k.units = reinterpret_cast<uint2*>(base + (size_t)k.units);
-    int dev = 0, sms = 148;
-    GNB_CUDA(cudaGetDevice(&dev));
-    GNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     k.hmat = reinterpret_cast<unsigned*>(base + pl.o_hmat);
     k.hstride = (BIN_MAXB + 31) / 32 * 32;
     // count / scatter: contiguous chunks of queries per block (a multiple of the block size), the same in both kernels
@@ -548,6 +534,53 @@ extern "C" int gnb_sample_features_binned(const GnbSampleParams* sp, void* scrat
     if (pl.smem_hist) bin_scatter_kernel<true><<<(unsigned)blocks, 1024, pl.hist_bytes, stream>>>(k);
     else bin_scatter_kernel<false><<<(unsigned)blocks, 1024, 0, stream>>>(k);
     GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+// Sort only (the fused decoder's prologue then walks the queries brick by brick: its gathers hit L1 / L2 instead of DRAM).
+// *sorted: [total] records (x, y, z, query index as int bits) inside `scratch`.
+namespace gnb {
+int64_t bin_sort_scratch_bytes(const GnbSampleParams* sp) {
+    BinPlan pl;
+    if (!sp || !plan_binned(sp, pl)) return 0;
+    return (int64_t)pl.total_bytes;
+}
+int bin_sort(const GnbSampleParams* sp, void* scratch, int64_t scratch_bytes, void* stream_, const float4** sorted) {
+    BinPlan pl;
+    GNB_CHECK_ARG(sp && sorted, "bin_sort: null argument");
+    GNB_CHECK_ARG(plan_binned(sp, pl), "bin_sort: needs a channels-last fp32 volume with C %% 4 == 0");
+    GNB_CHECK_ARG(scratch && aligned16(scratch) && scratch_bytes >= (int64_t)pl.total_bytes, "bin_sort: scratch too small");
+    int dev = 0, sms = 148;
+    GNB_CUDA(cudaGetDevice(&dev));
+    GNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int rc = launch_bin_sort(pl, scratch, (cudaStream_t)stream_, sms);
+    if (rc) return rc;
+    *sorted = pl.kp.sorted;
+    return 0;
+}
+}  // namespace gnb
+
+extern "C" int gnb_sample_features_binned(const GnbSampleParams* sp, void* scratch, int64_t scratch_bytes, void* stream_) {
+    BinPlan pl;
+    GNB_CHECK_ARG(sp, "sample_binned: null params");
+    {
+        SampleKP chk;
+        int rc = fill_sample_kp(sp, chk);
+        if (rc) return rc;
+        if (chk.total == 0) return 0;
+    }
+    GNB_CHECK_ARG(plan_binned(sp, pl), "sample_binned: needs a channels-last fp32 volume with C %% 4 == 0 (use gnb_sample_features)");
+    GNB_CHECK_ARG(sp->out && sp->out_stride >= pl.kp.s.C + pl.kp.s.Cp, "sample_binned: bad output");
+    GNB_CHECK_ARG(scratch && aligned16(scratch) && scratch_bytes >= (int64_t)pl.total_bytes, "sample_binned: scratch too small (gnb_sample_binned_scratch_bytes)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int dev = 0, sms = 148;
+    GNB_CUDA(cudaGetDevice(&dev));
+    GNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    {
+        int rc = launch_bin_sort(pl, scratch, stream, sms);
+        if (rc) return rc;
+    }
+    BinKP& k = pl.kp;
     // tensor map of the channels-last volume (C, z, y, x, scene): a brick's tile is one TMA box
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));

@@ -418,9 +418,13 @@ def decode(weights, xyz, feat, precision="fp32"):
 
 @_nvtx
 def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
-                want_feat=True, precision="fp16"):
+                want_feat=True, precision="fp16", presort="auto"):
     """GenNerf.forward in one kernel (sampler fused into the tcgen05 decoder).
-    Returns out (B,Q,d_out), tsdf (B,Q,1), feat (B,Q,C_lat) or None."""
+    Returns out (B,Q,d_out), tsdf (B,Q,1), feat (B,Q,C_lat) or None.
+
+    presort: "auto" first counting-sorts the queries by voxel brick (same bits, outputs in the caller's order) when there is
+    at least one query per three voxels -- the sampling prologue then reads the volume brick by brick; True forces it
+    (raises when there is no channels-last volume to sort by), False never."""
     s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
     feat = None
     if want_feat:
@@ -430,8 +434,19 @@ def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
     tsdf = torch.empty((B, Q, 1), device=xyz.device, dtype=torch.float32)
     packed = weights.tc_image(precision)
     with torch.cuda.device(xyz.device):
-        check(lib().gnb_query_fused_tc(C.byref(s), C.byref(weights.w), packed.data_ptr(), out.data_ptr(),
-                                         tsdf.data_ptr(), _stream()), "gnb_query_fused_tc")
+        nbytes = 0
+        if presort and volume is not None and Q > 0:
+            dense = presort is True or (B * Q >= (1 << 16) and 3 * Q >= volume.shape[2] * volume.shape[3] * volume.shape[4])
+            nbytes = lib().gnb_query_fused_sorted_scratch_bytes(C.byref(s)) if dense else 0
+            if presort is True and nbytes == 0:
+                raise RuntimeError("gennerf_b200: presort needs a channels-last fp32 volume with C % 4 == 0")
+        if nbytes > 0:
+            scratch = torch.empty(nbytes, device=xyz.device, dtype=torch.uint8)
+            check(lib().gnb_query_fused_sorted_tc(C.byref(s), C.byref(weights.w), packed.data_ptr(), out.data_ptr(),
+                                                    tsdf.data_ptr(), scratch.data_ptr(), nbytes, _stream()), "gnb_query_fused_sorted_tc")
+        else:
+            check(lib().gnb_query_fused_tc(C.byref(s), C.byref(weights.w), packed.data_ptr(), out.data_ptr(),
+                                             tsdf.data_ptr(), _stream()), "gnb_query_fused_tc")
     return out, tsdf, feat
 
 

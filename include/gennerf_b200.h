@@ -349,6 +349,15 @@ int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, const float* x
 int gnb_query_fused_tc(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed,
                        float* out, float* tsdf, void* stream);
 
+/* The same with the queries first counting-sorted by the 8x8x8-voxel brick of the volume they fall into (the brick sort of
+ * gnb_sample_features_binned): the kernel's sampling prologue then walks the volume brick by brick, so its 8 corner reads
+ * per query hit L1 / L2 instead of DRAM when the volume is larger than L2 (config 4: 805 MB), and results are written to
+ * the rows the original query order names -- bit-identical outputs.  `scratch`: gnb_query_fused_sorted_scratch_bytes(s)
+ * bytes (0: these parameters cannot be sorted -- no channels-last volume; use gnb_query_fused_tc). */
+int64_t gnb_query_fused_sorted_scratch_bytes(const GnbSampleParams* s);
+int gnb_query_fused_sorted_tc(const GnbSampleParams* s, const GnbDecoderWeights* w, const void* packed,
+                              float* out, float* tsdf, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* Dense-grid extraction (GenNerf.predict_tsdf, model.py:752-790 with get_grid_coordinates, utils.py:926-935): the same
  * fused kernel, but the (nx*ny*nz, 3) query grid is never materialised -- query row r of a scene is the grid point
  * (axes[i], axes[nx + j], axes[nx + ny + k]) with r = (i*ny + j)*nz + k.  `axes` (device, nx + ny + nz floats) holds the

@@ -189,3 +189,26 @@ def test_decode_tc_cta_group2_variant():
         _lib.set_option("GNB_TC_TWO_CTA", old)
     assert ((a - b).abs().max() / a.abs().max()).item() < 2e-3
     assert (ta - tb).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("B,Q", [(1, 70001), (2, 9000)])
+def test_query_fused_presorted_is_bit_identical(B, Q):
+    """Brick-sorted fused query (gnb_query_fused_sorted_tc): the queries are processed in brick order, the results land in
+    the caller's order -- identical bits to the unsorted launch (rows are independent), features included."""
+    from gennerf_b200 import ops
+    wl = S.WORKLOADS["small"]
+    g = S.gen(47)
+    C, Cp, R = 32, 32, 32
+    P = torch.stack([S.projections(wl["T"], wl["H"], wl["W"], wl["voxel_dim"], VS, g, pull_back=0.8) for _ in range(B)])
+    feats = S.frame_features(wl["T"], C, wl["H"], wl["W"], g, B=B)
+    xyz = S.query_points(Q, wl["voxel_dim"], VS, g, B=B).to(DEV)
+    planes = {k: torch.randn(B, Cp, R, R, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) for k in O.PLANES}
+    w, hw, hb = S.decoder_weights(g, C + Cp, 15, 512, 5, 64, 32)
+    vol, cnt, valid = ops.backproject_frames(wl["voxel_dim"], VS, ORIGIN, P, [f.to(DEV) for f in feats])
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    a = ops.query_fused(dw, xyz, volume=vol, planes=planes, voxel_size=VS, origin=ORIGIN, padding=0.1, presort=False)
+    b = ops.query_fused(dw, xyz, volume=vol, planes=planes, voxel_size=VS, origin=ORIGIN, padding=0.1, presort=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    with pytest.raises(RuntimeError):
+        ops.query_fused(dw, xyz, volume=None, planes=planes, padding=0.1, presort=True)
