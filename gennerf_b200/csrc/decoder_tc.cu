@@ -547,8 +547,13 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
 // ---------------------------------------------------------------------------------------------
 // TWO = cta_group::2: ranks (2i, 2i+1) of the cluster form an MMA pair working on 256 query rows (128 each);
 // rank>>1 selects the N-half of the hidden width, the even rank ("leader") issues every MMA of the pair.
-template <bool BF16, bool TWO>
-__global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_constant__ TcKP p) {
+// STG: four extra warps (12..15) stage the next tile's inputs, 32 query rows each, instead of warp 3 alone.  One warp is a
+// chain of latency-bound gather batches (8 / 12 LDG.128 per lane and batch): enough for a volume-only prologue, but with volume
+// AND plane features (20 corner reads of 128 B per query) it needs ~140 k cycles per tile against ~110 k for the tile's layers.
+// 16 warps cap the kernel at 128 registers per thread (168 with 12), which costs the epilogue ~5 %: used only when both
+// feature sources are sampled.
+template <bool BF16, bool TWO, bool STG>
+__global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc_kernel(const __grid_constant__ TcKP p) {
     extern __shared__ unsigned char smem_raw[];
     const Dims& d = p.d;
     unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -590,7 +595,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
         for (int t = 0; t < 8; ++t) mbar_init(a_ready(t), warps_in);
         for (int sl = 0; sl < 4; ++sl) { mbar_init(rready(sl), both); mbar_init(rfree(sl), 1); }
         mbar_init(acc_ready, d.nsplit);                   // every issuing CTA of the cluster commits to every CTA
-        mbar_init(in_ready, d.early ? 1 : warps_in);
+        mbar_init(in_ready, d.early ? (STG ? 4 : 1) : warps_in);
         mbar_init(in_free, 1);
         mbar_init(feat_free, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -607,9 +612,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
     {   // fp32 bias table
         const GnbDecoderWeights& w = p.w;
         float* bo = bias_s + d.HN;
-        for (int i = threadIdx.x; i < d.NOUT; i += NTHREADS) bo[i] = i < d.d_out ? __ldg(w.lin_out_b + i) : 0.0f;
+        for (int i = threadIdx.x; i < d.NOUT; i += (int)blockDim.x) bo[i] = i < d.d_out ? __ldg(w.lin_out_b + i) : 0.0f;
         float* hw = bo + d.NOUT;
-        for (int i = threadIdx.x; i < d.d_geo; i += NTHREADS) hw[i] = __ldg(w.head_w + i);
+        for (int i = threadIdx.x; i < d.d_geo; i += (int)blockDim.x) hw[i] = __ldg(w.head_w + i);
         if (threadIdx.x == 0) hw[d.d_geo] = __ldg(w.head_b);
     }
     tc_fence_before();
@@ -838,23 +843,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
             }
         }
         }   // !TWO
-    } else if (!TWO && warp == ROLE_WARP0 + 3) {
+    } else if (!TWO && (STG ? warp >= EPI_WARP0 + 4 * EPI_GROUPS : warp == ROLE_WARP0 + 3)) {
         // =============================== input staging (early mode) ============================
         // One warp prepares the NEXT tile's lin_in / lin_z operands (xyz -> positional code, feature sampling or load,
         // fp16/bf16 pack into the swizzled chunks) while the current tile's layers run, so the tensor pipe does not idle
         // for a prologue between tiles.  Lane l stages rows l, l+32, l+64, l+96.
         if (d.early) {
+            const int rr0 = STG ? warp - (EPI_WARP0 + 4 * EPI_GROUPS) : 0, rr1 = STG ? rr0 + 1 : BM / 32;
             uint32_t it = 0, ovf = 0;
             for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++it) {
                 // features first (the slow part: gathers): their buffer is free as soon as the previous tile's lin_in has
                 // retired, almost a whole tile before they are needed; the code tile only after its last lin_z
                 if (it > 0) mbar_wait(feat_free, (it - 1) & 1);
-                for (int rr = 0; rr < BM / 32; ++rr) {
+                for (int rr = rr0; rr < rr1; ++rr) {
                     const int row = rr * 32 + lane;
                     stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 2, ovf);
                 }
                 if (it > 0) mbar_wait(in_free, (it - 1) & 1);
-                for (int rr = 0; rr < BM / 32; ++rr) {
+                for (int rr = rr0; rr < rr1; ++rr) {
                     const int row = rr * 32 + lane;
                     stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 1, ovf);
                 }
@@ -884,7 +890,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp >= EPI_WARP0) {
+    } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4 * EPI_GROUPS) {
         // =============================== prologue + epilogue ===================================
         const int q = warp & 3;                              // TMEM lane quadrant of this warp
         const int eg = (warp - EPI_WARP0) >> 2;              // epilogue group 0 / 1
@@ -1243,12 +1249,16 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
     }
     if (kp.n_clusters > kp.n_tiles) kp.n_clusters = kp.n_tiles;
     const size_t smem = smem_layout(d).total + 1024;
-    auto kernel = d.two ? ((w->tc_dtype == GNB_TC_BF16) ? decoder_tc_kernel<true, true> : decoder_tc_kernel<false, true>)
-                        : ((w->tc_dtype == GNB_TC_BF16) ? decoder_tc_kernel<true, false> : decoder_tc_kernel<false, false>);
+    const bool bf = w->tc_dtype == GNB_TC_BF16;
+    // extra staging warps: fused query that samples BOTH a volume and planes, single-CTA issue with early staging
+    const bool stg = !d.two && d.early && kp.fused && kp.s.volume && kp.s.Cp > 0 && !opt(OPT_TC_NO_STG);
+    auto kernel = d.two ? (bf ? decoder_tc_kernel<true, true, false> : decoder_tc_kernel<false, true, false>)
+                        : stg ? (bf ? decoder_tc_kernel<true, false, true> : decoder_tc_kernel<false, false, true>)
+                              : (bf ? decoder_tc_kernel<true, false, false> : decoder_tc_kernel<false, false, false>);
     GNB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kp.n_clusters * d.csize);
-    cfg.blockDim = dim3(NTHREADS);
+    cfg.blockDim = dim3(stg ? NTHREADS + 128 : NTHREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];

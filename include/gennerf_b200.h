@@ -43,7 +43,7 @@ const char* gnb_last_error(void);
 int gnb_struct_size(int which);
 /* Tuning / debugging switches (GNB_TC_TWO_CTA, GNB_TC_NO_EARLY, GNB_DEBUG_MAX_CLUSTERS, GNB_DEBUG_PRINT, GNB_LIFT_NVW,
  * GNB_SCATTER_SCALAR, GNB_FPS_SINGLE_CTA, GNB_FPS_CLUSTER, GNB_SAMPLE_GENERIC, GNB_BIN_UNIT, GNB_BIN_ROWCOPY,
- * GNB_SCATTER_TILED, GNB_BIN_PRESORTED).  Every option takes its default from the environment variable of the same name,
+ * GNB_SCATTER_TILED, GNB_BIN_PRESORTED, GNB_TC_NO_STG).  Every option takes its default from the environment variable of the same name,
  * read ONCE per process (never on a hot-path call); these two calls read / change it afterwards.  None of them changes
  * results beyond floating-point summation order. */
 int gnb_set_option(const char* name, int value);
