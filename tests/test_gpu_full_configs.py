@@ -189,7 +189,9 @@ def test_config5_training_step_at_full_size():
     xo = xyz.clone().requires_grad_(True)
     vleaf = vol_o.detach().clone().requires_grad_(True)
     pleaf = {k: v.detach().clone().requires_grad_(True) for k, v in pl_o.items()}
-    feat_o = O.map_features(xo, vleaf, valid_o, pleaf, VS, 0.1)
+    # (valid = all ones: the accumulated volume is already 0 where no frame saw the voxel; dividing a LEAF by the 0 / 1 mask
+    #  would put 0/0 into the reference's own autograd)
+    feat_o = O.map_features(xo, vleaf, torch.ones_like(valid_o), pleaf, VS, 0.1)
     (feat_o * Gf).sum().backward()
     (vol_o * Gv).sum().backward()
     Gp = {k: torch.randn(pl_o[k].shape, generator=g) for k in O.PLANES}
