@@ -450,12 +450,16 @@ class GenNerf(nn.Module):
     attributes (.volume, .valid, .c_plane).  The 2D CNN (`spatial`) and the FPS front end are
     outside the path: pass the CNN as `spatial=` (any nn.Module image -> (B,C,H,W)) and the
     sparse point cloud through `encode(..., sparse_xyz=)`; Lightning orchestration, losses and
-    logging stay in the reference.  `precision`: 'fp16' (tcgen05 decoder, default) | 'bf16'
-    (tcgen05, wider range, coarser) | 'fp32' (CUDA-core decoder, 1e-5 parity).
+    logging stay in the reference.  `precision`: 'fp16' (tcgen05 decoder, default; |dTSDF| <= 1e-2) |
+    'fp32' (CUDA-core decoder, 1e-5 parity).
     """
 
     def __init__(self, cfg, spatial=None, unet=None, precision="fp16", fused=True):
         super().__init__()
+        if precision not in ("fp16", "fp32"):
+            raise ValueError("gennerf_b200: precision is 'fp16' (tcgen05 decoder, |dTSDF| <= 1e-2, saturation reported by "
+                             "fp16_overflowed()) or 'fp32' (CUDA-core decoder, 1e-5); bf16 operands miss the 1e-2 bar on this "
+                             "network (8-bit significand: ~3e-2) and are not offered")
         self.cfg = cfg
         self.precision, self.fused = precision, fused
         encoder_latent = 0

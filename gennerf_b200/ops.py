@@ -394,7 +394,8 @@ class DecoderWeights:
 @_nvtx
 def decode(weights, xyz, feat, precision="fp32"):
     """PositionalEncoding -> ResnetFC -> TSDFHeadSimple (reference model.py:226-246).
-    precision: 'fp32' (CUDA cores, exact mode) | 'fp16' | 'bf16' (tcgen05, 16-bit operands).
+    precision: 'fp32' (CUDA cores, exact mode, 1e-5) | 'fp16' (tcgen05, fp32 accumulate, |dTSDF| <= 1e-2).
+    ('bf16' selects the C ABI's experimental GNB_TC_BF16 operand type: ~3e-2 TSDF on this network, outside the contract.)
     xyz (..., 3), feat (..., d_feat) -> out (..., d_out), tsdf (..., 1)."""
     _need_cuda(xyz, feat)
     lead = xyz.shape[:-1]

@@ -1,12 +1,13 @@
 """tcgen05/TMEM decoder and the fused query against the CPU oracle.
 
-Bar (north_star): |TSDF - oracle| <= 1e-2 absolute for the 16-bit tensor-core decoder.  With
-fp16 operands (11-bit significand; the default) the bar holds with margin on the synthetic
-weights of SURVEY 8d.  With bf16 operands (8-bit significand) the same network shows up to
-~3e-2 on these weights -- that is the format, not the kernel: a second, sharper check compares
-both formats with a CPU emulation of the kernel's exact numerics (16-bit operands, fp32
-accumulation, biases riding as a hi+lo pair of extra K columns), which must agree to ~1e-3 and
-catches layout / pipeline bugs the loose format bar could hide.
+Bar (north_star): |TSDF - oracle| <= 1e-2 absolute for the 16-bit tensor-core decoder.  The product's 16-bit mode is fp16
+operands with fp32 accumulation (11-bit significand): ~2e-3 on the synthetic weights of SURVEY 8d, with a saturation
+status word for inputs beyond fp16's range (test_gpu_dropin.py).  bf16 operands (8-bit significand) give ~2e-2 .. 3e-2 on
+the same network -- that is the format, not the kernel (a CPU emulation of bf16 operands with fp32 accumulation shows the
+same 2.3e-2; only a bf16x3 hi+lo split of BOTH operands gets to 5e-5, at three MMAs per product: DESIGN.md section 4.5) --
+so bf16 is NOT offered by the Python API as a precision that meets the contract; the C ABI keeps GNB_TC_BF16 as an
+experimental operand type, and the kernel's bf16 instantiation is only checked here against a CPU emulation of its own
+numerics (layout / pipeline regression test), with no claim about the 1e-2 bar.
 """
 import pytest
 import torch
@@ -55,7 +56,7 @@ CASES = [  # d_hidden, num_freqs, d_feat, d_out, d_geo, n_rows
 ]
 
 
-TSDF_BAR = {"fp16": 1e-2, "bf16": 6e-2}
+TSDF_BAR = 1e-2          # north_star: 16-bit tensor-core decoder within 1e-2 absolute TSDF (the fp16 mode)
 
 
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
@@ -80,8 +81,9 @@ def test_decode_tc(d_hidden, nf, d_feat, d_out, d_geo, n, dtype):
     scale = ref.abs().max()
     # (accumulation order differs from the emulation; one flipped bf16 rounding moves a value by 2^-9)
     assert ((o - emu).abs().max() / scale).item() < (2e-3 if dtype == "fp16" else 1e-2), "kernel != emulation of its own numerics"
-    assert (t - ref_t).abs().max().item() <= TSDF_BAR[dtype], "TSDF must be within the bar of the fp32 oracle"
-    assert ((o - ref).abs().max() / scale).item() < (4e-3 if dtype == "fp16" else 3e-2)
+    if dtype == "fp16":
+        assert (t - ref_t).abs().max().item() <= TSDF_BAR, "TSDF must be within 1e-2 of the fp32 oracle"
+        assert ((o - ref).abs().max() / scale).item() < 4e-3
 
 
 def test_decode_tc_deterministic_and_row_independent():

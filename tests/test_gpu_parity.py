@@ -2,7 +2,7 @@
 
 Bars (BASELINE.json north_star): voxel indices, validity masks and scatter counts bit-exact;
 fp32 features / TSDF within 1e-5 relative (stated per test as rtol plus an absolute floor
-of 1e-5 x the largest reference magnitude); the bf16 tcgen05 decoder within 1e-2 absolute TSDF.
+of 1e-5 x the largest reference magnitude); the 16-bit (fp16 operand) tcgen05 decoder within 1e-2 absolute TSDF.
 """
 import os
 
