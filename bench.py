@@ -404,12 +404,13 @@ def run_native(args):
             pl = {k: planes[i] for i, k in enumerate(ops.PLANES)}
             mark()
             # ---- queries of this rank's range
-            if precision == "fp32" or args.unfused:
+            if precision == "fp32" or args.query == "unfused":
                 feat = ops.sample_features(xyz, volume=vol, planes=pl, voxel_size=VS, origin=origin, padding=0.1)
                 tsdf = ops.decode(dw, xyz, feat, precision)[1]
             else:
+                # "image" = what the public op picks for this many queries: sampler kernel -> 16-bit operand image -> decoder
                 tsdf = ops.query_fused(dw, xyz, volume=vol, planes=pl, voxel_size=VS, origin=origin, padding=0.1, want_feat=False,
-                                       precision=precision)[1]
+                                       precision=precision, mode=args.query)[1]
             mark()
             self.out = (vol, cnt, planes, tsdf)
             return tsdf
@@ -504,7 +505,15 @@ def run_native(args):
         lb = lift_bytes(T, C_FEAT, H, W, V, n_valid)
         lift_gbs = lb / (ms_lift * 1e-3) / 1e9
         feat_bytes = T * C_FEAT * H * W * 4
-        fused = precision != "fp32" and not args.unfused
+        qmode = "unfused" if precision == "fp32" else args.query
+        n_chunks = -(-(q1 - q0) // ops.IMAGE_CHUNK)
+        # own kernels per step: transpose, lift, scatter, finalize + the query phase (image: per chunk of 4 Mi queries the
+        # brick sort [count, reduce, scan, scatter], the binned sampler and the decoder; fused: 1; unfused: sort + sampler + decoder)
+        q_launches = {"image": 6 * n_chunks, "fused": 1, "unfused": 6}[qmode]
+        q_desc = {"image": f"{precision} brick-binned sampler writing the decoder's 16-bit operand image + tcgen05 MLP decoder, "
+                           f"{n_chunks} chunk(s) of <= {ops.IMAGE_CHUNK} queries",
+                  "fused": f"{precision} tcgen05 fused sampler+MLP (one kernel)",
+                  "unfused": f"{precision} sampler (fp32 features) + decoder kernels"}[qmode]
         line = {
             "metric": "tsdf_query_points_per_s", "value": Q / (ms_step * 1e-3), "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -513,7 +522,7 @@ def run_native(args):
             "parallelism": {"gpus": world, "frames_per_rank": t1 - t0, "queries_per_rank": q1 - q0,
                             "features": args.features if world > 1 else "local", "lift": args.lift if world > 1 else "single GPU",
                             "planes": "points sharded, NCCL all-reduce of sums + counts", "queries": "contiguous ranges, no collective"},
-            "decoder": f"{precision} tcgen05 fused sampler+MLP" if fused else f"{precision} sampler + decoder kernels",
+            "decoder": q_desc,
             "phases_ms": {"features_transpose_and_gather": ms_feat, "lift": ms_lift, "planes_scatter_allreduce": ms_planes,
                           "query_range": ms_query, "step": ms_step},
             "collectives": {"feature_gather": {"bytes_total": feat_bytes, "bytes_received_per_gpu": feat_bytes * (world - 1) // world,
@@ -521,7 +530,7 @@ def run_native(args):
                                                "gbs_received_per_gpu": (feat_bytes * (world - 1) / world) / (ms_feat * 1e-3) / 1e9 if world > 1 else None,
                                                "nvlink_reference_gbs": 770.0},
                             "plane_allreduce_bytes": 3 * R_PLANE * R_PLANE * (C_PLANE + 1) * 4},
-            "roofline": {"kernel": "decoder_tc_kernel (fused sampler + MLP, one launch = this rank's query range)" if fused else "sampler + decoder",
+            "roofline": {"kernel": "decoder_tc_kernel; timed = the whole query phase of this rank's range (" + q_desc + ")",
                          "bound": "tensor", "achieved": tf, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": tf / pk["bf16_burst"],
                          "frac_of_sustained": tf / pk["bf16_sustained"], "traffic": None,
                          "peak_source": pk["source"] + ": bf16 cuBLAS burst (fp16 and bf16 share the tensor-core rate)",
@@ -537,7 +546,7 @@ def run_native(args):
                     "bytes_are": "per rank (every rank uploads its frames, its query range and the sparse points, downloads its TSDF range)",
                     "how": "drop-in GenNerf.shard_scene / encode(projection, image, sparse_xyz=) / forward(xyz) from pinned host "
                            "buffers: H2D, NCHW->NHWC, feature all-gather, lift, PointNet + scatter, fused query, D2H of the TSDF"},
-            "gpu_launches": args.steps * (5 + (1 if args.lift == "slab" and world > 1 else 0)),
+            "gpu_launches": args.steps * (4 + q_launches + (1 if args.lift == "slab" and world > 1 else 0)),
             "fp16_saturated": overflow,
             "clocks": clocks.summary(),
             "wall_s_timed_region": t_wall,
@@ -606,11 +615,16 @@ def main():
                     help="N > 1: every rank owns T/N frames and they are all-gathered (default), or rank 0 owns all and broadcasts")
     ap.add_argument("--lift", default="replicated", choices=["replicated", "slab"],
                     help="N > 1: every rank lifts the whole grid (default), or x-slabs + all-gather of the volume")
-    ap.add_argument("--unfused", action="store_true", help="separate sampler and decoder kernels")
+    ap.add_argument("--query", choices=["image", "fused", "unfused"], default="image",
+                    help="query phase: image = sampler -> 16-bit operand image -> decoder (default, what ops.query_fused picks); "
+                         "fused = one kernel; unfused = fp32 features between sampler and decoder")
+    ap.add_argument("--unfused", action="store_true", help="same as --query unfused")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-side", action="store_true", help="skip the side measurements (HBM kernels, eager-GPU baseline)")
     ap.add_argument("--no-parity", action="store_true", help="skip the bench-time parity check")
     args = ap.parse_args()
+    if args.unfused:
+        args.query = "unfused"
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)

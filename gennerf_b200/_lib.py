@@ -51,6 +51,7 @@ class GnbSampleParams(C.Structure):
         ("pl_stride_c", C.c_int64),
         ("padding", C.c_double),
         ("out", C.c_void_p), ("out_stride", C.c_int64),
+        ("image", C.c_void_p), ("image_kchunks", C.c_int32), ("image_dtype", C.c_int32), ("image_status", C.c_void_p),
     ]
 
 
@@ -131,6 +132,9 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p]),
     "gnb_decoder_packed_bytes": (C.c_int64, [C.POINTER(GnbDecoderWeights)]),
     "gnb_decoder_pack_tc": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p]),
+    "gnb_decoder_image_kchunks": (C.c_int, [C.POINTER(GnbDecoderWeights)]),
+    "gnb_decode_image_tc": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "gnb_decode_tc": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_query_fused_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(GnbDecoderWeights), C.c_void_p,
@@ -169,6 +173,16 @@ def check(rc, what):
     if rc != 0:
         msg = lib().gnb_last_error().decode(errors="replace")
         raise RuntimeError(f"gennerf_b200: {what} failed (code {rc}): {msg}")
+
+
+def last_error():
+    return lib().gnb_last_error().decode(errors="replace")
+
+
+def get_option(name):
+    v = C.c_int(0)
+    check(lib().gnb_get_option(name.encode(), C.byref(v)), "gnb_get_option")
+    return v.value
 
 
 def set_option(name, value):

@@ -297,6 +297,28 @@ __device__ __forceinline__ void umma_commit_mc_2cta(uint32_t bar, uint16_t mask)
                  "h"(mask)
                  : "memory");
 }
+// cta_group::2 from a converged warp (see umma_f16_x4_u)
+__device__ __forceinline__ void umma_f16_x4_2cta_u(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+        "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+        "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, 1;\n\t}" ::"r"(d_tmem),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_2cta_u(uint32_t bar, uint16_t mask) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
 // arrive on a barrier that lives in another CTA of the cluster (address from map_to_cta)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
@@ -371,6 +393,7 @@ struct TcKP {
     const float* gaxes;           // dense-grid mode (xyz == null): the gnx + gny + gnz axis coordinates; query row r of a
     int gnx, gny, gnz;            //   scene is the grid point (x[i], y[j], z[k]), r = (i*gny + j)*gnz + k  (utils.py:926-935)
     const float* feat;            // (n_rows,d_feat) when !fused
+    const unsigned char* feat_img;   // or (!fused) the 16-bit operand image of lin_in (GnbSampleParams.image): one bulk copy per tile
     int fused;
     SampleKP s;                   // sampler (fused); s.out = optional fp32 feature output
     long long n_rows;
@@ -378,6 +401,7 @@ struct TcKP {
     float* tsdf;                  // (n_rows) or null
     int n_tiles, n_clusters;
     long long* dbg;               // optional per-phase clock64() trace of cluster 0 (profiling aid), or null
+    int nocopy;                   // GNB_DEBUG_NO_WCOPY (timing experiment, WRONG results): weight stages are signalled but not copied
 };
 
 // shared-memory carve-up (offsets from the 1024-aligned base)
@@ -442,7 +466,8 @@ __host__ __device__ inline int act_kchunk(int nsplit, int own, int half, int t, 
 // sampled here (fused query) or read from the feature tensor.
 template <bool BF16>
 __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, const Smem& L, int half, int row, long long grow,
-                                             int u0, int ustep, int what, uint32_t& ovf) {      // what: 1 = code tile, 2 = feature chunks
+                                             int u0, int ustep, int what, uint32_t& ovf,       // what: 1 = code tile, 2 = feature chunks
+                                             int chunk_stride = CHUNK) {                          // bytes between 64-column chunks of a tile
     const Dims& d = p.d;
     const GnbDecoderWeights& w = p.w;
     const bool live = grow < p.n_rows;
@@ -488,7 +513,7 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
             const float* v = code + c * 64 + u * 8;
             uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
             if constexpr (!BF16) ovf |= sat_probe(pk.x, pk.y) | sat_probe(pk.z, pk.w);
-            *reinterpret_cast<uint4*>(sm + L.code + c * CHUNK + chunk_off(row, u)) = pk;
+            *reinterpret_cast<uint4*>(sm + L.code + c * chunk_stride + chunk_off(row, u)) = pk;
         }
     }
     if (!(what & 2)) return;
@@ -527,7 +552,7 @@ __device__ __forceinline__ void stage_inputs(const TcKP& p, unsigned char* sm, c
             }
             uint4 pk = make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
             if constexpr (!BF16) ovf |= sat_probe(pk.x, pk.y) | sat_probe(pk.z, pk.w);
-            *reinterpret_cast<uint4*>(sm + L.feat + c * CHUNK + chunk_off(row, u)) = pk;
+            *reinterpret_cast<uint4*>(sm + L.feat + c * chunk_stride + chunk_off(row, u)) = pk;
         }
 }
 
@@ -629,7 +654,7 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
 
     if (warp == ROLE_WARP0) {
         // =============================== weight producer ======================================
-        if (TWO ? (lane == 0) : true) {
+        {
             int stage = 0;
             uint32_t phase = 0;
             if constexpr (TWO) {
@@ -643,8 +668,7 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                         for (int kc = 0; kc < op.kchunks; kc += 2) {
                             const uint32_t bytes = (uint32_t)min(2, op.kchunks - kc) * (uint32_t)op.rows * 128u;
                             mbar_wait(w_empty(stage), phase ^ 1);
-                            mbar_expect_tx(w_full(stage), bytes);
-                            bulk_g2s(sbase + L.ring + stage * d.stage_bytes, src, bytes, w_full(stage));
+                            bulk_g2s_u(sbase + L.ring + stage * d.stage_bytes, src, bytes, w_full(stage));
                             src += bytes;
                             if (++stage == nst) { stage = 0; phase ^= 1; }
                         }
@@ -661,7 +685,8 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                         const uint32_t bytes = (uint32_t)op.rows * 128u;
                         for (int kc = 0; kc < op.kchunks; ++kc) {       // (the whole warp, converged: see umma_f16_x4_u)
                             mbar_wait(w_empty(stage), phase ^ 1);
-                            bulk_g2s_u(sbase + L.ring + stage * d.stage_bytes, src, bytes, w_full(stage));
+                            if (p.nocopy) mbar_expect_tx_u(w_full(stage), 0);
+                            else bulk_g2s_u(sbase + L.ring + stage * d.stage_bytes, src, bytes, w_full(stage));
                             src += bytes;
                             if (++stage == d.nstage) { stage = 0; phase ^= 1; }
                         }
@@ -712,6 +737,7 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                 mbar_wait_warp(in_ready, tiles_done & 1);
                 tc_fence_after();
                 int tk = tiles_done * 64;
+                [[maybe_unused]] int step_no = 0;
                 if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
                 for (int o = 0; o < nops; ++o) {
                     const Op op = get_op(d, o);
@@ -735,8 +761,7 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                                     a_addr[c] = sbase + L.a + r * CHUNK;
                                 } else {
                                     rslot = (int)(rtotal % (uint32_t)d.RS);
-                                    if (lane == 0) mbar_expect_tx(rready(rslot), CHUNK);
-                                    __syncwarp();
+                                    mbar_expect_tx_u(rready(rslot), CHUNK);
                                     a_bar[c] = rready(rslot), a_par[c] = (rtotal / (uint32_t)d.RS) & 1;
                                     a_addr[c] = sbase + L.a + (d.AOWN + rslot) * CHUNK;
                                     ++rtotal;
@@ -744,28 +769,29 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                             }
                         }
                         const long long c1 = GNB_TRACE_ON(p) ? clock64() : 0;
+#ifdef GNB_TC_TRACE
+                        // finer trace (role 3): per step [reached, own chunk seen, pushed chunk seen, weight stage seen]
+                        if (GNB_TRACE_ON(p)) {
+                            const int sk = (tiles_done * 96 + step_no) * 4;
+                            if (lane == 0) GNB_TRACE(3, sk);
+                            if (a_bar[0]) mbar_wait(a_bar[0], a_par[0]);
+                            if (lane == 0) GNB_TRACE(3, sk + 1);
+                            if (a_bar[1]) mbar_wait(a_bar[1], a_par[1]);
+                            if (lane == 0) GNB_TRACE(3, sk + 2);
+                            mbar_wait(w_full(stage), phase);
+                            if (lane == 0) GNB_TRACE(3, sk + 3);
+                            ++step_no;
+                        } else
+#endif
                         mbar_wait3_warp(a_bar[0], a_par[0], a_bar[1], a_par[1], w_full(stage), phase);
                         if (GNB_TRACE_ON(p)) wait_all += clock64() - c1;
                         tc_fence_after();
                         const uint32_t b_base = sbase + L.ring + stage * d.stage_bytes;
                         const uint32_t first = (op.first_overwrites && t == 0) ? 0u : 1u;
-                        if (elect_one()) {
-                            const uint64_t da0 = umma_desc(a_addr[0]), db0 = umma_desc(b_base);
-                            umma_f16_2cta(dcol, da0, db0, idesc, first);
-                            umma_f16_2cta(dcol, da0 + 2, db0 + 2, idesc, 1u);
-                            umma_f16_2cta(dcol, da0 + 4, db0 + 4, idesc, 1u);
-                            umma_f16_2cta(dcol, da0 + 6, db0 + 6, idesc, 1u);
-                            if (nchunk == 2) {
-                                const uint64_t da1 = umma_desc(a_addr[1]), db1 = umma_desc(b_base + op.rows * 128);
-                                umma_f16_2cta(dcol, da1, db1, idesc, 1u);
-                                umma_f16_2cta(dcol, da1 + 2, db1 + 2, idesc, 1u);
-                                umma_f16_2cta(dcol, da1 + 4, db1 + 4, idesc, 1u);
-                                umma_f16_2cta(dcol, da1 + 6, db1 + 6, idesc, 1u);
-                            }
-                            umma_commit_mc_2cta(w_empty(stage), pairmask);     // both CTAs of the pair refill this stage
-                            if (rslot >= 0) umma_commit_mc_2cta(rfree(rslot), othermask);
-                        }
-                        __syncwarp();
+                        umma_f16_x4_2cta_u(dcol, umma_desc(a_addr[0]), umma_desc(b_base), idesc, first);
+                        if (nchunk == 2) umma_f16_x4_2cta_u(dcol, umma_desc(a_addr[1]), umma_desc(b_base + op.rows * 128), idesc, 1u);
+                        umma_commit_mc_2cta_u(w_empty(stage), pairmask);     // both CTAs of the pair refill this stage
+                        if (rslot >= 0) umma_commit_mc_2cta_u(rfree(rslot), othermask);
                         if (++stage == nst) { stage = 0; phase ^= 1; }
                     }
                     if (lane == 0) { GNB_TRACE(0, tk); } ++tk;
@@ -775,8 +801,7 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                     }
                     if (op.a_kind == 2) ++round;
                     if (op.group_end) {
-                        if (elect_one()) umma_commit_mc_2cta(acc_ready, (uint16_t)((1u << d.csize) - 1));
-                        __syncwarp();
+                        umma_commit_mc_2cta_u(acc_ready, (uint16_t)((1u << d.csize) - 1));
                     }
                 }
             }
@@ -855,9 +880,20 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                 // features first (the slow part: gathers): their buffer is free as soon as the previous tile's lin_in has
                 // retired, almost a whole tile before they are needed; the code tile only after its last lin_z
                 if (it > 0) mbar_wait(feat_free, (it - 1) & 1);
-                for (int rr = rr0; rr < rr1; ++rr) {
-                    const int row = rr * 32 + lane;
-                    stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 2, ovf);
+                const uint32_t img_bytes = (uint32_t)d.KF * CHUNK;
+                if (p.feat_img) {
+                    // the tile's feature chunks exist as an image already: one bulk copy, counted on in_ready (the expect_tx
+                    // comes with this warp's arrival below; the transaction count may run negative inside the phase)
+                    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                                 "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(
+                                     sbase + L.feat),
+                                 "l"(p.feat_img + (long long)tile * img_bytes), "r"(img_bytes), "r"(in_ready)
+                                 : "memory");
+                } else {
+                    for (int rr = rr0; rr < rr1; ++rr) {
+                        const int row = rr * 32 + lane;
+                        stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 2, ovf);
+                    }
                 }
                 if (it > 0) mbar_wait(in_free, (it - 1) & 1);
                 for (int rr = rr0; rr < rr1; ++rr) {
@@ -866,7 +902,10 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(in_ready);
+                if (lane == 0) {
+                    if (p.feat_img) mbar_expect_tx(in_ready, img_bytes);
+                    else mbar_arrive(in_ready);
+                }
             }
             if (ovf && p.w.status) atomicOr(p.w.status, 1);
         }
@@ -882,10 +921,13 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                     for (int t = 0; t < own_chunks; ++t, ++ptotal) {
                         const uint32_t sl = ptotal % (uint32_t)d.RS, use = ptotal / (uint32_t)d.RS;
                         mbar_wait(a_ready(t), round & 1);     // every epilogue warp wrote + fenced chunk t
+                        if (lane == 0) GNB_TRACE(2, 1024 + (int)ptotal * 3);
                         if (use > 0) mbar_wait(rfree(sl), (use - 1) & 1);
+                        if (lane == 0) GNB_TRACE(2, 1024 + (int)ptotal * 3 + 1);
                         const uint32_t src = sbase + L.a + t * CHUNK;
                         const uint32_t dst = sbase + L.a + (d.AOWN + sl) * CHUNK;
                         bulk_s2peer_u(map_to_cta(dst, peer), src, CHUNK, map_to_cta(rready(sl), peer));
+                        if (lane == 0) GNB_TRACE(2, 1024 + (int)ptotal * 3 + 2);
                     }
                 }
             }
@@ -1147,12 +1189,18 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
 }  // namespace tc
 }  // namespace gnb
 
+#include "decoder_tp.cuh"
+
 using namespace gnb;
 using namespace gnb::tc;
 
 extern "C" int64_t gnb_decoder_packed_bytes(const GnbDecoderWeights* w) {
     Dims d;
     if (make_dims(w, d, "gnb_decoder_packed_bytes")) return 0;
+    {
+        TpDims td;
+        if (tp_applies(w, td)) return tp_packed_bytes(td);
+    }
     return d.packed_per_rank * d.csize;
 }
 
@@ -1162,6 +1210,10 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
     if (rc) return rc;
     GNB_CHECK_ARG(packed, "gnb_decoder_pack_tc: null output");
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        TpDims td;
+        if (tp_applies(w, td)) return tp_pack(w, td, packed, st);
+    }
     for (int rank = 0; rank < d.csize; ++rank) {
         const int half = d.two ? rank >> 1 : rank, mrow = d.two ? (rank & 1) : 0;
         unsigned char* dst = (unsigned char*)packed + (long long)rank * d.packed_per_rank;
@@ -1231,7 +1283,18 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
     int rc = make_dims(w, kp.d, "gnb_decode_tc");
     if (rc) return rc;
     GNB_CHECK_ARG(packed, "gnb_decode_tc: weights are not packed");
+    {
+        TpDims td;
+        if (!kp.feat_img && tp_applies(w, td)) {
+            if (kp.n_rows == 0) return 0;
+            return tp_launch(w, td, packed, kp, stream, g_trace);
+        }
+    }
     const Dims& d = kp.d;
+    if (kp.feat_img && (!d.early || d.two)) {
+        set_error("gnb_decode_image_tc: needs the default kernel (early staging, single-CTA issue)");
+        return GNB_E_UNSUPPORTED;
+    }
     kp.w = *w;
     kp.packed = (const unsigned char*)packed;
     if (kp.n_rows == 0) return 0;
@@ -1241,6 +1304,7 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
     GNB_CUDA(cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev));
     if (cc != 10) { set_error("gnb_decode_tc: needs an sm_100 device (found sm_%d0)", cc); return GNB_E_ARCH; }
     kp.dbg = g_trace;
+    kp.nocopy = opt(OPT_DEBUG_NO_WCOPY);
     const int rows_per_cluster = d.two ? 2 * BM : BM;
     kp.n_tiles = (int)((kp.n_rows + rows_per_cluster - 1) / rows_per_cluster);
     kp.n_clusters = sms / d.csize;
@@ -1286,6 +1350,24 @@ extern "C" int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, con
     GNB_CHECK_ARG(xyz && feat && (out || tsdf), "gnb_decode_tc: bad arguments");
     TcKP kp = {};
     kp.xyz = xyz, kp.feat = feat, kp.fused = 0, kp.n_rows = n_rows, kp.out = out, kp.tsdf = tsdf;
+    return launch_tc(w, packed, kp, stream);
+}
+
+extern "C" int gnb_decoder_image_kchunks(const GnbDecoderWeights* w) {
+    Dims d;
+    if (make_dims(w, d, "gnb_decoder_image_kchunks")) return 0;
+    if (!d.early || d.two) return 0;         // the image is read by the early-staging warp of the default kernel only
+    return d.KF;
+}
+
+extern "C" int gnb_decode_image_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz, const void* image,
+                                     int64_t n_rows, float* out, float* tsdf, void* stream) {
+    GNB_CHECK_ARG(n_rows >= 0, "gnb_decode_image_tc: bad arguments");
+    if (n_rows == 0) return 0;
+    GNB_CHECK_ARG(xyz && image && (out || tsdf), "gnb_decode_image_tc: bad arguments");
+    GNB_CHECK_ARG((reinterpret_cast<uintptr_t>(image) & 15) == 0, "gnb_decode_image_tc: the image must be 16-byte aligned");
+    TcKP kp = {};
+    kp.xyz = xyz, kp.feat = nullptr, kp.feat_img = (const unsigned char*)image, kp.fused = 0, kp.n_rows = n_rows, kp.out = out, kp.tsdf = tsdf;
     return launch_tc(w, packed, kp, stream);
 }
 

@@ -16,14 +16,14 @@ __global__ void __launch_bounds__(256) sample_kernel(const __grid_constant__ Sam
     if (q >= p.total) return;
     const int b = (int)(q / p.Q);
     const float x = __ldg(p.xyz + q * 3 + 0), y = __ldg(p.xyz + q * 3 + 1), z = __ldg(p.xyz + q * 3 + 2);
-    float* __restrict__ out = p.out + q * p.out_stride;
+    float* __restrict__ out = p.out + q * p.out_stride;          // (VEC == 1 only: the image needs the float4 layout)
     int c_off = 0;
     if (p.Cp > 0) {
         BiCorners bc[3];
         planes_setup(p, x, y, z, bc);
         for (int c = sub * VEC; c < p.Cp; c += G * VEC) {
             Vals<VEC> r = sample_planes<VEC>(p, bc, b, c);
-            if constexpr (VEC == 4) *reinterpret_cast<float4*>(out + c) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+            if constexpr (VEC == 4) store_feat4(p, q, c, make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
             else out[c] = r.v[0];
         }
         c_off = p.Cp;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const __grid_constant__ Sam
         trilinear_setup(p, x, y, z, tc);
         for (int c = sub * VEC; c < p.C; c += G * VEC) {
             Vals<VEC> r = sample_volume<VEC>(p, tc, b, c);
-            if constexpr (VEC == 4) *reinterpret_cast<float4*>(out + c_off + c) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+            if constexpr (VEC == 4) store_feat4(p, q, c_off + c, make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
             else out[c_off + c] = r.v[0];
         }
     }
@@ -48,7 +48,7 @@ constexpr int ST_WORDS = 20;     // per query: 8 offsets + 8 weights (+4 pad: co
 
 // volume part of 32 staged queries: tab = [32][ST_WORDS] corner table of this warp
 __device__ __forceinline__ void staged_volume(const SampleKP& p, float* __restrict__ tab, int lane, int G, long long q0,
-                                              long long nq, float* __restrict__ out_base, int c_off) {
+                                              long long nq, int c_off) {
     const int sub = lane % G, qpi = 32 / G;
     const int Cn = p.C;
     for (int it = 0; it < G; ++it) {
@@ -59,7 +59,6 @@ __device__ __forceinline__ void staged_volume(const SampleKP& p, float* __restri
         const int4 o0 = *reinterpret_cast<const int4*>(e), o1 = *reinterpret_cast<const int4*>(e + 4);
         const float4 w0 = *reinterpret_cast<const float4*>(e + 8), w1 = *reinterpret_cast<const float4*>(e + 12);
         const int b = (int)(q / p.Q);
-        float* out = out_base + q * p.out_stride + c_off;
         for (int c = sub * 4; c < Cn; c += G * 4) {
             {
                 const float* base = p.volume + b * p.vsb + c;
@@ -73,7 +72,7 @@ __device__ __forceinline__ void staged_volume(const SampleKP& p, float* __restri
                 r.x = fmaf(v5.x, w1.y, r.x), r.y = fmaf(v5.y, w1.y, r.y), r.z = fmaf(v5.z, w1.y, r.z), r.w = fmaf(v5.w, w1.y, r.w);
                 r.x = fmaf(v6.x, w1.z, r.x), r.y = fmaf(v6.y, w1.z, r.y), r.z = fmaf(v6.z, w1.z, r.z), r.w = fmaf(v6.w, w1.z, r.w);
                 r.x = fmaf(v7.x, w1.w, r.x), r.y = fmaf(v7.y, w1.w, r.y), r.z = fmaf(v7.z, w1.w, r.z), r.w = fmaf(v7.w, w1.w, r.w);
-                *reinterpret_cast<float4*>(out + c) = r;
+                store_feat4(p, q, c_off + c, r);
             }
         }
     }
@@ -142,7 +141,6 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 9) sample_staged_kernel(const _
                 const long long qq = q0 + ql;
                 if (qq >= p.total) continue;
                 const int b = (int)(qq / p.Q);
-                float* out = p.out + qq * p.out_stride;
                 for (int c = sub * 4; c < p.Cp; c += Gp * 4) {
                     float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -151,11 +149,11 @@ __global__ void __launch_bounds__(32 * ST_WARPS, 9) sample_staged_kernel(const _
                         const float4 a = staged_plane(p, tp + ql * PT_WORDS + pl * 8, p.plane[pl] + b * p.psb + c);
                         r.x = __fadd_rn(r.x, a.x), r.y = __fadd_rn(r.y, a.y), r.z = __fadd_rn(r.z, a.z), r.w = __fadd_rn(r.w, a.w);
                     }
-                    *reinterpret_cast<float4*>(out + c) = r;
+                    store_feat4(p, qq, c, r);
                 }
             }
         }
-        if (p.volume) staged_volume(p, tv, lane, Gv, q0, p.total, p.out, p.Cp);
+        if (p.volume) staged_volume(p, tv, lane, Gv, q0, p.total, p.Cp);
         __syncwarp();
     }
 }
@@ -358,6 +356,13 @@ int fill_sample_kp(const GnbSampleParams* s, SampleKP& kp) {
     }
     kp.out = s->out;
     kp.out_stride = s->out_stride;
+    kp.img = (unsigned char*)s->image;
+    kp.img_kf = s->image_kchunks, kp.img_bf16 = s->image_dtype == GNB_TC_BF16, kp.img_status = s->image_status;
+    if (kp.img) {
+        GNB_CHECK_ARG((reinterpret_cast<uintptr_t>(kp.img) & 15) == 0 && kp.img_kf >= 1 && 64 * kp.img_kf >= kp.C + kp.Cp,
+                      "sample: bad operand image (16-byte aligned, 64 * image_kchunks >= C_p + C)");
+        GNB_CHECK_ARG(s->image_dtype == GNB_TC_FP16 || s->image_dtype == GNB_TC_BF16, "sample: bad image_dtype");
+    }
     return 0;
 }
 
@@ -372,9 +377,9 @@ extern "C" int gnb_sample_features(const GnbSampleParams* s, void* stream) {
     int rc = fill_sample_kp(s, kp);
     if (rc) return rc;
     if (kp.total == 0) return 0;
-    GNB_CHECK_ARG(s->out && s->out_stride >= kp.C + kp.Cp, "sample: bad output");
+    GNB_CHECK_ARG((s->out && s->out_stride >= kp.C + kp.Cp) || (!s->out && s->image), "sample: bad output");
     // float4 path: unit channel stride, channel counts and every base/stride a multiple of 4
-    bool vec = (s->out_stride % 4 == 0) && aligned16(s->out);
+    bool vec = !s->out || ((s->out_stride % 4 == 0) && aligned16(s->out));
     if (kp.volume)
         vec = vec && kp.vsc == 1 && kp.C % 4 == 0 && aligned16(kp.volume) && kp.vsb % 4 == 0 && kp.vsx % 4 == 0 &&
               kp.vsy % 4 == 0 && kp.vsz % 4 == 0;
@@ -399,6 +404,10 @@ extern "C" int gnb_sample_features(const GnbSampleParams* s, void* stream) {
                                                                         pow2_lanes(kp.Cp / 4 > 0 ? kp.Cp / 4 : 1));
         GNB_LAUNCH_CHECK();
         return 0;
+    }
+    if (kp.img && !vec) {
+        set_error("sample: the operand image needs unit channel strides, channel counts % 4 == 0 and 16-byte aligned bases");
+        return GNB_E_UNSUPPORTED;
     }
     int cmax = kp.C > kp.Cp ? kp.C : kp.Cp;
     int lanes = vec ? cmax / 4 : cmax;

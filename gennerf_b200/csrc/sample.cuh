@@ -8,6 +8,9 @@
 //       = normalize_coordinate (utils.py:75-98) + F.grid_sample 2-D (ATen GridSamplerKernel.cpp)
 // with the same operation order; each coordinate step is a separately rounded fp32 op.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace gnb {
@@ -30,7 +33,32 @@ struct SampleKP {
     // output
     float* out;
     long long out_stride;
+    // optional 16-bit operand image of the tcgen05 decoder (GnbSampleParams.image)
+    unsigned char* img;
+    int img_kf, img_bf16;
+    int* img_status;
 };
+
+// Stores the 4 feature columns [c, c+4) (c % 4 == 0; plane columns first) of flat query q: fp32 row and / or operand image.
+__device__ __forceinline__ void store_feat4(const SampleKP& p, long long q, int c, float4 r) {
+    if (p.out) *reinterpret_cast<float4*>(p.out + q * p.out_stride + c) = r;
+    if (p.img) {
+        uint2 pk;
+        if (p.img_bf16) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(r.x, r.y), b = __floats2bfloat162_rn(r.z, r.w);
+            pk.x = *reinterpret_cast<uint32_t*>(&a), pk.y = *reinterpret_cast<uint32_t*>(&b);
+        } else {
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.x) : "f"(r.y), "f"(r.x));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk.y) : "f"(r.w), "f"(r.z));
+            // +-65504 exactly when satfinite clipped the value (decoder_tc.cu: sat_probe)
+            if (p.img_status && ((((pk.x & 0x7FFF7FFFu) + 0x04010401u) | ((pk.y & 0x7FFF7FFFu) + 0x04010401u)) & 0x80008000u))
+                atomicOr(p.img_status, 1);
+        }
+        const int row = (int)(q & 127), u = (c & 63) >> 3;
+        const long long off = ((q >> 7) * p.img_kf + (c >> 6)) * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((u ^ (row & 7)) << 4) + ((c & 4) ? 8 : 0);
+        *reinterpret_cast<uint2*>(p.img + off) = pk;
+    }
+}
 
 struct TriCorners {              // trilinear: base offsets and weights of the 8 corners
     long long off[8];

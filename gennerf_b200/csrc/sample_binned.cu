@@ -188,7 +188,7 @@ __device__ __forceinline__ void gather_volume(const SampleKP& s, const float* __
         const float4 wa = *reinterpret_cast<const float4*>(e + 4), wb = *reinterpret_cast<const float4*>(e + 8);
         const int ox = hd.y, oy = hd.z, oz = hd.w;          // (per-query steps also on the tile path: measured faster than the uniform ones at C = 128)
         const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-        float* out = s.out + *reinterpret_cast<const long long*>(e + 12);
+        const long long q = *reinterpret_cast<const long long*>(e + 12);
         const float* base = src + hd.x;
         for (int f0 = 0; f0 < CV; f0 += G * NV) {
             const int fa = f0 + fa0, fb = f0 + fb0;
@@ -201,8 +201,8 @@ __device__ __forceinline__ void gather_volume(const SampleKP& s, const float* __
                     if (ha) va[k] = *reinterpret_cast<const float4*>(base + o + fa * 4);
                     if (hb) vb[k] = *reinterpret_cast<const float4*>(base + o + fb * 4);
                 }
-                if (ha) *reinterpret_cast<float4*>(out + fa * 4) = corners8(va, w);
-                if (hb) *reinterpret_cast<float4*>(out + fb * 4) = corners8(vb, w);
+                if (ha) store_feat4(s, q, s.Cp + fa * 4, corners8(va, w));
+                if (hb) store_feat4(s, q, s.Cp + fb * 4, corners8(vb, w));
             } else {
 #pragma unroll 1
                 for (int h = 0; h < NV; ++h) {             // sparse bins: one float4 of channels at a time (64-bit addresses)
@@ -211,7 +211,7 @@ __device__ __forceinline__ void gather_volume(const SampleKP& s, const float* __
                     float4 v[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) v[k] = ldg4(base + ((k & 1) ? ox : 0) + ((k & 2) ? oy : 0) + ((k & 4) ? oz : 0) + f * 4);
-                    *reinterpret_cast<float4*>(out + f * 4) = corners8(v, w);
+                    store_feat4(s, q, s.Cp + f * 4, corners8(v, w));
                 }
             }
         }
@@ -232,7 +232,7 @@ __device__ __forceinline__ void gather_tile_c32(const SampleKP& s, const float* 
         const int base = *reinterpret_cast<const int*>(e);
         const float4 wa = *reinterpret_cast<const float4*>(e + 4), wb = *reinterpret_cast<const float4*>(e + 8);
         const float w[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-        float* out = s.out + *reinterpret_cast<const long long*>(e + 12);
+        const long long q = *reinterpret_cast<const long long*>(e + 12);
         const float* pa = tile + base + fa;
         const float* pb = tile + base + fb;
         float4 va[8], vb[8];
@@ -243,8 +243,8 @@ __device__ __forceinline__ void gather_tile_c32(const SampleKP& s, const float* 
             va[k] = *reinterpret_cast<const float4*>(pa + o);
             vb[k] = *reinterpret_cast<const float4*>(pb + o);
         }
-        *reinterpret_cast<float4*>(out + fa) = corners8(va, w);
-        *reinterpret_cast<float4*>(out + fb) = corners8(vb, w);
+        store_feat4(s, q, s.Cp + fa, corners8(va, w));
+        store_feat4(s, q, s.Cp + fb, corners8(vb, w));
     }
 }
 
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(
                     const int ql = pit * pqpi + lane / Gp;
                     if (ql >= nq) continue;
                     const float* e = tab + ql * BIN_TAB;
-                    float* out = s.out + (long long)reinterpret_cast<const int*>(e)[18] * s.out_stride;
+                    const long long q = (long long)reinterpret_cast<const int*>(e)[18];
                     for (int c = psub * 4; c < s.Cp; c += Gp * 4) {
                         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(
                             a.x = fmaf(v3.x, w3, a.x), a.y = fmaf(v3.y, w3, a.y), a.z = fmaf(v3.z, w3, a.z), a.w = fmaf(v3.w, w3, a.w);
                             r.x = __fadd_rn(r.x, a.x), r.y = __fadd_rn(r.y, a.y), r.z = __fadd_rn(r.z, a.z), r.w = __fadd_rn(r.w, a.w);
                         }
-                        *reinterpret_cast<float4*>(out + c) = r;
+                        store_feat4(s, q, c, r);
                     }
                 }
                 __syncwarp();
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(32 * (BIN_WARPS + 1), 1) sample_binned_kernel(
                 reinterpret_cast<int*>(e)[1] = (int)(tc.off[1] - tc.off[0]);   // 0 where the +1 corner is beyond the border
                 reinterpret_cast<int*>(e)[2] = (int)(tc.off[2] - tc.off[0]);
                 reinterpret_cast<int*>(e)[3] = (int)(tc.off[4] - tc.off[0]);
-                *reinterpret_cast<long long*>(e + 12) = (long long)qidx * s.out_stride + s.Cp;
+                *reinterpret_cast<long long*>(e + 12) = (long long)qidx;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) e[4 + k] = tc.w[k];
             }
@@ -570,7 +570,7 @@ extern "C" int gnb_sample_features_binned(const GnbSampleParams* sp, void* scrat
         if (chk.total == 0) return 0;
     }
     GNB_CHECK_ARG(plan_binned(sp, pl), "sample_binned: needs a channels-last fp32 volume with C %% 4 == 0 (use gnb_sample_features)");
-    GNB_CHECK_ARG(sp->out && sp->out_stride >= pl.kp.s.C + pl.kp.s.Cp, "sample_binned: bad output");
+    GNB_CHECK_ARG((sp->out && sp->out_stride >= pl.kp.s.C + pl.kp.s.Cp) || (!sp->out && sp->image), "sample_binned: bad output");
     GNB_CHECK_ARG(scratch && aligned16(scratch) && scratch_bytes >= (int64_t)pl.total_bytes, "sample_binned: scratch too small (gnb_sample_binned_scratch_bytes)");
     cudaStream_t stream = (cudaStream_t)stream_;
     int dev = 0, sms = 148;

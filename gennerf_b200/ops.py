@@ -417,15 +417,78 @@ def decode(weights, xyz, feat, precision="fp32"):
     return out.reshape(*lead, weights.w.d_out), tsdf.reshape(*lead, 1)
 
 
+IMAGE_CHUNK = 1 << 22          # queries per sampler + decoder launch pair of query_image (512 MB of operand image per 64 features)
+
+
+@_nvtx
+def query_image(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
+                want_feat=False, precision="fp16", chunk=None):
+    """GenNerf.forward as TWO kernels per chunk of queries: the sampler (brick-binned where the queries are dense) writes the
+    features straight as the decoder's 16-bit lin_in operand image, and the tcgen05 decoder brings each tile's image into
+    shared memory with one bulk copy.  Same bits as query_fused (same sampling arithmetic, same rounding to 16 bits); faster
+    for many queries, because the decoder no longer gathers and converts features between its tiles.
+    Returns out (B,Q,d_out), tsdf (B,Q,1), feat (B,Q,C_lat) or None."""
+    _need_cuda(xyz)
+    xyz = _f32(xyz).contiguous()
+    B, Q, _ = xyz.shape
+    dev = xyz.device
+    d_feat = weights.w.d_feat
+    out = torch.empty((B, Q, weights.w.d_out), device=dev, dtype=torch.float32)
+    tsdf = torch.empty((B, Q, 1), device=dev, dtype=torch.float32)
+    feat = torch.empty((B, Q, d_feat), device=dev, dtype=torch.float32) if want_feat else None
+    if B * Q == 0:
+        return out, tsdf, feat
+    packed = weights.tc_image(precision)
+    kf = lib().gnb_decoder_image_kchunks(C.byref(weights.w))
+    if kf <= 0:          # no early-staging variant for these dimensions / options: the single fused kernel
+        return query_fused(weights, xyz, volume, planes, voxel_size=voxel_size, origin=origin, padding=padding,
+                           want_feat=want_feat, precision=precision, mode="fused")
+    step = int(chunk or IMAGE_CHUNK)
+    rows = min(step, Q)
+    image = torch.zeros(((rows + 127) // 128) * kf * 16384, device=dev, dtype=torch.uint8)   # zeros: operand columns past d_feat
+    with torch.cuda.device(dev):
+        for b in range(B):
+            vol_b = volume[b:b + 1] if volume is not None else None
+            pl_b = {k: (v[b:b + 1] if v is not None else None) for k, v in planes.items()} if planes else None
+            for q0 in range(0, Q, step):
+                q1 = min(q0 + step, Q)
+                xq = xyz[b:b + 1, q0:q1]
+                s, keep, _, n, Cp, Cv = _fill_sample_params(xq, vol_b, pl_b, voxel_size, origin, padding)
+                if Cp + Cv != d_feat:
+                    raise RuntimeError(f"query_image: d_feat {d_feat} != C_p + C = {Cp + Cv}")
+                if feat is not None:
+                    s.out, s.out_stride = feat[b, q0:q1].data_ptr(), d_feat
+                s.image, s.image_kchunks = image.data_ptr(), kf
+                s.image_dtype = _lib.TC_BF16 if precision == "bf16" else _lib.TC_FP16
+                s.image_status = weights.status.data_ptr()
+                nbytes = 0
+                if vol_b is not None and n >= (1 << 16) and 3 * n >= vol_b.shape[2] * vol_b.shape[3] * vol_b.shape[4]:
+                    nbytes = lib().gnb_sample_binned_scratch_bytes(C.byref(s))
+                if nbytes > 0:
+                    scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+                    check(lib().gnb_sample_features_binned(C.byref(s), scratch.data_ptr(), nbytes, _stream()), "gnb_sample_features_binned")
+                else:
+                    check(lib().gnb_sample_features(C.byref(s), _stream()), "gnb_sample_features")
+                check(lib().gnb_decode_image_tc(C.byref(weights.w), packed.data_ptr(), xq.data_ptr(), image.data_ptr(), n,
+                                                  out[b, q0:q1].data_ptr(), tsdf[b, q0:q1].data_ptr(), _stream()), "gnb_decode_image_tc")
+    return out, tsdf, feat
+
+
 @_nvtx
 def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
-                want_feat=True, precision="fp16", presort="auto"):
+                want_feat=True, precision="fp16", presort="auto", mode="auto"):
     """GenNerf.forward in one kernel (sampler fused into the tcgen05 decoder).
     Returns out (B,Q,d_out), tsdf (B,Q,1), feat (B,Q,C_lat) or None.
 
-    presort: "auto" first counting-sorts the queries by voxel brick (same bits, outputs in the caller's order) when there is
-    at least one query per three voxels -- the sampling prologue then reads the volume brick by brick; True forces it
-    (raises when there is no channels-last volume to sort by), False never."""
+    mode: "auto" hands 65 536 queries or more to query_image (sampler kernel writing the decoder's operand image, then the
+    decoder: same bits, less time per query); "fused" always runs the single fused kernel; "image" always query_image.
+    presort (fused kernel): "auto" first counting-sorts the queries by voxel brick (same bits, outputs in the caller's order)
+    when there is at least one query per three voxels -- the sampling prologue then reads the volume brick by brick; True
+    forces it (raises when there is no channels-last volume to sort by), False never."""
+    if mode == "image" or (mode == "auto" and presort == "auto" and xyz.shape[0] * xyz.shape[1] >= (1 << 16)
+                           and not _lib.get_option("GNB_QUERY_FUSED")):
+        return query_image(weights, xyz, volume, planes, voxel_size=voxel_size, origin=origin, padding=padding,
+                           want_feat=want_feat, precision=precision)
     s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
     feat = None
     if want_feat:

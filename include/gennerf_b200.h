@@ -43,7 +43,8 @@ const char* gnb_last_error(void);
 int gnb_struct_size(int which);
 /* Tuning / debugging switches (GNB_TC_TWO_CTA, GNB_TC_NO_EARLY, GNB_DEBUG_MAX_CLUSTERS, GNB_DEBUG_PRINT, GNB_LIFT_NVW,
  * GNB_SCATTER_SCALAR, GNB_FPS_SINGLE_CTA, GNB_FPS_CLUSTER, GNB_SAMPLE_GENERIC, GNB_BIN_UNIT, GNB_BIN_ROWCOPY,
- * GNB_SCATTER_TILED, GNB_BIN_PRESORTED, GNB_TC_NO_STG).  Every option takes its default from the environment variable of the same name,
+ * GNB_SCATTER_TILED, GNB_BIN_PRESORTED, GNB_TC_NO_STG, GNB_TC_PAIR, GNB_DEBUG_NO_WCOPY,
+ * GNB_QUERY_FUSED [read by the Python host: always the single fused query kernel]).  Every option takes its default from the environment variable of the same name,
  * read ONCE per process (never on a hot-path call); these two calls read / change it afterwards.  None of them changes
  * results beyond floating-point summation order. */
 int gnb_set_option(const char* name, int value);
@@ -138,6 +139,17 @@ typedef struct GnbSampleParams {
     /* output */
     float* out;                    /* (B,Q,out_stride), plane part first                    */
     int64_t out_stride;            /* >= Cp + C                                             */
+    /* optional second output (may replace `out`): the features as the tcgen05 decoder's 16-bit lin_in OPERAND IMAGE, which
+     * gnb_decode_image_tc copies into shared memory with one bulk copy per tile instead of converting fp32 rows.
+     * Tile t = q / 128 of the flat query index q is image_kchunks blocks of 16 KB; block k holds columns [64k, 64k+64) of
+     * the tile's 128 rows, 128 bytes per row, 128B-swizzled in 8-row atoms:
+     *   byte offset of the 8 columns [8u, 8u+8) of row r  =  (r/8)*1024 + (r%8)*128 + ((u ^ (r%8)) * 16).
+     * The caller zero-fills the image first when Cp + C < 64*image_kchunks or B*Q is not a multiple of 128 (operand columns /
+     * rows the sampler does not write).  Needs the float4 layout (unit channel strides, Cp % 4 == 0, C % 4 == 0). */
+    void* image;                   /* NULL = none; ceil(B*Q/128) * image_kchunks * 16384 bytes */
+    int32_t image_kchunks;         /* 64*image_kchunks >= Cp + C                            */
+    int32_t image_dtype;           /* GNB_TC_FP16 / GNB_TC_BF16                             */
+    int32_t* image_status;         /* optional: bit 0 is set when a feature saturated fp16   */
 } GnbSampleParams;
 
 int gnb_sample_features(const GnbSampleParams* p, void* stream);
@@ -341,6 +353,12 @@ int gnb_decode_fp32(const GnbDecoderWeights* w, const float* xyz, const float* f
  * bytes); it must be re-packed after the fp32 parameters change. */
 int64_t gnb_decoder_packed_bytes(const GnbDecoderWeights* w);
 int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, void* stream);
+/* gnb_decode_tc with the features given as the 16-bit operand image a sampler wrote (GnbSampleParams.image, with
+ * image_kchunks = gnb_decoder_image_kchunks(w) and image_dtype = w->tc_dtype): the kernel brings a tile's features into
+ * shared memory with one bulk copy instead of converting 128 fp32 rows.  Same results as gnb_query_fused_tc. */
+int gnb_decoder_image_kchunks(const GnbDecoderWeights* w);   /* 0: these weights / options do not take an image */
+int gnb_decode_image_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz, const void* image,
+                        int64_t n_rows, float* out, float* tsdf, void* stream);
 int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz,
                   const float* feat, int64_t n_rows, float* out, float* tsdf, void* stream);
 

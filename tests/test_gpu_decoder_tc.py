@@ -214,3 +214,81 @@ def test_query_fused_presorted_is_bit_identical(B, Q):
         assert torch.equal(x, y)
     with pytest.raises(RuntimeError):
         ops.query_fused(dw, xyz, volume=None, planes=planes, padding=0.1, presort=True)
+
+
+@pytest.mark.parametrize("n", [100, 128 * 74 * 2 + 5, 40000])
+def test_decode_pair_kernel_matches_query_major_kernel(n):
+    """decoder_tp_kernel (cta_group::2, hidden units on M, activations as the MN-major B operand shared by the pair) against
+    decoder_tc_kernel (queries on M, N-halves exchanged through DSMEM): same 16-bit operands and fp32 accumulation, so they
+    agree to accumulation order; and the pair kernel against the fp32 oracle at the 1e-2 TSDF bar."""
+    from gennerf_b200 import _lib, ops
+    g = S.gen(48)
+    w, hw, hb = S.decoder_weights(g, 64, 15, 512, 5, 64, 32, alpha=0.9)
+    xyz = S.query_points(n, (96, 96, 48), VS, g)[0]
+    feat = torch.randn(n, 64, generator=g)
+    dw2 = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    b, tb = ops.decode(dw2, xyz.to(DEV), feat.to(DEV), "fp16")
+    old = _lib.set_option("GNB_TC_PAIR", 1)               # the pair kernel is opt-in
+    try:
+        dw1 = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+        a, ta = ops.decode(dw1, xyz.to(DEV), feat.to(DEV), "fp16")
+        a2, _ = ops.decode(dw1, xyz.to(DEV), feat.to(DEV), "fp16")
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("GNB_TC_PAIR", old)
+    assert torch.equal(a, a2), "two runs of the pair kernel differ"
+    assert dw1.packed.numel() != dw2.packed.numel(), "the two kernels have different weight images: both must have run"
+    assert ((a - b).abs().max() / b.abs().max()).item() < 2e-3
+    assert (ta - tb).abs().max().item() < 5e-3
+    m = min(n, 4000)
+    code = O.positional_encoding(xyz[:m], 2, 0.5, True)
+    ref = O.resnetfc_forward(torch.cat((code, feat[:m]), -1), w, 5, 15)
+    ref_t = O.tsdf_head(ref[..., :32], hw, hb)
+    assert (ta.cpu()[:m] - ref_t).abs().max().item() <= TSDF_BAR
+    assert ((a.cpu()[:m] - ref).abs().max() / ref.abs().max()).item() < 4e-3
+    assert not dw1.overflowed()
+
+
+@pytest.mark.parametrize("B,Q,use_vol,use_pl,Cv,Cp,dtype,chunk", [
+    (1, 70001, True, True, 32, 32, "fp16", None),        # binned sampler, one chunk, ragged last tile
+    (2, 9000, True, True, 32, 32, "fp16", 4000),         # staged sampler, chunks that split scenes and tiles
+    (1, 20000, True, False, 32, 0, "fp16", None),        # volume only: half-empty 64-column operand chunk
+    (1, 20000, False, True, 0, 32, "bf16", 7777),        # planes only, bf16 image
+    (1, 66000, True, True, 64, 32, "fp16", None),        # 96 features: two operand chunks per tile
+])
+def test_query_image_is_bit_identical_to_fused(B, Q, use_vol, use_pl, Cv, Cp, dtype, chunk):
+    """query_image (sampler kernel -> 16-bit operand image -> decoder with one bulk copy per tile) against the single fused
+    kernel: same sampling arithmetic, same rounding to 16 bits, so outputs and features match bit for bit."""
+    from gennerf_b200 import ops
+    wl = S.WORKLOADS["small"]
+    g = S.gen(49)
+    R = 32
+    xyz = S.query_points(Q, wl["voxel_dim"], VS, g, B=B).to(DEV)
+    vol = torch.randn(B, *wl["voxel_dim"], Cv, generator=g).to(DEV).permute(0, 4, 1, 2, 3) if use_vol else None
+    planes = ({k: torch.randn(B, Cp, R, R, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) for k in O.PLANES}
+              if use_pl else None)
+    w, hw, hb = S.decoder_weights(g, Cv + Cp, 15, 512, 5, 64, 32)
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    kw = dict(volume=vol, planes=planes, voxel_size=VS, origin=ORIGIN, padding=0.1, precision=dtype)
+    a = ops.query_fused(dw, xyz, want_feat=True, mode="fused", presort=False, **kw)
+    b = ops.query_image(dw, xyz, want_feat=True, chunk=chunk, **kw)
+    for x, y, name in zip(a, b, ("out", "tsdf", "feat")):
+        assert torch.equal(x, y), name
+    c = ops.query_image(dw, xyz, want_feat=False, chunk=chunk, **kw)
+    assert torch.equal(c[1], a[1]) and c[2] is None
+    if B * Q >= (1 << 16):      # what mode="auto" picks for this many queries
+        d = ops.query_fused(dw, xyz, want_feat=False, **kw)
+        assert torch.equal(d[1], a[1])
+
+
+def test_query_image_reports_fp16_saturation():
+    from gennerf_b200 import ops
+    wl = S.WORKLOADS["small"]
+    g = S.gen(50)
+    xyz = S.query_points(5000, wl["voxel_dim"], VS, g).to(DEV)
+    vol = (torch.randn(1, *wl["voxel_dim"], 32, generator=g) * 1e5).to(DEV).permute(0, 4, 1, 2, 3)
+    w, hw, hb = S.decoder_weights(g, 32, 15, 512, 5, 64, 32)
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    assert not dw.overflowed()
+    ops.query_image(dw, xyz, volume=vol, voxel_size=VS, origin=ORIGIN)
+    assert dw.overflowed()

@@ -8,7 +8,10 @@ VARIANTS = {
     "default": {},
     "two_cta": {"GNB_TC_TWO_CTA": "1"},
     "one_cta": {"GNB_TC_TWO_CTA": "0"},
-    "no_early": {"GNB_TC_NO_EARLY": "1"},   # inputs of a tile staged by the epilogue warps between tiles (no staging warp)
+    "no_early": {"GNB_TC_NO_EARLY": "1"},
+    "nocopy": {"GNB_DEBUG_NO_WCOPY": "1"},                         # timing experiment: weight stages signalled, not copied (wrong results)
+    "pair_nocopy": {"GNB_TC_PAIR": "1", "GNB_DEBUG_NO_WCOPY": "1"},
+    "pair": {"GNB_TC_PAIR": "1"},           # the transposed-pair kernel (decoder_tp_kernel) instead of the query-major kernel
 }
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
