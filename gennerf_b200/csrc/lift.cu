@@ -53,9 +53,27 @@ __device__ __forceinline__ int project_voxel(const float* __restrict__ P, float 
         if (!(cz > 0.0f)) return -1;
         if (cx < -0.75f * cz || cx > ((float)W - 0.25f) * cz || cy < -0.75f * cz || cy > ((float)H - 0.25f) * cz) return -1;
     }
-    float fx = rintf(__fdiv_rn(cx, cz));
-    float fy = rintf(__fdiv_rn(cy, cz));
-    if (fx_out) { *fx_out = fx; *fy_out = fy; }
+    float fx, fy;
+    if (fx_out) {
+        fx = rintf(__fdiv_rn(cx, cz));
+        fy = rintf(__fdiv_rn(cy, cz));
+        *fx_out = fx, *fy_out = fy;
+    } else {
+        // Only the ROUNDED pixel matters, so the two IEEE divisions are replaced by one reciprocal: qa = c * rcp(cz) is within
+        // a few ulp of the exact quotient (MUFU.RCP: 1 ulp, two roundings), hence within 2^-20 |qa| of the correctly rounded
+        // one; if qa is farther than that from a half-integer, both round to the same integer.  Near a tie (and for
+        // NaN / inf / |qa| >= 2^19, where the test below is false) the IEEE division decides, as in the reference.
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(cz));
+        const float qx = __fmul_rn(cx, r), qy = __fmul_rn(cy, r);
+        fx = rintf(qx), fy = rintf(qy);
+        const float mx = 0.5f - fabsf(qx - fx), my = 0.5f - fabsf(qy - fy);       // margins to the nearest tie
+        const bool safe = (mx > fabsf(qx) * 9.5367431640625e-7f + 1e-30f) && (my > fabsf(qy) * 9.5367431640625e-7f + 1e-30f);
+        if (!safe) {
+            fx = rintf(__fdiv_rn(cx, cz));
+            fy = rintf(__fdiv_rn(cy, cz));
+        }
+    }
     // float comparisons == the reference's int64 comparisons for every finite value; NaN/inf
     // (cz == 0) compare false here and convert to INT64_MIN (invalid) there.
     bool ok = (fx >= 0.0f) && (fy >= 0.0f) && (fx < (float)W) && (fy < (float)H) && (cz > 0.0f);
@@ -133,13 +151,18 @@ __global__ void __launch_bounds__(256, (G <= 8 ? 6 : 5)) lift_kernel(const __gri
     const int c0 = (blockIdx.y * G + sub) * VEC;           // first channel of this lane
     const bool c_ok = c0 < p.C;
 
-    // lane i (< NVW) owns voxel i of this warp's part of the brick for the projection
-    const int iv = warp * NVW + lane;
+    // lane i (< NVW) owns voxel i of this warp's part of the brick for the projection; with NVW <= 16 the lanes
+    // [NVW, 2 NVW) project the same voxels by the trip's SECOND frame (SPLIT), so a trip of two frames costs the issue
+    // slots of one projection
+    constexpr bool SPLIT = NVW <= 16;
+    const int pl = lane & (NVW - 1), ph = lane / NVW;      // projection voxel / which frame of the trip
+    const int iv = warp * NVW + pl;
     const int vx = x0 + iv / (BZ * BY), vy = y0 + (iv / BZ) % BY, vz = z0 + iv % BZ;
-    const bool own = (lane < NVW) && vx < p.x_end && vy < p.ny && vz < p.nz;
+    const bool proj = (SPLIT ? ph < 2 : true) && vx < p.x_end && vy < p.ny && vz < p.nz;
+    const bool own = (lane < NVW) && proj;
     const int v_own = own ? (vx * p.ny + vy) * p.nz + vz : -1;
     float wx = 0.f, wy = 0.f, wz = 0.f;
-    if (own) {
+    if (proj) {
         // world = fl(i) * voxel_size + origin: two separately rounded operations (utils.py:974)
         wx = __fadd_rn(__fmul_rn((float)vx, p.vs), p.ox);
         wy = __fadd_rn(__fmul_rn((float)vy, p.vs), p.oy);
@@ -174,7 +197,13 @@ __global__ void __launch_bounds__(256, (G <= 8 ? 6 : 5)) lift_kernel(const __gri
         const int t1 = vis ? __ffsll((long long)vis) - 1 : -1;
         if (t1 >= 0) vis &= vis - 1;
         int off0 = -1, off1 = -1;
-        if (own) {
+        if constexpr (SPLIT) {
+            const int t = ph == 0 ? t0 : t1;
+            int off = -1;
+            if (proj && t >= 0) off = project_voxel(p.P[t], wx, wy, wz, p.H, p.W);
+            off0 = __shfl_sync(FULL, off, pl);
+            off1 = __shfl_sync(FULL, off, pl + NVW);
+        } else if (own) {
             off0 = project_voxel(p.P[t0], wx, wy, wz, p.H, p.W);
             if (t1 >= 0) off1 = project_voxel(p.P[t1], wx, wy, wz, p.H, p.W);
         }
