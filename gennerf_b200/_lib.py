@@ -135,6 +135,8 @@ SIGNATURES = {
     "gnb_decoder_image_kchunks": (C.c_int, [C.POINTER(GnbDecoderWeights)]),
     "gnb_decode_image_tc": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "gnb_decode_tc_save": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_decode_tc": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_query_fused_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(GnbDecoderWeights), C.c_void_p,

@@ -393,6 +393,8 @@ struct TcKP {
     const float* gaxes;           // dense-grid mode (xyz == null): the gnx + gny + gnz axis coordinates; query row r of a
     int gnx, gny, gnz;            //   scene is the grid point (x[i], y[j], z[k]), r = (i*gny + j)*gnz + k  (utils.py:926-935)
     const float* feat;            // (n_rows,d_feat) when !fused
+    uint16_t* save;               // optional (training forward): the 16-bit activations every layer consumed, [2 nb + 1][n_rows][Hd]:
+                                  //   slab 2i = relu(x_i + alpha lin_z_i), 2i + 1 = relu(fc_0 of block i), 2 nb = relu(x) into lin_out
     const unsigned char* feat_img;   // or (!fused) the 16-bit operand image of lin_in (GnbSampleParams.image): one bulk copy per tile
     int fused;
     SampleKP s;                   // sampler (fused); s.out = optional fp32 feature output
@@ -1002,6 +1004,9 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                                                   pack16_relu<BF16>(f[4], f[5]), pack16_relu<BF16>(f[6], f[7]));
                             if constexpr (!BF16) ovf |= sat_probe(pk.x, pk.y) | sat_probe(pk.z, pk.w);
                             *reinterpret_cast<uint4*>(dst + chunk_off(row, eg * 4 + u)) = pk;
+                            if (p.save && live)          // the backward pass reads what the next layer's MMAs read
+                                *reinterpret_cast<uint4*>(p.save + ((long long)r * p.n_rows + grow) * d.Hd + half * d.HN + (t + h) * 64 +
+                                                          eg * 32 + u * 8) = pk;
                         }
                         tc_fence_before();
                         fence_proxy_async();
@@ -1285,7 +1290,7 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
     GNB_CHECK_ARG(packed, "gnb_decode_tc: weights are not packed");
     {
         TpDims td;
-        if (!kp.feat_img && tp_applies(w, td)) {
+        if (!kp.feat_img && !kp.save && tp_applies(w, td)) {
             if (kp.n_rows == 0) return 0;
             return tp_launch(w, td, packed, kp, stream, g_trace);
         }
@@ -1350,6 +1355,19 @@ extern "C" int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, con
     GNB_CHECK_ARG(xyz && feat && (out || tsdf), "gnb_decode_tc: bad arguments");
     TcKP kp = {};
     kp.xyz = xyz, kp.feat = feat, kp.fused = 0, kp.n_rows = n_rows, kp.out = out, kp.tsdf = tsdf;
+    return launch_tc(w, packed, kp, stream);
+}
+
+extern "C" int gnb_decode_tc_save(const GnbDecoderWeights* w, const void* packed, const float* xyz, const float* feat,
+                                    int64_t n_rows, float* out, float* tsdf, void* activations, void* stream) {
+    GNB_CHECK_ARG(n_rows >= 0, "gnb_decode_tc_save: bad arguments");
+    if (n_rows == 0) return 0;
+    GNB_CHECK_ARG(xyz && feat && (out || tsdf) && activations, "gnb_decode_tc_save: bad arguments");
+    GNB_CHECK_ARG((reinterpret_cast<uintptr_t>(activations) & 15) == 0 && w && w->d_hidden % 8 == 0,
+                  "gnb_decode_tc_save: the activation buffer must be 16-byte aligned");
+    TcKP kp = {};
+    kp.xyz = xyz, kp.feat = feat, kp.fused = 0, kp.n_rows = n_rows, kp.out = out, kp.tsdf = tsdf;
+    kp.save = (uint16_t*)activations;
     return launch_tc(w, packed, kp, stream);
 }
 

@@ -451,11 +451,16 @@ class GenNerf(nn.Module):
     outside the path: pass the CNN as `spatial=` (any nn.Module image -> (B,C,H,W)) and the
     sparse point cloud through `encode(..., sparse_xyz=)`; Lightning orchestration, losses and
     logging stay in the reference.  `precision`: 'fp16' (tcgen05 decoder, default; |dTSDF| <= 1e-2) |
-    'fp32' (CUDA-core decoder, 1e-5 parity).
+    'fp32' (CUDA-core decoder, 1e-5 parity).  `train_precision` (training steps, i.e. forward with grad enabled):
+    'fp32' = nn.Linear under autograd (the reference's arithmetic, default) | 'fp16' = the tcgen05 kernel with saved
+    activations and a backward built on them (train_decode.py).
     """
 
-    def __init__(self, cfg, spatial=None, unet=None, precision="fp16", fused=True):
+    def __init__(self, cfg, spatial=None, unet=None, precision="fp16", fused=True, train_precision="fp32"):
         super().__init__()
+        if train_precision not in ("fp16", "fp32"):
+            raise ValueError("gennerf_b200: train_precision is 'fp32' or 'fp16'")
+        self.train_precision = train_precision
         if precision not in ("fp16", "fp32"):
             raise ValueError("gennerf_b200: precision is 'fp16' (tcgen05 decoder, |dTSDF| <= 1e-2, saturation reported by "
                              "fp16_overflowed()) or 'fp32' (CUDA-core decoder, 1e-5); bf16 operands miss the 1e-2 bar on this "
@@ -717,15 +722,18 @@ class GenNerf(nn.Module):
             planes=self.c_plane if self.cfg.encoder.use_pointnet else None,
             voxel_size=self.cfg.voxel_size, origin=self.origin,
             padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1)
-        out, tsdf = decode_train(self.mlp, self.head_geo, self.code if self.cfg.use_code else None, xyz, feat)
+        out, tsdf = decode_train(self.mlp, self.head_geo, self.code if self.cfg.use_code else None, xyz, feat,
+                                 precision=getattr(self, "train_precision", "fp32"))
         feat_geo, feat_sem = out[..., :d_geo], out[..., d_geo:d_geo + d_sem]
         return {"feat_geo": feat_geo, "feat_sem": feat_sem, "tsdf": tsdf, "feat": feat}
 
 
-def decode_train(mlp, head, code, xyz, feat):
+def decode_train(mlp, head, code, xyz, feat, precision="fp32"):
     """Differentiable decoder of a training step (reference model.py:226-246 under autograd): positional encoding with
-    torch ops so that d/dxyz flows, ResnetFC.forward_torch, tanh head.  xyz (B,N,3), feat (B,N,C_lat) ->
-    out (B,N,d_out), tsdf (B,N,1).  `code`: the PositionalEncoding module or None (cfg.use_code False)."""
+    torch ops so that d/dxyz flows, then the MLP and the tanh head.  xyz (B,N,3), feat (B,N,C_lat) ->
+    out (B,N,d_out), tsdf (B,N,1).  `code`: the PositionalEncoding module or None (cfg.use_code False).
+    precision "fp32": ResnetFC.forward_torch (nn.Linear under autograd, the reference's arithmetic);
+    "fp16": the tcgen05 kernel with saved activations and a backward built on them (train_decode.py)."""
     B, N, _ = xyz.shape
     z = xyz
     if code is not None:
@@ -734,6 +742,11 @@ def decode_train(mlp, head, code, xyz, feat):
         x2 = xyz.reshape(-1, 3)
         emb = torch.sin(torch.addcmul(ph, x2.unsqueeze(1).repeat(1, code.num_freqs * 2, 1), f)).view(x2.shape[0], -1)
         z = (torch.cat((x2, emb), dim=-1) if code.include_input else emb).reshape(B, N, -1)
+    if precision == "fp16":
+        from .train_decode import decode_train_tc
+        return decode_train_tc(mlp, head, z, feat)
+    if precision != "fp32":
+        raise ValueError(f"train precision {precision!r}: 'fp32' or 'fp16'")
     out = mlp.forward_torch(torch.cat((z, feat), dim=-1))
     d_geo = head.fc.weight.shape[1]
     tsdf = torch.tanh(torch.nn.functional.linear(out[..., :d_geo], head.fc.weight, head.fc.bias))

@@ -417,6 +417,26 @@ def decode(weights, xyz, feat, precision="fp32"):
     return out.reshape(*lead, weights.w.d_out), tsdf.reshape(*lead, 1)
 
 
+@_nvtx
+def decode_save(weights, xyz, feat, precision="fp16"):
+    """ops.decode on the tcgen05 kernel that also returns the 16-bit activations every layer consumed -- the ReLU masks and
+    left operands the backward pass of a training step needs (gnb_decode_tc_save).  Flat inputs: xyz (n,3) [or (n,d_code)
+    codes when the weights were built with use_code=2], feat (n,d_feat).  Returns out (n,d_out), tsdf (n,1),
+    activations (2*n_blocks+1, n, d_hidden) fp16 / bf16."""
+    _need_cuda(xyz, feat)
+    xyz2, feat2 = _f32(xyz).contiguous(), _f32(feat).contiguous()
+    n = xyz2.shape[0]
+    out = torch.empty((n, weights.w.d_out), device=xyz.device, dtype=torch.float32)
+    tsdf = torch.empty((n, 1), device=xyz.device, dtype=torch.float32)
+    acts = torch.empty((2 * weights.w.n_blocks + 1, n, weights.w.d_hidden), device=xyz.device,
+                       dtype=torch.float16 if precision == "fp16" else torch.bfloat16)
+    packed = weights.tc_image(precision)
+    with torch.cuda.device(xyz.device):
+        check(lib().gnb_decode_tc_save(C.byref(weights.w), packed.data_ptr(), xyz2.data_ptr(), feat2.data_ptr(), n,
+                                       out.data_ptr(), tsdf.data_ptr(), acts.data_ptr(), _stream()), "gnb_decode_tc_save")
+    return out, tsdf, acts
+
+
 IMAGE_CHUNK = 1 << 22          # queries per sampler + decoder launch pair of query_image (512 MB of operand image per 64 features)
 
 

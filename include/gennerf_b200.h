@@ -359,6 +359,12 @@ int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, void* stream);
 int gnb_decoder_image_kchunks(const GnbDecoderWeights* w);   /* 0: these weights / options do not take an image */
 int gnb_decode_image_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz, const void* image,
                         int64_t n_rows, float* out, float* tsdf, void* stream);
+/* gnb_decode_tc that also stores the 16-bit activations every layer consumed -- what the backward pass of a training step
+ * needs (ReLU masks for dgrad, left operands for wgrad): activations is [2*n_blocks + 1][n_rows][d_hidden] in w->tc_dtype;
+ * slab 2i = relu(x_i + alpha*lin_z_i(code)) (input of blocks.i.fc_0), slab 2i+1 = relu(fc_0 output) (input of fc_1),
+ * slab 2*n_blocks = relu(x) (input of lin_out).  resnetfc.py:134-189 under autograd. */
+int gnb_decode_tc_save(const GnbDecoderWeights* w, const void* packed, const float* xyz, const float* feat,
+                       int64_t n_rows, float* out, float* tsdf, void* activations, void* stream);
 int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz,
                   const float* feat, int64_t n_rows, float* out, float* tsdf, void* stream);
 

@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--matmul-precision", default="high", choices=["highest", "high"],
                     help="torch.set_float32_matmul_precision for the PyTorch part (the MLP's dgrad/wgrad): 'high' (TF32) is what "
                          "the reference's training sets (src/utils/utils.py:48); 'highest' = fp32 SIMT GEMMs")
+    ap.add_argument("--train-precision", default="fp16", choices=["fp16", "fp32"],
+                    help="MLP of the training step: fp16 = tcgen05 forward kernel with saved activations + backward built on them "
+                         "(gennerf_b200/train_decode.py); fp32 = nn.Linear under autograd (ResnetFC.forward_torch)")
     args = ap.parse_args()
     torch.set_float32_matmul_precision(args.matmul_precision)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -63,7 +66,7 @@ def main():
         "use_code": True, "code": {"num_freqs": 2, "freq_factor": 0.5, "include_input": True},
     })
     torch.manual_seed(7)                                        # same initial weights on every rank
-    model = GenNerf(cfg, precision="fp16", fused=True).to(dev).train()
+    model = GenNerf(cfg, precision="fp16", fused=True, train_precision=args.train_precision).to(dev).train()
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-4)
     g = S.gen(5000 + rank)                                      # a different scene per rank
@@ -146,7 +149,7 @@ def main():
             "config": {"workload": "BASELINE config 5: fwd + L1 TSDF loss + bwd + Adam, one scene per GPU: 8 frames 480x640x32ch, "
                                    "160x160x64 grid, FPS 512 pts/frame -> 3x128^2x32 planes, 23200 queries, MLP 512x5",
                        "parallelism": f"dp{world} (NCCL all-reduce of {flat.numel()} gradient elements)",
-                       "float32_matmul_precision": args.matmul_precision},
+                       "float32_matmul_precision": args.matmul_precision, "train_precision": args.train_precision},
             "phases_ms_rank0": phases, "loss": float(loss), "grad_feature_norm": float(gf.norm())}))
     if world > 1:
         dist.destroy_process_group()
