@@ -442,7 +442,7 @@ IMAGE_CHUNK = 1 << 22          # queries per sampler + decoder launch pair of qu
 
 @_nvtx
 def query_image(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
-                want_feat=False, precision="fp16", chunk=None):
+                want_feat=False, precision="fp16", chunk=None, out=None, tsdf=None, want_out=True):
     """GenNerf.forward as TWO kernels per chunk of queries: the sampler (brick-binned where the queries are dense) writes the
     features straight as the decoder's 16-bit lin_in operand image, and the tcgen05 decoder brings each tile's image into
     shared memory with one bulk copy.  Same bits as query_fused (same sampling arithmetic, same rounding to 16 bits); faster
@@ -453,16 +453,23 @@ def query_image(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
     B, Q, _ = xyz.shape
     dev = xyz.device
     d_feat = weights.w.d_feat
-    out = torch.empty((B, Q, weights.w.d_out), device=dev, dtype=torch.float32)
-    tsdf = torch.empty((B, Q, 1), device=dev, dtype=torch.float32)
+    packed = weights.tc_image(precision)
+    kf = lib().gnb_decoder_image_kchunks(C.byref(weights.w))
+    if kf <= 0 and B * Q > 0:          # no early-staging variant for these dimensions / options: the single fused kernel
+        o, t, f = query_fused(weights, xyz, volume, planes, voxel_size=voxel_size, origin=origin, padding=padding,
+                              want_feat=want_feat, precision=precision, mode="fused")
+        if out is not None:
+            out.copy_(o)
+        if tsdf is not None:
+            tsdf.copy_(t)
+        return (o if out is None else out), (t if tsdf is None else tsdf), f
+    # (out / tsdf: optional contiguous fp32 destinations of shape (B,Q,d_out) / (B,Q,1), e.g. slices of a larger result)
+    if out is None and want_out:
+        out = torch.empty((B, Q, weights.w.d_out), device=dev, dtype=torch.float32)
+    tsdf = torch.empty((B, Q, 1), device=dev, dtype=torch.float32) if tsdf is None else tsdf
     feat = torch.empty((B, Q, d_feat), device=dev, dtype=torch.float32) if want_feat else None
     if B * Q == 0:
         return out, tsdf, feat
-    packed = weights.tc_image(precision)
-    kf = lib().gnb_decoder_image_kchunks(C.byref(weights.w))
-    if kf <= 0:          # no early-staging variant for these dimensions / options: the single fused kernel
-        return query_fused(weights, xyz, volume, planes, voxel_size=voxel_size, origin=origin, padding=padding,
-                           want_feat=want_feat, precision=precision, mode="fused")
     step = int(chunk or IMAGE_CHUNK)
     rows = min(step, Q)
     image = torch.zeros(((rows + 127) // 128) * kf * 16384, device=dev, dtype=torch.uint8)   # zeros: operand columns past d_feat
@@ -490,7 +497,8 @@ def query_image(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
                 else:
                     check(lib().gnb_sample_features(C.byref(s), _stream()), "gnb_sample_features")
                 check(lib().gnb_decode_image_tc(C.byref(weights.w), packed.data_ptr(), xq.data_ptr(), image.data_ptr(), n,
-                                                  out[b, q0:q1].data_ptr(), tsdf[b, q0:q1].data_ptr(), _stream()), "gnb_decode_image_tc")
+                                                  out[b, q0:q1].data_ptr() if out is not None else None,
+                                                  tsdf[b, q0:q1].data_ptr(), _stream()), "gnb_decode_image_tc")
     return out, tsdf, feat
 
 
@@ -536,7 +544,7 @@ def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
 
 @_nvtx
 def query_grid_fused(weights, grid_dim, axes, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
-                     want_out=False, precision="fp16"):
+                     want_out=False, precision="fp16", mode="auto"):
     """GenNerf.predict_tsdf's query (reference model.py:752-790) in one kernel without a materialised query grid:
     `axes` = (ax (nx,), ay (ny,), az (nz,)) CUDA fp32 coordinate axes (torch.linspace of get_grid_coordinates,
     utils.py:926-935).  Returns tsdf (B,nx,ny,nz) and, with want_out, out (B,nx*ny*nz,d_out)."""
@@ -552,6 +560,24 @@ def query_grid_fused(weights, grid_dim, axes, volume=None, planes=None, *, voxel
     out = torch.empty((B, Q, weights.w.d_out), device=dev, dtype=torch.float32) if want_out else None
     tsdf = torch.empty((B, nx, ny, nz), device=dev, dtype=torch.float32)
     packed = weights.tc_image(precision)
+    if (mode == "image" or (mode == "auto" and B * Q >= (1 << 16) and not _lib.get_option("GNB_QUERY_FUSED"))) and \
+            lib().gnb_decoder_image_kchunks(C.byref(weights.w)) > 0:
+        # many grid points: the two-kernel query (query_image) is faster than the fused kernel's in-kernel sampling.  The
+        # points of a chunk are generated on the device from the axes (same values, so the same bits) and never exist
+        # for more than one chunk (48 MB per 4 Mi points).
+        axd = (ax[:nx], ax[nx:nx + ny], ax[nx + ny:])
+        tflat = tsdf.view(B, Q, 1)
+        for q0 in range(0, Q, IMAGE_CHUNK):
+            q1 = min(q0 + IMAGE_CHUNK, Q)
+            idx = torch.arange(q0, q1, device=dev)
+            xyz = torch.stack((axd[0][idx // (ny * nz)], axd[1][(idx // nz) % ny], axd[2][idx % nz]), dim=-1).unsqueeze(0)
+            for b in range(B):
+                scratch_out = out[b:b + 1, q0:q1] if out is not None else None
+                query_image(weights, xyz, volume[b:b + 1] if volume is not None else None,
+                            {k: (v[b:b + 1] if v is not None else None) for k, v in planes.items()} if planes else None,
+                            voxel_size=voxel_size, origin=origin, padding=padding, precision=precision,
+                            out=scratch_out, tsdf=tflat[b:b + 1, q0:q1], want_out=out is not None)
+        return tsdf, out
     g3 = (C.c_int32 * 3)(nx, ny, nz)
     with torch.cuda.device(dev):
         check(lib().gnb_query_grid_fused_tc(C.byref(s), g3, ax.data_ptr(), C.byref(weights.w), packed.data_ptr(),

@@ -292,3 +292,23 @@ def test_query_image_reports_fp16_saturation():
     assert not dw.overflowed()
     ops.query_image(dw, xyz, volume=vol, voxel_size=VS, origin=ORIGIN)
     assert dw.overflowed()
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_dense_grid_query_image_path_is_bit_identical_to_the_grid_kernel(B):
+    """query_grid_fused picks the two-kernel query (points of a chunk generated from the axes on the device) from 65 536 grid
+    points on: same TSDF and outputs, bit for bit, as the kernel that derives the points from the row index."""
+    from gennerf_b200 import ops
+    g = S.gen(51)
+    vd = (24, 24, 12)
+    grid = (47, 45, 33)                                                     # 69 795 points, ragged last tile
+    vol = torch.randn(B, *vd, 32, generator=g).to(DEV).permute(0, 4, 1, 2, 3)
+    planes = {k: torch.randn(B, 32, 32, 32, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) for k in O.PLANES}
+    w, hw, hb = S.decoder_weights(g, 64, 15, 512, 5, 64, 32)
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    axes = [torch.linspace(0, vd[i] * VS, n, device=DEV) for i, n in enumerate(grid)]
+    kw = dict(volume=vol, planes=planes, voxel_size=VS, origin=ORIGIN, padding=0.1, want_out=True)
+    ta, oa = ops.query_grid_fused(dw, grid, axes, mode="fused", **kw)
+    tb, ob = ops.query_grid_fused(dw, grid, axes, mode="image", **kw)
+    tc, _ = ops.query_grid_fused(dw, grid, axes, volume=vol, planes=planes, voxel_size=VS, origin=ORIGIN, padding=0.1)   # auto
+    assert torch.equal(ta, tb) and torch.equal(oa, ob) and torch.equal(ta, tc)
