@@ -106,6 +106,8 @@ SIGNATURES = {
     "gnb_backproject_frames_bwd": (C.c_int, [C.POINTER(GnbLiftParams), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
     "gnb_sample_features_bwd": (C.c_int, [C.POINTER(GnbSampleParams), C.c_void_p, C.c_int64, C.c_void_p,
                                           C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
+    "gnb_sample_features_bwd2": (C.c_int, [C.POINTER(GnbSampleParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "gnb_scatter_mean_planes_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,
                                               C.c_double, C.c_void_p, C.c_void_p]),
     "gnb_pool_bwd_scratch_bytes": (C.c_int64, [C.c_int, C.c_int64, C.c_int, C.c_int]),

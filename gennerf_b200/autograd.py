@@ -2,8 +2,9 @@
 
 Thin wrappers over the `torch.ops.gennerf_b200.*` custom ops (gennerf_b200/torch_ops.py): the forward is the same C-ABI
 kernel the inference path uses, the autograd formula calls the matching `gnb_*_bwd` kernel.  Scatter-add gradients are
-atomic (order-nondeterministic), like the reference's CUDA index_put_ / grid_sampler backward.  The formulas are
-once-differentiable: a double backward (create_graph=True, reference utils.py:636-649) raises instead of dropping terms.
+atomic (order-nondeterministic), like the reference's CUDA index_put_ / grid_sampler backward.  The sampler's
+backward is differentiable again (gnb_sample_features_bwd2: the eikonal / gradient losses' create_graph=True, reference
+utils.py:636-649); the other formulas are once-differentiable: a double backward raises instead of dropping terms.
 """
 import torch
 

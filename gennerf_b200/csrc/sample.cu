@@ -324,6 +324,186 @@ __global__ void __launch_bounds__(256) sample_bwd_kernel(const __grid_constant__
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Double backward of the sampler: what torch.autograd.grad(tsdf, xyz, create_graph=True) followed by
+// loss.backward() needs (the eikonal / gradient losses, reference utils.py:636-649, model.py:385-400).
+// The reference gets it for the planes from its pure-PyTorch grid_sample_2d (utils.py:1117-1174, model.py:157-158);
+// for the volume ATen has no grid_sampler_3d double backward at all.
+// sample_bwd_kernel is linear in grad_out.  With a = d L / d grad_xyz (B,Q,3), s_d = d i_d / d xyz_d (the chain through
+// the normalisation and the border clip: piecewise constant), w_k the corner weights in pixel coordinates i:
+//   g_gout[q,c]    = sum_k Dw_k V[k,c],          Dw_k = sum_d a_d s_d dw_k/di_d
+//   g_volume[k,:] += Dw_k * grad_out[q,:]        (same for the planes)
+//   g_xyz[q,e]     = s_e sum_{d != e} a_d s_d sum_k d2w_k/(di_d di_e) <grad_out[q,:], V[k,:]>
+// (d2w/di_d^2 = 0: the weights are multilinear).  Same lane-group layout as sample_bwd_kernel.
+// ---------------------------------------------------------------------------------------
+struct SampleBwd2KP {
+    SampleKP s;
+    const float* gout;             // (B,Q,gout_stride): [planes C_p | volume C]
+    long long gout_stride;
+    const float* ggxyz;            // (B,Q,3): gradient w.r.t. the first backward's grad_xyz
+    float* g_gout;                 // (B,Q,g_gout_stride) or null: overwritten
+    long long g_gout_stride;
+    float* g_volume;               // forward strides, accumulated into, or null
+    float* g_plane[3];
+    float* g_xyz;                  // (B,Q,3) or null: overwritten
+};
+
+__global__ void __launch_bounds__(256) sample_bwd2_kernel(const __grid_constant__ SampleBwd2KP p, int G) {
+    const SampleKP& s = p.s;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long q = tid / G;
+    const int sub = (int)(tid % G);
+    const bool live = q < s.total;
+    const long long qq = live ? q : 0;
+    const int b = (int)(qq / s.Q);
+    const float x = __ldg(s.xyz + qq * 3 + 0), y = __ldg(s.xyz + qq * 3 + 1), z = __ldg(s.xyz + qq * 3 + 2);
+    const float av[3] = {__ldg(p.ggxyz + qq * 3 + 0), __ldg(p.ggxyz + qq * 3 + 1), __ldg(p.ggxyz + qq * 3 + 2)};
+    const float* __restrict__ go = p.gout + qq * p.gout_stride;
+    float* __restrict__ ggo = p.g_gout ? p.g_gout + qq * p.g_gout_stride : nullptr;
+    float h[3] = {0.f, 0.f, 0.f};                         // g_xyz, partial over this lane's channels
+    if (s.Cp > 0 && live) {
+        BiCorners bc[3];
+        planes_setup(s, x, y, z, bc);
+        const float xyz3[3] = {x, y, z};
+        float u[3], sc[3];                                // unit coordinates and d u / d p (0 where normalize_coordinate clamps)
+        for (int d = 0; d < 3; ++d) {
+            u[d] = plane_unit(xyz3[d], s.den);
+            const float raw = __fadd_rn(__fdiv_rn(xyz3[d], s.den), 0.5f);
+            sc[d] = (raw >= 1.0f || raw < 0.0f) ? 0.0f : __fdiv_rn(1.0f, s.den);
+        }
+        const int a0[3] = {0, 0, 1}, a1[3] = {2, 1, 2};
+        float dw[3][4], cr[3][4], s0[3], s1[3], A0[3], A1[3], cross[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float vg0 = __fsub_rn(__fmul_rn(2.0f, u[a0[k]]), 1.0f), vg1 = __fsub_rn(__fmul_rn(2.0f, u[a1[k]]), 1.0f);
+            const float ix = unnorm_clip(vg0, s.R), iy = unnorm_clip(vg1, s.R);
+            const float w = ix - floorf(ix), e = 1.0f - w, n = iy - floorf(iy), sth = 1.0f - n;
+            s0[k] = 2.0f * unnorm_clip_grad(vg0, s.R) * sc[a0[k]];
+            s1[k] = 2.0f * unnorm_clip_grad(vg1, s.R) * sc[a1[k]];
+            A0[k] = av[a0[k]] * s0[k], A1[k] = av[a1[k]] * s1[k];
+            const float m1 = bc[k].off[1] != bc[k].off[0] ? 1.f : 0.f, m2 = bc[k].off[2] != bc[k].off[0] ? 1.f : 0.f;
+            const float m3 = (m1 != 0.f && m2 != 0.f) ? 1.f : 0.f;
+            // nw = e*s, ne = w*s, sw = e*n, se = w*n
+            dw[k][0] = -A0[k] * sth - A1[k] * e;
+            dw[k][1] = m1 * (A0[k] * sth - A1[k] * w);
+            dw[k][2] = m2 * (-A0[k] * n + A1[k] * e);
+            dw[k][3] = m3 * (A0[k] * n + A1[k] * w);
+            cr[k][0] = 1.0f, cr[k][1] = -m1, cr[k][2] = -m2, cr[k][3] = m3;
+        }
+        for (int c = sub * 4; c < s.Cp; c += G * 4) {
+            float g4[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) g4[e] = (c + e < s.Cp) ? __ldg(go + c + e) : 0.0f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (s.plane[k] == nullptr) continue;
+                const float* pb = s.plane[k] + b * s.psb + c * s.psc;
+                float* gb = p.g_plane[k] ? p.g_plane[k] + b * s.psb + c * s.psc : nullptr;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (cr[k][j] == 0.0f) continue;       // corner beyond the border: no value in the forward
+                    float dot = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        if (c + ch >= s.Cp) continue;
+                        const float v = __ldg(pb + bc[k].off[j] + ch * s.psc);
+                        acc[ch] = fmaf(dw[k][j], v, acc[ch]);
+                        dot = fmaf(g4[ch], v, dot);
+                    }
+                    cross[k] = fmaf(cr[k][j], dot, cross[k]);
+                    if (gb && dw[k][j] != 0.0f) {
+                        if (s.psc == 1 && (c + 3 < s.Cp) && ((reinterpret_cast<uintptr_t>(gb + bc[k].off[j]) & 15) == 0)) {
+                            atomicAdd(reinterpret_cast<float4*>(gb + bc[k].off[j]),
+                                      make_float4(dw[k][j] * g4[0], dw[k][j] * g4[1], dw[k][j] * g4[2], dw[k][j] * g4[3]));
+                        } else {
+#pragma unroll
+                            for (int ch = 0; ch < 4; ++ch)
+                                if (c + ch < s.Cp) atomicAdd(gb + bc[k].off[j] + ch * s.psc, dw[k][j] * g4[ch]);
+                        }
+                    }
+                }
+            }
+            if (ggo) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    if (c + ch < s.Cp) ggo[c + ch] = acc[ch];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            h[a0[k]] = fmaf(s0[k] * A1[k], cross[k], h[a0[k]]);
+            h[a1[k]] = fmaf(s1[k] * A0[k], cross[k], h[a1[k]]);
+        }
+    }
+    if (s.volume && live) {
+        TriCorners tc;
+        trilinear_setup(s, x, y, z, tc);
+        const float gxn = query_grid(x, s.ox, s.ext_x), gyn = query_grid(y, s.oy, s.ext_y), gzn = query_grid(z, s.oz, s.ext_z);
+        const float ix = unnorm_clip(gxn, s.nx), iy = unnorm_clip(gyn, s.ny), iz = unnorm_clip(gzn, s.nz);
+        const float fx = ix - floorf(ix), fy = iy - floorf(iy), fz = iz - floorf(iz);
+        const float wx[2] = {1.0f - fx, fx}, wy[2] = {1.0f - fy, fy}, wz[2] = {1.0f - fz, fz};
+        const float sx = __fdiv_rn(2.0f * unnorm_clip_grad(gxn, s.nx), s.ext_x), sy = __fdiv_rn(2.0f * unnorm_clip_grad(gyn, s.ny), s.ext_y),
+                    sz = __fdiv_rn(2.0f * unnorm_clip_grad(gzn, s.nz), s.ext_z);
+        const float Ax = av[0] * sx, Ay = av[1] * sy, Az = av[2] * sz;
+        float dw[8], cxy[8], cxz[8], cyz[8];
+        bool inb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int bx = k & 1, byy = (k >> 1) & 1, bzz = (k >> 2) & 1;
+            inb[k] = (!bx || tc.off[k] != tc.off[k & ~1]) && (!byy || tc.off[k] != tc.off[k & ~2]) && (!bzz || tc.off[k] != tc.off[k & ~4]);
+            const float gx = bx ? 1.0f : -1.0f, gy = byy ? 1.0f : -1.0f, gz = bzz ? 1.0f : -1.0f;
+            dw[k] = inb[k] ? Ax * gx * wy[byy] * wz[bzz] + Ay * gy * wx[bx] * wz[bzz] + Az * gz * wx[bx] * wy[byy] : 0.0f;
+            cxy[k] = gx * gy * wz[bzz], cxz[k] = gx * gz * wy[byy], cyz[k] = gy * gz * wx[bx];
+        }
+        float Sxy = 0.f, Sxz = 0.f, Syz = 0.f;
+        for (int c = sub * 4; c < s.C; c += G * 4) {
+            float g4[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) g4[e] = (c + e < s.C) ? __ldg(go + s.Cp + c + e) : 0.0f;
+            const float* vb = s.volume + b * s.vsb + c * s.vsc;
+            float* gb = p.g_volume ? p.g_volume + b * s.vsb + c * s.vsc : nullptr;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (!inb[k]) continue;
+                float dot = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    if (c + ch >= s.C) continue;
+                    const float v = __ldg(vb + tc.off[k] + ch * s.vsc);
+                    acc[ch] = fmaf(dw[k], v, acc[ch]);
+                    dot = fmaf(g4[ch], v, dot);
+                }
+                Sxy = fmaf(cxy[k], dot, Sxy), Sxz = fmaf(cxz[k], dot, Sxz), Syz = fmaf(cyz[k], dot, Syz);
+                if (gb && dw[k] != 0.0f) {
+                    if (s.vsc == 1 && (c + 3 < s.C) && ((reinterpret_cast<uintptr_t>(gb + tc.off[k]) & 15) == 0)) {
+                        atomicAdd(reinterpret_cast<float4*>(gb + tc.off[k]), make_float4(dw[k] * g4[0], dw[k] * g4[1], dw[k] * g4[2], dw[k] * g4[3]));
+                    } else {
+#pragma unroll
+                        for (int ch = 0; ch < 4; ++ch)
+                            if (c + ch < s.C) atomicAdd(gb + tc.off[k] + ch * s.vsc, dw[k] * g4[ch]);
+                    }
+                }
+            }
+            if (ggo) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    if (c + ch < s.C) ggo[s.Cp + c + ch] = acc[ch];
+            }
+        }
+        h[0] += sx * (Ay * Sxy + Az * Sxz);
+        h[1] += sy * (Ax * Sxy + Az * Syz);
+        h[2] += sz * (Ax * Sxz + Ay * Syz);
+    }
+    if (p.g_xyz) {
+        for (int d = G >> 1; d > 0; d >>= 1) {
+            h[0] += __shfl_xor_sync(FULL, h[0], d);
+            h[1] += __shfl_xor_sync(FULL, h[1], d);
+            h[2] += __shfl_xor_sync(FULL, h[2], d);
+        }
+        if (live && sub == 0) p.g_xyz[q * 3 + 0] = h[0], p.g_xyz[q * 3 + 1] = h[1], p.g_xyz[q * 3 + 2] = h[2];
+    }
+}
+
 int fill_sample_kp(const GnbSampleParams* s, SampleKP& kp) {
     GNB_CHECK_ARG(s, "sample: null params");
     GNB_CHECK_ARG(s->batch >= 1 && s->n_query >= 0 && (s->xyz || s->n_query == 0), "sample: bad batch / n_query / xyz");
@@ -440,6 +620,30 @@ extern "C" int gnb_sample_features_bwd(const GnbSampleParams* s, const float* gr
     while (G < lanes && G < 32) G <<= 1;
     long long threads = kp.s.total * G;
     sample_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kp, G);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_sample_features_bwd2(const GnbSampleParams* s, const float* grad_out, int64_t grad_out_stride, const float* gg_xyz,
+                                        float* g_grad_out, int64_t g_grad_out_stride, float* g_volume, float* const* h_g_planes3,
+                                        float* g_xyz, void* stream) {
+    SampleBwd2KP kp;
+    int rc = fill_sample_kp(s, kp.s);
+    if (rc) return rc;
+    GNB_CHECK_ARG(grad_out && grad_out_stride >= kp.s.C + kp.s.Cp && gg_xyz, "gnb_sample_features_bwd2: bad grad_out / gg_xyz");
+    GNB_CHECK_ARG(g_grad_out || g_volume || h_g_planes3 || g_xyz, "gnb_sample_features_bwd2: nothing to compute");
+    GNB_CHECK_ARG(!g_grad_out || g_grad_out_stride >= kp.s.C + kp.s.Cp, "gnb_sample_features_bwd2: bad g_grad_out stride");
+    if (kp.s.total == 0) return 0;
+    kp.gout = grad_out, kp.gout_stride = grad_out_stride, kp.ggxyz = gg_xyz;
+    kp.g_gout = g_grad_out, kp.g_gout_stride = g_grad_out_stride;
+    kp.g_volume = kp.s.volume ? g_volume : nullptr;
+    for (int k = 0; k < 3; ++k) kp.g_plane[k] = (h_g_planes3 && kp.s.plane[k]) ? h_g_planes3[k] : nullptr;
+    kp.g_xyz = g_xyz;
+    int cmax = kp.s.C > kp.s.Cp ? kp.s.C : kp.s.Cp;
+    int lanes = (cmax + 3) / 4, G = 1;
+    while (G < lanes && G < 32) G <<= 1;
+    long long threads = kp.s.total * G;
+    sample_bwd2_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kp, G);
     GNB_LAUNCH_CHECK();
     return 0;
 }

@@ -718,6 +718,37 @@ def sample_features_bwd(grad_out, xyz, volume=None, planes=None, *, voxel_size=0
 
 
 @_nvtx
+def sample_features_bwd2(grad_out, gg_xyz, xyz, volume=None, planes=None, *, voxel_size=0.04, origin=None, padding=0.1,
+                         need_grad_out=True, need_volume=True, need_planes=True, need_xyz=True):
+    """Double backward of sample_features (gnb_sample_features_bwd2): the gradients of <gg_xyz, grad_xyz> where grad_xyz
+    is sample_features_bwd's coordinate gradient (eikonal / gradient losses, reference utils.py:636-649).
+    Returns (g_grad_out | None, g_volume | None, {plane: g} | None, g_xyz | None)."""
+    s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
+    go, gg = _f32(grad_out).contiguous(), _f32(gg_xyz).contiguous()
+    _need_cuda(go, gg)
+    ggo = torch.empty((B, Q, Cp + Cv), device=go.device, dtype=torch.float32) if need_grad_out else None
+    gvol = torch.zeros_like(volume, memory_format=torch.preserve_format) if (volume is not None and need_volume) else None
+    if gvol is not None and gvol.stride() != volume.stride():
+        raise RuntimeError("gradient volume must share the forward strides")
+    gpl, ptrs = None, None
+    if planes and need_planes:
+        gpl, ptrs = {}, (C.c_void_p * 3)()
+        fwd = {t.data_ptr(): t for t in keep}
+        for k, name in enumerate(PLANES):
+            if planes.get(name) is not None:
+                g = torch.zeros_like(fwd[s.plane[k]], memory_format=torch.preserve_format)
+                gpl[name] = g
+                ptrs[k] = g.data_ptr()
+    gx = torch.empty((B, Q, 3), device=go.device, dtype=torch.float32) if need_xyz else None
+    with torch.cuda.device(go.device):
+        check(lib().gnb_sample_features_bwd2(C.byref(s), go.data_ptr(), go.shape[-1], gg.data_ptr(),
+                                             ggo.data_ptr() if ggo is not None else None, Cp + Cv,
+                                             gvol.data_ptr() if gvol is not None else None, ptrs,
+                                             gx.data_ptr() if gx is not None else None, _stream()), "gnb_sample_features_bwd2")
+    return ggo, gvol, gpl, gx
+
+
+@_nvtx
 def scatter_mean_planes_bwd(p, grad_planes, count, padding=0.1):
     """grad_planes (3,B,C_p,R,R) logical -> grad_c (B,N,C_p)."""
     _need_cuda(p, grad_planes, count)

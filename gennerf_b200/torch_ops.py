@@ -5,9 +5,10 @@ Every hot op of the path is registered as `torch.ops.gennerf_b200.<name>` with
   * a fake (meta) implementation = output shapes / strides only, so FakeTensor tracing, `torch.compile`
     (the `compile:` switch of configs/model/gen_nerf.yaml:121-122) and `torch.export` see through the ops, and
   * an autograd formula wired to the `gnb_*_bwd` kernels.
-The backward ops are custom ops themselves and have NO autograd formula: differentiating a backward (create_graph=True,
-the reference's eikonal / gradient losses, src/models/utils.py:636-649) raises PyTorch's "no autograd formula registered"
-error instead of silently dropping the second-order term.  CUDA tensors only; there is no CPU implementation.
+The backward ops are custom ops themselves.  The sampler's backward HAS an autograd formula (`sample_features_bwd2`, the
+double backward the reference's eikonal / gradient losses need: create_graph=True, src/models/utils.py:636-649); the other
+backward ops have none, so differentiating them raises PyTorch's "no autograd formula registered" error instead of
+silently dropping a second-order term.  CUDA tensors only; there is no CPU implementation.
 """
 from typing import List, Optional, Tuple
 
@@ -119,6 +120,71 @@ def _(grad_out, xyz, volume, p_xz, p_xy, p_yz, voxel_size, origin, padding, need
     for p in (p_xz, p_xy, p_yz):
         out.append(torch.empty_like(p) if (need_planes and p is not None) else e())
     return out
+
+
+@_op(f"{NS}::sample_features_bwd2", mutates_args=())
+def sample_features_bwd2(grad_out: Tensor, gg_xyz: Tensor, xyz: Tensor, volume: Optional[Tensor], p_xz: Optional[Tensor],
+                         p_xy: Optional[Tensor], p_yz: Optional[Tensor], voxel_size: float, origin: List[float], padding: float,
+                         need_grad_out: bool, need_xyz: bool, need_volume: bool, need_planes: bool) -> List[Tensor]:
+    """Double backward (gnb_sample_features_bwd2) -> [g_grad_out, g_xyz, g_volume, g_xz, g_xy, g_yz]; entries that were not
+    asked for are empty.  No autograd formula of its own: a third derivative raises."""
+    ggo, gvol, gpl, gx = ops.sample_features_bwd2(grad_out, gg_xyz, xyz, volume, _planes(p_xz, p_xy, p_yz), voxel_size=voxel_size,
+                                                  origin=origin, padding=padding, need_grad_out=need_grad_out,
+                                                  need_volume=need_volume and volume is not None, need_planes=need_planes,
+                                                  need_xyz=need_xyz)
+    gs = [ggo, gx, gvol] + [(gpl.get(k) if gpl else None) for k in ops.PLANES]
+    return [g if g is not None else grad_out.new_empty(0) for g in gs]
+
+
+@sample_features_bwd2.register_fake
+def _(grad_out, gg_xyz, xyz, volume, p_xz, p_xy, p_yz, voxel_size, origin, padding, need_grad_out, need_xyz, need_volume, need_planes):
+    e = lambda: grad_out.new_empty(0)      # noqa: E731
+    out = [torch.empty_like(grad_out, dtype=torch.float32, memory_format=torch.contiguous_format) if need_grad_out else e(),
+           torch.empty_like(xyz, dtype=torch.float32) if need_xyz else e(),
+           torch.empty_like(volume) if (need_volume and volume is not None) else e()]
+    for p in (p_xz, p_xy, p_yz):
+        out.append(torch.empty_like(p) if (need_planes and p is not None) else e())
+    return out
+
+
+def _sample_bwd_setup(ctx, inputs, output):
+    grad_out, xyz, volume, p_xz, p_xy, p_yz, voxel_size, origin, padding = inputs[:9]
+    ctx.save_for_backward(grad_out, xyz, volume, p_xz, p_xy, p_yz)
+    ctx.meta = (float(voxel_size), list(origin), float(padding))
+    ctx.set_materialize_grads(False)
+
+
+def _sample_bwd_bwd(ctx, grads):
+    """Backward of the sampler's backward (create_graph=True: eikonal / gradient losses, reference utils.py:636-649,
+    model.py:385-400).  The coordinate gradient's derivative is one kernel; the (rare) derivatives of grad_volume /
+    grad_planes are the sampler and its backward applied to the incoming gradients, because
+    grad_volume = sum_q w(xyz_q) grad_out_q is the adjoint of the sampler itself."""
+    gg_xyz, gg_vol, gg_xz, gg_xy, gg_yz = grads
+    grad_out, xyz, volume, p_xz, p_xy, p_yz = ctx.saved_tensors
+    voxel_size, origin, padding = ctx.meta
+    need = ctx.needs_input_grad                    # grad_out, xyz, volume, p_xz, p_xy, p_yz, ...
+    planes = (p_xz, p_xy, p_yz)
+    out = [None] * 6
+    if gg_xyz is not None and gg_xyz.numel() > 0 and any(need[:6]):
+        r = sample_features_bwd2(grad_out, gg_xyz, xyz, volume, p_xz, p_xy, p_yz, voxel_size, origin, padding,
+                                 need[0], need[1], need[2], any(need[3:6]))
+        for i in range(6):
+            if need[i] and r[i].numel() > 0:
+                out[i] = r[i]
+    ggp = (gg_xz, gg_xy, gg_yz)
+    if (gg_vol is not None and gg_vol.numel() > 0) or any(g is not None and g.numel() > 0 for g in ggp):
+        zv = None if volume is None else (gg_vol if (gg_vol is not None and gg_vol.numel() > 0) else torch.zeros_like(volume))
+        zp = [None if p is None else (g if (g is not None and g.numel() > 0) else torch.zeros_like(p)) for g, p in zip(ggp, planes)]
+        if need[0]:
+            t = sample_features(xyz, zv, zp[0], zp[1], zp[2], voxel_size, origin, padding)
+            out[0] = t if out[0] is None else out[0] + t
+        if need[1]:
+            t = sample_features_bwd(grad_out, xyz, zv, zp[0], zp[1], zp[2], voxel_size, origin, padding, True, False, False)[0]
+            out[1] = t if out[1] is None else out[1] + t
+    return tuple(out) + (None,) * 6
+
+
+sample_features_bwd.register_autograd(_sample_bwd_bwd, setup_context=_sample_bwd_setup)
 
 
 def _sample_setup(ctx, inputs, output):

@@ -173,6 +173,18 @@ int gnb_sample_features_bwd(const GnbSampleParams* s, const float* grad_out, int
                             float* grad_volume, float* const* h_grad_planes3, float* grad_xyz,
                             void* stream);
 
+/* Double backward of the sampler: the backward of gnb_sample_features_bwd's grad_xyz output, i.e. what
+ * torch.autograd.grad(tsdf, xyz, create_graph=True) (calculate_grad, src/models/utils.py:636-649) followed by
+ * loss.backward() needs for the eikonal / gradient losses (src/models/model.py:385-400).  The reference gets it for the
+ * planes from its pure-PyTorch grid_sample_2d (src/models/utils.py:1117-1174, chosen in model.py:157-158); ATen has no
+ * double backward for the 3-D grid sampler, so for the volume this goes beyond the reference.
+ * gg_xyz (B,Q,3) = gradient w.r.t. grad_xyz.  Outputs (any may be null): g_grad_out (B,Q,g_grad_out_stride)
+ * overwritten; g_volume / g_planes (forward strides) accumulated into; g_xyz (B,Q,3) overwritten (the second-order
+ * cross terms of the multilinear weights). */
+int gnb_sample_features_bwd2(const GnbSampleParams* s, const float* grad_out, int64_t grad_out_stride,
+                             const float* gg_xyz, float* g_grad_out, int64_t g_grad_out_stride,
+                             float* g_volume, float* const* h_g_planes3, float* g_xyz, void* stream);
+
 /* -------------------------------------------------------------------------------------
  * Plane coordinates and cell indices.  Replaces normalize_coordinate() + coordinate2index()
  * src/models/utils.py:57-98 for the three planes at once.

@@ -331,6 +331,60 @@ def sample_plane_feature_explicit(p, c, plane, padding=0.1):
     return out
 
 
+def grid_sample_2d(image, optical):
+    """The reference's double-differentiable stand-in for F.grid_sample 2-D (bilinear, border, align_corners=True):
+    src/models/utils.py:1117-1174, chosen by model.py:157-158 when loss.use_eikonal / loss.use_gradient is set.
+    image (N,C,IH,IW), optical (N,H,W,2) -> (N,C,H,W).  Unlike ATen's kernel it does not clip the coordinates, only the
+    corner indices; inside [-1,1] (where normalize_coordinate keeps vgrid) both agree."""
+    N, C, IH, IW = image.shape
+    _, H, W, _ = optical.shape
+    ix = ((optical[..., 0] + 1) / 2) * (IW - 1)
+    iy = ((optical[..., 1] + 1) / 2) * (IH - 1)
+    with torch.no_grad():
+        ix_nw, iy_nw = torch.floor(ix), torch.floor(iy)
+        ix_ne, iy_ne = ix_nw + 1, iy_nw
+        ix_sw, iy_sw = ix_nw, iy_nw + 1
+        ix_se, iy_se = ix_nw + 1, iy_nw + 1
+    nw = (ix_se - ix) * (iy_se - iy)
+    ne = (ix - ix_sw) * (iy_sw - iy)
+    sw = (ix_ne - ix) * (iy - iy_ne)
+    se = (ix - ix_nw) * (iy - iy_nw)
+    flat = image.view(N, C, IH * IW)
+
+    def corner(cx, cy):
+        with torch.no_grad():
+            idx = (cy.clamp(0, IH - 1) * IW + cx.clamp(0, IW - 1)).long().view(N, 1, H * W).repeat(1, C, 1)
+        return torch.gather(flat, 2, idx).view(N, C, H, W)
+
+    return (corner(ix_nw, iy_nw) * nw.view(N, 1, H, W) + corner(ix_ne, iy_ne) * ne.view(N, 1, H, W) +
+            corner(ix_sw, iy_sw) * sw.view(N, 1, H, W) + corner(ix_se, iy_se) * se.view(N, 1, H, W))
+
+
+def sample_plane_feature_eikonal(p, c, plane, padding=0.1):
+    """model.py:153-161 with loss.use_eikonal / use_gradient: normalize_coordinate + grid_sample_2d -> (B,C_p,Q)."""
+    xy = normalize_coordinate(p.clone(), plane=plane, padding=padding)
+    vgrid = 2.0 * xy[:, :, None].float() - 1.0
+    return grid_sample_2d(c, vgrid).squeeze(-1)
+
+
+def map_features_twice_differentiable(xyz, volume=None, planes=None, voxel_size=0.04, padding=0.1, origin=None):
+    """map_features (model.py:163-204) from operations autograd can differentiate twice: the planes through the reference's
+    own grid_sample_2d, the volume through the written-out 8-corner sum (ATen has no double backward for grid_sampler_3d,
+    so the reference itself cannot run its eikonal loss with a volume that requires grad).  Checker of
+    gnb_sample_features_bwd2."""
+    feats = []
+    if planes is not None:
+        fp = 0
+        for name in PLANES:
+            if name in planes:
+                fp = fp + sample_plane_feature_eikonal(xyz, planes[name], name, padding)
+        feats.append(fp.transpose(1, 2))
+    if volume is not None:
+        org = torch.zeros(3, dtype=torch.long) if origin is None else origin
+        feats.append(trilinear_interpolation_explicit(volume.permute(0, 2, 3, 4, 1), xyz, org, voxel_size))
+    return torch.cat(feats, dim=-1)
+
+
 # ----------------------------------------------------------------------------------------
 # a10  feature lookup                                        src/models/model.py:163-204
 # ----------------------------------------------------------------------------------------
@@ -406,9 +460,14 @@ def tsdf_head(feat_geo, weight, bias):
 def gennerf_forward(xyz, mlp_w, head_w, head_b, *, volume=None, valid=None, planes=None,
                     voxel_size=0.04, padding=0.1, num_freqs=2, freq_factor=0.5,
                     include_input=True, use_code=True, n_blocks=5, d_out_geo=32, d_out_sem=32,
-                    beta=0.0):
+                    beta=0.0, twice_differentiable=False):
+    """twice_differentiable: the feature lookup the eikonal / gradient losses need (model.py:157-158: grid_sample_2d for
+    the planes; written-out trilinear sum for an already normalised volume, `valid` ignored)."""
     B, Q, _ = xyz.shape
-    feat = map_features(xyz, volume, valid, planes, voxel_size, padding)
+    if twice_differentiable:
+        feat = map_features_twice_differentiable(xyz, volume, planes, voxel_size, padding)
+    else:
+        feat = map_features(xyz, volume, valid, planes, voxel_size, padding)
     code = xyz
     if use_code:
         code = positional_encoding(xyz.reshape(-1, 3), num_freqs, freq_factor, include_input).reshape(B, Q, -1)

@@ -117,11 +117,12 @@ def test_custom_ops_registered_with_fake_impls():
         assert out.shape == (2, 100, 16) and tsdf.shape == (2, 100, 1) and feat.shape == (2, 100, 40)
 
 
-def test_backward_ops_have_no_autograd_formula():
-    """The formulas are once-differentiable by construction: the *_bwd ops carry no autograd registration, so a double
-    backward (create_graph=True) raises in PyTorch instead of silently dropping the second-order term."""
+def test_backward_ops_autograd_registrations():
+    """The sampler's backward is differentiable again (sample_features_bwd2: the eikonal / gradient losses, reference
+    utils.py:636-649).  The other *_bwd ops carry no autograd registration, so a double backward through them raises in
+    PyTorch instead of silently dropping the second-order term."""
     from gennerf_b200 import torch_ops as T
-    for fwd in (T.backproject_frames, T.sample_features, T.scatter_mean_planes, T.pool_local):
+    for fwd in (T.backproject_frames, T.sample_features, T.scatter_mean_planes, T.pool_local, T.sample_features_bwd):
         assert fwd._backward_fn is not None
-    for bwd in (T.backproject_frames_bwd, T.sample_features_bwd, T.scatter_mean_planes_bwd, T.pool_local_bwd):
+    for bwd in (T.backproject_frames_bwd, T.sample_features_bwd2, T.scatter_mean_planes_bwd, T.pool_local_bwd):
         assert getattr(bwd, "_backward_fn", None) is None

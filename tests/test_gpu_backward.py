@@ -77,6 +77,82 @@ def test_sampler_backward(with_planes, with_volume):
             close(pd[k].grad, po[k].grad, 1e-4, f"grad plane {k}")
 
 
+@pytest.mark.parametrize("with_planes,with_volume", [(True, False), (False, True), (True, True)])
+def test_sampler_double_backward(with_planes, with_volume):
+    """The eikonal / gradient losses (reference utils.py:636-649 `calculate_grad(create_graph=True)`, model.py:385-400)
+    differentiate d tsdf / d xyz once more.  CUDA: sample_features -> sample_features_bwd -> gnb_sample_features_bwd2;
+    checker: CPU autograd through the reference's grid_sample_2d (planes) and the written-out trilinear sum (volume)."""
+    from gennerf_b200 import autograd as ag
+    g = S.gen(57)
+    dims, R, Cp, C, Q = (12, 10, 6), 16, 8, 16, 1500
+    vol = torch.randn(2, C, *dims, generator=g)
+    planes = {k: torch.randn(2, Cp, R, R, generator=g) for k in O.PLANES}
+    xyz = S.query_points(Q, dims, VS, g, B=2)                                   # some outside the grid (border clip)
+    xyz[:, :600] = S.plane_points(600, g, "unit", B=2) * 1.15                   # plane domain, some clamped by normalize_coordinate
+    D = (Cp if with_planes else 0) + (C if with_volume else 0)
+    wgt = torch.randn(D, generator=g) * 0.3
+    bdir = torch.randn(3, generator=g)
+
+    def loss_of(feat, x):
+        t = torch.tanh((feat * wgt.to(feat.device)).sum(-1) + (x * bdir.to(x.device)).sum(-1))
+        (gx,) = torch.autograd.grad(t.sum(), x, create_graph=True)
+        return ((gx.norm(dim=-1) - 1) ** 2).mean() + t.mean(), gx
+
+    # checker
+    xo = xyz.clone().requires_grad_(True)
+    vo = vol.clone().requires_grad_(True)
+    po = {k: v.clone().requires_grad_(True) for k, v in planes.items()}
+    ref = O.map_features_twice_differentiable(xo, vo if with_volume else None, po if with_planes else None, VS, 0.1)
+    lo, gxo = loss_of(ref, xo)
+    lo.backward()
+    # kernels
+    xd = xyz.to(DEV).requires_grad_(True)
+    vd = vol.to(DEV).permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    pd = {k: v.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for k, v in planes.items()}
+    out = ag.sample_features(xd, volume=vd if with_volume else None, planes=pd if with_planes else None, voxel_size=VS,
+                             origin=ORIGIN, padding=0.1)
+    ld, gxd = loss_of(out, xd)
+    ld.backward()
+    close(gxd, gxo, 1e-4, "d tsdf / d xyz")
+    assert abs(ld.item() - lo.item()) <= 1e-4 * max(1.0, abs(lo.item()))
+    assert xo.grad.abs().max() > 0
+    close(xd.grad, xo.grad, 2e-4, "grad xyz (second order)")
+    if with_volume:
+        close(vd.grad, vo.grad, 2e-4, "grad volume (second order)")
+    if with_planes:
+        for k in O.PLANES:
+            close(pd[k].grad, po[k].grad, 2e-4, f"grad plane {k} (second order)")
+
+
+def test_sampler_double_backward_through_grad_volume():
+    """The other half of the sampler backward's derivative: a loss on grad_volume / grad_planes (create_graph=True)
+    flows back into grad_out and xyz through the sampler and its backward applied to the incoming gradients."""
+    from gennerf_b200 import autograd as ag
+    g = S.gen(58)
+    dims, R, Cp, C, Q = (8, 6, 5), 8, 4, 8, 400
+    vol = torch.randn(1, C, *dims, generator=g)
+    planes = {k: torch.randn(1, Cp, R, R, generator=g) for k in O.PLANES}
+    xyz = S.query_points(Q, dims, VS, g, B=1) * 0.9 + 0.01
+    wv, wp = torch.randn(1, C, *dims, generator=g), torch.randn(1, Cp, R, R, generator=g)
+    wgt = torch.randn(Cp + C, generator=g)
+
+    def run(sample, dev, x, v, pl):
+        t = torch.tanh((sample(x, v, pl) * wgt.to(dev)).sum(-1)).sum()
+        gv, gp = torch.autograd.grad(t, [v, pl["xy"]], create_graph=True)
+        loss = (gv * wv.to(dev)).sum() + (gp * wp.to(dev)).sum()
+        return torch.autograd.grad(loss, [x, v, pl["xy"]], allow_unused=True)
+
+    xo, vo = xyz.clone().requires_grad_(True), vol.clone().requires_grad_(True)
+    po = {k: v.clone().requires_grad_(True) for k, v in planes.items()}
+    a = run(lambda x, v, pl: O.map_features_twice_differentiable(x, v, pl, VS, 0.1), "cpu", xo, vo, po)
+    xd = xyz.to(DEV).requires_grad_(True)
+    vd = vol.to(DEV).permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    pd = {k: v.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for k, v in planes.items()}
+    b = run(lambda x, v, pl: ag.sample_features(x, volume=v, planes=pl, voxel_size=VS, origin=ORIGIN, padding=0.1), DEV, xd, vd, pd)
+    for name, u, w in zip(("xyz", "volume", "plane xy"), b, a):
+        close(u, w, 2e-4, f"grad {name} through grad_volume / grad_planes")
+
+
 @pytest.mark.parametrize("scatter_type", ["max", "mean"])
 def test_triplane_backward(scatter_type):
     from gennerf_b200 import autograd as ag

@@ -1,6 +1,6 @@
 """Drop-in boundary on the GPU: a reference-built checkpoint loaded into the drop-in GenNerf gives
 the reference's outputs; cached decoder weights follow the parameters; plane layouts a U-Net produces are accepted; the
-backward formulas refuse a double backward; dense extraction generates its query grid in the kernel; the fp16 decoder
+sampler's backward is differentiable again (eikonal losses); dense extraction generates its query grid in the kernel; the fp16 decoder
 reports saturation instead of returning clipped results silently."""
 import os
 
@@ -118,14 +118,64 @@ def test_unet_style_nchw_planes_run_fused(SD):
     assert (out["tsdf"] - ref["tsdf"]).abs().max().item() <= 3e-2
 
 
-def test_double_backward_raises(SD):
+def _eikonal_loss(tsdf, xyz):
+    """reference utils.py:636-649 (calculate_grad, create_graph=True) + model.py:385-400 (|grad| -> 1)."""
+    (grad,) = torch.autograd.grad(tsdf, xyz, grad_outputs=torch.ones_like(tsdf), create_graph=True, retain_graph=True)
+    return ((grad.norm(dim=-1) - 1) ** 2).mean() + tsdf.abs().mean(), grad
+
+
+def test_eikonal_double_backward_matches_the_oracle(SD):
     """The reference's eikonal / gradient losses differentiate d(tsdf)/d(xyz) again (utils.py:636-649, create_graph=True).
-    The sampler's backward kernel is once-differentiable: that must fail loudly, not drop the second-order term."""
+    Through the drop-in: sampler -> its backward kernel -> the double-backward kernel (gnb_sample_features_bwd2); the MLP is
+    nn.Linear under autograd.  Checker: CPU autograd through the oracle with the reference's grid_sample_2d lookup."""
     model = _small_model(SD, "fp32").train()
+    small = SD["small"]
+    i = small["in"]
+    xyz = i["xyz"][:, :600].clone()
+    for t in (model.volume, *model.c_plane.values()):
+        t.requires_grad_(True)
+    xd = xyz.to(DEV).requires_grad_(True)
+    loss, grad = _eikonal_loss(model(xd)["tsdf"], xd)
+    loss.backward()
+    # checker
+    sd = {k: v.clone().requires_grad_(True) for k, v in small["state_dict"].items() if v.is_floating_point()}
+    w = {k[4:]: v for k, v in sd.items() if k.startswith("mlp.")}
+    cfg = small["cfg"]
+    xo = xyz.clone().requires_grad_(True)
+    vo = (i["volume"] * i["valid"]).clone().requires_grad_(True)
+    po = {k: v.clone().requires_grad_(True) for k, v in i["planes"].items()}
+    ref = O.gennerf_forward(xo, w, sd["head_geo.fc.weight"], sd["head_geo.fc.bias"], volume=vo, planes=po,
+                            voxel_size=cfg["voxel_size"], padding=cfg["encoder"]["pointnet"]["padding"],
+                            num_freqs=cfg["code"]["num_freqs"], freq_factor=cfg["code"]["freq_factor"],
+                            include_input=cfg["code"]["include_input"], use_code=cfg["use_code"], n_blocks=cfg["mlp"]["n_blocks"],
+                            d_out_geo=cfg["mlp"]["d_out_geo"], d_out_sem=cfg["mlp"]["d_out_sem"], twice_differentiable=True)
+    lo, go = _eikonal_loss(ref["tsdf"], xo)
+    lo.backward()
+
+    def close(a, b, what, tol=2e-3):
+        b = b.float()
+        err = ((a.detach().cpu().float() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+        assert err <= tol, f"{what}: {err:.2e}"
+
+    assert go.abs().max() > 0 and xo.grad.abs().max() > 0
+    close(grad, go, "d tsdf / d xyz")
+    close(xd.grad, xo.grad, "eikonal grad xyz")
+    close(model.volume.grad, vo.grad, "eikonal grad volume")
+    for k in PLANES:
+        close(model.c_plane[k].grad, po[k].grad, f"eikonal grad plane {k}")
+    for k in ("mlp.lin_in.weight", "mlp.blocks.1.fc_0.weight", "mlp.lin_z.0.weight", "mlp.lin_out.weight", "head_geo.fc.weight"):
+        close(dict(model.named_parameters())[k].grad, sd[k].grad, f"eikonal grad {k}")
+
+
+def test_double_backward_through_the_fp16_training_decoder_raises(SD):
+    """train_precision='fp16' (tcgen05 forward + hand-written backward, train_decode.py) is once-differentiable: an eikonal
+    loss through it must fail loudly, not drop the second-order term."""
+    model = _small_model(SD, "fp32").train()
+    model.train_precision = "fp16"
     xyz = SD["small"]["in"]["xyz"].to(DEV).requires_grad_(True)
     tsdf = model(xyz)["tsdf"]
-    (grad,) = torch.autograd.grad(tsdf.sum(), xyz, create_graph=True)
     with pytest.raises(RuntimeError):
+        (grad,) = torch.autograd.grad(tsdf.sum(), xyz, create_graph=True)
         grad.pow(2).sum().backward()
 
 

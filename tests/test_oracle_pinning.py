@@ -131,6 +131,35 @@ def test_plane_query(ref):
         assert torch.allclose(a, d, rtol=1e-5, atol=1e-6)
 
 
+def test_plane_query_eikonal_variant_and_its_double_backward(ref):
+    """model.py:157-158 with loss.use_eikonal: the reference's grid_sample_2d (utils.py:1117-1174).  The oracle's restatement
+    equals it bit for bit -- values, first derivatives and the double backward of an eikonal-style loss."""
+    g = S.gen(53)
+    Cp, R = 8, 16
+    xyz = S.plane_points(300, g, "unit", B=2) * 1.2
+    GenNerf = ref_shim.ref_gennerf()
+    fake = type("F", (), {})()
+    fake.cfg = ref_shim.to_attr({"encoder": {"pointnet": {"padding": 0.1, "sample_mode": "bilinear"}},
+                                 "loss": {"use_eikonal": True, "use_gradient": False}})
+    wgt = torch.randn(Cp, generator=g)
+
+    def run(sample):
+        x = xyz.clone().requires_grad_(True)
+        pl = {k: torch.randn(2, Cp, R, R, generator=S.gen(54 + i)).requires_grad_(True) for i, k in enumerate(O.PLANES)}
+        f = sum(sample(x, pl[k], k) for k in O.PLANES)                     # (B,Cp,Q)
+        t = torch.tanh((f * wgt.view(1, -1, 1)).sum(1))
+        (gx,) = torch.autograd.grad(t.sum(), x, create_graph=True)
+        loss = ((gx.norm(dim=-1) - 1) ** 2).mean() + t.mean()
+        grads = torch.autograd.grad(loss, [x] + [pl[k] for k in O.PLANES])
+        return [f.detach(), gx.detach()] + list(grads)
+
+    a = run(lambda x, c, k: GenNerf.sample_plane_feature(fake, x, c, plane=k))
+    b = run(lambda x, c, k: O.sample_plane_feature_eikonal(x, c, k, 0.1))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    assert a[2].abs().max() > 0 and a[3].abs().max() > 0
+
+
 @pytest.mark.parametrize("num_freqs,ff", [(2, 0.5), (6, 1.5)])
 def test_positional_encoding(ref, num_freqs, ff):
     x = torch.randn(100, 3, generator=S.gen(61)) * 3
