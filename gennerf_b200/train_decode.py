@@ -45,8 +45,18 @@ class _DecodeTC(torch.autograd.Function):
         return out, tsdf
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, g_out, g_tsdf):
+        # create_graph=True (the eikonal / gradient losses, reference utils.py:636-649) runs this with grad mode ON.
+        # once_differentiable alone only raises when the INCOMING gradients carry history; the dependence of this backward
+        # on the saved activations would be dropped without a word.
+        if torch.is_grad_enabled():
+            raise RuntimeError("gennerf_b200: the fp16 training decoder (train_precision='fp16') is once-differentiable; "
+                               "use train_precision='fp32' with loss.use_eikonal / loss.use_gradient (create_graph=True)")
+        return _DecodeTC._backward_once(ctx, g_out, g_tsdf)
+
+    @staticmethod
+    @once_differentiable
+    def _backward_once(ctx, g_out, g_tsdf):
         code, feat, out, tsdf, acts, head_w, *params = ctx.saved_tensors
         nb, d_geo = ctx.n_blocks, ctx.d_geo
         P = dict(zip(mlp_keys(nb), params))
