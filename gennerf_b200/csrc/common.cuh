@@ -13,7 +13,7 @@ void set_error(const char* fmt, ...);
 // tuning / debugging options (error.cu): defaults read from the environment once, changed with gnb_set_option
 enum Opt : int { OPT_TC_TWO_CTA = 0, OPT_TC_NO_EARLY, OPT_DEBUG_MAX_CLUSTERS, OPT_DEBUG_PRINT, OPT_LIFT_NVW, OPT_SCATTER_SCALAR,
                  OPT_FPS_SINGLE_CTA, OPT_FPS_CLUSTER, OPT_SAMPLE_GENERIC, OPT_BIN_UNIT, OPT_BIN_ROWCOPY, OPT_SCATTER_TILED,
-                 OPT_BIN_PRESORTED, OPT_TC_NO_STG, OPT_TC_PAIR, OPT_DEBUG_NO_WCOPY, OPT_QUERY_FUSED, OPT_COUNT };
+                 OPT_BIN_PRESORTED, OPT_TC_NO_STG, OPT_TC_PAIR, OPT_DEBUG_NO_WCOPY, OPT_QUERY_FUSED, OPT_FPS_GRID, OPT_COUNT };
 int opt(int which);
 
 #define GNB_CHECK_ARG(cond, ...)                 \

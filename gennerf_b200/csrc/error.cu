@@ -22,7 +22,7 @@ void set_error(const char* fmt, ...) {
 static const char* const kOptNames[OPT_COUNT] = {
     "GNB_TC_TWO_CTA", "GNB_TC_NO_EARLY", "GNB_DEBUG_MAX_CLUSTERS", "GNB_DEBUG_PRINT", "GNB_LIFT_NVW", "GNB_SCATTER_SCALAR",
     "GNB_FPS_SINGLE_CTA", "GNB_FPS_CLUSTER", "GNB_SAMPLE_GENERIC", "GNB_BIN_UNIT", "GNB_BIN_ROWCOPY", "GNB_SCATTER_TILED",
-    "GNB_BIN_PRESORTED", "GNB_TC_NO_STG", "GNB_TC_PAIR", "GNB_DEBUG_NO_WCOPY", "GNB_QUERY_FUSED"};
+    "GNB_BIN_PRESORTED", "GNB_TC_NO_STG", "GNB_TC_PAIR", "GNB_DEBUG_NO_WCOPY", "GNB_QUERY_FUSED", "GNB_FPS_GRID"};
 static std::atomic<int> g_opt[OPT_COUNT];
 static std::once_flag g_opt_once;
 static void opt_init() {

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     float dist[FPS_PPT];
 #pragma unroll
     for (int j = 0; j < FPS_PPT; ++j) dist[j] = 1e10f;
+    const int jmax = (n_local + FPS_THREADS - 1) / FPS_THREADS;
     int far = (int)start[b];
     float cx = __ldg(p + far * 3LL), cy = __ldg(p + far * 3LL + 1), cz = __ldg(p + far * 3LL + 2);
     if (threadIdx.x == 0) {
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
         int besti = 0x7fffffff;
 #pragma unroll
         for (int j = 0; j < FPS_PPT; ++j) {
+            if (j >= jmax) break;                 // block-uniform: predicated-off trips would still cost their issue slots
             const int i = j * FPS_THREADS + threadIdx.x;
             if (i < n_local) {
                 const float dx = __fsub_rn(sx[i], cx), dy = __fsub_rn(sy[i], cy), dz = __fsub_rn(sz[i], cz);
@@ -221,6 +223,138 @@ __global__ void __launch_bounds__(FPS_THREADS, 1) fps_cluster_kernel(const float
     }
     // no CTA may exit while a peer can still write into its shared memory
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Grid version: CPC co-resident CTAs ANYWHERE on the GPU share one cloud and exchange their candidates through global memory
+// (L2), launched cooperatively.  Thread-block clusters must sit inside one GPC: at most seven 16-CTA clusters are co-resident
+// on a B200, so the 8 clouds of a scene (480x640 points each: 16 CTAs' worth of shared memory) took two waves of the cluster
+// kernel.  Here 8 clouds x 18 CTAs = 144 of the 148 SMs run in ONE wave.  Per iteration every CTA publishes {value, index, xyz}
+// into its slot of the cloud's exchange buffer as (word, iteration number) pairs -- 8-byte units are written and read atomically,
+// so a reader that sees the iteration number next to every word has the whole record, without a fence on either side (the
+// release store / acquire poll version cost 5.8 us per iteration) --.  Every slot has ONE writer and ONE reader (32 CTAs polling the same lines cost 5 us per iteration): CTA r sends
+// its candidate to the cloud's leader (rank 0), whose lane r polls it; the leader reduces and sends the result back, one slot per CTA.  Slots are double-buffered by iteration parity: a CTA overwrites its parity-p slot two iterations later,
+// after it has seen every peer's record of the iteration in between, which those peers published only after reading parity p.
+// Same arithmetic, same slices in ascending rank order and the same tie rule as the cluster kernel: identical indices.
+constexpr int FPS_XWORDS = 8;               // words per slot (one 32-byte sector): value, index | tag, 6 pad
+constexpr int FPS_MAX_CPC = 32;
+// A record travels as (word, sequence number) pairs in three 16-byte stores: 8-byte units are written and read atomically, so a
+// reader that finds the iteration's number next to every word has the whole record -- no fence on either side.
+__device__ __forceinline__ void fps_ll_store(unsigned* s, const FpsCand& c, unsigned seq) {
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %2};" ::"l"(s), "r"(__float_as_uint(c.val)), "r"(seq), "r"((unsigned)c.idx) : "memory");
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %2};" ::"l"(s + 4), "r"(__float_as_uint(c.x)), "r"(seq), "r"(__float_as_uint(c.y)) : "memory");
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %2};" ::"l"(s + 8), "r"(__float_as_uint(c.z)), "r"(seq), "r"(0u) : "memory");
+}
+__device__ __forceinline__ FpsCand fps_ll_poll(const unsigned* s, unsigned seq) {
+    unsigned a0, f0, a1, f1, b0, g0, b1, g1, c0, h0, c1, h1;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(f0), "=r"(a1), "=r"(f1) : "l"(s) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(g0), "=r"(b1), "=r"(g1) : "l"(s + 4) : "memory");
+        asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(c0), "=r"(h0), "=r"(c1), "=r"(h1) : "l"(s + 8) : "memory");
+        if (f0 == seq && f1 == seq && g0 == seq && g1 == seq && h0 == seq && h1 == seq) break;
+        if (spin > (1u << 24)) __trap();                     // a peer that never arrives must not hang the GPU
+    }
+    FpsCand c;
+    c.val = __uint_as_float(a0), c.idx = (int)a1, c.x = __uint_as_float(b0), c.y = __uint_as_float(b1), c.z = __uint_as_float(c0);
+    return c;
+}
+__global__ void __launch_bounds__(FPS_THREADS, 1) fps_grid_kernel(const float* __restrict__ xyz, long long N, int npoint,
+                                                                  const long long* __restrict__ start, int cpc, int chunk, int b0,
+                                                                  unsigned* __restrict__ xbuf, long long* __restrict__ out_idx,
+                                                                  float* __restrict__ out_xyz) {
+    extern __shared__ float fps_sm[];
+    __shared__ FpsCand s_res;
+    __shared__ float s_val[32];
+    __shared__ int s_idx[32];
+    float* sx = fps_sm, *sy = fps_sm + chunk, *sz = fps_sm + 2 * chunk;
+    const int b = b0 + blockIdx.x / cpc, rank = blockIdx.x % cpc;
+    const float* __restrict__ p = xyz + (long long)b * N * 3;
+    unsigned* xb = xbuf + (long long)b * 2 * cpc * FPS_XWORDS;
+    const long long lo = (long long)rank * chunk;
+    const int n_local = (int)max(0LL, min((long long)chunk, N - lo));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < n_local; i += FPS_THREADS) {
+        sx[i] = p[(lo + i) * 3], sy[i] = p[(lo + i) * 3 + 1], sz[i] = p[(lo + i) * 3 + 2];
+    }
+    float dist[FPS_PPT];
+#pragma unroll
+    for (int j = 0; j < FPS_PPT; ++j) dist[j] = 1e10f;
+    const int jmax = (n_local + FPS_THREADS - 1) / FPS_THREADS;
+    int far = (int)start[b];
+    float cx = __ldg(p + far * 3LL), cy = __ldg(p + far * 3LL + 1), cz = __ldg(p + far * 3LL + 2);
+    __syncthreads();
+    for (int it = 0; it < npoint; ++it) {
+        if (rank == 0 && threadIdx.x == 0) {
+            out_idx[(long long)b * npoint + it] = far;
+            out_xyz[((long long)b * npoint + it) * 3 + 0] = cx;
+            out_xyz[((long long)b * npoint + it) * 3 + 1] = cy;
+            out_xyz[((long long)b * npoint + it) * 3 + 2] = cz;
+        }
+        float best = -1.0f;
+        int besti = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < FPS_PPT; ++j) {
+            if (j >= jmax) break;                 // block-uniform: predicated-off trips would still cost their issue slots
+            const int i = j * FPS_THREADS + threadIdx.x;
+            if (i < n_local) {
+                const float dx = __fsub_rn(sx[i], cx), dy = __fsub_rn(sy[i], cy), dz = __fsub_rn(sz[i], cz);
+                const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                if (d < dist[j]) dist[j] = d;
+                if (dist[j] > best) { best = dist[j]; besti = i; }       // ascending i: keeps the first maximum
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, best, o);
+            const int oi = __shfl_xor_sync(FULL, besti, o);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (lane == 0) { s_val[warp] = best; s_idx[warp] = besti; }
+        __syncthreads();
+        if (warp == 0) {
+            best = s_val[lane];
+            besti = s_idx[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, best, o);
+                const int oi = __shfl_xor_sync(FULL, besti, o);
+                if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+            }
+            const unsigned seq = (unsigned)it + 1u;
+            // this CTA's candidate: ONE 8-byte record {value, index | iteration number in the top byte} -- 8-byte accesses are
+            // single-copy atomic, so there is no fence and no flag on either side; slot r is written by CTA r and polled by
+            // lane r of every CTA of the cloud
+            const unsigned tag = (seq & 0xffu) << 24;
+            if (lane == 0) {
+                const unsigned gi = besti == 0x7fffffff ? 0x00ffffffu : (unsigned)(lo + besti);
+                asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(xb + ((it & 1) * cpc + rank) * FPS_XWORDS),
+                             "r"(__float_as_uint(best)), "r"(gi | tag) : "memory");
+            }
+            float cv = -2.0f;
+            unsigned ci = 0x00ffffffu;
+            if (lane < cpc) {
+                const unsigned* s = xb + ((it & 1) * cpc + lane) * FPS_XWORDS;
+                unsigned v0, v1;
+                for (unsigned spin = 0;; ++spin) {
+                    asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(v0), "=r"(v1) : "l"(s) : "memory");
+                    if ((v1 & 0xff000000u) == tag) break;
+                    if (spin > (1u << 24)) __trap();         // a peer that never arrives must not hang the GPU
+                }
+                cv = __uint_as_float(v0), ci = v1 & 0x00ffffffu;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(FULL, cv, o);
+                const unsigned oi = __shfl_xor_sync(FULL, ci, o);
+                if (ov > cv || (ov == cv && oi < ci)) { cv = ov; ci = oi; }
+            }
+            FpsCand c;
+            c.val = cv, c.idx = (int)ci;
+            c.x = __ldg(p + ci * 3LL), c.y = __ldg(p + ci * 3LL + 1), c.z = __ldg(p + ci * 3LL + 2);
+            if (lane == 0) s_res = c;
+        }
+        __syncthreads();
+        far = s_res.idx, cx = s_res.x, cy = s_res.y, cz = s_res.z;
+    }
 }
 
 // Training-time ray sampler: sample_points_on_rays(), reference src/models/utils.py:458-540 (iSDF).
@@ -330,6 +464,33 @@ extern "C" int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int
         GNB_CUDA(cudaFuncSetAttribute(fps_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         int best_cs = 0;
         double best_t = 1e30;
+        // grid kernel (co-operative launch, exchange through L2): as many clouds per launch as fit the GPU with the fewest CTAs a
+        // cloud needs, the CTAs of a wave spread evenly over its clouds; several launches when the batch needs more than one wave
+        int grid_cpc = 0, grid_per_wave = 0;
+        double grid_t = 1e30;
+        {
+            int dev = 0, sms = 0, coop = 0;
+            GNB_CUDA(cudaGetDevice(&dev));
+            GNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            GNB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+            const long long by_smem = (N * 12 + 225 * 1024 - 1) / (225 * 1024), by_regs = (N + (long long)FPS_PPT * FPS_THREADS - 1) / ((long long)FPS_PPT * FPS_THREADS);
+            long long cpc_min = by_smem > by_regs ? by_smem : by_regs;
+            if (cpc_min < 2) cpc_min = 2;
+            const int forced = opt(OPT_FPS_GRID);             // tuning aid: > 0 forces the CTAs per cloud, < 0 switches the grid kernel off
+            if (forced > 0 && forced >= cpc_min) cpc_min = forced;
+            if (coop && forced >= 0 && cpc_min <= FPS_MAX_CPC && cpc_min <= sms && N < (1 << 24) - 1 &&
+                (long long)N * 4 >= 2LL * FPS_MAX_CPC * FPS_XWORDS * 4) {                       // (the exchange slots live in `scratch`)
+                int per_wave = sms / (int)cpc_min;
+                if (per_wave > B) per_wave = B;
+                const int waves = (B + per_wave - 1) / per_wave;
+                per_wave = (B + waves - 1) / waves;
+                int cpc = forced > 0 ? (int)cpc_min : sms / per_wave;
+                if (cpc > FPS_MAX_CPC) cpc = FPS_MAX_CPC;
+                const long long chunk = (N + cpc - 1) / cpc;
+                grid_cpc = cpc, grid_per_wave = per_wave;
+                grid_t = forced > 0 ? 0.0 : waves * (2.6 + 0.063e-3 * (double)chunk);          // (us per iteration; exchange latency measured on a B200)
+            }
+        }
         for (int cs = 2; cs <= 16; cs *= 2) {
             const long long chunk = (N + cs - 1) / cs;
             const size_t smem = (size_t)chunk * 12;
@@ -350,7 +511,33 @@ extern "C" int gnb_farthest_point_sample(const float* xyz, int B, int64_t N, int
             const double t = waves * (2.1 + 0.063e-3 * (double)chunk);
             if (t < best_t * 0.97) best_t = t, best_cs = cs;           // ties go to the smaller cluster
         }
-        if (const int e = opt(OPT_FPS_CLUSTER)) best_cs = e;    // tuning aid
+        if (const int e = opt(OPT_FPS_CLUSTER)) best_cs = e, grid_cpc = 0;    // tuning aid
+        if (grid_cpc > 1 && N > 2048 && grid_t < best_t * 0.97) {
+            const int cpc = grid_cpc;
+            int chunk = (int)((N + cpc - 1) / cpc);
+            const size_t smem = (size_t)chunk * 12;
+            GNB_CUDA(cudaFuncSetAttribute(fps_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            GNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fps_grid_kernel, FPS_THREADS, smem));
+            if (per_sm >= 1) {
+                unsigned* xbuf = reinterpret_cast<unsigned*>(scratch);
+                GNB_CUDA(cudaMemsetAsync(xbuf, 0, (size_t)B * 2 * cpc * FPS_XWORDS * 4, (cudaStream_t)stream));
+                long long NN = N;
+                const long long* st = (const long long*)start;
+                long long* oi = (long long*)out_idx;
+                bool ok = true;
+                for (int b0 = 0; b0 < B && ok; b0 += grid_per_wave) {
+                    const int nb = B - b0 < grid_per_wave ? B - b0 : grid_per_wave;
+                    void* args[] = {(void*)&xyz, (void*)&NN, (void*)&npoint, (void*)&st, (void*)&cpc, (void*)&chunk, (void*)&b0, (void*)&xbuf,
+                                    (void*)&oi, (void*)&out_xyz};
+                    ok = cudaLaunchCooperativeKernel((const void*)fps_grid_kernel, dim3((unsigned)(nb * cpc)), dim3(FPS_THREADS), args, smem,
+                                                     (cudaStream_t)stream) == cudaSuccess;
+                    if (!ok && b0 > 0) GNB_CUDA(cudaGetLastError());       // (a later wave cannot fail when the first one fitted)
+                }
+                if (ok) return 0;
+                (void)cudaGetLastError();                     // (e.g. not all CTAs co-resident right now: take the cluster kernel)
+            }
+        }
         if (best_cs > 1 && N > 2048) {
             const int cs = best_cs;
             const long long chunk = (N + cs - 1) / cs;

@@ -377,3 +377,14 @@ def test_fps_cluster_kernel_bit_identical(N, npoint, B):
     finally:
         _lib.set_option("GNB_FPS_SINGLE_CTA", old)
     assert torch.equal(c1.cpu(), c_o) and torch.equal(s1.cpu(), s_o)
+    # ... and both multi-CTA kernels when forced: thread-block clusters (DSMEM exchange) and the co-operative grid kernel
+    # (CTAs anywhere on the GPU, exchange through L2), with CTA counts that leave ragged / empty last slices
+    for name, val in (("GNB_FPS_GRID", -1), ("GNB_FPS_GRID", 5), ("GNB_FPS_GRID", 18), ("GNB_FPS_GRID", 32)):
+        if val > 0 and (B * val > 148 or -(-N // val) > 20 * 1024 or -(-N // val) * 12 > 225 * 1024):
+            continue
+        old = _lib.set_option(name, val)
+        try:
+            s2, c2 = ops().farthest_point_sample(xyz.to(DEV), npoint, start.to(DEV))
+        finally:
+            _lib.set_option(name, old)
+        assert torch.equal(c2.cpu(), c_o) and torch.equal(s2.cpu(), s_o), (name, val)
