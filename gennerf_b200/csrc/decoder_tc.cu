@@ -70,7 +70,11 @@ struct Dims {
     int stage_bytes;                  // bytes of one stage: the weight rows of one step x 64 k (single-CTA issue: one k-chunk
                                       // of <= 256 rows; cta_group::2: two k-chunks of <= 128 rows)
     int early;                        // 1: a dedicated warp stages the NEXT tile's lin_in / lin_z operands (sampling, encoding) while
-                                      // this tile's layers run; needs its own feature buffer (KF chunks) next to the code tile
+                                      // this tile's layers run; needs its own feature buffer (KFB chunks) next to the code tile
+    int wide;                         // 1: lin_in has more k-chunks than shared memory can hold next to the layers' operands (KF > 8, e.g.
+                                      // the reference's default latent 512 + 32): operand-image mode only, the chunks are streamed --
+                                      // chunk 0 waits in the feature buffer, the others pass through the tile's own activation slots
+    int KFB;                          // chunks of the feature buffer (KF, or 1 in wide mode)
     long long packed_per_rank;        // bytes
 };
 
@@ -416,7 +420,7 @@ __host__ __device__ inline Smem smem_layout(const Dims& d) {
     s.a = 0;
     s.code = s.a + d.ACH * CHUNK;
     s.feat = d.early ? s.code + d.KZ * CHUNK : s.a;          // lin_in operand: own buffer, or the first own chunk slots
-    s.ring = s.code + d.KZ * CHUNK + (d.early ? d.KF * CHUNK : 0);
+    s.ring = s.code + d.KZ * CHUNK + (d.early ? d.KFB * CHUNK : 0);
     s.bias = s.ring + d.nstage * d.stage_bytes;
     // fp32 table: bias[HN] | b_out[NOUT] | head_w[d_geo] | head_b.  bias[] is time-shared: the epilogue threads load
     // fc_0's bias of block i into it during round 2i (which adds no bias) for round 2i+1, and the last fc_1 bias
@@ -596,6 +600,11 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
     const uint32_t in_ready = acc_ready + 8;
     const uint32_t in_free = in_ready + 8;                   // (early staging) the code tile may be overwritten: the tile's last lin_z has retired
     const uint32_t feat_free = in_free + 8;                  // (early staging) the feature buffer may be overwritten: lin_in has retired
+    // wide latent (lin_in chunks 1.. streamed through the own activation slots): the slots are free for the next tile (lin_out
+    // has retired) / chunk landed in slot j / the MMAs that read slot j have retired
+    const uint32_t a_free = feat_free + 8;
+    auto s_full = [&](int j) { return a_free + 8u + 8u * j; };
+    auto s_empty = [&](int j) { return a_free + 8u + 8u * (4 + j); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L.bars + (2 * MAX_STAGES + MAX_CHUNKS + 2 + 12) * 8);
     float* bias_s = reinterpret_cast<float*>(sm + L.bias);
 
@@ -625,6 +634,8 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
         mbar_init(in_ready, d.early ? (STG ? 4 : 1) : warps_in);
         mbar_init(in_free, 1);
         mbar_init(feat_free, 1);
+        mbar_init(a_free, 1);
+        for (int j = 0; j < 4; ++j) { mbar_init(s_full(j), 1); mbar_init(s_empty(j), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == ROLE_WARP0 + 2) {
@@ -814,7 +825,7 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
         //      TMEM columns -- were tried in round 1: tcgen05.commit arrivals got lost and results were corrupted.)
         {
             int stage = 0;
-            uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0;
+            uint32_t phase = 0, round = 0, tiles_done = 0, rtotal = 0, wfill = 0;
             const uint16_t allmask = (uint16_t)((1u << d.nsplit) - 1);
             for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++tiles_done) {
                 mbar_wait(in_ready, tiles_done & 1);
@@ -829,7 +840,13 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                     for (int t = 0; t < op.kchunks; ++t) {
                         uint32_t a_addr;
                         int rslot = -1;                                // >= 0: this chunk sits in a remote slot
-                        if (op.a_kind == 0) {
+                        int wslot = -1;                                // >= 0: (wide latent) lin_in chunk streamed through own slot wslot
+                        if (op.a_kind == 0 && d.wide && t > 0) {
+                            wslot = (int)(wfill % (uint32_t)d.OWN);
+                            a_addr = sbase + L.a + wslot * CHUNK;
+                            mbar_wait2(s_full(wslot), (wfill / (uint32_t)d.OWN) & 1, w_full(stage), phase);
+                            ++wfill;
+                        } else if (op.a_kind == 0) {
                             a_addr = sbase + L.feat + t * CHUNK;
                             mbar_wait(w_full(stage), phase);
                         } else if (op.a_kind == 1) {
@@ -849,6 +866,7 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                         const uint64_t da = umma_desc(a_addr), db = umma_desc(sbase + L.ring + stage * d.stage_bytes);
                         umma_f16_x4_u(dcol, da, db, idesc, (op.first_overwrites && t == 0) ? 0u : 1u);
                         umma_commit_u(w_empty(stage));            // frees the ring stage when these MMAs retire
+                        if (wslot >= 0) umma_commit_u(s_empty(wslot));     // (wide latent) the staging warp may refill the slot
                         // MMAs that read a remote slot: tell the PEER it may push into it again
                         if (rslot >= 0) umma_commit_mc_u(rfree(rslot), (uint16_t)(1u << peer));
                         if (++stage == d.nstage) { stage = 0; phase ^= 1; }
@@ -859,6 +877,8 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
                     // overwrite the code tile and the feature buffer with the next tile's operands
                     if (d.early && op.mat == M_LIN_Z && op.blk == d.nb - 1) umma_commit_u(in_free);
                     if (d.early && o == 0) umma_commit_u(feat_free);
+                    // (wide latent) lin_out was the last reader of the own activation slots: the next tile's lin_in chunks may land
+                    if (d.wide && o == nops - 1) umma_commit_u(a_free);
                     if (op.group_end) {
                         // (early staging) this tile's first group may complete before the PEER has finished the previous
                         // tile: its arrival must not count for the previous tile's last phase of acc_ready
@@ -877,7 +897,35 @@ __global__ void __launch_bounds__(STG ? NTHREADS + 128 : NTHREADS, 1) decoder_tc
         // for a prologue between tiles.  Lane l stages rows l, l+32, l+64, l+96.
         if (d.early) {
             const int rr0 = STG ? warp - (EPI_WARP0 + 4 * EPI_GROUPS) : 0, rr1 = STG ? rr0 + 1 : BM / 32;
-            uint32_t it = 0, ovf = 0;
+            uint32_t it = 0, ovf = 0, wfill = 0;
+            if (d.wide) {
+                // wide latent (operand image only): chunk 0 goes into the feature buffer early, the code tile follows, and chunks
+                // 1.. are streamed through the tile's own activation slots once the previous tile's lin_out has retired
+                for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++it) {
+                    const unsigned char* img = p.feat_img + (long long)tile * d.KF * CHUNK;
+                    if (it > 0) mbar_wait(feat_free, (it - 1) & 1);
+                    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+                                 "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}" ::"r"(
+                                     sbase + L.feat),
+                                 "l"(img), "r"((uint32_t)CHUNK), "r"(in_ready)
+                                 : "memory");
+                    if (it > 0) mbar_wait(in_free, (it - 1) & 1);
+                    for (int rr = rr0; rr < rr1; ++rr) {
+                        const int row = rr * 32 + lane;
+                        stage_inputs<BF16>(p, sm, L, (int)half, row, (long long)tile * BM + row, 0, 1, 1, ovf);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_expect_tx(in_ready, (uint32_t)CHUNK);
+                    if (it > 0) mbar_wait(a_free, (it - 1) & 1);
+                    for (int c = 1; c < d.KF; ++c, ++wfill) {
+                        const int j = (int)(wfill % (uint32_t)d.OWN);
+                        const uint32_t use = wfill / (uint32_t)d.OWN;
+                        if (use > 0) mbar_wait(s_empty(j), (use - 1) & 1);
+                        bulk_g2s_u(sbase + L.a + j * CHUNK, img + (long long)c * CHUNK, (uint32_t)CHUNK, s_full(j));
+                    }
+                }
+            } else
             for (int tile = cluster_id; tile < p.n_tiles; tile += p.n_clusters, ++it) {
                 // features first (the slow part: gathers): their buffer is free as soon as the previous tile's lin_in has
                 // retired, almost a whole tile before they are needed; the code tile only after its last lin_z
@@ -1156,12 +1204,18 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
     d.KH = d.Hd / 64;
     d.NOUT = d.two ? (d.d_out + 31) / 32 * 32 : (d.d_out + 15) / 16 * 16;     // each CTA of a pair holds NOUT/2 rows
     d.NOUTC = d.two ? d.NOUT / 2 : d.NOUT;
-    if (d.KZ > 4 || d.NOUT > 256 || d.KF > 8) {
+    if (d.KZ > 4 || d.NOUT > 256 || d.KF > 64) {
         set_error("%s: d_code %d / d_out %d / d_feat %d too large for the tcgen05 path", who, d.d_code, d.d_out, d.d_feat);
         return GNB_E_UNSUPPORTED;
     }
+    d.wide = d.KF > 8 ? 1 : 0;
+    d.KFB = d.wide ? 1 : d.KF;
+    if (d.wide && d.two) {
+        set_error("%s: d_feat %d (more than 8 k-chunks) needs the default kernel (GNB_TC_TWO_CTA off)", who, d.d_feat);
+        return GNB_E_UNSUPPORTED;
+    }
     d.OWN = d.HN / 64;
-    d.AOWN = d.KF > d.OWN ? d.KF : d.OWN;
+    d.AOWN = (!d.wide && d.KF > d.OWN) ? d.KF : d.OWN;
     d.RS = d.nsplit > 1 ? (d.OWN >= 2 ? 2 : 1) : 0;
     d.ACH = d.AOWN + d.RS;
     // ring stage: cta_group::2 = two k-chunks of WN <= 128 rows; otherwise one k-chunk of the widest op
@@ -1179,7 +1233,11 @@ static int make_dims(const GnbDecoderWeights* w, Dims& d, const char* who) {
         e.AOWN = e.OWN, e.ACH = e.AOWN + e.RS;             // the lin_in operand no longer borrows the own chunk slots
         e.nstage = MAX_STAGES;
         while (e.nstage >= 2 && smem_layout(e).total + 1024 > 227 * 1024) --e.nstage;
-        if (e.nstage >= d.nstage || e.nstage >= 4) d = e;
+        if (e.nstage >= d.nstage || e.nstage >= 4 || d.wide) d = e;
+    }
+    if (d.wide && (!d.early || opt(OPT_TC_NO_EARLY))) {
+        set_error("%s: d_feat %d (more than 8 k-chunks) needs the early-staging kernel (GNB_TC_NO_EARLY off)", who, d.d_feat);
+        return GNB_E_UNSUPPORTED;
     }
     if (d.nstage < 2) { set_error("%s: tile does not fit in shared memory", who); return GNB_E_UNSUPPORTED; }
     long long bytes = 0;
@@ -1296,6 +1354,11 @@ static int launch_tc(const GnbDecoderWeights* w, const void* packed, TcKP& kp, v
         }
     }
     const Dims& d = kp.d;
+    if (d.wide && !kp.feat_img) {
+        set_error("gnb_decode_tc: d_feat %d (more than 8 k-chunks of lin_in) is served through the operand image only: "
+                  "gnb_features_to_image / the sampler's image output + gnb_decode_image_tc", d.d_feat);
+        return GNB_E_UNSUPPORTED;
+    }
     if (kp.feat_img && (!d.early || d.two)) {
         set_error("gnb_decode_image_tc: needs the default kernel (early staging, single-CTA issue)");
         return GNB_E_UNSUPPORTED;

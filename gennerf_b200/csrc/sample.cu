@@ -504,6 +504,30 @@ __global__ void __launch_bounds__(256) sample_bwd2_kernel(const __grid_constant_
     }
 }
 
+// fp32 feature rows -> the tcgen05 decoder's 16-bit lin_in operand image (the layout store_feat4 writes): every column of
+// every tile is written, columns >= d_feat and the rows past n of the last tile as zeros (they meet zero weights, but
+// 0 * NaN of an uninitialised buffer would still poison the accumulator).
+__global__ void __launch_bounds__(256) features_to_image_kernel(const __grid_constant__ SampleKP p, const float* __restrict__ feat, long long n,
+                                                                int d_feat, long long stride, int vec) {
+    const int groups = p.img_kf * 16;                        // 4-column groups per row
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long q = idx / groups;
+    const int c = (int)(idx % groups) * 4;
+    if (q >= ((n + 127) >> 7 << 7)) return;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < n && c < d_feat) {
+        const float* src = feat + q * stride + c;
+        if (vec && c + 3 < d_feat) r = ldg4(src);
+        else {
+            r.x = __ldg(src);
+            if (c + 1 < d_feat) r.y = __ldg(src + 1);
+            if (c + 2 < d_feat) r.z = __ldg(src + 2);
+            if (c + 3 < d_feat) r.w = __ldg(src + 3);
+        }
+    }
+    store_feat4(p, q, c, r);
+}
+
 int fill_sample_kp(const GnbSampleParams* s, SampleKP& kp) {
     GNB_CHECK_ARG(s, "sample: null params");
     GNB_CHECK_ARG(s->batch >= 1 && s->n_query >= 0 && (s->xyz || s->n_query == 0), "sample: bad batch / n_query / xyz");
@@ -644,6 +668,23 @@ extern "C" int gnb_sample_features_bwd2(const GnbSampleParams* s, const float* g
     while (G < lanes && G < 32) G <<= 1;
     long long threads = kp.s.total * G;
     sample_bwd2_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kp, G);
+    GNB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int gnb_features_to_image(const float* feat, int64_t n_rows, int d_feat, int64_t feat_stride, int image_kchunks, int image_dtype,
+                                     void* image, int32_t* status, void* stream) {
+    GNB_CHECK_ARG(n_rows >= 0 && d_feat >= 1 && feat_stride >= d_feat && image_kchunks >= 1 && 64 * image_kchunks >= d_feat,
+                  "gnb_features_to_image: bad shape (64 * image_kchunks >= d_feat, feat_stride >= d_feat)");
+    if (n_rows == 0) return 0;
+    GNB_CHECK_ARG(feat && image && (reinterpret_cast<uintptr_t>(image) & 15) == 0, "gnb_features_to_image: null / unaligned pointer");
+    GNB_CHECK_ARG(image_dtype == GNB_TC_FP16 || image_dtype == GNB_TC_BF16, "gnb_features_to_image: bad image_dtype");
+    SampleKP kp = {};
+    kp.img = (unsigned char*)image, kp.img_kf = image_kchunks, kp.img_bf16 = image_dtype == GNB_TC_BF16, kp.img_status = status;
+    const int vec = (feat_stride % 4 == 0) && aligned16(feat);
+    const long long rows = (n_rows + 127) / 128 * 128;
+    const long long threads = rows * image_kchunks * 16;
+    features_to_image_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kp, feat, n_rows, d_feat, feat_stride, vec);
     GNB_LAUNCH_CHECK();
     return 0;
 }

@@ -385,6 +385,12 @@ class DecoderWeights:
             self.status.zero_()
         return hit
 
+    @property
+    def wide(self):
+        """More than 8 k-chunks of lin_in (d_feat > 512, e.g. the reference's default latent 512 + 32): the tcgen05 decoder
+        takes such features through the operand image only (gnb_features_to_image / the sampler's image output)."""
+        return self.w.d_feat > 512
+
     def tc_image(self, dtype):
         if self.packed is None or getattr(self, "packed_dtype", None) != dtype:
             self.pack(dtype)
@@ -408,6 +414,21 @@ def decode(weights, xyz, feat, precision="fp32"):
         if precision == "fp32":
             check(lib().gnb_decode_fp32(C.byref(weights.w), xyz2.data_ptr(), feat2.data_ptr(), n, out.data_ptr(),
                                         tsdf.data_ptr(), _stream()), "gnb_decode_fp32")
+        elif precision in ("fp16", "bf16") and weights.wide:
+            # wide latent: fp32 rows -> 16-bit operand image (chunks of <= 512 MB) -> decoder streaming the image's k-chunks
+            packed = weights.tc_image(precision)
+            kf = lib().gnb_decoder_image_kchunks(C.byref(weights.w))
+            if kf <= 0:
+                raise RuntimeError("gennerf_b200: no tcgen05 path for these decoder dimensions / options: " + lib().gnb_last_error().decode())
+            step = _image_rows(kf)
+            image = torch.empty(((min(step, n) + 127) // 128) * kf * 16384, device=xyz.device, dtype=torch.uint8)
+            dt = _lib.TC_BF16 if precision == "bf16" else _lib.TC_FP16
+            for r0 in range(0, n, step):
+                r1 = min(r0 + step, n)
+                check(lib().gnb_features_to_image(feat2[r0:r1].data_ptr(), r1 - r0, feat2.shape[1], feat2.stride(0), kf, dt,
+                                                  image.data_ptr(), weights.status.data_ptr(), _stream()), "gnb_features_to_image")
+                check(lib().gnb_decode_image_tc(C.byref(weights.w), packed.data_ptr(), xyz2[r0:r1].data_ptr(), image.data_ptr(), r1 - r0,
+                                                  out[r0:r1].data_ptr(), tsdf[r0:r1].data_ptr(), _stream()), "gnb_decode_image_tc")
         elif precision in ("fp16", "bf16"):
             packed = weights.tc_image(precision)
             check(lib().gnb_decode_tc(C.byref(weights.w), packed.data_ptr(), xyz2.data_ptr(), feat2.data_ptr(), n,
@@ -424,6 +445,9 @@ def decode_save(weights, xyz, feat, precision="fp16"):
     codes when the weights were built with use_code=2], feat (n,d_feat).  Returns out (n,d_out), tsdf (n,1),
     activations (2*n_blocks+1, n, d_hidden) fp16 / bf16."""
     _need_cuda(xyz, feat)
+    if weights.wide:
+        raise RuntimeError("gennerf_b200: the activation-saving decoder (train_precision='fp16') takes latent codes up to 512 wide; "
+                           "train this model with train_precision='fp32'")
     xyz2, feat2 = _f32(xyz).contiguous(), _f32(feat).contiguous()
     n = xyz2.shape[0]
     out = torch.empty((n, weights.w.d_out), device=xyz.device, dtype=torch.float32)
@@ -438,6 +462,11 @@ def decode_save(weights, xyz, feat, precision="fp16"):
 
 
 IMAGE_CHUNK = 1 << 22          # queries per sampler + decoder launch pair of query_image (512 MB of operand image per 64 features)
+
+
+def _image_rows(kf):
+    """Rows per operand-image chunk: IMAGE_CHUNK for up to 64 features, fewer for wider latents (the image stays ~512 MB)."""
+    return max(128, (IMAGE_CHUNK // max(1, int(kf))) // 128 * 128)
 
 
 @_nvtx
@@ -470,7 +499,7 @@ def query_image(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
     feat = torch.empty((B, Q, d_feat), device=dev, dtype=torch.float32) if want_feat else None
     if B * Q == 0:
         return out, tsdf, feat
-    step = int(chunk or IMAGE_CHUNK)
+    step = int(chunk or _image_rows(kf))
     rows = min(step, Q)
     image = torch.zeros(((rows + 127) // 128) * kf * 16384, device=dev, dtype=torch.uint8)   # zeros: operand columns past d_feat
     with torch.cuda.device(dev):
@@ -513,8 +542,8 @@ def query_fused(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
     presort (fused kernel): "auto" first counting-sorts the queries by voxel brick (same bits, outputs in the caller's order)
     when there is at least one query per three voxels -- the sampling prologue then reads the volume brick by brick; True
     forces it (raises when there is no channels-last volume to sort by), False never."""
-    if mode == "image" or (mode == "auto" and presort == "auto" and xyz.shape[0] * xyz.shape[1] >= (1 << 16)
-                           and not _lib.get_option("GNB_QUERY_FUSED")):
+    if mode == "image" or (weights.wide and mode != "fused") or (mode == "auto" and presort == "auto" and xyz.shape[0] * xyz.shape[1] >= (1 << 16)
+                                           and not _lib.get_option("GNB_QUERY_FUSED")):
         return query_image(weights, xyz, volume, planes, voxel_size=voxel_size, origin=origin, padding=padding,
                            want_feat=want_feat, precision=precision)
     s, keep, B, Q, Cp, Cv = _fill_sample_params(xyz, volume, planes, voxel_size, origin, padding)
@@ -560,7 +589,7 @@ def query_grid_fused(weights, grid_dim, axes, volume=None, planes=None, *, voxel
     out = torch.empty((B, Q, weights.w.d_out), device=dev, dtype=torch.float32) if want_out else None
     tsdf = torch.empty((B, nx, ny, nz), device=dev, dtype=torch.float32)
     packed = weights.tc_image(precision)
-    if (mode == "image" or (mode == "auto" and B * Q >= (1 << 16) and not _lib.get_option("GNB_QUERY_FUSED"))) and \
+    if (mode == "image" or weights.wide or (mode == "auto" and B * Q >= (1 << 16) and not _lib.get_option("GNB_QUERY_FUSED"))) and \
             lib().gnb_decoder_image_kchunks(C.byref(weights.w)) > 0:
         # many grid points: the two-kernel query (query_image) is faster than the fused kernel's in-kernel sampling.  The
         # points of a chunk are generated on the device from the axes (same values, so the same bits) and never exist

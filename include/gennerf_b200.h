@@ -43,7 +43,7 @@ const char* gnb_last_error(void);
 int gnb_struct_size(int which);
 /* Tuning / debugging switches (GNB_TC_TWO_CTA, GNB_TC_NO_EARLY, GNB_DEBUG_MAX_CLUSTERS, GNB_DEBUG_PRINT, GNB_LIFT_NVW,
  * GNB_SCATTER_SCALAR, GNB_FPS_SINGLE_CTA, GNB_FPS_CLUSTER, GNB_SAMPLE_GENERIC, GNB_BIN_UNIT, GNB_BIN_ROWCOPY,
- * GNB_SCATTER_TILED, GNB_BIN_PRESORTED, GNB_TC_NO_STG, GNB_TC_PAIR, GNB_DEBUG_NO_WCOPY,
+ * GNB_SCATTER_TILED, GNB_BIN_PRESORTED, GNB_TC_NO_STG, GNB_TC_PAIR, GNB_DEBUG_NO_WCOPY, GNB_FPS_GRID,
  * GNB_QUERY_FUSED [read by the Python host: always the single fused query kernel]).  Every option takes its default from the environment variable of the same name,
  * read ONCE per process (never on a hot-path call); these two calls read / change it afterwards.  None of them changes
  * results beyond floating-point summation order. */
@@ -371,6 +371,14 @@ int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, void* stream);
 int gnb_decoder_image_kchunks(const GnbDecoderWeights* w);   /* 0: these weights / options do not take an image */
 int gnb_decode_image_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz, const void* image,
                         int64_t n_rows, float* out, float* tsdf, void* stream);
+/* Wide latent codes (d_feat > 512, i.e. more than 8 k-chunks of lin_in -- the reference's default Hydra config has
+ * encoder_latent = 512 + 32, configs/model/gen_nerf.yaml:43,56 and src/models/model.py:35-44): the tensor-core decoder takes
+ * the features through the operand image ONLY and streams its chunks through shared memory; gnb_decode_tc / gnb_query_fused_tc
+ * return GNB_E_UNSUPPORTED for such weights.  gnb_features_to_image converts fp32 feature rows (n_rows, feat_stride) into that
+ * image (all image_kchunks * 64 columns of every 128-row tile are written, padding as zeros; image bytes =
+ * ceil(n_rows / 128) * image_kchunks * 16384); status as GnbSampleParams.image_status. */
+int gnb_features_to_image(const float* feat, int64_t n_rows, int d_feat, int64_t feat_stride, int image_kchunks,
+                          int image_dtype, void* image, int32_t* status, void* stream);
 /* gnb_decode_tc that also stores the 16-bit activations every layer consumed -- what the backward pass of a training step
  * needs (ReLU masks for dgrad, left operands for wgrad): activations is [2*n_blocks + 1][n_rows][d_hidden] in w->tc_dtype;
  * slab 2i = relu(x_i + alpha*lin_z_i(code)) (input of blocks.i.fc_0), slab 2i+1 = relu(fc_0 output) (input of fc_1),

@@ -53,6 +53,9 @@ CASES = [  # d_hidden, num_freqs, d_feat, d_out, d_geo, n_rows
     (512, 2, 160, 64, 32, 777),            # C_lat = 128 + 32
     (384, 2, 32, 64, 32, 129),
     (512, 2, 32, 64, 32, 148 * 128 * 2 + 77),   # persistent loop: > 2 tiles per cluster, ragged tail
+    (512, 2, 544, 64, 32, 148 * 128 + 300),     # the reference's DEFAULT latent: spatial 512 + pointnet 32 (gen_nerf.yaml:43,56): lin_in streamed
+    (256, 6, 1056, 65, 64, 2000),               # spatial num_layers 5 (1024) + 32: 17 k-chunks through ONE-CTA clusters (4 own slots)
+    (64, 2, 576, 16, 8, 700),                   # one own slot: every streamed chunk waits for the previous one's MMAs
 ]
 
 
@@ -279,6 +282,40 @@ def test_query_image_is_bit_identical_to_fused(B, Q, use_vol, use_pl, Cv, Cp, dt
     if B * Q >= (1 << 16):      # what mode="auto" picks for this many queries
         d = ops.query_fused(dw, xyz, want_feat=False, **kw)
         assert torch.equal(d[1], a[1])
+
+
+@pytest.mark.parametrize("B,Q,Cv,Cp", [(1, 3000, 512, 32), (2, 70000, 512, 32), (1, 1500, 576, 0)])
+def test_wide_latent_query(B, Q, Cv, Cp):
+    """The reference's default Hydra config has encoder_latent = 512 + 32 (configs/model/gen_nerf.yaml:43,56, model.py:35-44):
+    more lin_in k-chunks than fit shared memory next to the layers' operands.  Every query entry point then goes through the
+    operand image, whose chunks the decoder streams; sampler-written image == image converted from the sampler's fp32 rows
+    (bit for bit), and the TSDF meets the 1e-2 bar against the fp32 oracle."""
+    from gennerf_b200 import ops
+    g = S.gen(59)
+    dims, R = (12, 10, 6), 16
+    xyz = S.query_points(Q, dims, VS, g, B=B)
+    vol = torch.randn(B, *dims, Cv, generator=g) * 0.3
+    planes = {k: torch.randn(B, Cp, R, R, generator=g) * 0.3 for k in O.PLANES} if Cp else None
+    w, hw, hb = S.decoder_weights(g, Cv + Cp, 15, 512, 5, 64, 32)
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=DEV)
+    assert dw.wide
+    vd = vol.to(DEV).permute(0, 4, 1, 2, 3)
+    pd = {k: v.to(DEV).contiguous(memory_format=torch.channels_last) for k, v in planes.items()} if planes else None
+    kw = dict(volume=vd, planes=pd, voxel_size=VS, origin=ORIGIN, padding=0.1)
+    out, tsdf, feat = ops.query_fused(dw, xyz.to(DEV), want_feat=True, **kw)             # -> query_image
+    feat2 = ops.sample_features(xyz.to(DEV), **kw)
+    assert torch.equal(feat, feat2)
+    out2, tsdf2 = ops.decode(dw, xyz.to(DEV), feat2, "fp16")                              # -> gnb_features_to_image + decoder
+    assert torch.equal(out, out2) and torch.equal(tsdf, tsdf2)
+    assert not dw.overflowed()
+    with pytest.raises(RuntimeError):
+        ops.query_fused(dw, xyz.to(DEV), mode="fused", presort=False, **kw)               # the single fused kernel cannot stream
+    m = min(Q, 1500)
+    ref = O.gennerf_forward(xyz[:, :m], w, hw, hb, volume=vol.permute(0, 4, 1, 2, 3), valid=torch.ones(B, 1, *dims, dtype=torch.bool),
+                            planes=planes, voxel_size=VS, padding=0.1, num_freqs=2, freq_factor=0.5)
+    assert (tsdf[:, :m].cpu() - ref["tsdf"]).abs().max().item() <= TSDF_BAR
+    o32, t32 = ops.decode(dw, xyz.to(DEV)[:, :m], feat2[:, :m], "fp32")
+    assert ((o32.cpu() - torch.cat((ref["feat_geo"], ref["feat_sem"]), -1)).abs().max() / ref["feat_geo"].abs().max()).item() <= 2e-5
 
 
 def test_query_image_reports_fp16_saturation():

@@ -21,11 +21,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     dev = "cuda"
     Hd = int(os.environ.get("TD_HIDDEN", "512"))
     n = int(os.environ.get("TD_ROWS", str(1 << 20)))
+    DF = int(os.environ.get("TD_FEAT", "32"))        # latent width (544 = the reference's default yaml: streamed lin_in)
     g = S.gen(1)
-    w, hw, hb = S.decoder_weights(g, 32, 15, Hd, 5, 64, 32)
+    w, hw, hb = S.decoder_weights(g, DF, 15, Hd, 5, 64, 32)
     dw = ops.DecoderWeights(w, hw, hb, n_blocks=5, d_geo=32, device=dev)
     xyz = S.query_points(n, (96, 96, 48), 0.04, g)[0].to(dev)
-    feat = torch.randn(n, 32, generator=g).to(dev)
+    feat = torch.randn(n, DF, generator=g).to(dev)
     fused = os.environ.get("TD_FUSED") == "1"       # sample the features from a volume inside the kernel (the bench's path)
     if fused:
         vd = (96, 96, 48)
@@ -44,7 +45,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         a.record(); run(); b.record(); b.synchronize()
         ms.append(a.elapsed_time(b))
     m = sorted(ms)[len(ms) // 2]
-    flops = 2.0 * (32 * Hd + 5 * (15 * Hd + 2 * Hd * Hd) + Hd * 64 + 32) * n
+    flops = 2.0 * (DF * Hd + 5 * (15 * Hd + 2 * Hd * Hd) + Hd * 64 + 32) * n
     ck = os.environ.get("TD_CHECK")
     diff = ""
     if ck and os.path.exists(ck):
@@ -52,7 +53,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         diff = f"  max|tsdf - default| {(tsdf.cpu() - ref['tsdf']).abs().max().item():.2e}  max|out - default| {(out.cpu() - ref['out']).abs().max().item():.2e}"
     elif ck:
         torch.save({"tsdf": tsdf.cpu(), "out": out.cpu()}, ck)
-    print(f"  Hd={Hd} rows={n}: {m:.3f} ms  {flops / m / 1e9:.1f} TFLOP/s  ({flops / m / 1e9 / 1389.9:.3f} of sustained bf16 peak){diff}", flush=True)
+    print(f"  Hd={Hd} d_feat={DF} rows={n}: {m:.3f} ms  {flops / m / 1e9:.1f} TFLOP/s  ({flops / m / 1e9 / 1389.9:.3f} of sustained bf16 peak){diff}", flush=True)
 else:
     names = sys.argv[1:] or list(VARIANTS)
     ck = "/tmp/td_check.pt"
