@@ -118,6 +118,50 @@ def test_unet_style_nchw_planes_run_fused(SD):
     assert (out["tsdf"] - ref["tsdf"]).abs().max().item() <= 3e-2
 
 
+def test_default_yaml_model_runs_on_the_tensor_cores(SD):
+    """configs/model/gen_nerf.yaml unmodified: encoder_latent = 512 (spatial, num_layers 4) + 32 (pointnet) = 544
+    (model.py:35-44) -- nine k-chunks of lin_in, more than shared memory holds next to the layers' operands.  The drop-in's
+    default precision (fp16, tcgen05) must serve it: forward and predict_tsdf go through the operand image whose chunks the
+    decoder streams.  TSDF within 1e-2 of the fp32 oracle on the same randomly initialised weights."""
+    from gennerf_b200.dropin import GenNerf
+    cfg = to_attr(SD["default"]["cfg"])
+    torch.manual_seed(7)
+    model = GenNerf(cfg, unet=nn.Identity()).eval().to(DEV)
+    assert model.mlp.lin_in.weight.shape[1] == 544
+    with torch.no_grad():
+        model.head_geo.fc.weight.mul_(0.3)                  # default init saturates tanh: keep the TSDF in its sensitive range
+    g = S.gen(71)
+    dims, Cp = (16, 12, 8), cfg.encoder.pointnet.c_dim
+    R = 16
+    vol = torch.randn(1, 512, *dims, generator=g) * 0.3
+    valid = torch.ones(1, 1, *dims, dtype=torch.bool)
+    planes = {k: torch.randn(1, Cp, R, R, generator=g) * 0.3 for k in PLANES}
+    model.volume = vol.to(DEV).contiguous(memory_format=torch.channels_last_3d)
+    model.valid = valid.to(DEV)
+    model.c_plane = {k: v.to(DEV) for k, v in planes.items()}
+    xyz = S.query_points(4000, dims, cfg.voxel_size, g)
+    with torch.no_grad():
+        out = model(xyz.to(DEV))
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    w = {k[4:]: v for k, v in sd.items() if k.startswith("mlp.")}
+    ref = O.gennerf_forward(xyz, w, sd["head_geo.fc.weight"], sd["head_geo.fc.bias"], volume=vol, valid=valid, planes=planes,
+                            voxel_size=cfg.voxel_size, padding=cfg.encoder.pointnet.padding, num_freqs=cfg.code.num_freqs,
+                            freq_factor=cfg.code.freq_factor, include_input=cfg.code.include_input, use_code=cfg.use_code,
+                            n_blocks=cfg.mlp.n_blocks, d_out_geo=cfg.mlp.d_out_geo, d_out_sem=cfg.mlp.d_out_sem)
+    assert rel(out["feat"], ref["feat"]) <= 1e-5
+    assert ref["tsdf"].abs().max() < 0.999 and ref["tsdf"].std() > 0.05
+    assert (out["tsdf"].cpu() - ref["tsdf"]).abs().max().item() <= 1e-2
+    assert rel(out["feat_geo"], ref["feat_geo"]) <= 5e-3
+    assert not model.fp16_overflowed()
+    t = model.predict_tsdf(9, 7, 5)
+    grid = O.get_grid_coordinates(9, 7, 5, [cfg.voxel_size * d for d in cfg.voxel_dim_test]).reshape(1, -1, 3)
+    rg = O.gennerf_forward(grid, w, sd["head_geo.fc.weight"], sd["head_geo.fc.bias"], volume=vol, valid=valid, planes=planes,
+                           voxel_size=cfg.voxel_size, padding=cfg.encoder.pointnet.padding, num_freqs=cfg.code.num_freqs,
+                           freq_factor=cfg.code.freq_factor, include_input=cfg.code.include_input, use_code=cfg.use_code,
+                           n_blocks=cfg.mlp.n_blocks, d_out_geo=cfg.mlp.d_out_geo, d_out_sem=cfg.mlp.d_out_sem)
+    assert (t.cpu().reshape(-1) - rg["tsdf"].reshape(-1)).abs().max().item() <= 1e-2
+
+
 def _eikonal_loss(tsdf, xyz):
     """reference utils.py:636-649 (calculate_grad, create_graph=True) + model.py:385-400 (|grad| -> 1)."""
     (grad,) = torch.autograd.grad(tsdf, xyz, grad_outputs=torch.ones_like(tsdf), create_graph=True, retain_graph=True)
