@@ -261,6 +261,40 @@ def hbm_side_kernels(ops, dev, pk):
         c = torch.randn(1, N, C_PLANE, generator=g).to(dev)
         byt = N * (12 + 4 * C_PLANE) + 3 * R_PLANE * R_PLANE * (4 * C_PLANE + 4)
         out[f"scatter_mean_planes_N{N}"] = roof(byt, timed(lambda: ops.scatter_mean_planes(p, c, R_PLANE, 0.1, "atomic")))
+    del vol, feats, feats_cl
+    # ... and the lift at the default yaml's 512 spatial channels (4 channel chunks of 128 per voxel brick), config-2 shape
+    g = S.gen(1006)
+    f512 = [torch.randn(1, wl["H"], wl["W"], 512, generator=g).to(dev).permute(0, 3, 1, 2) for _ in range(wl["T"])]
+    lb512 = lift_bytes(wl["T"], 512, wl["H"], wl["W"], V, int(cnt.sum().item()))
+    out["lift_cfg2_512_channels_last"] = dict(roof(lb512, timed(lambda: ops.backproject_frames(wl["voxel_dim"], VS, origin, P, f512))),
+                                              includes="lift kernel only, C = 512", voxel_frames=V * wl["T"])
+    del f512
+    # The reference's DEFAULT Hydra config (configs/model/gen_nerf.yaml:43,56): 512 spatial + 32 plane channels = latent 544,
+    # nine lin_in k-chunks streamed from the operand image.  1 Mi queries against a 512-channel volume on the config-2 grid.
+    g = S.gen(1004)
+    Cw = 512
+    volw = (torch.randn(1, *wl["voxel_dim"], Cw, generator=g) * 0.2).to(dev).permute(0, 4, 1, 2, 3)
+    plw = {k: (torch.randn(1, C_PLANE, R_PLANE, R_PLANE, generator=g) * 0.2).to(dev).contiguous(memory_format=torch.channels_last)
+           for k in ops.PLANES}
+    ww, hww, hbw = S.decoder_weights(S.gen(1005), Cw + C_PLANE, D_CODE, MLP["d_hidden"], MLP["n_blocks"], MLP["d_out"], MLP["d_geo"])
+    dww = ops.DecoderWeights(ww, hww, hbw, n_blocks=MLP["n_blocks"], d_geo=MLP["d_geo"], num_freqs=MLP["num_freqs"], freq_factor=MLP["freq_factor"], device=dev)
+    run = lambda: ops.query_fused(dww, xyz, volume=volw, planes=plw, voxel_size=VS, origin=origin, padding=0.1, want_feat=False)    # noqa: E731
+    run()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); run(); b.record(); b.synchronize()
+        ms.append(a.elapsed_time(b))
+    m = sorted(ms)[len(ms) // 2]
+    Hd = MLP["d_hidden"]
+    fl = 2.0 * ((Cw + C_PLANE) * Hd + MLP["n_blocks"] * (D_CODE * Hd + 2 * Hd * Hd) + Hd * MLP["d_out"] + MLP["d_geo"]) * Q
+    out["query_default_yaml_latent_544"] = {
+        "ms": m, "queries": Q, "points_per_s": Q / (m * 1e-3), "includes": "sampler (512-channel volume + 32-channel planes) writing the 9-chunk "
+        "operand image + tcgen05 decoder streaming it, 3 chunks of queries", "fp16_saturated": bool(dww.overflowed()),
+        "roofline": {"bound": "tensor", "achieved": fl / (m * 1e-3) / 1e12, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                     "frac": fl / (m * 1e-3) / 1e12 / pk["bf16_burst"]}}
     return out
 
 

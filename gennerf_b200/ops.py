@@ -233,7 +233,10 @@ def sample_features(xyz, volume=None, planes=None, *, voxel_size=0.04, origin=No
     with torch.cuda.device(out.device):
         use = False
         if binned and volume is not None and Q > 0:
-            dense = binned is True or (B * Q >= (1 << 16) and 3 * Q >= volume.shape[2] * volume.shape[3] * volume.shape[4])
+            # (above 256 channels a brick's tile arrives as row copies instead of one tensor-map copy and the staged kernel, which
+            #  already runs at the bandwidth of its random 8-line gathers, is faster: C = 512, 1 Mi queries 2.5 vs 3.5 ms)
+            dense = binned is True or (B * Q >= (1 << 16) and 3 * Q >= volume.shape[2] * volume.shape[3] * volume.shape[4]
+                                       and volume.shape[1] <= 256)
             nbytes = lib().gnb_sample_binned_scratch_bytes(C.byref(s)) if dense else 0
             if binned is True and nbytes == 0:
                 raise RuntimeError("gennerf_b200: the binned sampler needs a channels-last fp32 volume with C % 4 == 0")
@@ -465,8 +468,13 @@ IMAGE_CHUNK = 1 << 22          # queries per sampler + decoder launch pair of qu
 
 
 def _image_rows(kf):
-    """Rows per operand-image chunk: IMAGE_CHUNK for up to 64 features, fewer for wider latents (the image stays ~512 MB)."""
-    return max(128, (IMAGE_CHUNK // max(1, int(kf))) // 128 * 128)
+    """Rows per operand-image chunk: IMAGE_CHUNK (a 512 MB image) for up to 64 features; for wider latents as many rows as a
+    2 GB image holds -- the brick-binned sampler stages a tile per brick, so the more queries of a brick are in one chunk the
+    fewer bytes it moves per query, and fewer launches either way."""
+    kf = max(1, int(kf))
+    if kf <= 1:
+        return IMAGE_CHUNK
+    return max(128, min(IMAGE_CHUNK, ((2 << 30) // (kf * 128 * 128)) * 128))
 
 
 @_nvtx
@@ -518,7 +526,7 @@ def query_image(weights, xyz, volume=None, planes=None, *, voxel_size=0.04, orig
                 s.image_dtype = _lib.TC_BF16 if precision == "bf16" else _lib.TC_FP16
                 s.image_status = weights.status.data_ptr()
                 nbytes = 0
-                if vol_b is not None and n >= (1 << 16) and 3 * n >= vol_b.shape[2] * vol_b.shape[3] * vol_b.shape[4]:
+                if vol_b is not None and n >= (1 << 16) and 3 * n >= vol_b.shape[2] * vol_b.shape[3] * vol_b.shape[4] and Cv <= 256:
                     nbytes = lib().gnb_sample_binned_scratch_bytes(C.byref(s))
                 if nbytes > 0:
                     scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)

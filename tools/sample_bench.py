@@ -16,6 +16,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     if mode != "generic":
         cases.append(((256, 256, 96), 32, 0, 0, 1 << 24))
         cases.append(((256, 256, 96), 32, 0, 0, 1 << 21))
+    if os.environ.get("SAMPLE_WIDE"):        # the reference's default yaml: 512 spatial channels
+        cases = [((96, 96, 48), 512, 0, 0, 1 << 20), ((96, 96, 48), 512, 32, 256, 1 << 20), ((96, 96, 48), 256, 0, 0, 1 << 20)]
     cases = cases[:int(os.environ.get('SAMPLE_CASES', len(cases)))]
     for dims, C, Cp, R, Q in cases:
         vol = torch.randn(1, *dims, C, device=dev).permute(0, 4, 1, 2, 3)
