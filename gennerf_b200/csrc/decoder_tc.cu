@@ -98,6 +98,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // hardware between polls, so waiting roles do not take issue slots from the warps that have work.
 // Before trapping, the first thread to time out leaves {1, block, thread, source line, barrier, parity} in the
 // host-mapped report buffer (gnb_debug_hang_report), which stays readable after the context has died.
+// Suspend-time hint of mbarrier.try_wait (ns; 0 = none, the default).  Without a hint a waiting warp comes back from the hardware
+// wait every ~80 cycles and re-issues its poll loop: ncu counts 21 M polls x 10 instructions of the 8 epilogue warps on acc_ready
+// alone, a quarter of all instructions the kernel executes.  With CUTLASS's 0x989680 the polls all but vanish -- and the kernel
+// gets SLOWER (1 Mi rows 6.52 -> 6.66 ms, the bench's query phase 114.9 -> 116.3 ms, A/B on one box): a suspended warp wakes up
+// later than a polling one notices the phase flip, and every layer waits on exactly those wake-ups.  Kept as a build switch.
+#ifndef GNB_TRYWAIT_HINT
+#define GNB_TRYWAIT_HINT 0
+#endif
 __device__ int* g_hang_report = nullptr;
 __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity, int line) {
     int* r = g_hang_report;
@@ -117,10 +125,14 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity, int li
     for (uint32_t spin = 0; !done; ++spin) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
+#if GNB_TRYWAIT_HINT
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(GNB_TRYWAIT_HINT)
             : "memory");
         if (!done && spin > (1u << 22)) mbar_timeout(bar, parity, line);
     }
@@ -142,12 +154,17 @@ __device__ __forceinline__ void mbar_wait2_(uint32_t bar_a, uint32_t par_a, uint
     for (uint32_t spin = 0; !(da & db); ++spin) {
         asm volatile(
             "{\n\t.reg .pred p, q;\n\t"
+#if GNB_TRYWAIT_HINT
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3, %6;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5, %6;\n\t"
+#else
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+#endif
             "selp.u32 %0, 1, 0, p;\n\t"
             "selp.u32 %1, 1, 0, q;\n\t}"
             : "=r"(da), "=r"(db)
-            : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b)
+            : "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b), "r"(GNB_TRYWAIT_HINT)
             : "memory");
         if (!(da & db) && spin > (1u << 22)) mbar_timeout(da ? bar_b : bar_a, da ? par_b : par_a, line);
     }
