@@ -77,8 +77,9 @@ def test_sampler_backward(with_planes, with_volume):
             close(pd[k].grad, po[k].grad, 1e-4, f"grad plane {k}")
 
 
-@pytest.mark.parametrize("with_planes,with_volume", [(True, False), (False, True), (True, True)])
-def test_sampler_double_backward(with_planes, with_volume):
+@pytest.mark.parametrize("with_planes,with_volume,layout", [(True, False, "cl"), (False, True, "cl"), (True, True, "cl"),
+                                                            (True, True, "reference")])
+def test_sampler_double_backward(with_planes, with_volume, layout):
     """The eikonal / gradient losses (reference utils.py:636-649 `calculate_grad(create_graph=True)`, model.py:385-400)
     differentiate d tsdf / d xyz once more.  CUDA: sample_features -> sample_features_bwd -> gnb_sample_features_bwd2;
     checker: CPU autograd through the reference's grid_sample_2d (planes) and the written-out trilinear sum (volume)."""
@@ -107,8 +108,12 @@ def test_sampler_double_backward(with_planes, with_volume):
     lo.backward()
     # kernels
     xd = xyz.to(DEV).requires_grad_(True)
-    vd = vol.to(DEV).permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3).requires_grad_(True)
-    pd = {k: v.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for k, v in planes.items()}
+    if layout == "cl":
+        vd = vol.to(DEV).permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3).requires_grad_(True)
+        pd = {k: v.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True) for k, v in planes.items()}
+    else:               # the reference's own layouts (B,C,nx,ny,nz) / (B,C,R,R): strided scalar gathers and reductions
+        vd = vol.to(DEV).requires_grad_(True)
+        pd = {k: v.to(DEV).requires_grad_(True) for k, v in planes.items()}
     out = ag.sample_features(xd, volume=vd if with_volume else None, planes=pd if with_planes else None, voxel_size=VS,
                              origin=ORIGIN, padding=0.1)
     ld, gxd = loss_of(out, xd)

@@ -56,6 +56,7 @@ CASES = [  # d_hidden, num_freqs, d_feat, d_out, d_geo, n_rows
     (512, 2, 544, 64, 32, 148 * 128 + 300),     # the reference's DEFAULT latent: spatial 512 + pointnet 32 (gen_nerf.yaml:43,56): lin_in streamed
     (256, 6, 1056, 65, 64, 2000),               # spatial num_layers 5 (1024) + 32: 17 k-chunks through ONE-CTA clusters (4 own slots)
     (64, 2, 576, 16, 8, 700),                   # one own slot: every streamed chunk waits for the previous one's MMAs
+    (128, 2, 515, 16, 8, 300),                  # ragged last chunk (515 = 8 * 64 + 3): padded operand columns must be zeros
 ]
 
 
