@@ -69,6 +69,20 @@ class GnbDecoderWeights(C.Structure):
         ("head_w", C.c_void_p), ("head_b", C.c_void_p),
         ("tc_dtype", C.c_int32),
         ("status", C.c_void_p),
+        ("alpha_dev", C.c_void_p),
+    ]
+
+
+class GnbDecoderGrads(C.Structure):
+    _fields_ = [
+        ("lin_in_w", C.c_void_p), ("lin_in_b", C.c_void_p),
+        ("lin_z_w", C.c_void_p * 8), ("lin_z_b", C.c_void_p * 8),
+        ("fc0_w", C.c_void_p * 8), ("fc0_b", C.c_void_p * 8),
+        ("fc1_w", C.c_void_p * 8), ("fc1_b", C.c_void_p * 8),
+        ("lin_out_w", C.c_void_p), ("lin_out_b", C.c_void_p),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+        ("alpha", C.c_void_p),
+        ("g_code", C.c_void_p), ("g_feat", C.c_void_p),
     ]
 
 
@@ -142,6 +156,14 @@ SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_decode_tc": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnb_mlp_grad_link": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "gnb_mlp_grad_head": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gnb_decode_train_bwd_workspace_bytes": (C.c_int64, [C.POINTER(GnbDecoderWeights), C.c_int64]),
+    "gnb_decode_train_bwd": (C.c_int, [C.POINTER(GnbDecoderWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(GnbDecoderGrads), C.c_void_p, C.c_int64, C.c_int,
+                                       C.c_void_p]),
     "gnb_query_fused_tc": (C.c_int, [C.POINTER(GnbSampleParams), C.POINTER(GnbDecoderWeights), C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "gnb_query_fused_sorted_scratch_bytes": (C.c_int64, [C.POINTER(GnbSampleParams)]),
@@ -166,7 +188,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError if the symbol is not exported
             fn.restype, fn.argtypes = res, args
-        for which, st in enumerate((GnbLiftParams, GnbSampleParams, GnbDecoderWeights, GnbFusionParams)):
+        for which, st in enumerate((GnbLiftParams, GnbSampleParams, GnbDecoderWeights, GnbFusionParams, GnbDecoderGrads)):
             if L.gnb_struct_size(which) != C.sizeof(st):
                 raise RuntimeError(f"gennerf_b200: ABI mismatch for {st.__name__}: library "
                                    f"{L.gnb_struct_size(which)} bytes, binding {C.sizeof(st)} bytes")

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgennerf_b200.so")
-SOURCES = ["error.cu", "lift.cu", "sample.cu", "sample_binned.cu", "planes.cu", "points.cu", "fusion.cu", "decoder_simt.cu", "decoder_tc.cu"]
+SOURCES = ["error.cu", "lift.cu", "sample.cu", "sample_binned.cu", "planes.cu", "points.cu", "fusion.cu", "decoder_simt.cu", "decoder_tc.cu", "mlp_grad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
@@ -58,7 +58,7 @@ def build(force=False, verbose=False, trace=False):
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout)

@@ -116,11 +116,12 @@ __global__ void __launch_bounds__(512) decode_fp32_kernel(const __grid_constant_
     __syncthreads();
 
     float x[DM], t[DM];
+    const float alpha = w.alpha_dev ? __ldg(w.alpha_dev) : w.alpha;
     linear_col(w.lin_in_w, w.lin_in_b, n, w.d_feat, featb, lda_f, x);          // resnetfc.py:149
     for (int blk = 0; blk < w.n_blocks; ++blk) {
         linear_col(w.lin_z_w[blk], w.lin_z_b[blk], n, w.d_code, codeb, lda_c, t);   // resnetfc.py:175
 #pragma unroll
-        for (int m = 0; m < DM; ++m) x[m] = __fadd_rn(x[m], __fmul_rn(w.alpha, t[m]));   // x + alpha * tz (:180)
+        for (int m = 0; m < DM; ++m) x[m] = __fadd_rn(x[m], __fmul_rn(alpha, t[m]));   // x + alpha * tz (:180)
 #pragma unroll
         for (int m = 0; m < DM; ++m) act[m * Hd + n] = fmaxf(x[m], 0.0f);
         __syncthreads();

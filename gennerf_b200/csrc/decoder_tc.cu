@@ -1157,6 +1157,7 @@ struct PackOp {
     int order_half;       // activation ops: N-half whose visiting order (act_kchunk) is used; -1 = identity
     int nsplit, own, interleave;
     float scale;          // multiplies W and biasA
+    const float* scale_dev;   // optional: the scale is read from the device instead (GnbDecoderWeights.alpha_dev)
     const float* biasA;   // bias columns at k == K_true (hi) and K_true + 1 (lo): scale*biasA[n] + biasB[n]
     const float* biasB;
     int bias_cols;
@@ -1177,14 +1178,15 @@ __global__ void pack_kernel(PackOp op, unsigned char* __restrict__ dst_rank) {
     const int kc = op.order_half < 0 ? t : act_kchunk(op.nsplit, op.own, op.order_half, t, op.interleave);
     const int n = op.n0 + n_in_op;
     float v[8];
+    const float scale = op.scale_dev ? __ldg(op.scale_dev) : op.scale;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = kc * 64 + u * 8 + e;
         float x = 0.0f;
         if (n < op.rows_true) {
-            if (k < op.K_true) x = op.scale * op.W[(long long)n * op.K_true + k];
+            if (k < op.K_true) x = scale * op.W[(long long)n * op.K_true + k];
             else if (op.bias_cols && k < op.K_true + 2) {
-                float b = (op.biasA ? op.scale * op.biasA[n] : 0.0f) + (op.biasB ? op.biasB[n] : 0.0f);
+                float b = (op.biasA ? scale * op.biasA[n] : 0.0f) + (op.biasB ? op.biasB[n] : 0.0f);
                 float hi = round16<BF16>(b);
                 x = (k == op.K_true) ? hi : (b - hi);
             }
@@ -1313,23 +1315,23 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
             PackOp op;
             switch (g.mat) {
             case M_LIN_IN:
-                op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.WN, d.KF, -1, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
+                op = PackOp{w->lin_in_w, d.Hd, d.d_feat, n0, d.WN, d.KF, -1, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, nullptr, 0, 0};
                 break;
             case M_LIN_Z:
                 // x += alpha * (Wz code + bz)   [+ b1 of the previous block, or lin_in's bias for block 0: lin_in and lin_z_0
                 // accumulate into x in the same group, so one pair of bias columns serves both and a 64-wide feature vector
                 // (volume 32 + planes 32) stays ONE k-chunk]
-                op = PackOp{w->lin_z_w[g.blk], d.Hd, d.d_code, n0, d.WN, d.KZ, -1, d.nsplit, d.OWN, d.two, w->alpha, w->lin_z_b[g.blk],
+                op = PackOp{w->lin_z_w[g.blk], d.Hd, d.d_code, n0, d.WN, d.KZ, -1, d.nsplit, d.OWN, d.two, w->alpha, w->alpha_dev, w->lin_z_b[g.blk],
                             g.blk > 0 ? w->fc1_b[g.blk - 1] : w->lin_in_b, 1, 0};
                 break;
             case M_FC0:
-                op = PackOp{w->fc0_w[g.blk], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
+                op = PackOp{w->fc0_w[g.blk], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, nullptr, 0, 0};
                 break;
             case M_FC1:
-                op = PackOp{w->fc1_w[g.blk], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
+                op = PackOp{w->fc1_w[g.blk], d.Hd, d.Hd, n0, d.WN, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, nullptr, 0, 0};
                 break;
             default:
-                op = PackOp{w->lin_out_w, d.d_out, d.Hd, mrow * d.NOUTC, d.NOUTC, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, 0, 0};
+                op = PackOp{w->lin_out_w, d.d_out, d.Hd, mrow * d.NOUTC, d.NOUTC, d.KH, half, d.nsplit, d.OWN, d.two, 1.0f, nullptr, nullptr, nullptr, 0, 0};
                 break;
             }
             if ((rc = launch(op))) return rc;

@@ -521,6 +521,7 @@ struct TpPackOp {
     int rows;                // rows written (<= 128)
     int kc;                  // 64-wide k-chunk
     float scale;
+    const float* scale_dev;  // optional device copy of the scale (GnbDecoderWeights.alpha_dev)
     long long dst_off;
 };
 template <bool BF16>
@@ -532,7 +533,7 @@ __global__ void tp_pack_kernel(TpPackOp op, unsigned char* __restrict__ dst) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = op.kc * 64 + u * 8 + e;
-        v[e] = (n < op.rows_true && k < op.K_true) ? op.scale * op.W[(long long)n * op.K_true + k] : 0.0f;
+        v[e] = (n < op.rows_true && k < op.K_true) ? (op.scale_dev ? __ldg(op.scale_dev) : op.scale) * op.W[(long long)n * op.K_true + k] : 0.0f;
     }
     *reinterpret_cast<uint4*>(dst + op.dst_off + tp_off(r, u)) =
         make_uint4(pack16<BF16>(v[0], v[1]), pack16<BF16>(v[2], v[3]), pack16<BF16>(v[4], v[5]), pack16<BF16>(v[6], v[7]));
@@ -544,8 +545,9 @@ __global__ void tp_table_kernel(GnbDecoderWeights w, float* __restrict__ table) 
     if (h >= w.d_hidden) return;
     const int nb = w.n_blocks, stride = 2 * nb + 1;
     float cb = w.lin_in_b[h];
+    const float alpha = w.alpha_dev ? __ldg(w.alpha_dev) : w.alpha;
     for (int i = 0; i <= nb; ++i) {
-        if (i < nb) cb += w.alpha * w.lin_z_b[i][h];
+        if (i < nb) cb += alpha * w.lin_z_b[i][h];
         if (i > 0) cb += w.fc1_b[i - 1][h];
         table[(long long)h * stride + i] = cb;
     }
@@ -585,7 +587,7 @@ static int tp_pack(const GnbDecoderWeights* w, const TpDims& d, void* packed, cu
                 op.n0 = sg.j * 256 + rank * 128;
                 op.rows_true = d.Hd;
                 if (sg.kind == 0) op.W = w->lin_in_w, op.K_true = d.d_feat;
-                else if (sg.kind == 1) op.W = w->lin_z_w[sg.blk], op.K_true = d.d_code, op.scale = w->alpha;
+                else if (sg.kind == 1) op.W = w->lin_z_w[sg.blk], op.K_true = d.d_code, op.scale = w->alpha, op.scale_dev = w->alpha_dev;
                 else if (sg.is_out) op.W = w->lin_out_w, op.K_true = d.Hd, op.rows_true = d.d_out, op.n0 = 0;
                 else {
                     // stage index inside the block tells fc_0 from fc_1: d_col >= 256 <-> net accumulator <-> fc_0

@@ -67,6 +67,7 @@ extern "C" int gnb_struct_size(int which) {
         case 1: return (int)sizeof(GnbSampleParams);
         case 2: return (int)sizeof(GnbDecoderWeights);
         case 3: return (int)sizeof(GnbFusionParams);
+        case 4: return (int)sizeof(GnbDecoderGrads);
         default: return -1;
     }
 }

@@ -335,7 +335,9 @@ class DecoderWeights:
     """
 
     def __init__(self, mlp_sd, head_w, head_b, *, n_blocks, d_geo, use_code=True, num_freqs=2,
-                 freq_factor=0.5, include_input=True, d_code=None, device="cuda"):
+                 freq_factor=0.5, include_input=True, d_code=None, device="cuda", alpha_on_device=False):
+        """alpha_on_device: the kernels read ResnetFC.alpha from the parameter's device memory (GnbDecoderWeights.alpha_dev)
+        instead of a host copy -- no `.item()`, i.e. no stream sync when the weights object is built inside a training step."""
         def dev(t):
             return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
@@ -345,7 +347,10 @@ class DecoderWeights:
         w.d_hidden, w.d_feat = self.t["lin_in.weight"].shape
         w.d_out = self.t["lin_out.weight"].shape[0]
         w.n_blocks, w.d_geo = int(n_blocks), int(d_geo)
-        w.alpha = float(self.t["alpha"].item()) if "alpha" in self.t else 1.0
+        if alpha_on_device and "alpha" in self.t:
+            w.alpha, w.alpha_dev = 1.0, self.t["alpha"].data_ptr()
+        else:
+            w.alpha = float(self.t["alpha"].item()) if "alpha" in self.t else 1.0
         w.use_code, w.num_freqs, w.freq_factor, w.include_input = int(use_code), int(num_freqs), float(freq_factor), int(include_input)
         if int(use_code) == 2:         # codes are given (stand-alone ResnetFC.forward)
             w.d_code = int(d_code)
@@ -462,6 +467,137 @@ def decode_save(weights, xyz, feat, precision="fp16"):
         check(lib().gnb_decode_tc_save(C.byref(weights.w), packed.data_ptr(), xyz2.data_ptr(), feat2.data_ptr(), n,
                                        out.data_ptr(), tsdf.data_ptr(), acts.data_ptr(), _stream()), "gnb_decode_tc_save")
     return out, tsdf, acts
+
+
+def _row_major(t, what):
+    if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16:
+        raise ValueError(f"gennerf_b200: {what} must be a 2-D row-major tensor (or a column slice of one) with a row stride that is a "
+                         "multiple of 4 elements and a 16-byte aligned start")
+    return t
+
+
+def mlp_grad_link(pre, act, res=None, *, out=None, colsum=None, want_act32=False):
+    """One Linear + ReLU link of the ResNet-MLP's backward pass (gnb_mlp_grad_link; reference resnetfc.py:54-63 under autograd:
+    threshold_backward, the skip connection's add and the bias gradient's column sum in ONE pass):
+    out = where(act > 0, pre, 0) [+ res];  colsum (d,) += out.sum(0) (atomic order; must arrive zeroed).
+    pre / res / out (n,d) fp32, act (n,d) fp16 / bf16 as saved by decode_save; all may be column slices of wider row-major
+    tensors.  Returns out, or (out, act.float()) with want_act32 (the fp32 left operand of the weight-gradient GEMM)."""
+    _need_cuda(pre, act, res, out, colsum)
+    n, d = pre.shape
+    if act.dtype not in (torch.float16, torch.bfloat16) or tuple(act.shape) != (n, d) or act.stride(1) != 1:
+        raise ValueError("gennerf_b200: mlp_grad_link takes (n,d) fp16 / bf16 activations")
+    if pre.dtype != torch.float32 or (res is not None and (res.dtype != torch.float32 or tuple(res.shape) != (n, d))):
+        raise ValueError("gennerf_b200: mlp_grad_link takes fp32 gradients of one shape")
+    _row_major(pre, "pre")
+    if res is not None:
+        _row_major(res, "res")
+    if out is None:
+        out = torch.empty((n, d), device=pre.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or tuple(out.shape) != (n, d):
+        raise ValueError("gennerf_b200: mlp_grad_link: out must be (n,d) fp32")
+    _row_major(out, "out")
+    if colsum is not None and (colsum.dtype != torch.float32 or colsum.numel() != d or not colsum.is_contiguous()):
+        raise ValueError("gennerf_b200: mlp_grad_link: colsum must be a contiguous fp32 vector of d elements")
+    a32 = torch.empty((n, d), device=pre.device, dtype=torch.float32) if want_act32 else None
+    with torch.cuda.device(pre.device):
+        check(lib().gnb_mlp_grad_link(pre.data_ptr(), pre.stride(0), act.data_ptr(), act.stride(0),
+                                      _lib.TC_FP16 if act.dtype == torch.float16 else _lib.TC_BF16,
+                                      res.data_ptr() if res is not None else None, res.stride(0) if res is not None else 0,
+                                      out.data_ptr(), out.stride(0), a32.data_ptr() if want_act32 else None, d,
+                                      colsum.data_ptr() if colsum is not None else None, n, d, _stream()), "gnb_mlp_grad_link")
+    return (out, a32) if want_act32 else out
+
+
+def mlp_grad_head(g_out, g_tsdf, out, tsdf, head_w, d_geo):
+    """Gradient entering the decoder from its outputs (gnb_mlp_grad_head; reference heads3d.py:36-50 + model.py:226-246 under
+    autograd).  g_out (n,d_out) or None, g_tsdf (n,1) or None.  Returns G (n,d_out), d_head_w (d_geo,), d_head_b (1,),
+    d_lin_out_b (d_out,)."""
+    _need_cuda(g_out, g_tsdf, out, tsdf, head_w)
+    n, d_out = out.shape
+    dev = out.device
+    g_out = None if g_out is None else _f32(g_out).contiguous()
+    g_tsdf = None if g_tsdf is None else _f32(g_tsdf).contiguous()
+    out, tsdf, hw = _f32(out).contiguous(), _f32(tsdf).contiguous(), _f32(head_w).reshape(-1).contiguous()
+    G = torch.empty((n, d_out), device=dev, dtype=torch.float32)
+    sums = torch.zeros(d_geo + 1 + d_out, device=dev, dtype=torch.float32)
+    d_hw, d_hb, d_lb = sums[:d_geo], sums[d_geo:d_geo + 1], sums[d_geo + 1:]
+    with torch.cuda.device(dev):
+        check(lib().gnb_mlp_grad_head(g_out.data_ptr() if g_out is not None else None,
+                                      g_tsdf.data_ptr() if g_tsdf is not None else None, out.data_ptr(), tsdf.data_ptr(),
+                                      hw.data_ptr(), n, d_out, int(d_geo), G.data_ptr(), d_hw.data_ptr(), d_hb.data_ptr(),
+                                      d_lb.data_ptr(), _stream()), "gnb_mlp_grad_head")
+    return G, d_hw, d_hb, d_lb
+
+
+@_nvtx
+def decode_train_bwd(weights, code, feat, out, tsdf, acts, g_out, g_tsdf, *, need_code=True, need_feat=True, tf32=None):
+    """The decoder's whole backward pass in ONE library call (gnb_decode_train_bwd; loss.backward() through ResnetFC +
+    TSDFHeadSimple in the reference, resnetfc.py:134-189 + heads3d.py:36-50): own kernels for the output head, the ReLU masks /
+    skip connections / bias sums of every link and the lin_z tail, cuBLAS SGEMMs (TF32 when torch's float32 matmul precision is
+    not "highest", the reference's training setting) for the dgrad / wgrad products.  `weights`: the DecoderWeights of the
+    forward (use_code=2); code (n,d_code), feat (n,d_feat), out / tsdf / acts as decode_save returned them; g_out (n,d_out) /
+    g_tsdf (n,1) or None.  Returns (grads: dict keyed like the ResnetFC state_dict, d_head_w (d_geo,) | None, d_head_b (1,) |
+    None, g_code | None, g_feat | None)."""
+    _need_cuda(code, feat, out, tsdf, acts, g_out, g_tsdf)
+    w = weights.w
+    n = code.shape[0]
+    H, nb, dc, df, dout, dgeo = w.d_hidden, w.n_blocks, w.d_code, w.d_feat, w.d_out, w.d_geo
+    dev = code.device
+    code, feat = _f32(code).contiguous(), _f32(feat).contiguous()
+    out, tsdf = _f32(out).contiguous(), _f32(tsdf).contiguous()
+    g_out = None if g_out is None else _f32(g_out).contiguous()
+    g_tsdf = None if g_tsdf is None else _f32(g_tsdf).contiguous()
+    if tuple(acts.shape) != (2 * nb + 1, n, H) or not acts.is_contiguous():
+        raise ValueError("gennerf_b200: decode_train_bwd takes the activations decode_save returned")
+    if tf32 is None:
+        tf32 = torch.get_float32_matmul_precision() != "highest" or torch.backends.cuda.matmul.allow_tf32
+    r4 = lambda v: (v + 3) & ~3                                       # noqa: E731  (16-byte aligned slices)
+    # accumulated (zeroed) gradients in one buffer, overwritten ones in another
+    zsizes = [("lin_in.bias", H)] + [(f"blocks.{i}.fc_0.bias", H) for i in range(nb)] + [(f"blocks.{i}.fc_1.bias", H) for i in range(nb)] \
+        + [("lin_out.bias", dout), ("head_w", max(dgeo, 1)), ("head_b", 1), ("alpha", 1)]
+    esizes = [("lin_in.weight", H * df), ("lin_out.weight", dout * H)] + [(f"lin_z.{i}.weight", H * dc) for i in range(nb)] \
+        + [(f"lin_z.{i}.bias", H) for i in range(nb)] + [(f"blocks.{i}.fc_0.weight", H * H) for i in range(nb)] \
+        + [(f"blocks.{i}.fc_1.weight", H * H) for i in range(nb)]
+    zbuf = torch.zeros(sum(r4(s) for _, s in zsizes), device=dev, dtype=torch.float32)
+    ebuf = torch.empty(sum(r4(s) for _, s in esizes), device=dev, dtype=torch.float32)
+    t = {}
+    for buf, sizes in ((zbuf, zsizes), (ebuf, esizes)):
+        o = 0
+        for k, s in sizes:
+            t[k] = buf[o:o + s]
+            o += r4(s)
+    g = _lib.GnbDecoderGrads()
+    ptr = lambda k: t[k].data_ptr()                                   # noqa: E731
+    g.lin_in_w, g.lin_in_b, g.lin_out_w, g.lin_out_b = ptr("lin_in.weight"), ptr("lin_in.bias"), ptr("lin_out.weight"), ptr("lin_out.bias")
+    for i in range(nb):
+        g.lin_z_w[i], g.lin_z_b[i] = ptr(f"lin_z.{i}.weight"), ptr(f"lin_z.{i}.bias")
+        g.fc0_w[i], g.fc0_b[i] = ptr(f"blocks.{i}.fc_0.weight"), ptr(f"blocks.{i}.fc_0.bias")
+        g.fc1_w[i], g.fc1_b[i] = ptr(f"blocks.{i}.fc_1.weight"), ptr(f"blocks.{i}.fc_1.bias")
+    g.head_w, g.head_b, g.alpha = ptr("head_w"), ptr("head_b"), ptr("alpha")
+    g_code = torch.empty((n, dc), device=dev, dtype=torch.float32) if need_code else None
+    g_feat = torch.empty((n, df), device=dev, dtype=torch.float32) if need_feat else None
+    g.g_code = g_code.data_ptr() if need_code else None
+    g.g_feat = g_feat.data_ptr() if need_feat else None
+    nbytes = lib().gnb_decode_train_bwd_workspace_bytes(C.byref(w), n)
+    ws = torch.empty(max(nbytes, 256), device=dev, dtype=torch.uint8)
+    saved_dtype = w.tc_dtype
+    w.tc_dtype = _lib.TC_FP16 if acts.dtype == torch.float16 else _lib.TC_BF16
+    try:
+        with torch.cuda.device(dev):
+            check(lib().gnb_decode_train_bwd(C.byref(w), code.data_ptr(), feat.data_ptr(), out.data_ptr(), tsdf.data_ptr(), acts.data_ptr(),
+                                             g_out.data_ptr() if g_out is not None else None,
+                                             g_tsdf.data_ptr() if g_tsdf is not None else None, n, C.byref(g), ws.data_ptr(), nbytes,
+                                             int(bool(tf32)), _stream()), "gnb_decode_train_bwd")
+    finally:
+        w.tc_dtype = saved_dtype
+    grads = {"lin_in.weight": t["lin_in.weight"].view(H, df), "lin_in.bias": t["lin_in.bias"],
+             "lin_out.weight": t["lin_out.weight"].view(dout, H), "lin_out.bias": t["lin_out.bias"], "alpha": t["alpha"]}
+    for i in range(nb):
+        grads[f"lin_z.{i}.weight"], grads[f"lin_z.{i}.bias"] = t[f"lin_z.{i}.weight"].view(H, dc), t[f"lin_z.{i}.bias"]
+        grads[f"blocks.{i}.fc_0.weight"], grads[f"blocks.{i}.fc_0.bias"] = t[f"blocks.{i}.fc_0.weight"].view(H, H), t[f"blocks.{i}.fc_0.bias"]
+        grads[f"blocks.{i}.fc_1.weight"], grads[f"blocks.{i}.fc_1.bias"] = t[f"blocks.{i}.fc_1.weight"].view(H, H), t[f"blocks.{i}.fc_1.bias"]
+    has_t = g_tsdf is not None
+    return grads, (t["head_w"][:dgeo] if has_t else None), (t["head_b"] if has_t else None), g_code, g_feat
 
 
 IMAGE_CHUNK = 1 << 22          # queries per sampler + decoder launch pair of query_image (512 MB of operand image per 64 features)

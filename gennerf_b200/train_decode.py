@@ -10,6 +10,8 @@ is needed because no gradient is ever stored in 16 bits.
 The gradients are those of the network the kernel evaluated (fp16-rounded operands); against fp32 autograd of the fp32
 network they differ by the fp16 rounding of the activations (tests/test_gpu_train_decode.py states the bar).
 """
+import os
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -17,16 +19,37 @@ from . import ops
 from .torch_ops import mlp_keys
 
 
-_pending_status = []          # status words of earlier forwards, not read yet
+# backward of the decoder: True = ONE library call (gnb_decode_train_bwd: own kernels + cuBLAS SGEMMs behind the C ABI);
+# False = the same chain spelled out here with torch.matmul between the own kernels (what the tests compare it with)
+NATIVE_BACKWARD = os.environ.get("GNB_TRAIN_BWD", "native") != "python"
+
+_pending_status = []          # (pinned host copy of a forward's status word, event after the copy), not read yet
 
 
-def check_saturation():
+def _watch_status(status):
+    """Queues an asynchronous copy of a forward's device status word into pinned host memory; check_saturation reads it once
+    the copy's event has completed -- the training step itself never waits for the device."""
+    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(status, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _pending_status.append((host, ev))
+
+
+def check_saturation(wait=False):
     """Raises if an fp16 operand of an earlier training forward saturated at +-65504 (that step's gradients are those of a
-    clipped network).  Called at the start of every decode_train_tc, i.e. one step late but without a device sync inside
-    the step; call it yourself after the last step."""
+    clipped network).  Called at the start of every decode_train_tc: only status words whose copy has already arrived are
+    looked at (no device sync inside a step, so the report can come a step or two late); `wait=True` -- call it yourself
+    after the last step -- waits for all of them."""
     hit = False
-    while _pending_status:
-        hit |= bool(_pending_status.pop().item())
+    for item in list(_pending_status):
+        host, ev = item
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            continue
+        _pending_status.remove(item)
+        hit |= bool(host.item())
     if hit:
         raise FloatingPointError("gennerf_b200: an fp16 operand of a training forward saturated at +-65504; "
                                  "use train_precision='fp32' for this model")
@@ -37,10 +60,12 @@ class _DecodeTC(torch.autograd.Function):
     def forward(ctx, code, feat, head_w, head_b, n_blocks, d_geo, *params):
         sd = dict(zip(mlp_keys(n_blocks), params))
         dw = ops.DecoderWeights(sd, head_w, head_b, n_blocks=n_blocks, d_geo=d_geo, use_code=2, num_freqs=0, freq_factor=0.0,
-                                include_input=False, d_code=code.shape[1], device=code.device)
+                                include_input=False, d_code=code.shape[1], device=code.device, alpha_on_device=True)
         out, tsdf, acts = ops.decode_save(dw, code, feat, "fp16")
         ctx.n_blocks, ctx.d_geo = n_blocks, d_geo
-        _pending_status.append(dw.status)            # read at the NEXT call (by then the step is over: no stall of the launch queue)
+        ctx.dw = dw
+        ctx.set_materialize_grads(False)             # an output the loss does not use arrives as None, not as a tensor of zeros
+        _watch_status(dw.status)                     # read at a later call, when its copy has arrived: no stall of the launch queue
         ctx.save_for_backward(code, feat, out, tsdf, acts, head_w, *params)
         return out, tsdf
 
@@ -59,49 +84,66 @@ class _DecodeTC(torch.autograd.Function):
     def _backward_once(ctx, g_out, g_tsdf):
         code, feat, out, tsdf, acts, head_w, *params = ctx.saved_tensors
         nb, d_geo = ctx.n_blocks, ctx.d_geo
-        P = dict(zip(mlp_keys(nb), params))
+        keys = mlp_keys(nb)
+        if NATIVE_BACKWARD:
+            need = ctx.needs_input_grad
+            grads, d_hw, d_hb, g_code, g_feat = ops.decode_train_bwd(ctx.dw, code, feat, out, tsdf, acts, g_out, g_tsdf,
+                                                                     need_code=need[0], need_feat=need[1])
+            plist = [grads[k].reshape(p.shape) if need[6 + j] else None for j, (k, p) in enumerate(zip(keys, params))]
+            return (g_code, g_feat, d_hw.reshape(head_w.shape) if (d_hw is not None and need[2]) else None,
+                    d_hb if (d_hb is not None and need[3]) else None, None, None, *plist)
+        P = dict(zip(keys, params))
         alpha = P["alpha"]
         grads = {k: None for k in P}
-        f32 = torch.float32
-        G = torch.zeros_like(out) if g_out is None else g_out.to(f32).clone()
-        d_hw = d_hb = None
-        if g_tsdf is not None:
-            s = g_tsdf.to(f32) * (1.0 - tsdf * tsdf)                     # (n,1): through tanh
-            d_hw = s.t() @ out[:, :d_geo]                                # (1,d_geo)
-            d_hb = s.sum(0)
-            G[:, :d_geo] += s @ head_w.reshape(1, -1)
-        relu_bwd = torch.ops.aten.threshold_backward          # grad * (activation > 0) in one kernel
-        a_f = acts[2 * nb].to(f32)
-        grads["lin_out.weight"] = G.t() @ a_f
-        grads["lin_out.bias"] = G.sum(0)
-        gx = relu_bwd(G @ P["lin_out.weight"], a_f, 0.0)                 # grad wrt x_nb
-        g_code = torch.zeros_like(code)
-        d_alpha = torch.zeros((), device=code.device, dtype=f32)
+        n, H = acts.shape[1], acts.shape[2]
+        dc = code.shape[1]
+        # every link below = one library GEMM (grad @ W, fp32 storage / TF32) + ONE pass of gnb_mlp_grad_link (ReLU mask from
+        # the saved 16-bit activation, skip-connection add, bias column sum, fp32 copy of the activation for the wgrad GEMM)
+        G, d_hw, d_hb, d_lob = ops.mlp_grad_head(g_out, g_tsdf, out, tsdf, head_w, d_geo)
+        colsum = torch.zeros((2 * nb + 1, H), device=code.device, dtype=torch.float32)
+        S, a32 = ops.mlp_grad_link(G @ P["lin_out.weight"], acts[2 * nb], colsum=colsum[2 * nb], want_act32=True)
+        grads["lin_out.weight"] = G.t() @ a32
+        grads["lin_out.bias"] = d_lob
+        # S = gradient w.r.t. the residual stream; the one entering block i's lin_z sits in column slab i of GX, so that the
+        # five K = d_code GEMMs of lin_z (weights and codes) are ONE GEMM each over the concatenation
+        GX = torch.empty((n, max(nb, 1) * H), device=code.device, dtype=torch.float32)
         for i in reversed(range(nb)):
-            h, a = acts[2 * i + 1].to(f32), acts[2 * i].to(f32)
-            grads[f"blocks.{i}.fc_1.weight"] = gx.t() @ h
-            grads[f"blocks.{i}.fc_1.bias"] = gx.sum(0)
-            gn = relu_bwd(gx @ P[f"blocks.{i}.fc_1.weight"], h, 0.0)
-            grads[f"blocks.{i}.fc_0.weight"] = gn.t() @ a
-            grads[f"blocks.{i}.fc_0.bias"] = gn.sum(0)
-            gx = gx + relu_bwd(gn @ P[f"blocks.{i}.fc_0.weight"], a, 0.0)  # grad wrt u_i = x_i + alpha * lin_z_i(code)
-            gsum = gx.sum(0)
-            Wz, bz = P[f"lin_z.{i}.weight"], P[f"lin_z.{i}.bias"]
-            grads[f"lin_z.{i}.weight"] = alpha * (gx.t() @ code)
-            grads[f"lin_z.{i}.bias"] = alpha * gsum
-            gz = gx @ Wz                                                  # (n, d_code)
-            g_code.add_(gz, alpha=1.0)
-            d_alpha = d_alpha + (gz * code).sum() + (gsum * bz).sum()
-        g_code = g_code * alpha
-        grads["lin_in.weight"] = gx.t() @ feat
-        grads["lin_in.bias"] = gx.sum(0)
-        g_feat = gx @ P["lin_in.weight"]
-        grads["alpha"] = d_alpha.reshape(alpha.shape)
+            grads[f"blocks.{i}.fc_1.bias"] = colsum[2 * i + 2]
+            gn, h32 = ops.mlp_grad_link(S @ P[f"blocks.{i}.fc_1.weight"], acts[2 * i + 1], colsum=colsum[2 * i + 1], want_act32=True)
+            grads[f"blocks.{i}.fc_1.weight"] = S.t() @ h32
+            grads[f"blocks.{i}.fc_0.bias"] = colsum[2 * i + 1]
+            Sn = GX[:, i * H:(i + 1) * H]
+            _, a32 = ops.mlp_grad_link(gn @ P[f"blocks.{i}.fc_0.weight"], acts[2 * i], S, out=Sn, colsum=colsum[2 * i], want_act32=True)
+            grads[f"blocks.{i}.fc_0.weight"] = gn.t() @ a32
+            S = Sn
+        g_code = None
+        if nb:
+            pad = (-dc) % 4                                              # K = 15 would put cuBLAS on its unaligned kernels
+            code_p = torch.nn.functional.pad(code, (0, pad))
+            wz = torch.nn.functional.pad(torch.cat([P[f"lin_z.{i}.weight"] for i in range(nb)], 0), (0, pad))   # (nb*H, dc+pad)
+            gz = GX @ wz                                                  # (n, dc+pad) = sum_i S_i @ Wz_i
+            g_code = (gz[:, :dc] * alpha) if ctx.needs_input_grad[0] else None
+            d_wz = ((GX.t() @ code_p)[:, :dc] * alpha).reshape(nb, H, dc) # contiguous (H, dc) gradients per block
+            gsum = colsum[0:2 * nb:2]                                     # (nb, H): column sums of S_i
+            for i in range(nb):
+                grads[f"lin_z.{i}.weight"] = d_wz[i]
+            d_zb = gsum * alpha
+            for i in range(nb):
+                grads[f"lin_z.{i}.bias"] = d_zb[i]
+            bz = torch.stack([P[f"lin_z.{i}.bias"] for i in range(nb)], 0)
+            grads["alpha"] = ((gz * code_p).sum() + (gsum * bz).sum()).reshape(alpha.shape)
+        else:
+            grads["alpha"] = torch.zeros_like(alpha)
+        grads["lin_in.weight"] = S.t() @ feat
+        grads["lin_in.bias"] = colsum[0]
         need = ctx.needs_input_grad
-        plist = [grads[k] if need[6 + j] else None for j, k in enumerate(mlp_keys(nb))]
-        return (g_code if need[0] else None, g_feat if need[1] else None,
-                d_hw.reshape(head_w.shape) if (d_hw is not None and need[2]) else None,
-                d_hb if (d_hb is not None and need[3]) else None, None, None, *plist)
+        g_feat = (S @ P["lin_in.weight"]) if need[1] else None
+        if g_code is None and need[0]:
+            g_code = torch.zeros_like(code)
+        plist = [grads[k] if need[6 + j] else None for j, k in enumerate(keys)]
+        has_t = g_tsdf is not None
+        return (g_code if need[0] else None, g_feat, d_hw.reshape(head_w.shape) if (has_t and need[2]) else None,
+                d_hb if (has_t and need[3]) else None, None, None, *plist)
 
 
 def decode_train_tc(mlp, head, z, feat):

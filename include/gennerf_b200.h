@@ -347,6 +347,9 @@ typedef struct GnbDecoderWeights {
     int32_t* status;               /* optional device int32 (NULL = off): the tensor-core kernels OR bit 0 into it when an  */
                                    /* fp16 operand (input feature, code or activation) saturated at +-65504, i.e. the      */
                                    /* result is outside the 1e-2 contract and the fp32 decoder should be used instead      */
+    const float* alpha_dev;        /* optional device float (NULL = use `alpha`): ResnetFC.alpha read on the device by the  */
+                                   /* pack / fp32 kernels -- a training step (the scalar is a learnable parameter that      */
+                                   /* changes every step) then needs no device-to-host read of it, i.e. no stream sync      */
 } GnbDecoderWeights;
 
 /* Stand-alone pieces (the reference's modules called on their own). */
@@ -387,6 +390,50 @@ int gnb_decode_tc_save(const GnbDecoderWeights* w, const void* packed, const flo
                        int64_t n_rows, float* out, float* tsdf, void* activations, void* stream);
 int gnb_decode_tc(const GnbDecoderWeights* w, const void* packed, const float* xyz,
                   const float* feat, int64_t n_rows, float* out, float* tsdf, void* stream);
+
+/* Backward links of the ResNet-MLP in a training step (row a15: resnetfc.py:54-63, 134-189 under autograd, where every
+ * Linear + ReLU link costs threshold_backward + the skip connection's add + a column sum for the bias gradient).  With the
+ * 16-bit activations gnb_decode_tc_save stored, one pass over the (n_rows, d) gradient:
+ *   out[r,c] = (act[r,c] > 0 ? pre[r,c] : 0) + (res ? res[r,c] : 0);  colsum[c] += sum_r out[r,c]  (atomic order; NULL = off);
+ *   act32[r,c] = (float)act[r,c]  (NULL = off: the fp32 left operand of the layer's weight-gradient GEMM).
+ * `pre` is the dgrad GEMM's result (grad @ W).  Row strides (ld_*) in elements, multiples of 4; pointers 16-byte aligned
+ * (act: 8); d % 4 == 0; act_dtype GNB_TC_FP16 / GNB_TC_BF16; out may alias pre or res.  colsum must be zeroed by the caller. */
+int gnb_mlp_grad_link(const float* pre, int64_t ld_pre, const void* act, int64_t ld_act, int act_dtype,
+                      const float* res, int64_t ld_res, float* out, int64_t ld_out, float* act32, int64_t ld_act32,
+                      float* colsum, int64_t n_rows, int d, void* stream);
+/* Gradient entering the decoder from its two outputs (heads3d.py:36-50 and model.py:226-246 under autograd):
+ *   s[r] = g_tsdf[r] * (1 - tsdf[r]^2);  G[r,c] = g_out[r,c] + (c < d_geo ? s[r] * head_w[c] : 0);
+ *   d_head_w[c] += sum_r s[r] * out[r,c];  d_head_b += sum_r s[r];  d_lin_out_b[c] += sum_r G[r,c]   (atomic order).
+ * g_out or g_tsdf may be NULL (that output received no gradient); the three sums must be zeroed by the caller. */
+int gnb_mlp_grad_head(const float* g_out, const float* g_tsdf, const float* out, const float* tsdf, const float* head_w,
+                      int64_t n_rows, int d_out, int d_geo, float* G, float* d_head_w, float* d_head_b,
+                      float* d_lin_out_b, void* stream);
+
+/* The decoder's whole backward pass in ONE call (row a15; loss.backward() through ResnetFC + TSDFHeadSimple in the reference,
+ * resnetfc.py:134-189, heads3d.py:36-50): the two kernels above around plain library GEMMs (cuBLAS SGEMM, TF32 tensor cores
+ * when `tf32` != 0 -- the reference trains with torch.set_float32_matmul_precision("high"), src/utils/utils.py:48; no gradient
+ * is ever stored in 16 bits).  cuBLAS is bound with dlopen at the first call (GNB_E_UNSUPPORTED if it cannot be loaded); the
+ * rest of the library does not depend on it.
+ * Inputs: `w` as given to gnb_decode_tc_save (use_code = 2: `code` holds the (n_rows, d_code) codes; w->alpha or w->alpha_dev);
+ * feat (n_rows, d_feat); out / tsdf / activations as gnb_decode_tc_save wrote them; g_out (n_rows, d_out) and g_tsdf (n_rows)
+ * = d loss / d outputs, either may be NULL.
+ * Outputs (fp32, shapes of the parameters): the weight gradients, lin_z biases, g_code (n_rows, d_code) and g_feat
+ * (n_rows, d_feat) [either may be NULL] are overwritten; the other bias gradients, head_w / head_b and alpha are ACCUMULATED
+ * into (atomic order) and must be zeroed by the caller.  head_w / head_b are only touched when g_tsdf is given. */
+typedef struct GnbDecoderGrads {
+    float* lin_in_w;  float* lin_in_b;
+    float* lin_z_w[8]; float* lin_z_b[8];
+    float* fc0_w[8];   float* fc0_b[8];
+    float* fc1_w[8];   float* fc1_b[8];
+    float* lin_out_w; float* lin_out_b;
+    float* head_w;    float* head_b;
+    float* alpha;
+    float* g_code;    float* g_feat;
+} GnbDecoderGrads;
+int64_t gnb_decode_train_bwd_workspace_bytes(const GnbDecoderWeights* w, int64_t n_rows);
+int gnb_decode_train_bwd(const GnbDecoderWeights* w, const float* code, const float* feat, const float* out, const float* tsdf,
+                         const void* activations, const float* g_out, const float* g_tsdf, int64_t n_rows,
+                         const GnbDecoderGrads* grads, void* workspace, int64_t workspace_bytes, int tf32, void* stream);
 
 /* Fused sampler + tensor-core decoder (GenNerf.forward, model.py:207-248): xyz -> feat
  * (optional output), out (feat_geo|feat_sem), tsdf, in one kernel. */

@@ -74,7 +74,70 @@ def test_tensor_core_training_step_is_as_accurate_as_tf32_autograd(n):
     assert not bad, bad
 
 
-def test_tensor_core_training_backward_is_exact_for_its_own_forward():
+@pytest.fixture(params=["native", "python"])
+def backward_path(request):
+    """Both spellings of the decoder's backward: ONE library call (gnb_decode_train_bwd, cuBLAS inside) and the chain of own
+    kernels + torch.matmul in train_decode.py."""
+    from gennerf_b200 import train_decode
+    old = train_decode.NATIVE_BACKWARD
+    train_decode.NATIVE_BACKWARD = request.param == "native"
+    yield request.param
+    train_decode.NATIVE_BACKWARD = old
+
+
+def test_native_backward_equals_the_python_chain():
+    """gnb_decode_train_bwd against the same chain written with torch.matmul (fp32 GEMMs on both sides): same kernels, same
+    operands -- only cuBLAS's choice of algorithm for a shape may differ, and the atomic order of the bias sums."""
+    from gennerf_b200 import train_decode
+    from gennerf_b200.dropin import decode_train
+    n = 5000
+    mlp, head, code, xyz, feat, g = _setup(n, seed=77)
+    gout = torch.randn(1, n, 64, generator=g).to(DEV)
+    gts = torch.randn(1, n, 1, generator=g).to(DEV)
+    res = {}
+    old, old_tf = train_decode.NATIVE_BACKWARD, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for which in (True, False):
+            train_decode.NATIVE_BACKWARD = which
+            for p in list(mlp.parameters()) + list(head.parameters()):
+                p.grad = None
+            x1, f1 = xyz.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+            out, tsdf = decode_train(mlp, head, code, x1, f1, precision="fp16")
+            ((out * gout).sum() + (tsdf * gts).sum()).backward()
+            r = {"xyz": x1.grad, "feat": f1.grad}
+            r.update({k: p.grad.clone() for k, p in mlp.named_parameters()})
+            r.update({"head." + k: p.grad.clone() for k, p in head.named_parameters()})
+            res[which] = r
+    finally:
+        train_decode.NATIVE_BACKWARD, torch.backends.cuda.matmul.allow_tf32 = old, old_tf
+    bad = {k: _rel2(res[True][k], res[False][k]) for k in res[False] if not _rel2(res[True][k], res[False][k]) <= 2e-5}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("which", ["out", "tsdf"])
+def test_native_backward_with_one_output_unused(which, backward_path):
+    """Only one of the decoder's two outputs enters the loss: the other arrives as None (materialize_grads off) or zeros."""
+    from gennerf_b200.dropin import decode_train
+    n = 700
+    mlp, head, code, xyz, feat, g = _setup(n, seed=78)
+    gout = torch.randn(1, n, 64, generator=g).to(DEV)
+    res = {}
+    for prec in ("fp16", "fp32"):
+        for p in list(mlp.parameters()) + list(head.parameters()):
+            p.grad = None
+        f1 = feat.clone().requires_grad_(True)
+        out, tsdf = decode_train(mlp, head, code, xyz, f1, precision=prec)
+        ((out * gout).sum() if which == "out" else tsdf.sum()).backward()
+        res[prec] = {"feat": f1.grad, **{k: p.grad for k, p in mlp.named_parameters()},
+                     **{"head." + k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in head.named_parameters()}}
+    # (fp16 vs fp32 forward: kinks move, see the test above; the scalar alpha is a sum with heavy cancellation)
+    bad = {k: _rel2(res["fp16"][k], res["fp32"][k]) for k in res["fp32"]
+           if not _rel2(res["fp16"][k], res["fp32"][k]) <= (0.3 if k == "alpha" else 6e-2)}
+    assert not bad, bad
+
+
+def test_tensor_core_training_backward_is_exact_for_its_own_forward(backward_path):
     """The hand-written backward against torch autograd through the SAME piecewise-linear network: relu(v) replaced by
     v * mask with the masks the kernel's forward saved (activation > 0).  What is left is the fp16 rounding of the saved
     activation VALUES in the weight gradients (2^-11 per element)."""
@@ -154,13 +217,120 @@ def test_dropin_train_precision_fp16_step():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
 
 
-def test_training_forward_saturation_is_reported_one_call_later():
+def test_training_forward_saturation_is_reported_without_a_sync():
+    """The status word of a training forward travels to pinned host memory asynchronously; a later call (or
+    check_saturation(wait=True) after the last step) raises -- the step itself never waits for the device."""
     from gennerf_b200 import train_decode
     from gennerf_b200.dropin import decode_train
     mlp, head, code, xyz, feat, g = _setup(500, seed=74)
-    train_decode.check_saturation()
+    train_decode.check_saturation(wait=True)
     decode_train(mlp, head, code, xyz, feat * 1e5, precision="fp16")
+    torch.cuda.synchronize()                                            # the copy has arrived: the next call sees it
     with pytest.raises(FloatingPointError):
         decode_train(mlp, head, code, xyz, feat, precision="fp16")
     decode_train(mlp, head, code, xyz, feat, precision="fp16")          # the flag was consumed; a clean forward passes
-    train_decode.check_saturation()
+    train_decode.check_saturation(wait=True)
+    decode_train(mlp, head, code, xyz, feat * 1e5, precision="fp16")
+    with pytest.raises(FloatingPointError):
+        train_decode.check_saturation(wait=True)
+
+
+def test_alpha_is_read_on_the_device():
+    """GnbDecoderWeights.alpha_dev: the pack kernel reads ResnetFC.alpha from the parameter itself (no .item() in a training
+    step); same bits as the host-copy path, and an in-place update of the parameter is seen by the next pack."""
+    from gennerf_b200 import ops
+    g = S.gen(75)
+    w, hw, hb = S.decoder_weights(g, 64, 15, 512, 5, 64, 32)
+    w = {k: v.to(DEV) for k, v in w.items()}
+    w["alpha"] = torch.tensor(0.7, device=DEV)
+    xyz = S.query_points(1000, (96, 96, 48), 0.04, g).to(DEV).reshape(-1, 3)
+    feat = torch.randn(1000, 64, generator=g).to(DEV)
+    kw = dict(n_blocks=5, d_geo=32, use_code=True, num_freqs=2, freq_factor=0.5, device=DEV)
+    host = ops.DecoderWeights(w, hw, hb, **kw)
+    devw = ops.DecoderWeights(w, hw, hb, alpha_on_device=True, **kw)
+    for prec in ("fp16", "fp32"):
+        a, b = ops.decode(host, xyz, feat, prec), ops.decode(devw, xyz, feat, prec)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), prec
+    w["alpha"].fill_(0.3)
+    devw.pack("fp16")
+    host2 = ops.DecoderWeights(w, hw, hb, **kw)
+    for prec in ("fp16", "fp32"):
+        a, b = ops.decode(host2, xyz, feat, prec), ops.decode(devw, xyz, feat, prec)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), prec
+    assert not torch.equal(ops.decode(host, xyz, feat, "fp16")[1], ops.decode(host2, xyz, feat, "fp16")[1])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("n,d,slab", [(1, 4, 1), (300, 512, 1), (23200, 512, 5), (1000, 132, 2), (200000, 64, 1)])
+def test_mlp_grad_link_matches_aten(n, d, slab, dtype):
+    """gnb_mlp_grad_link against the three ATen ops the reference's autograd runs per link (threshold_backward, add, sum(0)),
+    evaluated on the CPU in fp32: values bit-exact (a select and one add), column sums within the atomic-order bar."""
+    from gennerf_b200 import ops
+    g = S.gen(5 + n)
+    pre = torch.randn(n, d, generator=g)
+    res = torch.randn(n, d, generator=g)
+    act = torch.relu(torch.randn(n, d, generator=g)).to(dtype)
+    act[::7] = 0
+    want = torch.ops.aten.threshold_backward(pre, act.float(), 0.0)
+    # column slices of wider row-major buffers, as train_decode.py uses them
+    wide_res = torch.zeros(n, slab * d + 4).to(DEV)
+    wide_res[:, 4:4 + d] = res.to(DEV)
+    wide_out = torch.full((n, slab * d), 7.0, device=DEV)
+    col = torch.zeros(2, d, device=DEV)
+    o1, a32 = ops.mlp_grad_link(pre.to(DEV), act.to(DEV), colsum=col[0], want_act32=True)
+    o2 = ops.mlp_grad_link(pre.to(DEV), act.to(DEV), wide_res[:, 4:4 + d], out=wide_out[:, (slab - 1) * d:], colsum=col[1])
+    assert torch.equal(o1.cpu(), want)
+    assert torch.equal(a32.cpu(), act.float())
+    assert torch.equal(o2.cpu(), want + res)
+    if slab > 1:
+        assert (wide_out[:, :(slab - 1) * d] == 7.0).all()           # nothing outside the slab was written
+    for got, ref in ((col[0], want.double().sum(0)), (col[1], (want + res).double().sum(0))):
+        scale = max(1.0, float((want.abs() + res.abs()).double().sum(0).max()))
+        assert (got.cpu().double() - ref).abs().max() <= 1e-5 * scale
+    # in place on the GEMM result
+    p = pre.to(DEV).clone()
+    ops.mlp_grad_link(p, act.to(DEV), out=p)
+    assert torch.equal(p.cpu(), want)
+
+
+def test_mlp_grad_link_rejects_what_it_cannot_vectorise():
+    from gennerf_b200 import ops
+    pre = torch.zeros(8, 10, device=DEV)
+    act = torch.zeros(8, 10, device=DEV, dtype=torch.float16)
+    with pytest.raises((RuntimeError, ValueError)):
+        ops.mlp_grad_link(pre, act)                                  # d % 4 != 0
+    pre = torch.zeros(8, 17, device=DEV)[:, 1:]
+    act = torch.zeros(8, 16, device=DEV, dtype=torch.float16)
+    with pytest.raises((RuntimeError, ValueError)):
+        ops.mlp_grad_link(pre, act)                                  # row stride 17, start not 16-byte aligned
+
+
+@pytest.mark.parametrize("n,d_out,d_geo", [(1, 64, 32), (23200, 64, 32), (777, 40, 40), (5000, 96, 0)])
+@pytest.mark.parametrize("which", ["both", "out", "tsdf"])
+def test_mlp_grad_head_matches_autograd(n, d_out, d_geo, which):
+    """gnb_mlp_grad_head against CPU autograd through tanh(fc(out[:, :d_geo])) (reference heads3d.py:36-50)."""
+    from gennerf_b200 import ops
+    if d_geo == 0 and which != "out":
+        pytest.skip("no head without geometric features")
+    g = S.gen(11 + n)
+    out = torch.randn(n, d_out, generator=g).requires_grad_(True)
+    hw = (torch.randn(1, max(d_geo, 1), generator=g) * 0.2).requires_grad_(True)
+    hb = torch.zeros(1, requires_grad=True)
+    g_out = torch.randn(n, d_out, generator=g) if which != "tsdf" else None
+    g_tsdf = torch.randn(n, 1, generator=g) if which != "out" else None
+    tsdf = torch.tanh(torch.nn.functional.linear(out[:, :max(d_geo, 1)], hw, hb))
+    loss = 0
+    if g_out is not None:
+        loss = loss + (out * g_out).sum()
+    if g_tsdf is not None:
+        loss = loss + (tsdf * g_tsdf).sum()
+    loss.backward()
+    dv = lambda t: None if t is None else t.to(DEV)                  # noqa: E731
+    G, d_hw, d_hb, d_lb = ops.mlp_grad_head(dv(g_out), dv(g_tsdf), out.detach().to(DEV), tsdf.detach().to(DEV), hw.detach().to(DEV),
+                                            d_geo if g_tsdf is not None else min(d_geo, d_out))
+    assert (G.cpu() - out.grad).abs().max() <= 1e-6 * max(1.0, out.grad.abs().max().item())
+    sc = lambda t: max(1.0, t.abs().max().item())                    # noqa: E731
+    assert (d_lb.cpu() - out.grad.sum(0)).abs().max() <= 1e-4 * sc(out.grad.abs().sum(0))
+    if g_tsdf is not None:
+        assert (d_hw.cpu() - hw.grad.reshape(-1)).abs().max() <= 1e-4 * sc(hw.grad) + 1e-5 * n ** 0.5
+        assert (d_hb.cpu() - hb.grad).abs().max() <= 1e-4 * sc(hb.grad) + 1e-5 * n ** 0.5

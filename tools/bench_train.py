@@ -117,6 +117,8 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         loss, gf = step()
+        if os.environ.get("TRAIN_TRACE"):
+            print(f"warm-up step: loss {float(loss):.6f} grad_feature_norm {float(gf.norm()):.6e}", file=sys.stderr)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
