@@ -31,6 +31,7 @@ def _watch_status(status):
     the copy's event has completed -- the training step itself never waits for the device."""
     host = torch.empty(1, dtype=torch.int32, pin_memory=True)
     host.copy_(status, non_blocking=True)
+    status.zero_()                                # the weights view (and its status word) lives on across steps
     ev = torch.cuda.Event()
     ev.record()
     _pending_status.append((host, ev))
@@ -55,12 +56,31 @@ def check_saturation(wait=False):
                                  "use train_precision='fp32' for this model")
 
 
-class _DecodeTC(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, code, feat, head_w, head_b, n_blocks, d_geo, *params):
+_views = {}                   # (device, d_code, parameter addresses) -> DecoderWeights: pointers only, rebuilt when a tensor moves
+
+
+def _weights_view(code, head_w, head_b, n_blocks, d_geo, params):
+    """The pointer view of the live fp32 parameters (ops.DecoderWeights) is the same object step after step as long as the
+    optimiser updates the parameters in place; only the 16-bit operand image is re-packed per forward."""
+    ok = all(p.dtype == torch.float32 and p.is_contiguous() and p.device == code.device for p in (head_w, head_b, *params))
+    key = (code.device, code.shape[1], n_blocks, d_geo, head_w.data_ptr(), head_b.data_ptr(), *(p.data_ptr() for p in params)) if ok else None
+    dw = _views.get(key) if ok else None
+    if dw is None:
         sd = dict(zip(mlp_keys(n_blocks), params))
         dw = ops.DecoderWeights(sd, head_w, head_b, n_blocks=n_blocks, d_geo=d_geo, use_code=2, num_freqs=0, freq_factor=0.0,
                                 include_input=False, d_code=code.shape[1], device=code.device, alpha_on_device=True)
+        if ok:
+            if len(_views) >= 8:
+                _views.clear()
+            _views[key] = dw
+    return dw
+
+
+class _DecodeTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, code, feat, head_w, head_b, n_blocks, d_geo, *params):
+        dw = _weights_view(code, head_w, head_b, n_blocks, d_geo, params)
+        dw.pack("fp16")                              # the parameters changed since the last step: new operand image
         out, tsdf, acts = ops.decode_save(dw, code, feat, "fp16")
         ctx.n_blocks, ctx.d_geo = n_blocks, d_geo
         ctx.dw = dw
