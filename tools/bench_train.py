@@ -88,7 +88,7 @@ def main():
     depth = S.surface_depth_maps(T, H, W, g, mean=1.5, holes=False).unsqueeze(0).to(dev)
     xyz = S.query_points(Q, vd, VS, g).to(dev)
     target = (torch.rand(1, Q, 1, generator=g) * 2 - 1).to(dev)
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    sizes = [p.numel() for p in params]
 
     ev = lambda: torch.cuda.Event(enable_timing=True)           # noqa: E731
 
@@ -110,19 +110,14 @@ def main():
         loss.backward()
         mark("backward")
         if world > 1:                                           # data-parallel: average the gradients over the scenes
-            o = 0
+            # one flat bucket: a concatenation (one kernel), ONE NCCL all-reduce, one multi-tensor copy back
             for p_ in params:
-                n = p_.numel()
-                flat[o:o + n].copy_((p_.grad if p_.grad is not None else torch.zeros_like(p_)).reshape(-1))
-                o += n
-            dist.all_reduce(flat)
-            flat.div_(world)
-            o = 0
-            for p_ in params:
-                n = p_.numel()
-                if p_.grad is not None:
-                    p_.grad.copy_(flat[o:o + n].view_as(p_))
-                o += n
+                if p_.grad is None:
+                    p_.grad = torch.zeros_like(p_)
+            bucket = torch.cat([p_.grad.reshape(-1) for p_ in params])
+            dist.all_reduce(bucket)
+            bucket.div_(world)
+            torch._foreach_copy_([p_.grad for p_ in params], [c.view_as(p_) for c, p_ in zip(bucket.split(sizes), params)])
             mark("allreduce")
         opt.step()
         mark("adam")
@@ -165,7 +160,7 @@ def main():
             "steps": args.steps, "ms_per_step": t.item(), "host_issue_ms_per_step_rank0": host_ms, "scaling": "weak",
             "config": {"workload": "BASELINE config 5: fwd + L1 TSDF loss + bwd + Adam, one scene per GPU: 8 frames 480x640x32ch, "
                                    "160x160x64 grid, FPS 512 pts/frame -> 3x128^2x32 planes, 23200 queries, MLP 512x5",
-                       "parallelism": f"dp{world} (NCCL all-reduce of {flat.numel()} gradient elements)",
+                       "parallelism": f"dp{world} (NCCL all-reduce of {sum(sizes)} gradient elements)",
                        "float32_matmul_precision": args.matmul_precision, "train_precision": args.train_precision, "adam": args.adam,
                        "pointnet_cuda_graph": bool(args.graph_pointnet)},
             "phases_ms_rank0": phases, "loss": float(loss), "grad_feature_norm": float(gf.norm())}))
