@@ -1164,8 +1164,14 @@ struct PackOp {
     long long dst_off;    // byte offset of the op inside the rank's stream
 };
 
+// all ops of one CTA rank's weight stream in ONE launch (blockIdx.y = op): a training step re-packs the image every forward
+constexpr int MAX_PACK_OPS = 3 * 8 + 2;
+struct PackBatch {
+    PackOp op[MAX_PACK_OPS];
+};
 template <bool BF16>
-__global__ void pack_kernel(PackOp op, unsigned char* __restrict__ dst_rank) {
+__global__ void pack_kernel(const __grid_constant__ PackBatch batch, unsigned char* __restrict__ dst_rank) {
+    const PackOp& op = batch.op[blockIdx.y];
     // one thread per 16-byte unit: (t, nt, n_local, u)
     const int ntile = n_tiles_of(op.rows);
     const long long units_per_k = (long long)op.rows * 8;
@@ -1299,13 +1305,15 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
     for (int rank = 0; rank < d.csize; ++rank) {
         const int half = d.two ? rank >> 1 : rank, mrow = d.two ? (rank & 1) : 0;
         unsigned char* dst = (unsigned char*)packed + (long long)rank * d.packed_per_rank;
-        long long off = 0;
+        long long off = 0, max_units = 0;
+        PackBatch batch;
+        int n_batch = 0;
+        if (num_ops(d) > MAX_PACK_OPS) { set_error("gnb_decoder_pack_tc: too many ops"); return GNB_E_INVALID; }
         auto launch = [&](PackOp op) -> int {
             op.dst_off = off;
-            long long units = (long long)op.rows * 8 * op.kchunks;
-            if (w->tc_dtype == GNB_TC_BF16) pack_kernel<true><<<ceil_div(units, 256), 256, 0, st>>>(op, dst);
-            else pack_kernel<false><<<ceil_div(units, 256), 256, 0, st>>>(op, dst);
-            GNB_LAUNCH_CHECK();
+            const long long units = (long long)op.rows * 8 * op.kchunks;
+            max_units = units > max_units ? units : max_units;
+            batch.op[n_batch++] = op;
             off += (long long)op.kchunks * op.rows * 128;
             return 0;
         };
@@ -1337,6 +1345,10 @@ extern "C" int gnb_decoder_pack_tc(const GnbDecoderWeights* w, void* packed, voi
             if ((rc = launch(op))) return rc;
         }
         if (off != d.packed_per_rank) { set_error("gnb_decoder_pack_tc: internal size mismatch"); return GNB_E_INVALID; }
+        const dim3 grid((unsigned)ceil_div(max_units, 256), (unsigned)n_batch);
+        if (w->tc_dtype == GNB_TC_BF16) pack_kernel<true><<<grid, 256, 0, st>>>(batch, dst);
+        else pack_kernel<false><<<grid, 256, 0, st>>>(batch, dst);
+        GNB_LAUNCH_CHECK();
     }
     return 0;
 }

@@ -133,3 +133,29 @@ def test_dense_grid_query_guard_bands(guarded):
     grid = tuple(2 * n - 1 for n in vd)
     ops.query_grid_fused(dw, grid, axes, volume=vol, voxel_size=VS, origin=ORIGIN, want_out=True)
     assert guarded.check() >= 2
+
+
+def test_training_decoder_backward_guard_bands(guarded):
+    """gnb_decode_tc_save + gnb_decode_train_bwd (and the stand-alone link / head kernels) at ragged row counts: activations,
+    gradient buffers and the workspace sit between canaries."""
+    from gennerf_b200 import ops
+    g = S.gen(67)
+    n = 333
+    w, hw, hb = S.decoder_weights(g, 24, 15, 128, 3, 40, 12)
+    w = {k: v.to(DEV) for k, v in w.items()}
+    dw = ops.DecoderWeights(w, hw, hb, n_blocks=3, d_geo=12, use_code=2, num_freqs=0, freq_factor=0.0, include_input=False,
+                            d_code=15, device=DEV, alpha_on_device=True)
+    code = torch.randn(n, 15, generator=g).to(DEV)
+    feat = torch.randn(n, 24, generator=g).to(DEV)
+    out, tsdf, acts = ops.decode_save(dw, code, feat, "fp16")
+    assert guarded.check() >= 3
+    g_out = torch.randn(n, 40, generator=g).to(DEV)
+    g_tsdf = torch.randn(n, 1, generator=g).to(DEV)
+    grads, d_hw, d_hb, g_code, g_feat = ops.decode_train_bwd(dw, code, feat, out, tsdf, acts, g_out, g_tsdf)
+    assert guarded.check() >= 5
+    assert all(torch.isfinite(v).all() for v in grads.values()) and torch.isfinite(g_code).all() and torch.isfinite(g_feat).all()
+    pre = torch.randn(n, 128, generator=g).to(DEV)
+    col = ops.torch.zeros(128, device=DEV)
+    o, a32 = ops.mlp_grad_link(pre, acts[1], colsum=col, want_act32=True)
+    G, *_ = ops.mlp_grad_head(g_out, g_tsdf, out, tsdf, hw.to(DEV), 12)
+    assert guarded.check() >= 4
