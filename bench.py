@@ -401,6 +401,27 @@ def run_native(args):
     if precision != "fp32":
         dw.pack(precision)                                          # raises if the tcgen05 path is unavailable: no fallback
     fb = parallel.FrameBuffer(T, 1, C_FEAT, H, W, dev)
+    # feature exchange: "p2p" = pulls over NVLink by the copy engines between symmetric-memory buffers, issued one scene ahead
+    # (parallel.P2PFrameBuffer); "allgather" / "broadcast" = one NCCL collective inside the step.  "auto" takes p2p when every
+    # rank could set it up.
+    feat_mode, p2p = args.features, None
+    if world > 1 and feat_mode in ("auto", "p2p"):
+        ok = 1
+        try:
+            p2p = parallel.P2PFrameBuffer(T, 1, C_FEAT, H, W, dev)
+        except Exception as e:                                      # noqa: BLE001  (no symmetric memory on this box / build)
+            ok = 0
+            print(f"[bench] rank {rank}: symmetric-memory exchange unavailable ({type(e).__name__}: {e}); NCCL all-gather instead",
+                  file=sys.stderr)
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if feat_mode == "p2p":
+                raise RuntimeError("--features p2p: symmetric memory could not be set up on every rank")
+            p2p = None
+        feat_mode = "p2p" if p2p is not None else "allgather"
+    elif feat_mode == "auto":
+        feat_mode = "allgather"
     ev = lambda: torch.cuda.Event(enable_timing=True)               # noqa: E731
 
     def barrier():
@@ -411,7 +432,11 @@ def run_native(args):
     class Step:
         """One pass of the path; `marks` = events at the phase boundaries."""
 
-        def __call__(self, marks=None):
+        slot, ahead = 0, False                                      # p2p: the slot of this scene; is it already on its way?
+
+        def __call__(self, marks=None, prefetch=False):
+            """prefetch (p2p only): a further scene follows -- its frames are transposed and their exchange is started before
+            this scene's lift, so that the copy engines move them while this scene's queries run."""
             def mark():
                 if marks is not None:
                     e = ev()
@@ -419,19 +444,33 @@ def run_native(args):
                     marks.append(e)
             mark()
             # ---- features: own frames NCHW -> NHWC into the flat buffer, all ranks' frames gathered over NVLink
-            if frames_d:
-                ops.nchw_to_nhwc(frames_d, out=fb.flat[t0:t1])
-            if args.features == "broadcast" and world > 1:
-                # (alternative: rank 0 ran the CNN alone -- only its buffer is meaningful; one broadcast of 1.26 GB)
-                fb.broadcast(src=0)
+            if p2p is not None:
+                k = self.slot
+                if not self.ahead:                                  # first scene of a stream: nothing was sent ahead
+                    ops.nchw_to_nhwc(frames_d, out=p2p.own(k))
+                    p2p.exchange(k)
+                p2p.wait(k)
+                self.ahead = bool(prefetch)
+                if prefetch:
+                    ops.nchw_to_nhwc(frames_d, out=p2p.own(k ^ 1))
+                    p2p.exchange(k ^ 1)
+                self.slot = k ^ 1
+                frames = p2p.frames(k)
             else:
-                fb.all_gather()
+                if frames_d:
+                    ops.nchw_to_nhwc(frames_d, out=fb.flat[t0:t1])
+                if feat_mode == "broadcast" and world > 1:
+                    # (alternative: rank 0 ran the CNN alone -- only its buffer is meaningful; one broadcast of 1.26 GB)
+                    fb.broadcast(src=0)
+                else:
+                    fb.all_gather()
+                frames = fb.frames
             mark()
             # ---- lift
             if args.lift == "slab" and world > 1:
-                vol, cnt, valid = parallel.lift_sharded(ops, WL["voxel_dim"], VS, origin, P, fb.frames, gather=True)
+                vol, cnt, valid = parallel.lift_sharded(ops, WL["voxel_dim"], VS, origin, P, frames, gather=True)
             else:
-                vol, cnt, valid = ops.backproject_frames(WL["voxel_dim"], VS, origin, P, fb.frames)
+                vol, cnt, valid = ops.backproject_frames(WL["voxel_dim"], VS, origin, P, frames)
             mark()
             # ---- triplanes: own points -> partial sums -> all-reduce -> divide
             planes, pcnt = parallel.scatter_planes_sharded(ops, pts, cpt, R_PLANE, 0.1)
@@ -450,12 +489,13 @@ def run_native(args):
             return tsdf
 
     step = Step()
-    if args.features == "broadcast" and world > 1 and rank == 0:    # rank 0 "ran the CNN": it holds every frame
+    if feat_mode == "broadcast" and world > 1 and rank == 0:        # rank 0 "ran the CNN": it holds every frame
         frames_all = [frame(t).to(dev) for t in range(T)]
         ops.nchw_to_nhwc(frames_all, out=fb.flat)
         del frames_all
-    for _ in range(max(args.warmup, 3)):
-        step()
+    n_warm = max(args.warmup, 3)
+    for i in range(n_warm):
+        step(prefetch=p2p is not None and i + 1 < n_warm)
     barrier()
 
     clocks = ClockSampler(local)
@@ -465,9 +505,9 @@ def run_native(args):
     barrier()
     t_wall0 = time.perf_counter()
     a.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):                                     # a stream of K scenes: every exchange is inside the region
         m = []
-        step(m)
+        step(m, prefetch=p2p is not None and i + 1 < args.steps)
         marks_all.append(m)
     b.record()
     barrier()
@@ -476,6 +516,25 @@ def run_native(args):
     ph = torch.tensor([[m[i].elapsed_time(m[i + 1]) for i in range(4)] for m in marks_all], dtype=torch.float64).mean(0)
     vol, cnt, planes, tsdf = step.out
     n_valid = int(cnt.sum().item())
+    # the exchange timed alone (nothing to hide behind), max over ranks: the GB/s a GPU receives over NVLink
+    ms_exchange_alone = None
+    if world > 1:
+        barrier()
+        xa, xb = ev(), ev()
+        xa.record()
+        for i in range(3):
+            if p2p is not None:
+                p2p.exchange(i & 1)
+                p2p.wait(i & 1)
+            elif feat_mode == "broadcast":
+                fb.broadcast(src=0)
+            else:
+                fb.all_gather()
+        xb.record()
+        barrier()
+        tx = torch.tensor([xa.elapsed_time(xb) / 3], device=dev, dtype=torch.float64)
+        dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        ms_exchange_alone = float(tx.item())
     overflow = dw.overflowed() if precision == "fp16" else False
 
     # ---- end to end through the drop-in API with pinned host buffers -----------------------------------------------
@@ -579,14 +638,20 @@ def run_native(args):
             "scaling": "strong", "vs_baseline": None, "dtype": {"fp16": "f16", "fp32": "f32"}[precision],
             "data": "synthetic", "config": config_dict(),
             "parallelism": {"gpus": world, "frames_per_rank": t1 - t0, "queries_per_rank": q1 - q0,
-                            "features": args.features if world > 1 else "local", "lift": args.lift if world > 1 else "single GPU",
+                            "features": {"p2p": "p2p pulls over NVLink by the copy engines (symmetric memory), issued one scene ahead: they run under "
+                                                "the previous scene's query kernels; the first scene of the timed stream waits for its own",
+                                         "allgather": "NCCL all-gather inside the step", "broadcast": "NCCL broadcast inside the step"}[feat_mode]
+                            if world > 1 else "local", "lift": args.lift if world > 1 else "single GPU",
                             "planes": "points sharded, NCCL all-reduce of sums + counts", "queries": "contiguous ranges, no collective"},
             "decoder": q_desc,
             "phases_ms": {"features_transpose_and_gather": ms_feat, "lift": ms_lift, "planes_scatter_allreduce": ms_planes,
                           "query_range": ms_query, "step": ms_step},
             "collectives": {"feature_gather": {"bytes_total": feat_bytes, "bytes_received_per_gpu": feat_bytes * (world - 1) // world,
-                                               "ms_incl_local_transpose": ms_feat,
-                                               "gbs_received_per_gpu": (feat_bytes * (world - 1) / world) / (ms_feat * 1e-3) / 1e9 if world > 1 else None,
+                                               "how": feat_mode if world > 1 else "local",
+                                               "ms_in_step_incl_local_transpose": ms_feat,
+                                               "ms_alone": ms_exchange_alone,
+                                               "gbs_received_per_gpu": (feat_bytes * (world - 1) / world) / (ms_exchange_alone * 1e-3) / 1e9
+                                               if world > 1 else None,
                                                "nvlink_reference_gbs": 770.0},
                             "plane_allreduce_bytes": 3 * R_PLANE * R_PLANE * (C_PLANE + 1) * 4},
             "roofline": {"kernel": "decoder_tc_kernel; timed = the whole query phase of this rank's range (" + q_desc + ")",
@@ -614,7 +679,7 @@ def run_native(args):
         }
         if not args.no_parity:
             try:
-                line["parity"] = parity_check(ops, dev, P, fb.frames, vol, planes, tsdf, xyz_h, (w, hw, hb))
+                line["parity"] = parity_check(ops, dev, P, p2p.frames(0) if p2p is not None else fb.frames, vol, planes, tsdf, xyz_h, (w, hw, hb))
                 line["parity_checked"] = line["parity"]["ok"]
             except Exception as e:                                  # noqa: BLE001
                 line["parity"] = {"parity_checked": False, "error": repr(e)}
@@ -672,8 +737,10 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"],
                     help="decoder operands: fp16 = tcgen05 tensor cores (fp32 accumulate; the 1e-2 TSDF mode), fp32 = CUDA cores "
                          "(1e-5 mode)")
-    ap.add_argument("--features", default="allgather", choices=["allgather", "broadcast"],
-                    help="N > 1: every rank owns T/N frames and they are all-gathered (default), or rank 0 owns all and broadcasts")
+    ap.add_argument("--features", default="auto", choices=["auto", "p2p", "allgather", "broadcast"],
+                    help="N > 1: every rank owns T/N frames.  p2p = every rank pulls the others' frames over NVLink with the copy "
+                         "engines (symmetric memory), one scene ahead; allgather = one NCCL all-gather inside the step; broadcast = "
+                         "rank 0 owns all frames and broadcasts; auto (default) = p2p when symmetric memory is available, else allgather")
     ap.add_argument("--lift", default="replicated", choices=["replicated", "slab"],
                     help="N > 1: every rank lifts the whole grid (default), or x-slabs + all-gather of the volume")
     ap.add_argument("--query", choices=["image", "fused", "unfused"], default="image",

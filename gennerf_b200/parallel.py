@@ -150,6 +150,64 @@ class FrameBuffer:
         return self
 
 
+class P2PFrameBuffer:
+    """FrameBuffer whose exchange does not use an SM: `depth` flat buffers in symmetric memory (every rank maps every peer's
+    buffer, torch.distributed._symmetric_memory); after a device-side barrier on the signal pads each rank PULLS the other
+    ranks' frame slices over NVLink with plain device-to-device copies, i.e. on the copy engines, on its own copy stream.
+    The kernels of the scene being processed (the persistent tcgen05 decoder fills every SM for the whole query phase: an NCCL
+    kernel launched beside it would wait for a free SM) therefore run undisturbed while the NEXT scene's frames arrive:
+
+        write(k) own frames into slots[k] -> exchange(k) [barrier on the current stream, pulls on the copy stream]
+        ... kernels of the current scene ...
+        wait(k) -> lift from slots[k].frames
+
+    Buffer reuse needs no second barrier: a rank rewrites its slice of slot k only after a later exchange() barrier, which every
+    peer reaches only after its own wait(k), i.e. after its pulls from slot k have completed."""
+
+    def __init__(self, T, B, C, H, W, device, group=None, depth=2, barrier_timeout_ms=20000):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = _ws(group)
+        if T % self.world:
+            raise ValueError("P2PFrameBuffer: the frames must split evenly over the ranks")
+        self.T, self.per = T, T // self.world
+        self.owned = shard_range(T, self.rank, self.world)
+        self.timeout = int(barrier_timeout_ms)
+        self.slots = []
+        for _ in range(depth):
+            flat = symm.empty((T, B, H, W, C), dtype=torch.float32, device=device)
+            hdl = symm.rendezvous(flat, self.group)
+            peers = [flat if r == self.rank else hdl.get_buffer(r, tuple(flat.shape), flat.dtype) for r in range(self.world)]
+            self.slots.append({"flat": flat, "hdl": hdl, "peers": peers, "done": torch.cuda.Event(),
+                               "frames": [flat[t].permute(0, 3, 1, 2) for t in range(T)]})
+        self.copy_stream = torch.cuda.Stream(device)
+
+    def own(self, k):
+        """This rank's slice of slot k (channels-last (T/N, B, H, W, C)): where its frames are written before exchange(k)."""
+        return self.slots[k]["flat"][self.owned[0]:self.owned[1]]
+
+    def frames(self, k):
+        return self.slots[k]["frames"]
+
+    def exchange(self, k):
+        """Every rank has written own(k) on its current stream.  Returns at once; wait(k) orders later work behind the pulls."""
+        s = self.slots[k]
+        if self.world > 1:
+            s["hdl"].barrier(channel=0, timeout_ms=self.timeout)          # on the current stream: all slices of slot k are written
+        go = torch.cuda.Event()
+        go.record()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(go)
+            for i in range(1, self.world):                                 # staggered sources: every GPU serves one reader at a time
+                r = (self.rank + i) % self.world
+                a, b = r * self.per, (r + 1) * self.per
+                s["flat"][a:b].copy_(s["peers"][r][a:b], non_blocking=True)
+            s["done"].record()
+
+    def wait(self, k):
+        torch.cuda.current_stream().wait_event(self.slots[k]["done"])
+
+
 def scatter_planes_sharded(backend, p, c, reso, padding=0.1, group=None):
     """p (B,N,3), c (B,N,C_p): every rank scatters ITS points (the caller passes the rank's
     shard); partial sums and counts are all-reduced, then divided locally.
