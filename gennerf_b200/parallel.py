@@ -164,7 +164,7 @@ class P2PFrameBuffer:
     Buffer reuse needs no second barrier: a rank rewrites its slice of slot k only after a later exchange() barrier, which every
     peer reaches only after its own wait(k), i.e. after its pulls from slot k have completed."""
 
-    def __init__(self, T, B, C, H, W, device, group=None, depth=2, barrier_timeout_ms=20000):
+    def __init__(self, T, B, C, H, W, device, group=None, depth=2, barrier_timeout_ms=60000):
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = _ws(group)

@@ -33,7 +33,8 @@ def test_header_symbols_exported(library):
 def test_struct_layout_matches(library):
     import ctypes as C
     L = library.lib()
-    for which, st in enumerate((library.GnbLiftParams, library.GnbSampleParams, library.GnbDecoderWeights, library.GnbFusionParams)):
+    for which, st in enumerate((library.GnbLiftParams, library.GnbSampleParams, library.GnbDecoderWeights, library.GnbFusionParams,
+                                library.GnbDecoderGrads)):
         assert L.gnb_struct_size(which) == C.sizeof(st)
 
 
@@ -112,3 +113,30 @@ def test_extent_arithmetic_matches_torch():
         den = np.float32(1 + pad + 10e-6)
         x = torch.randn(1000)
         assert torch.equal(x / (1 + pad + 10e-6), torch.from_numpy(x.numpy() / den))
+
+
+def test_training_backward_plan_and_argument_checks_are_host_only(library):
+    """gnb_decode_train_bwd_workspace_bytes is a host-side plan (G, the stream gradients of every block, one layer's
+    pre-activation / masked gradient / fp32 activation, the padded lin_z operands); the argument checks of the training entry
+    points return GNB_E_INVALID before any CUDA call, and cuBLAS is not a link-time dependency of the library."""
+    import ctypes as C
+    L = library.lib()
+    w = library.GnbDecoderWeights()
+    w.d_feat, w.d_code, w.d_hidden, w.n_blocks, w.d_out, w.d_geo, w.use_code = 64, 15, 512, 5, 64, 32, 2
+    n = 23200
+    b = L.gnb_decode_train_bwd_workspace_bytes(C.byref(w), n)
+    floats = n * 64 + n * 6 * 512 + 3 * n * 512 + 2 * n * 16 + 2 * 5 * 512 * 16
+    assert floats * 4 <= b <= floats * 4 + 16 * 64 * 4                       # each of the 9 regions rounded up to 64 floats
+    assert L.gnb_decode_train_bwd_workspace_bytes(C.byref(w), 2 * n) > b
+    assert L.gnb_decode_train_bwd_workspace_bytes(None, n) == -1
+    g = library.GnbDecoderGrads()
+    assert L.gnb_decode_train_bwd(C.byref(w), None, None, None, None, None, None, None, 10, C.byref(g), None, 0, 1, None) == -1
+    assert b"null pointer" in L.gnb_last_error()
+    w.use_code = 1
+    assert L.gnb_decode_train_bwd(C.byref(w), None, None, None, None, None, None, None, 10, C.byref(g), None, 0, 1, None) == -1
+    assert b"use_code" in L.gnb_last_error()
+    assert L.gnb_mlp_grad_link(None, 512, None, 512, 0, None, 0, None, 512, None, 0, None, 10, 510, None) == -1     # d % 4
+    assert L.gnb_mlp_grad_link(None, 512, None, 512, 0, None, 0, None, 512, None, 0, None, 10, 512, None) == -1     # null pointers
+    assert L.gnb_mlp_grad_head(None, None, None, None, None, 10, 64, 32, None, None, None, None, None) == -1
+    out = subprocess.run(["ldd", library.LIB_PATH], capture_output=True, text=True).stdout
+    assert "cublas" not in out and "libcuda.so" not in out
