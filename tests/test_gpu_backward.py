@@ -13,6 +13,17 @@ VS = 0.04
 ORIGIN = torch.tensor([0, 0, 0]).view(1, 3)
 
 
+@pytest.fixture(autouse=True, params=["eager_functions", "custom_ops"])
+def autograd_path(request):
+    """Every test of this file runs through both spellings of the autograd formulas (gennerf_b200/autograd.py): the plain
+    autograd.Functions of eager mode and the torch.library custom ops a tracer sees."""
+    from gennerf_b200 import autograd as ag
+    old = ag.EAGER_FUNCTIONS
+    ag.EAGER_FUNCTIONS = request.param == "eager_functions"
+    yield request.param
+    ag.EAGER_FUNCTIONS = old
+
+
 def close(a, b, rtol, what):
     a, b = a.detach().cpu().float(), b.detach().cpu().float()
     assert a.shape == b.shape, (what, a.shape, b.shape)
