@@ -1,4 +1,4 @@
-# Final check of round 2 on one GPU: all GPU tests, smoke, both bench arms, config-5 step, launch lists, ncu of the link kernel.
+# Round-end check on one GPU: all GPU tests, smoke, both bench arms, the config-5 training step, its launch list and an ncu capture of the link kernel.
 set -x
 T=${1:-r2z}
 mkdir -p gpurun_out
