@@ -561,7 +561,8 @@ def run_native(args):
     xyz_pin = xyz_h.pin_memory()
     pts_pin = pts_h.pin_memory()
     tsdf_pin = torch.empty((1, q1 - q0, 1), dtype=torch.float32).pin_memory()
-    Pd = P.to(dev)
+    # (the 32 camera matrices stay on the host: the lift takes them as kernel parameters, and a CUDA tensor would cost a
+    # device-to-host copy, i.e. a stream sync, in the middle of every step)
 
     # Double-buffered, as a user streaming scenes through the drop-in would write it: scene i+1's inputs are uploaded on a
     # copy stream while scene i's kernels run, scene i's TSDF is downloaded on a third stream.  In the steady state the timed
@@ -583,7 +584,7 @@ def run_native(args):
             t.record_stream(cur)
         model.initialize_volume()
         with torch.no_grad():
-            model.encode(Pd, img, None, "val", sparse_xyz=sp)
+            model.encode(P, img, None, "val", sparse_xyz=sp)
             out = model(xd)
         done = torch.cuda.Event()
         done.record(cur)
