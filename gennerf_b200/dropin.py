@@ -443,6 +443,15 @@ class FeaturePlaneMerger(nn.Module):
 # ------------------------------------------------------------------------------------------
 # src/models/model.py -- the hot-path methods of GenNerf
 # ------------------------------------------------------------------------------------------
+def _packed_bytes_ok(L, w):
+    import ctypes as C
+    for name in ("lin_in_w", "lin_in_b", "lin_out_w", "lin_out_b", "head_w", "head_b"):      # the plan checks for null parameters
+        setattr(w, name, 1)
+    for i in range(w.n_blocks):
+        w.lin_z_w[i] = w.lin_z_b[i] = w.fc0_w[i] = w.fc0_b[i] = w.fc1_w[i] = w.fc1_b[i] = 1
+    return L.gnb_decoder_packed_bytes(C.byref(w)) > 0
+
+
 class GenNerf(nn.Module):
     """Encoder/decoder interface of the reference's GenNerf (model.py:25-248) on the B200 path.
 
@@ -452,14 +461,17 @@ class GenNerf(nn.Module):
     sparse point cloud through `encode(..., sparse_xyz=)`; Lightning orchestration, losses and
     logging stay in the reference.  `precision`: 'fp16' (tcgen05 decoder, default; |dTSDF| <= 1e-2) |
     'fp32' (CUDA-core decoder, 1e-5 parity).  `train_precision` (training steps, i.e. forward with grad enabled):
-    'fp32' = nn.Linear under autograd (the reference's arithmetic, default) | 'fp16' = the tcgen05 kernel with saved
-    activations and a backward built on them (train_decode.py).
+    'fp32' = nn.Linear under autograd (the reference's arithmetic) | 'fp16' = the tcgen05 kernel with saved
+    activations and ONE library call for the backward (train_decode.py; once-differentiable) | 'auto' (default) = 'fp16' when
+    the config rules out second-order losses -- `cfg.loss.use_eikonal` and `cfg.loss.use_gradient` both False, the very switch
+    the reference uses to pick its double-differentiable plane lookup (model.py:157) -- and the decoder's dimensions have a
+    tensor-core training path (latent code <= 512 wide); 'fp32' otherwise, and whenever the config has no `loss` section.
     """
 
-    def __init__(self, cfg, spatial=None, unet=None, precision="fp16", fused=True, train_precision="fp32"):
+    def __init__(self, cfg, spatial=None, unet=None, precision="fp16", fused=True, train_precision="auto"):
         super().__init__()
-        if train_precision not in ("fp16", "fp32"):
-            raise ValueError("gennerf_b200: train_precision is 'fp32' or 'fp16'")
+        if train_precision not in ("fp16", "fp32", "auto"):
+            raise ValueError("gennerf_b200: train_precision is 'auto', 'fp32' or 'fp16'")
         self.train_precision = train_precision
         if precision not in ("fp16", "fp32"):
             raise ValueError("gennerf_b200: precision is 'fp16' (tcgen05 decoder, |dTSDF| <= 1e-2, saturation reported by "
@@ -487,6 +499,26 @@ class GenNerf(nn.Module):
         self._dw = None
         self._dw_key = None
         self.initialize_volume()
+
+    def resolved_train_precision(self):
+        """What `train_precision='auto'` means for this model and config (see the class docstring)."""
+        tp = getattr(self, "train_precision", "fp32")
+        if tp != "auto":
+            return tp
+        loss = getattr(self.cfg, "loss", None)
+        if loss is None or bool(getattr(loss, "use_eikonal", True)) or bool(getattr(loss, "use_gradient", True)):
+            return "fp32"                                   # create_graph=True needs the double-differentiable path
+        key = tuple(self.mlp.lin_in.weight.shape) + tuple(self.mlp.lin_out.weight.shape) + (str(self.mlp.lin_in.weight.device),)
+        if getattr(self, "_tc_train_key", None) != key:
+            from ._lib import GnbDecoderWeights, lib
+            w = GnbDecoderWeights()
+            w.d_hidden, w.d_feat = self.mlp.lin_in.weight.shape
+            w.d_out, w.n_blocks, w.d_geo = self.mlp.lin_out.weight.shape[0], self.mlp.n_blocks, self.cfg.mlp.d_out_geo
+            w.use_code, w.d_code = 2, (self.code.d_out if self.cfg.use_code else 3)
+            # (host-side plan only: packed bytes > 0 <=> these dimensions have a tcgen05 kernel; pointers are not looked at)
+            self._tc_train_ok = w.d_feat <= 512 and w.n_blocks >= 1 and self.mlp.lin_in.weight.is_cuda and _packed_bytes_ok(lib(), w)
+            self._tc_train_key = key
+        return "fp16" if self._tc_train_ok else "fp32"
 
     @property
     def device(self):
@@ -723,7 +755,7 @@ class GenNerf(nn.Module):
             voxel_size=self.cfg.voxel_size, origin=self.origin,
             padding=self.cfg.encoder.pointnet.padding if self.cfg.encoder.use_pointnet else 0.1)
         out, tsdf = decode_train(self.mlp, self.head_geo, self.code if self.cfg.use_code else None, xyz, feat,
-                                 precision=getattr(self, "train_precision", "fp32"))
+                                 precision=self.resolved_train_precision())
         feat_geo, feat_sem = out[..., :d_geo], out[..., d_geo:d_geo + d_sem]
         return {"feat_geo": feat_geo, "feat_sem": feat_sem, "tsdf": tsdf, "feat": feat}
 

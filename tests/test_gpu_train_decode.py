@@ -217,6 +217,53 @@ def test_dropin_train_precision_fp16_step():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
 
 
+def test_dropin_train_precision_auto_follows_the_loss_config():
+    """train_precision='auto' (the default): the tensor-core training path when the config rules out second-order losses
+    (cfg.loss.use_eikonal / use_gradient, the reference's own switch at model.py:157) and the decoder has one; nn.Linear under
+    autograd otherwise -- and always when the config carries no `loss` section."""
+    from gennerf_b200 import train_decode
+    from gennerf_b200.dropin import GenNerf
+    from oracle.ref_shim import to_attr
+    wl = S.WORKLOADS["small"]
+
+    def cfg(latent=32, loss=None, d_hidden=512):
+        c = {"voxel_size": 0.04, "voxel_dim_train": list(wl["voxel_dim"]), "voxel_dim_val": list(wl["voxel_dim"]),
+             "voxel_dim_test": list(wl["voxel_dim"]),
+             "encoder": {"use_spatial": True, "spatial": {"num_layers": 0, "latent_size": latent}, "use_pointnet": False, "use_auxiliary": False},
+             "mlp": {"d_out_sem": 32, "d_out_geo": 32, "n_blocks": 5, "d_hidden": d_hidden, "combine_layer": 1000, "combine_type": "average",
+                     "beta": 0.0, "use_spade": False, "use_layer_norm": False, "alpha": 1.0},
+             "use_code": True, "code": {"num_freqs": 2, "freq_factor": 0.5, "include_input": True}}
+        if loss is not None:
+            c["loss"] = loss
+        return to_attr(c)
+
+    off = {"use_eikonal": False, "use_gradient": False}
+    assert GenNerf(cfg()).to(DEV).resolved_train_precision() == "fp32"                                   # no loss section
+    assert GenNerf(cfg(loss={"use_eikonal": True, "use_gradient": False})).to(DEV).resolved_train_precision() == "fp32"
+    assert GenNerf(cfg(loss={"use_eikonal": False, "use_gradient": True})).to(DEV).resolved_train_precision() == "fp32"
+    assert GenNerf(cfg(loss=off, latent=544)).to(DEV).resolved_train_precision() == "fp32"               # wide latent
+    assert GenNerf(cfg(loss=off, d_hidden=500)).to(DEV).resolved_train_precision() == "fp32"             # no tcgen05 kernel
+    assert GenNerf(cfg(loss=off), train_precision="fp32").to(DEV).resolved_train_precision() == "fp32"
+    model = GenNerf(cfg(loss=off)).to(DEV).train()
+    assert model.resolved_train_precision() == "fp16"
+    # ... and the step really goes through the kernel: its backward is the native one
+    calls = []
+    orig = train_decode.ops.decode_train_bwd
+    train_decode.ops.decode_train_bwd = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        g = S.gen(79)
+        T, H, W = wl["T"], wl["H"], wl["W"]
+        P = S.projections(T, H, W, wl["voxel_dim"], 0.04, g, pull_back=0.8).unsqueeze(0)
+        img = torch.stack(S.frame_features(T, 32, H, W, g), dim=1).to(DEV).requires_grad_(True)
+        model.initialize_volume()
+        model.encode(P, img, None, "train")
+        res = model(S.query_points(1000, wl["voxel_dim"], 0.04, g).to(DEV))
+        res["tsdf"].abs().mean().backward()
+    finally:
+        train_decode.ops.decode_train_bwd = orig
+    assert calls and img.grad is not None and torch.isfinite(img.grad).all()
+
+
 def test_training_forward_saturation_is_reported_without_a_sync():
     """The status word of a training forward travels to pinned host memory asynchronously; a later call (or
     check_saturation(wait=True) after the last step) raises -- the step itself never waits for the device."""
