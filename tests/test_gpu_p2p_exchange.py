@@ -26,8 +26,11 @@ def test_p2p_frame_buffer_single_rank():
     from gennerf_b200 import ops, parallel
     own_group = not dist.is_initialized()
     if own_group:
-        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_port()}", world_size=1, rank=0,
-                                device_id=torch.device("cuda", 0))
+        try:
+            dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{_port()}", world_size=1, rank=0,
+                                    device_id=torch.device("cuda", 0))
+        except Exception as e:                                             # noqa: BLE001
+            pytest.skip(f"no 1-rank NCCL group on this box: {type(e).__name__}: {e}")
     try:
         T, B, C, H, W = 4, 1, 8, 12, 20
         try:
