@@ -556,7 +556,7 @@ def run_native(args):
     model.head_geo.load_state_dict({"fc.weight": hw, "fc.bias": hb})
     model = model.to(dev)
     if world > 1:
-        model.shard_scene()
+        model.shard_scene(p2p=feat_mode == "p2p")
     img_pin = torch.stack(frames_h, dim=1).pin_memory() if frames_h else torch.empty(1, 0, C_FEAT, H, W).pin_memory()
     xyz_pin = xyz_h.pin_memory()
     pts_pin = pts_h.pin_memory()
@@ -577,13 +577,19 @@ def run_native(args):
         return t, e
 
     def e2e_step(pre):
-        (img, xd, sp), e = pre
+        """pre = [scene i, scene i+1]: two scenes are on their way to the device.  Scene i+1's frames (uploaded during the previous
+        step) are handed to the model before scene i is encoded: with the p2p exchange (N > 1) they cross NVLink under scene i's
+        kernels; scene i+2's upload is issued here."""
+        ((img, xd, sp), e), ((img_n, _, _), e_n) = pre
         cur.wait_event(e)
-        nxt = upload()                                  # the NEXT scene's host-to-device copies overlap this scene's kernels
-        for t in (img, xd, sp):
+        cur.wait_event(e_n)
+        nxt = upload()                                  # a further scene's host-to-device copies overlap this scene's kernels
+        for t in (img, xd, sp, img_n):
             t.record_stream(cur)
         model.initialize_volume()
         with torch.no_grad():
+            if world > 1:
+                model.queue_next_frames(img_n)
             model.encode(P, img, None, "val", sparse_xyz=sp)
             out = model(xd)
         done = torch.cuda.Event()
@@ -592,9 +598,9 @@ def run_native(args):
             down.wait_event(done)
             tsdf_pin.copy_(out["tsdf"], non_blocking=True)
         out["tsdf"].record_stream(down)
-        return nxt
+        return [pre[1], nxt]
 
-    pre = upload()
+    pre = [upload(), upload()]
     for _ in range(2):
         pre = e2e_step(pre)
     cur.wait_stream(up)
@@ -670,9 +676,10 @@ def run_native(args):
                     "h2d_bytes_per_step": (img_pin.numel() + xyz_pin.numel() + pts_pin.numel()) * 4, "d2h_bytes_per_step": (q1 - q0) * 4,
                     "bytes_are": "per rank (every rank uploads its frames, its query range and the sparse points, downloads its TSDF range)",
                     "how": "drop-in GenNerf.shard_scene / encode(projection, image, sparse_xyz=) / forward(xyz) from pinned host "
-                           "buffers: H2D, NCHW->NHWC, feature all-gather, lift, PointNet + scatter, query, D2H of the TSDF; scenes are "
-                           "double-buffered (scene i+1 uploads on a copy stream while scene i computes, its TSDF downloads on a third "
-                           "stream): per step the timed region holds one full H2D, one pass and one D2H"},
+                           "buffers: H2D, NCHW->NHWC, feature exchange (" + (feat_mode if world > 1 else "none at N = 1") + "), lift, PointNet + "
+                           "scatter, query, D2H of the TSDF; scenes are streamed (uploads run two scenes ahead on a copy stream, the TSDF "
+                           "downloads on a third stream; with the p2p exchange the next scene's frames cross NVLink under this scene's "
+                           "kernels, model.queue_next_frames): per step the timed region holds one full H2D, one exchange, one pass and one D2H"},
             "gpu_launches": args.steps * (4 + q_launches + (1 if args.lift == "slab" and world > 1 else 0)),
             "fp16_saturated": overflow,
             "clocks": clocks.summary(),

@@ -570,15 +570,61 @@ class GenNerf(nn.Module):
             self._pl_key = key
         return self._pl_cl
 
-    def shard_scene(self, group=None, enabled=True):
+    def shard_scene(self, group=None, enabled=True, p2p=False):
         """ONE scene over the ranks of `group` (torch.distributed; SURVEY 8e, BASELINE config 4).  Afterwards
         `encode(projection, image, depth)` takes ALL T projections but only THIS rank's frames
         (parallel.shard_range(T, rank, world) of them, in frame order): every rank runs the 2D CNN and the farthest-point
         sampling on its own frames, the channels-last feature maps are all-gathered in one NCCL call over NVLink, the
         sampled points (a few KB) likewise, and every rank lifts the whole grid and builds the planes itself -- cheaper
         than moving the volume.  `forward(xyz)` then answers whatever range of the queries the caller hands to this rank
-        (parallel.shard_range(Q, ...)); no collective on the query path.  Inference only."""
+        (parallel.shard_range(Q, ...)); no collective on the query path.  Inference only.
+        `p2p=True`: the frames travel by copy-engine pulls over NVLink between symmetric-memory buffers
+        (parallel.P2PFrameBuffer; NCCL all-gather when symmetric memory cannot be set up on every rank), and a caller that
+        streams scenes can hand the NEXT scene's frames to `queue_next_frames()` before `encode()`: their exchange is started
+        inside that encode, right after this scene's frames have arrived, and runs under this scene's kernels."""
         self._scene_group = (group if group is not None else True) if enabled else None
+        self._scene_p2p = bool(p2p) and enabled
+        self._p2p = None                # (shape key, P2PFrameBuffer), created by the first encode (a collective call)
+        self._p2p_slot = 0              # slot of the next scene that was not sent ahead
+        self._p2p_ahead = {}            # data_ptr of a queued scene's frames -> the slot its exchange was started in
+        self._p2p_next = None
+
+    def queue_next_frames(self, image):
+        """shard_scene(p2p=True): `image` (B, T/N, C, H, W) = this rank's frames of the scene that will be encoded AFTER the next
+        encode() call.  Returns False (and does nothing) when the p2p exchange is not active."""
+        if not getattr(self, "_scene_p2p", False):
+            return False
+        self._p2p_next = image
+        return True
+
+    def _p2p_buffer(self, T, B, C, H, W, device, group):
+        """The model's symmetric-memory frame buffer (created once per shape; every rank calls this in the same encode)."""
+        import torch.distributed as dist
+
+        from . import parallel
+        key = (T, B, C, H, W, str(device))
+        if self._p2p is None or self._p2p[0] != key:
+            fb, ok = None, 1
+            try:
+                fb = parallel.P2PFrameBuffer(T, B, C, H, W, device, group)
+            except Exception:                                       # noqa: BLE001  (no symmetric memory here)
+                ok = 0
+            flag = torch.tensor([ok], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:                               # not on every rank: NCCL from now on
+                self._scene_p2p, self._p2p, self._p2p_next = False, None, None
+                return None
+            self._p2p, self._p2p_slot, self._p2p_ahead = (key, fb), 0, {}
+        return self._p2p[1]
+
+    def _p2p_send(self, fb, mine, t0, k):
+        """This rank's feature maps -> its slice of slot k (channels-last), then the exchange of slot k is started."""
+        if mine and all(f.is_contiguous() for f in mine):
+            ops.nchw_to_nhwc(mine, out=fb.own(k))                   # reference layout: transposed straight into the slot
+        else:
+            for i, f in enumerate(mine):
+                fb.frames(k)[t0 + i].copy_(f)
+        fb.exchange(k)
 
     def _encode_sharded(self, projection, image, depth, sparse_xyz):
         import torch.distributed as dist
@@ -597,17 +643,39 @@ class GenNerf(nn.Module):
             frames = image.unbind(1)
             mine = [self.spatial(f) if self.spatial is not None else f for f in frames]
             B, C, H, W = mine[0].shape if mine else (image.size(0), image.size(2), image.size(3), image.size(4))
-            fb = parallel.FrameBuffer(T, B, C, H, W, image.device, group)
-            nchw = [i for i, f in enumerate(mine) if f.is_contiguous()]
-            if len(nchw) == len(mine) and mine:
-                ops.nchw_to_nhwc(mine, out=fb.flat[t0:t1])                  # reference layout: transposed straight into the slot
+            pfb = None
+            if getattr(self, "_scene_p2p", False) and world > 1 and T % world == 0 and mine:
+                pfb = self._p2p_buffer(T, B, C, H, W, image.device, group)
+            if pfb is not None:
+                k = self._p2p_ahead.pop(image.data_ptr(), None)
+                if k is None:
+                    if self._p2p_ahead:
+                        raise RuntimeError("gennerf_b200: a scene whose frames were queued ahead is pending: encode it first")
+                    k = self._p2p_slot
+                    self._p2p_send(pfb, mine, t0, k)
+                pfb.wait(k)
+                self._p2p_slot = k ^ 1
+                nxt, self._p2p_next = self._p2p_next, None
+                if nxt is not None:
+                    # this scene's frames have arrived (every peer's pulls from the other slot completed before its own wait):
+                    # the other slot is free, and the next scene's exchange runs under this scene's kernels
+                    nmine = [self.spatial(f) if self.spatial is not None else f for f in nxt.unbind(1)]
+                    self._p2p_send(pfb, nmine, t0, k ^ 1)
+                    self._p2p_ahead[nxt.data_ptr()] = k ^ 1
+                all_frames = pfb.frames(k)
             else:
-                for i, f in enumerate(mine):
-                    fb.frames[t0 + i].copy_(f)
-            fb.all_gather()
+                fb = parallel.FrameBuffer(T, B, C, H, W, image.device, group)
+                nchw = [i for i, f in enumerate(mine) if f.is_contiguous()]
+                if len(nchw) == len(mine) and mine:
+                    ops.nchw_to_nhwc(mine, out=fb.flat[t0:t1])              # reference layout: transposed straight into the slot
+                else:
+                    for i, f in enumerate(mine):
+                        fb.frames[t0 + i].copy_(f)
+                fb.all_gather()
+                all_frames = fb.frames
             out = None if self.volume is None else (self.volume, self.count, self.valid)
             self.volume, self.count, self.valid = ops.backproject_frames(
-                voxel_dim, self.cfg.voxel_size, self.origin, projection, fb.frames, out=out)
+                voxel_dim, self.cfg.voxel_size, self.origin, projection, all_frames, out=out)
         if self.cfg.encoder.use_pointnet:
             if sparse_xyz is None:
                 if depth is None:
