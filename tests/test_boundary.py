@@ -126,3 +126,64 @@ def test_backward_ops_autograd_registrations():
         assert fwd._backward_fn is not None
     for bwd in (T.backproject_frames_bwd, T.sample_features_bwd2, T.scatter_mean_planes_bwd, T.pool_local_bwd):
         assert getattr(bwd, "_backward_fn", None) is None
+
+
+def test_sharded_encode_p2p_slot_protocol(monkeypatch):
+    """GenNerf.shard_scene(p2p=True) + queue_next_frames: the ORDER of the frame-buffer calls inside encode is what makes the
+    two-slot symmetric-memory exchange safe (parallel.P2PFrameBuffer): this scene's wait(k) comes before the next scene's
+    frames are written into slot k^1 and its barrier / pulls are started, and only then the lift.  Host logic only: the
+    buffer and the kernels are stand-ins that record the calls."""
+    from gennerf_b200 import dropin, ops, parallel
+    from gennerf_b200.dropin import GenNerf
+    cfg = to_attr({
+        "voxel_size": 0.04, "voxel_dim_train": [8, 8, 8], "voxel_dim_val": [8, 8, 8], "voxel_dim_test": [8, 8, 8],
+        "encoder": {"use_spatial": True, "spatial": {"num_layers": 0, "latent_size": 4}, "use_pointnet": False, "use_auxiliary": False},
+        "mlp": {"d_out_sem": 8, "d_out_geo": 8, "n_blocks": 1, "d_hidden": 64, "combine_layer": 1000, "combine_type": "average",
+                "beta": 0.0, "use_spade": False, "use_layer_norm": False, "alpha": 1.0},
+        "use_code": True, "code": {"num_freqs": 2, "freq_factor": 0.5, "include_input": True}})
+    log = []
+
+    class FakeBuffer:
+        def own(self, k):
+            log.append(("own", k))
+            return None
+
+        def frames(self, k):
+            return [("frames", k)]
+
+        def exchange(self, k):
+            log.append(("exchange", k))
+
+        def wait(self, k):
+            log.append(("wait", k))
+
+    fake = FakeBuffer()
+    monkeypatch.setattr(parallel, "_ws", lambda group: (0, 2))
+    monkeypatch.setattr(GenNerf, "_p2p_buffer", lambda self, *a: fake)
+    monkeypatch.setattr(ops, "nchw_to_nhwc", lambda frames, out=None: log.append(("transpose", len(frames))))
+    monkeypatch.setattr(ops, "backproject_frames",
+                        lambda vd, vs, o, P, frames, out=None: (log.append(("lift",) + frames[0]), (None, None, None))[1])
+    assert dropin.ops is ops
+    model = GenNerf(cfg).eval()
+    model.shard_scene(p2p=True)
+    P = torch.zeros(1, 4, 3, 4)
+    scenes = [torch.zeros(1, 2, 4, 6, 5) for _ in range(4)]           # this rank's 2 of T = 4 frames
+    with torch.no_grad():
+        assert model.queue_next_frames(scenes[1])
+        model.encode(P, scenes[0])
+        assert log == [("own", 0), ("transpose", 2), ("exchange", 0), ("wait", 0),
+                       ("own", 1), ("transpose", 2), ("exchange", 1), ("lift", "frames", 0)]
+        del log[:]
+        model.queue_next_frames(scenes[2])
+        model.encode(P, scenes[1])                                    # sent ahead: no transpose / exchange of its own
+        assert log == [("wait", 1), ("own", 0), ("transpose", 2), ("exchange", 0), ("lift", "frames", 1)]
+        del log[:]
+        with pytest.raises(RuntimeError, match="queued ahead"):
+            model.encode(P, scenes[3])                                # scene 2 is pending in slot 0
+        model.encode(P, scenes[2])                                    # nothing queued behind it
+        assert log == [("wait", 0), ("lift", "frames", 0)]
+        del log[:]
+        model.encode(P, scenes[3])                                    # back to one exchange per encode, alternating slots
+        assert log == [("own", 1), ("transpose", 2), ("exchange", 1), ("wait", 1), ("lift", "frames", 1)]
+    model.shard_scene(p2p=False)
+    assert model.queue_next_frames(scenes[0]) is False
